@@ -1,0 +1,208 @@
+"""Host-side mesh mirror: OpenFOAM polyMesh layout as numpy arrays.
+
+`PolyMesh` holds exactly what constant/polyMesh/{points,faces,owner,neighbour,
+boundary} hold; `hex_block` is the blockMesh equivalent used by the reference's
+test case (tutorials/test/plicVofAdvectionFoam/system/blockMeshDict:17-90) and
+can also emit one sub-block of a decomposed box with processor patches in
+OpenFOAM's convention (physical patches first, processor patches after, faces
+of a processor patch in the same order on both sides).
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import capi
+
+
+@dataclass
+class Patch:
+    name: str
+    start: int
+    size: int
+    kind: int = capi.PATCH_GENERIC
+    nbr_rank: int = -1
+    alpha_bc: int = capi.BC_ZERO_GRADIENT
+    alpha_value: float = 0.0
+
+
+@dataclass
+class PolyMesh:
+    points: np.ndarray          # [nP,3] f64
+    face_offsets: np.ndarray    # [nF+1] i32
+    face_points: np.ndarray     # [sum] i32
+    owner: np.ndarray           # [nF] i32
+    neighbour: np.ndarray       # [nIF] i32
+    patches: list = field(default_factory=list)
+    n_cells: int = 0
+    # global addressing of a decomposed block (cellProcAddressing-style), optional
+    cell_global: np.ndarray = None
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_points(self):
+        return self.points.shape[0]
+
+    @property
+    def n_faces(self):
+        return self.owner.shape[0]
+
+    @property
+    def n_internal_faces(self):
+        return self.neighbour.shape[0]
+
+    @property
+    def n_boundary_faces(self):
+        return self.n_faces - self.n_internal_faces
+
+    def to_c(self):
+        """svof_mesh struct (+ keep-alive list for the arrays it points into)."""
+        pts = capi.f64(self.points.reshape(-1))
+        fo, fp = capi.i32(self.face_offsets), capi.i32(self.face_points)
+        own, nei = capi.i32(self.owner), capi.i32(self.neighbour)
+        parr = (capi.SvofPatch * max(1, len(self.patches)))()
+        for i, p in enumerate(self.patches):
+            parr[i] = capi.SvofPatch(p.start, p.size, p.kind, p.nbr_rank, p.alpha_bc, 0, p.alpha_value)
+        m = capi.SvofMesh()
+        m.n_points, m.n_faces, m.n_internal_faces = self.n_points, self.n_faces, self.n_internal_faces
+        m.n_cells, m.n_patches = self.n_cells, len(self.patches)
+        m.points, m.face_offsets, m.face_points = capi.dptr(pts), capi.iptr(fo), capi.iptr(fp)
+        m.owner, m.neighbour = capi.iptr(own), capi.iptr(nei)
+        m.patches = C.cast(parr, C.POINTER(capi.SvofPatch))
+        m.Cf = m.Sf = m.C = m.V = None
+        return m, [pts, fo, fp, own, nei, parr]
+
+    def face_centres_simple(self):
+        """Vertex-mean face centres (exact for planar parallelograms); used only to
+        sample analytic velocity fields in the harness, never by the solver."""
+        n = np.diff(self.face_offsets)
+        s = np.add.reduceat(self.points[self.face_points], self.face_offsets[:-1], axis=0)
+        return s / n[:, None]
+
+
+# patch order and names of tutorials/test/plicVofAdvectionFoam/system/blockMeshDict:44-90
+_HEX_PATCHES = [("top", 2, 1), ("left", 1, 0), ("back", 0, 0), ("right", 1, 1), ("bottom", 2, 0), ("front", 0, 1)]
+
+
+def hex_block(n, lo=(0, 0, 0), hi=None, length=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), proc_nbr=None):
+    """Uniform hex mesh of cells [lo,hi) out of a global n=(Nx,Ny,Nz) box.
+
+    Natural cell order c = i + nx*j + nx*ny*k, upper-triangular face order (what
+    blockMesh emits).  `proc_nbr` maps (axis, side) -> neighbour rank for sides
+    that are cut by a decomposition; those become processor patches listed after
+    the six physical patches (zero-sized where the side is not physical).
+    """
+    N = np.array(n if np.ndim(n) else (n, n, n), dtype=np.int64)
+    lo = np.array(lo, dtype=np.int64)
+    hi = N.copy() if hi is None else np.array(hi, dtype=np.int64)
+    nx, ny, nz = (hi - lo).tolist()
+    proc_nbr = dict(proc_nbr or {})
+    h = np.array(length, dtype=np.float64) / N
+
+    # points: coordinates computed from GLOBAL indices so sub-blocks are bit-identical to the full mesh
+    # (blockMesh-like: vertices at exact fractions i/N of the edge)
+    gx = origin[0] + length[0] * ((lo[0] + np.arange(nx + 1)) / N[0])
+    gy = origin[1] + length[1] * ((lo[1] + np.arange(ny + 1)) / N[1])
+    gz = origin[2] + length[2] * ((lo[2] + np.arange(nz + 1)) / N[2])
+    px, py, pz = nx + 1, ny + 1, nz + 1
+    pts = np.empty((pz, py, px, 3), dtype=np.float64)
+    pts[..., 0] = gx[None, None, :]
+    pts[..., 1] = gy[None, :, None]
+    pts[..., 2] = gz[:, None, None]
+    pts = pts.reshape(-1, 3)
+
+    def pid(i, j, k):
+        return (i + px * (j + py * k)).astype(np.int32)
+
+    def cid(i, j, k):
+        return (i + nx * (j + ny * k)).astype(np.int32)
+
+    K, J, I = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
+    c = cid(I, J, K)
+
+    # internal faces: per cell (ascending) the faces towards +x, +y, +z neighbours
+    def xface(i, j, k):   # plane i (point index), normal +x
+        return np.stack([pid(i, j, k), pid(i, j + 1, k), pid(i, j + 1, k + 1), pid(i, j, k + 1)], axis=1)
+
+    def yface(i, j, k):   # plane j, normal +y
+        return np.stack([pid(i, j, k), pid(i, j, k + 1), pid(i + 1, j, k + 1), pid(i + 1, j, k)], axis=1)
+
+    def zface(i, j, k):   # plane k, normal +z
+        return np.stack([pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)], axis=1)
+
+    mx, my, mz = I < nx - 1, J < ny - 1, K < nz - 1
+    # slot = 3*cell + axis keeps (owner asc, neighbour asc) order
+    slot = np.concatenate([3 * c[mx].astype(np.int64), 3 * c[my].astype(np.int64) + 1, 3 * c[mz].astype(np.int64) + 2])
+    fpts = np.concatenate([xface(I[mx] + 1, J[mx], K[mx]), yface(I[my], J[my] + 1, K[my]), zface(I[mz], J[mz], K[mz] + 1)])
+    own = np.concatenate([c[mx], c[my], c[mz]])
+    nei = np.concatenate([cid(I[mx] + 1, J[mx], K[mx]), cid(I[my], J[my] + 1, K[my]), cid(I[mz], J[mz], K[mz] + 1)])
+    order = np.argsort(slot, kind="stable")
+    fpts, own, nei = fpts[order], own[order], nei[order]
+    n_if = own.shape[0]
+
+    # boundary faces (outward normals), per side
+    def side_faces(axis, side):
+        if axis == 0:
+            k, j = np.meshgrid(np.arange(nz), np.arange(ny), indexing="ij")
+            j, k = j.reshape(-1), k.reshape(-1)
+            i = np.full_like(j, 0 if side == 0 else nx - 1)
+            f = xface(i + side, j, k)
+        elif axis == 1:
+            k, i = np.meshgrid(np.arange(nz), np.arange(nx), indexing="ij")
+            i, k = i.reshape(-1), k.reshape(-1)
+            j = np.full_like(i, 0 if side == 0 else ny - 1)
+            f = yface(i, j + side, k)
+        else:
+            j, i = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
+            i, j = i.reshape(-1), j.reshape(-1)
+            k = np.full_like(i, 0 if side == 0 else nz - 1)
+            f = zface(i, j, k + side)
+        if side == 0:
+            f = f[:, [0, 3, 2, 1]]  # reverse to point outward (-axis)
+        return f, cid(i, j, k)
+
+    b_fpts, b_own, patches = [], [], []
+    start = n_if
+    for name, axis, side in _HEX_PATCHES:
+        physical = (lo[axis] == 0) if side == 0 else (hi[axis] == N[axis])
+        if physical and (axis, side) not in proc_nbr:
+            f, o = side_faces(axis, side)
+        else:
+            f, o = np.zeros((0, 4), np.int32), np.zeros((0,), np.int32)
+        patches.append(Patch(name, start, f.shape[0]))
+        b_fpts.append(f)
+        b_own.append(o)
+        start += f.shape[0]
+    for (axis, side), nbr in sorted(proc_nbr.items(), key=lambda kv: kv[1]):
+        f, o = side_faces(axis, side)
+        patches.append(Patch("procBoundaryTo%d" % nbr, start, f.shape[0], kind=capi.PATCH_PROCESSOR, nbr_rank=int(nbr)))
+        b_fpts.append(f)
+        b_own.append(o)
+        start += f.shape[0]
+
+    face_points = np.concatenate([fpts] + b_fpts).astype(np.int32).reshape(-1)
+    owner = np.concatenate([own] + b_own).astype(np.int32)
+    n_f = owner.shape[0]
+    face_offsets = (4 * np.arange(n_f + 1, dtype=np.int64)).astype(np.int32)
+    gi, gj, gk = I + lo[0], J + lo[1], K + lo[2]
+    cell_global = (gi + N[0] * (gj + N[1] * gk)).astype(np.int64)
+    return PolyMesh(points=pts, face_offsets=face_offsets, face_points=face_points, owner=owner,
+                    neighbour=nei.astype(np.int32), patches=patches, n_cells=nx * ny * nz, cell_global=cell_global,
+                    meta={"kind": "hex_block", "N": N.tolist(), "lo": lo.tolist(), "hi": hi.tolist(),
+                          "h": h.tolist(), "origin": list(origin), "length": list(length)})
+
+
+def cell_centres_hex(mesh):
+    """Cell centres of a hex_block mesh from its metadata (harness use only)."""
+    N, lo, hi = (np.array(mesh.meta[k]) for k in ("N", "lo", "hi"))
+    L, o = np.array(mesh.meta["length"]), np.array(mesh.meta["origin"])
+    nx, ny, nz = (hi - lo).tolist()
+    cx = o[0] + L[0] * ((lo[0] + np.arange(nx) + 0.5) / N[0])
+    cy = o[1] + L[1] * ((lo[1] + np.arange(ny) + 0.5) / N[1])
+    cz = o[2] + L[2] * ((lo[2] + np.arange(nz) + 0.5) / N[2])
+    C3 = np.empty((nz, ny, nx, 3))
+    C3[..., 0] = cx[None, None, :]
+    C3[..., 1] = cy[None, :, None]
+    C3[..., 2] = cz[:, None, None]
+    return C3.reshape(-1, 3)

@@ -1,0 +1,286 @@
+/*
+ * svof.h -- C ABI of the B200-native SimPLIC volume-fraction transport step.
+ *
+ * This is the drop-in boundary for the one hot path of daidezhi/geometricVofExt:
+ *     geometricVofExt::SimPLIC::solveVofEqu::reconstruct() + advect(Sp, Su)
+ * Everything crossing it is a plain pointer + size (SoA, int32 labels, IEEE
+ * double scalars: the reference's `arch "LSB;label=32;scalar=64"`).  There are
+ * no C++/torch types in any signature, so it can be bound from C++ (the
+ * OpenFOAM adapter in INTEGRATION.md), ctypes, cgo or JNI alike.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative
+ * to the reference tree).  Every function returns 0 on success or a negative
+ * svof_status; the library never calls exit()/abort() (the reference would
+ * FatalError-abort, e.g. reconstruction.C:610-625, advectionTemplates.C:58-63;
+ * the adapter turns a non-zero return into FatalErrorInFunction).
+ *
+ * Two shared objects implement this header with identical semantics:
+ *   geometricvofext_b200/lib/libsvof_b200.so   -- the product: CUDA, sm_100a
+ *   oracle/_build/libsvof_oracle.so            -- test infrastructure only: a
+ *        single-threaded CPU restatement of the reference algorithm
+ */
+#ifndef SVOF_H
+#define SVOF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVOF_ABI_VERSION 1
+
+typedef struct svof_handle svof_handle;
+
+typedef enum {
+    SVOF_OK = 0,
+    SVOF_ERR_INVALID_ARG = -1,   /* null pointer, bad size, unknown key      */
+    SVOF_ERR_BAD_MESH = -2,      /* inconsistent connectivity / patch table  */
+    SVOF_ERR_BAD_CONFIG = -3,    /* e.g. invalid orientationMethod           */
+    SVOF_ERR_CUDA = -4,          /* CUDA runtime error (text in last_error)  */
+    SVOF_ERR_COMM = -5,          /* halo exchange / peer mapping error       */
+    SVOF_ERR_CAPACITY = -6,      /* polygon/polyhedron exceeds a device cap  */
+    SVOF_ERR_STATE = -7,         /* call order (advect before fields set...) */
+    SVOF_ERR_UNSUPPORTED = -8
+} svof_status;
+
+/* polyPatch classes that matter to the path (advectionTemplates.C:66-70,
+ * advection.C:403,425).  Everything that is neither empty nor processor is
+ * GENERIC (wall, patch, ...). */
+typedef enum {
+    SVOF_PATCH_GENERIC = 0,
+    SVOF_PATCH_EMPTY = 1,
+    SVOF_PATCH_PROCESSOR = 2
+} svof_patch_kind;
+
+/* alpha boundary conditions used by the reference's cases:
+ * zeroGradient (tutorials/test/plicVofAdvectionFoam/0.orig/alpha.water),
+ * inletOutlet (tutorials/solvers/interPlicFoam/damBreakWithObstacle/0.orig/alpha.water),
+ * fixedValue. */
+typedef enum {
+    SVOF_BC_ZERO_GRADIENT = 0,
+    SVOF_BC_FIXED_VALUE = 1,
+    SVOF_BC_INLET_OUTLET = 2
+} svof_alpha_bc;
+
+typedef struct {
+    int32_t start;        /* first face (global face index, >= n_internal_faces) */
+    int32_t size;         /* number of faces                                      */
+    int32_t kind;         /* svof_patch_kind                                      */
+    int32_t nbr_rank;     /* processor patches: neighbour rank, else -1           */
+    int32_t alpha_bc;     /* svof_alpha_bc (GENERIC patches)                      */
+    int32_t reserved;
+    double alpha_value;   /* fixedValue value / inletOutlet inletValue            */
+} svof_patch;
+
+/* polyMesh in OpenFOAM's own layout (constant/polyMesh/{points,faces,owner,
+ * neighbour,boundary}): faces [0,n_internal_faces) are internal, boundary
+ * faces follow patch by patch. */
+typedef struct {
+    int32_t n_points;
+    int32_t n_faces;
+    int32_t n_internal_faces;
+    int32_t n_cells;
+    int32_t n_patches;
+    int32_t reserved;
+    const double* points;        /* [3*n_points] xyz interleaved              */
+    const int32_t* face_offsets; /* [n_faces+1] CSR into face_points          */
+    const int32_t* face_points;  /* point labels, owner-outward orientation   */
+    const int32_t* owner;        /* [n_faces]                                 */
+    const int32_t* neighbour;    /* [n_internal_faces]                        */
+    const svof_patch* patches;   /* [n_patches], ascending start              */
+    /* Optional host geometry (fvMesh::Cf/Sf/C/V).  NULL => derived with
+     * OpenFOAM's primitiveMeshTools formulas. */
+    const double* Cf;            /* [3*n_faces] or NULL */
+    const double* Sf;            /* [3*n_faces] or NULL */
+    const double* C;             /* [3*n_cells] or NULL */
+    const double* V;             /* [n_cells]   or NULL */
+} svof_mesh;
+
+/* orientationMethod (reconstruction.C:60-68) */
+typedef enum {
+    SVOF_ORIENT_ALPHA_GRAD = 0,     /* "alphaGrad"                       */
+    SVOF_ORIENT_ISO_ALPHA_GRAD = 1, /* "isoAlphaGrad" | "LS"  (default)  */
+    SVOF_ORIENT_ISO_RDF = 2         /* "isoRDF" | "RDF"                  */
+} svof_orientation;
+
+/* The fvSolution solvers."alpha.*" keys the path reads
+ * (reconstruction.C:502-516, advection.C:455-457) plus the two isoAdvector
+ * names the north star lists (surfCellTol -> alias of mixedCellTol,
+ * isoFaceTol -> accepted and ignored: SimPLIC's plane position is analytic). */
+typedef struct {
+    double mixed_cell_tol;      /* mixedCellTol   1e-8   */
+    double snap_tol;            /* snapTol        0      */
+    double iso_face_tol;        /* isoFaceTol     (ignored, recorded)      */
+    double rdf_tol;             /* tol            1e-6   (isoRDF only)     */
+    double rdf_rel_tol;         /* relTol         0.1    (isoRDF only)     */
+    int32_t n_alpha_bounds;     /* nAlphaBounds   10     */
+    int32_t clip;               /* clip           true   */
+    int32_t orientation_method; /* svof_orientation, default ISO_ALPHA_GRAD */
+    int32_t split_warped_face;  /* splitWarpedFace false */
+    int32_t map_alpha_field;    /* mapAlphaField  false  */
+    int32_t write_plic_fields;  /* writePlicFields false */
+    int32_t rdf_iterations;     /* iterations     5      (isoRDF only)     */
+    int32_t mixed_cell_tol_set; /* internal: explicit mixedCellTol wins over surfCellTol */
+} svof_params;
+
+/* One handle <-> one rank <-> one GPU (one MPI rank of the reference).
+ * Peer-memory halo exchange is bootstrapped by the host however it likes
+ * (torch.distributed in bench.py, MPI inside OpenFOAM): see svof_comm_*. */
+typedef struct {
+    int32_t rank;
+    int32_t world_size;
+    int32_t device;   /* CUDA device ordinal, -1 => rank % deviceCount */
+    int32_t reserved;
+} svof_comm;
+
+/* ---- configuration -------------------------------------------------------- */
+
+/* Defaults of reconstruction.C:502-516 / advection.C:455-457. */
+int svof_params_default(svof_params* p);
+
+/* Set one fvSolution key from its dictionary text ("nAlphaBounds","3"),
+ * ("clip","false"), ("orientationMethod","LS"), ("surfCellTol","1e-8")...
+ * Unknown keys return SVOF_ERR_INVALID_ARG; keys of the same dictionary that
+ * belong to the caller (nAlphaSubCycles, cAlpha, period, reverseTime) are
+ * accepted and ignored. */
+int svof_params_set(svof_params* p, const char* key, const char* value);
+
+/* ---- life cycle ------------------------------------------------------------ */
+
+/* Replaces the solveVofEqu constructor (solveVofEqu.C:55-91), i.e. the
+ * reconstruction ctor (reconstruction.C:478-629, incl. updateFaceFlatness
+ * :408-473) and the advection ctor (advection.C:437-522). */
+int svof_create(const svof_mesh* mesh, const svof_params* params,
+                const svof_comm* comm, svof_handle** out);
+int svof_destroy(svof_handle* h);
+
+/* Text of the last error on this handle (or of the last failed svof_create
+ * when h == NULL).  Never NULL. */
+const char* svof_last_error(const svof_handle* h);
+
+/* ---- fields in (host pointers) ------------------------------------------- */
+
+/* alpha1 internal field [n_cells]; boundary values are evaluated from the patch
+ * BCs (volScalarField::correctBoundaryConditions).  Also resets alpha.oldTime. */
+int svof_set_alpha(svof_handle* h, const double* alpha);
+/* phi: face volume flux [n_faces] (internal then boundary faces, patch order;
+ * surfaceScalarField primitive + boundary fields flattened). */
+int svof_set_phi(svof_handle* h, const double* phi);
+/* U: cell values [3*n_cells] and boundary-face values [3*(n_faces-n_internal)]
+ * (volVectorField internal + boundary field after correctBoundaryConditions),
+ * consumed by the interface-velocity interpolation (advection.C:91,126). */
+int svof_set_U(svof_handle* h, const double* U, const double* Ub);
+
+/* ---- the step --------------------------------------------------------------- */
+
+/* solveVofEqu::reconstruct()  (solveVofEqu.C:96-99 -> reconstruction.C:680-722) */
+int svof_reconstruct(svof_handle* h);
+
+/* solveVofEqu::advect(Sp,Su)  (solveVofEquTemplates.C:35-43 ->
+ * advectionTemplates.C:352-418).  Sp/Su: [n_cells] or NULL for zeroField
+ * (interPlicFoam/alphaSuSp.H:1-2).  alpha.oldTime() is the alpha held at entry. */
+int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su);
+
+/* Host-pointer convenience = set_phi + set_U + reconstruct + advect + read back
+ * alpha (and alphaPhi if non-NULL): the end-to-end call bench.py times. */
+int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U,
+                   const double* Ub, double* alpha_out, double* alpha_phi_out);
+
+/* ---- fields out -------------------------------------------------------------- */
+
+typedef enum {
+    SVOF_F_ALPHA = 0,        /* f64 [n_cells]                                     */
+    SVOF_F_ALPHA_PHI = 1,    /* f64 [n_faces]   advection::alphaPhi()             */
+    SVOF_F_DVF = 2,          /* f64 [n_faces]   dVf_ after the step               */
+    SVOF_F_INTERFACE_N = 3,  /* f64 [3*n_cells] reconstruction::interfaceN()      */
+    SVOF_F_INTERFACE_D = 4,  /* f64 [n_cells]                                     */
+    SVOF_F_INTERFACE_C = 5,  /* f64 [3*n_cells]                                   */
+    SVOF_F_INTERFACE_S = 6,  /* f64 [3*n_cells]                                   */
+    SVOF_F_MIXED_CELLS = 7,  /* i32 [n_mixed]   reconstruction::mixedCells()      */
+    SVOF_F_CELL_STATUS = 8,  /* i32 [n_mixed]   reconstruction::cellStatus()      */
+    SVOF_F_FACE_FLATNESS = 9,/* f64 [n_faces]   reconstruction::faceFlatness()    */
+    SVOF_F_CF = 10,          /* f64 [3*n_faces] mesh geometry as used             */
+    SVOF_F_SF = 11,          /* f64 [3*n_faces]                                   */
+    SVOF_F_C = 12,           /* f64 [3*n_cells]                                   */
+    SVOF_F_V = 13,           /* f64 [n_cells]                                     */
+    SVOF_F_ALPHA_BOUNDARY = 14, /* f64 [n_faces-n_internal] alpha patch values    */
+    SVOF_F_UN0 = 15,         /* f64 [n_mixed] interface normal speed (advection.C:126) */
+    SVOF_F_COUNT_
+} svof_field;
+
+/* Copy a field to host memory.  capacity is in ELEMENTS of the field's type;
+ * returns the number of elements written (>= 0) or a negative status. */
+int64_t svof_get_field(svof_handle* h, int which, void* dst, int64_t capacity);
+
+typedef enum {
+    SVOF_I_N_MIXED = 0,          /* mixedCells().size() of the last reconstruct   */
+    SVOF_I_MIN_ALPHA_BEFORE = 1, /* "Before conservative bounding" log values     */
+    SVOF_I_MAX_ALPHA_M1_BEFORE = 2,
+    SVOF_I_MIN_ALPHA_AFTER = 3,  /* "After  conservative bounding"                */
+    SVOF_I_MAX_ALPHA_M1_AFTER = 4,
+    SVOF_I_N_BOUND_SWEEPS = 5,   /* sweeps executed by limitFlux                  */
+    SVOF_I_RECONSTRUCTION_TIME = 6, /* s, cumulative (reconstruction.C:721)       */
+    SVOF_I_ADVECTION_TIME = 7,      /* s, cumulative (advectionTemplates.C:415)   */
+    SVOF_I_ALPHA_MAPPING_TIME = 8,
+    SVOF_I_VOLUME = 9,           /* sum(alpha*V) (plicVof.H:44-46)                */
+    SVOF_I_GPU_LAUNCHES = 10,    /* kernels launched so far (0 for the oracle)    */
+    SVOF_I_FLATNESS_MIN = 11, SVOF_I_FLATNESS_MAX = 12, SVOF_I_FLATNESS_AVG = 13,
+    SVOF_I_DEVICE_BYTES = 14,
+    SVOF_I_ERROR_FLAGS = 15,     /* device-side capacity flags, 0 = clean         */
+    SVOF_I_COUNT_
+} svof_info;
+
+int svof_get_info(svof_handle* h, int which, double* out);
+
+/* Device-resident access for callers that already live on the GPU (the
+ * benchmark's roofline leg).  Returns a CUDA device pointer valid until
+ * svof_destroy.  The oracle returns SVOF_ERR_UNSUPPORTED. */
+int svof_device_ptr(svof_handle* h, int which, void** dptr);
+/* Tell the handle that a device-resident input (ALPHA, via svof_device_ptr) was
+ * overwritten in place by the caller. */
+int svof_device_touch(svof_handle* h, int which);
+/* phi/U staged on device already: same as svof_set_phi/svof_set_U but
+ * device-to-device (CUDA library only). */
+int svof_set_phi_device(svof_handle* h, const void* dphi);
+int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
+/* Block until all device work queued by this handle has finished. */
+int svof_synchronize(svof_handle* h);
+/* Elapsed device time (ms, CUDA events on the handle's own stream) of the
+ * most recent svof_reconstruct + svof_advect pair. */
+int svof_last_step_ms(svof_handle* h, double* reconstruct_ms, double* advect_ms);
+
+/* ---- geometry primitives (unit-test / utility surface) -------------------- */
+/* These expose the L1 geometry kernels of the reference on caller-supplied
+ * polygons/planes, for known-answer tests and for utilities such as
+ * setVofField/exportPlicSurface.H:20-27 that call cutCell directly. */
+
+/* cutFace::calcSubFace (cutFace.C:136-259) on n_polys polygons sharing one
+ * vertex count n_verts: pts[n_polys][n_verts][3], plane (normal[3], dist) per
+ * polygon.  Out: status[n_polys], centre[3*n_polys], area[3*n_polys]. */
+int svof_cut_faces(svof_handle* h, int32_t n_polys, int32_t n_verts, const double* pts,
+                   const double* normals, const double* dists, int32_t* status,
+                   double* centres, double* areas);
+
+/* cutCell::calcSubCell (cutCell.C:343-542) for a list of mesh cells with given
+ * planes.  Out per cell: status, VOF, sub-cell volume, interface centre[3], area[3]. */
+int svof_cut_cells(svof_handle* h, int32_t n, const int32_t* cells, const double* normals,
+                   const double* dists, int32_t* status, double* vof, double* sub_volume,
+                   double* iface_centre, double* iface_area);
+
+/* cutCell::findSignedDistance (cutCell.C:611-799) for a list of mesh cells
+ * with given volume fractions and (unit) normals.  Out: status, D, C[3], S[3]. */
+int svof_find_signed_distance(svof_handle* h, int32_t n, const int32_t* cells,
+                              const double* alphas, const double* normals, int32_t* status,
+                              double* dists, double* iface_centre, double* iface_area);
+
+/* cutFace::timeIntegratedFaceFlux (cutFace.C:262-389) for a list of mesh
+ * faces.  Out: dVf[n]. */
+int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const double* normals,
+                     const double* dists, const double* Un0, double dt, const double* phi,
+                     double* dVf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVOF_H */

@@ -1,0 +1,55 @@
+"""Build recipe for the test oracle (TEST INFRASTRUCTURE ONLY).
+
+  oracle/_build/libsvof_oracle.so  -- CPU restatement of the reference algorithm
+                                      (oracle/*.hpp, svof_oracle.cpp), g++ only.
+  oracle/_ref/libref_overlap.so    -- the reference's own vendored overlap.hpp +
+                                      Eigen compiled from /root/reference (only
+                                      when that tree is present, i.e. in the build
+                                      container; the GPU box uses the prebuilt file).
+
+Both directories are git-ignored and are NOT gpurun-ignored.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_APP = "/root/reference/applications/test/calcExactVofFieldForSphericalShapeInHexMesh"
+ORACLE_SO = os.path.join(HERE, "_build", "libsvof_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_overlap.so")
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
+
+
+def build_oracle(force=False):
+    srcs = [os.path.join(HERE, f) for f in
+            ("svof_oracle.cpp", "ora_vec.hpp", "ora_mesh.hpp", "ora_cut.hpp", "ora_solver.hpp")]
+    srcs.append(os.path.join(HERE, "..", "include", "svof.h"))
+    if force or _stale(ORACLE_SO, srcs):
+        os.makedirs(os.path.dirname(ORACLE_SO), exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+               "-Wall", "-o", ORACLE_SO, srcs[0]]
+        subprocess.check_call(cmd)
+    return ORACLE_SO
+
+
+def build_ref(force=False):
+    """Compile the reference's overlap.hpp where it lies; returns path or None."""
+    if not os.path.isdir(REF_APP):
+        return REF_SO if os.path.exists(REF_SO) else None
+    src = os.path.join(HERE, "ref_sphere_overlap.cpp")
+    if force or _stale(REF_SO, [src]):
+        os.makedirs(os.path.dirname(REF_SO), exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-w", "-I", REF_APP, "-o", REF_SO, src]
+        subprocess.check_call(cmd)
+    return REF_SO
+
+
+if __name__ == "__main__":
+    print(build_oracle(force="--force" in sys.argv))
+    print(build_ref(force="--force" in sys.argv))
