@@ -1,0 +1,1078 @@
+// svof_b200.cu -- host side of the B200-native SimPLIC step: the handle, the one-off mesh
+// precompute, the per-step launch sequence and the C ABI of include/svof.h.
+//
+// One handle <-> one rank <-> one GPU <-> one CUDA stream.  All numerics run in the kernels of
+// svof_kernels.cuh; this file only builds CSR tables, owns device memory and orders launches.
+// There is no CPU fallback: every entry point either runs on the device or returns an error.
+//
+// Build (see geometricvofext_b200/build.py):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xcompiler -fPIC -shared
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/svof.h"
+#include "svof_geom_kernels.cuh"
+
+using namespace svof;
+
+namespace {
+
+thread_local std::string g_createError;
+
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kind = -1;  // 0 reconstruct, 1 advect
+    bool pending = false;
+};
+
+}  // namespace
+
+struct svof_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
+    std::vector<svof_patch> patches;
+    svof_params prm;
+    StepParams sp;
+    MeshDev md;
+    int variant = 0;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    std::string err;
+
+    // fields
+    double* alphaBuf[2] = {nullptr, nullptr};
+    int cur = 0;
+    double* alphaBBuf[2] = {nullptr, nullptr};
+    int cb = 0;
+    double *phi = nullptr, *alphaPhi = nullptr, *U = nullptr, *Ub = nullptr, *Sp = nullptr, *Su = nullptr;
+    double *iN = nullptr, *iD = nullptr, *iC = nullptr, *iS = nullptr, *Un0 = nullptr;
+    int *cellSlot = nullptr, *mixedCells = nullptr, *cellStatus = nullptr;
+    unsigned int *mixedBits = nullptr, *near1 = nullptr, *near2 = nullptr, *blockSums = nullptr;
+    int* near2List = nullptr;
+    int2* work = nullptr;
+    int capWork = 0, capMixed = 0, capNear = 0, nWords = 0, nScanBlocks = 0;
+    double *dVfGeo = nullptr, *dVf = nullptr, *corr = nullptr, *scratchF = nullptr;
+    int *corrBy = nullptr, *corrPos = nullptr, *oobList = nullptr;
+    unsigned char* oobState = nullptr;
+    Ctl* ctl = nullptr;
+    Ctl* hctl = nullptr;  // pinned mirror
+    PatchDev* dPatches = nullptr;
+    int* bPatch = nullptr;
+    double* partial = nullptr;
+    double* hpartial = nullptr;
+
+    bool haveAlpha = false, havePhi = false, haveU = false, bitsValid = false, advected = false;
+    double lastDt = 0.0;
+    long long launches = 0;
+    double reconTime = 0, advTime = 0, lastReconMs = 0, lastAdvMs = 0;
+    double flatMin = 1, flatMax = 1, flatAvg = 1;
+    std::vector<EventPair> events;
+    size_t evNext = 0;
+    int sms = 148;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw std::runtime_error(buf_);                                                        \
+        }                                                                                          \
+    } while (0)
+
+template <class T>
+T* dalloc(svof_handle* h, size_t n, bool zero = true)
+{
+    void* p = nullptr;
+    const size_t b = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&p, b));
+    if (zero) CK(cudaMemsetAsync(p, 0, b, h->stream));
+    h->allocs.push_back(p);
+    h->bytes += b;
+    return (T*)p;
+}
+template <class T>
+T* dupload(svof_handle* h, const T* src, size_t n)
+{
+    T* p = dalloc<T>(h, n, false);
+    if (n) CK(cudaMemcpyAsync(p, src, n * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return p;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline int sparseGrid(svof_handle* h, int threads) { return h->sms * (1024 / threads > 0 ? 1024 / threads : 1); }
+
+#define LAUNCH(h, kern, grid, block, ...)                        \
+    do {                                                         \
+        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);  \
+        (h)->launches++;                                         \
+    } while (0)
+
+// dispatch a capacity-variant launcher (explicitly instantiated in svof_inst.cu)
+#define GEO(h, fn, ...)                                               \
+    do {                                                              \
+        switch ((h)->variant) {                                       \
+            case 0: GeoLaunch<CapsHex>::fn(__VA_ARGS__); break;       \
+            case 1: GeoLaunch<CapsSmall>::fn(__VA_ARGS__); break;     \
+            case 2: GeoLaunch<CapsPoly>::fn(__VA_ARGS__); break;      \
+            default: GeoLaunch<CapsSplit>::fn(__VA_ARGS__); break;    \
+        }                                                             \
+        (h)->launches++;                                              \
+    } while (0)
+
+void buildMesh(svof_handle* h, const svof_mesh& m)
+{
+    if (!m.points || !m.face_offsets || !m.face_points || !m.owner || (m.n_internal_faces > 0 && !m.neighbour) ||
+        (m.n_patches > 0 && !m.patches))
+        throw std::invalid_argument("svof_mesh: null connectivity pointer");
+    const int nP = m.n_points, nF = m.n_faces, nIF = m.n_internal_faces, nC = m.n_cells, nBF = nF - nIF;
+    if (nP <= 0 || nF <= 0 || nC <= 0 || nIF < 0 || nIF > nF) throw std::invalid_argument("svof_mesh: bad sizes");
+    h->nP = nP; h->nF = nF; h->nIF = nIF; h->nC = nC; h->nBF = nBF;
+    h->patches.assign(m.patches, m.patches + m.n_patches);
+    const int* fo = m.face_offsets;
+    const int* fp = m.face_points;
+    const int* own = m.owner;
+    const int* nei = m.neighbour;
+    int maxFV = 0;
+    for (int f = 0; f < nF; ++f) {
+        const int nv = fo[f + 1] - fo[f];
+        if (nv < 3) throw std::invalid_argument("svof_mesh: face with < 3 points");
+        if (own[f] < 0 || own[f] >= nC) throw std::invalid_argument("svof_mesh: owner out of range");
+        if (f < nIF && (nei[f] < 0 || nei[f] >= nC)) throw std::invalid_argument("svof_mesh: neighbour out of range");
+        maxFV = std::max(maxFV, nv);
+    }
+    if (maxFV > 255) throw std::invalid_argument("svof_mesh: face with > 255 points");
+    const long long nFP = fo[nF];
+    for (long long i = 0; i < nFP; ++i)
+        if (fp[i] < 0 || fp[i] >= nP) throw std::invalid_argument("svof_mesh: point label out of range");
+
+    // patch table must tile the boundary faces in order
+    std::vector<unsigned char> bKind(std::max(nBF, 1), 0);
+    std::vector<int> bPatch(std::max(nBF, 1), 0);
+    std::vector<PatchDev> pd(std::max<size_t>(h->patches.size(), 1));
+    int expect = nIF;
+    for (size_t pi = 0; pi < h->patches.size(); ++pi) {
+        const svof_patch& p = h->patches[pi];
+        if (p.start != expect || p.size < 0 || p.start + p.size > nF)
+            throw std::invalid_argument("svof_mesh: patches must tile the boundary faces in order");
+        if (p.kind < 0 || p.kind > 2) throw std::invalid_argument("svof_mesh: unknown patch kind");
+        for (int k = 0; k < p.size; ++k) {
+            bKind[p.start - nIF + k] = (unsigned char)p.kind;
+            bPatch[p.start - nIF + k] = (int)pi;
+        }
+        pd[pi].start = p.start; pd[pi].size = p.size; pd[pi].kind = p.kind; pd[pi].bc = p.alpha_bc; pd[pi].value = p.alpha_value;
+        expect += p.size;
+    }
+    if (expect != nF) throw std::invalid_argument("svof_mesh: patches do not cover all boundary faces");
+
+    // cells(): owned faces ascending, then neighbour-side faces ascending (primitiveMesh::calcCells)
+    std::vector<int> cellOff(nC + 1, 0);
+    for (int f = 0; f < nF; ++f) cellOff[own[f] + 1]++;
+    for (int f = 0; f < nIF; ++f) cellOff[nei[f] + 1]++;
+    for (int c = 0; c < nC; ++c) cellOff[c + 1] += cellOff[c];
+    const int nCF = cellOff[nC];
+    std::vector<int> cellFaces(nCF);
+    std::vector<int> nOwned(nC, 0);
+    {
+        std::vector<int> fill(cellOff.begin(), cellOff.end() - 1);
+        for (int f = 0; f < nF; ++f) { cellFaces[fill[own[f]]++] = f; nOwned[own[f]]++; }
+        for (int f = 0; f < nIF; ++f) cellFaces[fill[nei[f]]++] = f;
+    }
+    // ascending-face rows for the streaming kernel: merge of the two sorted runs
+    std::vector<int2> cellAsc(nCF);
+    int maxCF = 0;
+    for (int c = 0; c < nC; ++c) {
+        const int b = cellOff[c], e = cellOff[c + 1], mid = b + nOwned[c];
+        maxCF = std::max(maxCF, e - b);
+        int i = b, j = mid, o = b;
+        while (i < mid || j < e) {
+            const bool takeOwned = (j >= e) || (i < mid && cellFaces[i] < cellFaces[j]);
+            if (takeOwned) {
+                const int f = cellFaces[i++];
+                cellAsc[o++] = make_int2(f, f < nIF ? nei[f] : (-1 - (f - nIF)));
+            } else {
+                const int f = cellFaces[j++];
+                cellAsc[o++] = make_int2(f | (int)0x80000000, own[f]);
+            }
+        }
+    }
+    // cellPoints ascending; pointCells ascending
+    std::vector<int> cellPtOff(nC + 1, 0), cellPts;
+    cellPts.reserve((size_t)nC * 8);
+    int maxCP = 0;
+    {
+        std::vector<int> tmp;
+        for (int c = 0; c < nC; ++c) {
+            tmp.clear();
+            for (int k = cellOff[c]; k < cellOff[c + 1]; ++k) {
+                const int f = cellFaces[k];
+                tmp.insert(tmp.end(), fp + fo[f], fp + fo[f + 1]);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            cellPts.insert(cellPts.end(), tmp.begin(), tmp.end());
+            cellPtOff[c + 1] = (int)cellPts.size();
+            maxCP = std::max(maxCP, (int)tmp.size());
+        }
+    }
+    std::vector<int> ptCellOff(nP + 1, 0);
+    for (int p : cellPts) ptCellOff[p + 1]++;
+    for (int p = 0; p < nP; ++p) ptCellOff[p + 1] += ptCellOff[p];
+    std::vector<int> ptCells(ptCellOff[nP]);
+    {
+        std::vector<int> fill(ptCellOff.begin(), ptCellOff.end() - 1);
+        for (int c = 0; c < nC; ++c)
+            for (int k = cellPtOff[c]; k < cellPtOff[c + 1]; ++k) ptCells[fill[cellPts[k]]++] = c;
+    }
+    // boundary point -> boundary faces (ascending), patch points
+    std::vector<int> ptBFOff(nP + 1, 0);
+    std::vector<unsigned char> isPatchPoint(nP, 0);
+    for (int bf = 0; bf < nBF; ++bf) {
+        const int f = nIF + bf;
+        for (int k = fo[f]; k < fo[f + 1]; ++k) {
+            ptBFOff[fp[k] + 1]++;
+            if (bKind[bf] == SVOF_PATCH_GENERIC) isPatchPoint[fp[k]] = 1;
+        }
+    }
+    for (int p = 0; p < nP; ++p) ptBFOff[p + 1] += ptBFOff[p];
+    std::vector<int> ptBFaces(std::max(ptBFOff[nP], 1));
+    {
+        std::vector<int> fill(ptBFOff.begin(), ptBFOff.end() - 1);
+        for (int bf = 0; bf < nBF; ++bf) {
+            const int f = nIF + bf;
+            for (int k = fo[f]; k < fo[f + 1]; ++k) ptBFaces[fill[fp[k]]++] = bf;
+        }
+    }
+
+    // capacity variant
+    const bool split = h->prm.split_warped_face != 0;
+    int maxLocalFaces = maxCF, maxLocalPts = maxCP;
+    if (split) {  // worst case: every face triangulated
+        maxLocalFaces = 0;
+        for (int c = 0; c < nC; ++c) {
+            int s = 0;
+            for (int k = cellOff[c]; k < cellOff[c + 1]; ++k) s += fo[cellFaces[k] + 1] - fo[cellFaces[k]];
+            maxLocalFaces = std::max(maxLocalFaces, s);
+        }
+        maxLocalPts = maxCP + maxCF;
+    }
+    auto fits = [&](int fv, int cf, int cp) { return maxFV <= fv && maxLocalFaces <= cf && maxLocalPts <= cp; };
+    if (fits(CapsHex::MAXFV, CapsHex::MAXCF, CapsHex::MAXCP)) h->variant = 0;
+    else if (fits(CapsSmall::MAXFV, CapsSmall::MAXCF, CapsSmall::MAXCP)) h->variant = 1;
+    else if (fits(CapsPoly::MAXFV, CapsPoly::MAXCF, CapsPoly::MAXCP)) h->variant = 2;
+    else if (fits(CapsSplit::MAXFV, CapsSplit::MAXCF, CapsSplit::MAXCP)) h->variant = 3;
+    else {
+        char b[256];
+        snprintf(b, sizeof(b), "mesh exceeds the compiled polyhedron caps: face verts %d, cell faces %d, cell points %d",
+                 maxFV, maxLocalFaces, maxLocalPts);
+        throw std::length_error(b);
+    }
+    if (maxCF > 64) throw std::length_error("cells with more than 64 faces are not supported");
+
+    // upload
+    MeshDev& d = h->md;
+    d.nPoints = nP; d.nFaces = nF; d.nIF = nIF; d.nCells = nC; d.nBF = nBF;
+    d.points = dupload(h, m.points, (size_t)3 * nP);
+    d.faceOff = dupload(h, fo, (size_t)nF + 1);
+    d.facePts = dupload(h, fp, (size_t)nFP);
+    d.owner = dupload(h, own, (size_t)nF);
+    d.neighbour = dupload(h, nei, (size_t)nIF);
+    d.cellOff = dupload(h, cellOff.data(), cellOff.size());
+    d.cellFaces = dupload(h, cellFaces.data(), cellFaces.size());
+    d.cellAsc = dupload(h, cellAsc.data(), cellAsc.size());
+    d.cellPtOff = dupload(h, cellPtOff.data(), cellPtOff.size());
+    d.cellPts = dupload(h, cellPts.data(), cellPts.size());
+    d.ptCellOff = dupload(h, ptCellOff.data(), ptCellOff.size());
+    d.ptCells = dupload(h, ptCells.data(), ptCells.size());
+    d.ptBFOff = dupload(h, ptBFOff.data(), ptBFOff.size());
+    d.ptBFaces = dupload(h, ptBFaces.data(), ptBFaces.size());
+    d.bKind = dupload(h, bKind.data(), bKind.size());
+    d.isPatchPoint = dupload(h, isPatchPoint.data(), isPatchPoint.size());
+    h->dPatches = dupload(h, pd.data(), pd.size());
+    h->bPatch = dupload(h, bPatch.data(), bPatch.size());
+
+    double* Cf = dalloc<double>(h, (size_t)3 * nF);
+    double* Sf = dalloc<double>(h, (size_t)3 * nF);
+    double* magSf = dalloc<double>(h, nF);
+    double* C = dalloc<double>(h, (size_t)3 * nC);
+    double* V = dalloc<double>(h, nC);
+    double* flat = dalloc<double>(h, nF);
+    unsigned char* tetBase = dalloc<unsigned char>(h, nF);
+    const int haveFaceGeom = (m.Cf && m.Sf) ? 1 : 0;
+    if (haveFaceGeom) {
+        CK(cudaMemcpyAsync(Cf, m.Cf, sizeof(double) * 3 * nF, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(Sf, m.Sf, sizeof(double) * 3 * nF, cudaMemcpyHostToDevice, h->stream));
+    }
+    d.Cf = Cf; d.Sf = Sf; d.magSf = magSf; d.C = C; d.V = V; d.flat = flat; d.tetBase = tetBase;
+    LAUNCH(h, k_face_geom, cdiv(nF, 256), 256, d, Cf, Sf, magSf, haveFaceGeom);
+    if (m.C && m.V) {
+        CK(cudaMemcpyAsync(C, m.C, sizeof(double) * 3 * nC, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(V, m.V, sizeof(double) * nC, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        LAUNCH(h, k_cell_geom, cdiv(nC, 256), 256, d, C, V);
+    }
+    LAUNCH(h, k_flatness_tetbase, cdiv(nF, 256), 256, d, flat, tetBase);
+    CK(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
+
+    // "SimPLIC::Mesh face flatness: min/max/avg" (reconstruction.C:442-447)
+    {
+        std::vector<double> hf(nF), hm(nF);
+        CK(cudaMemcpy(hf.data(), flat, sizeof(double) * nF, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hm.data(), magSf, sizeof(double) * nF, cudaMemcpyDeviceToHost));
+        double mn = SV_VGREAT, mx = -SV_VGREAT, sfa = 0, sa = 0;
+        for (int f = 0; f < nF; ++f) {
+            mn = std::min(mn, hf[f]); mx = std::max(mx, hf[f]);
+            sfa += hf[f] * hm[f]; sa += hm[f];
+        }
+        h->flatMin = mn; h->flatMax = mx; h->flatAvg = sfa / sa;
+    }
+
+    // polyMesh::geometricD(): directions normal to empty patches are excluded (OF, recalled)
+    h->sp.geomD[0] = h->sp.geomD[1] = h->sp.geomD[2] = 1;
+    {
+        bool anyEmpty = false;
+        for (const svof_patch& p : h->patches) anyEmpty |= (p.kind == SVOF_PATCH_EMPTY && p.size > 0);
+        if (anyEmpty) {
+            std::vector<double> hs((size_t)3 * nF);
+            CK(cudaMemcpy(hs.data(), Sf, sizeof(double) * 3 * nF, cudaMemcpyDeviceToHost));
+            double e[3] = {0, 0, 0};
+            for (const svof_patch& p : h->patches) {
+                if (p.kind != SVOF_PATCH_EMPTY) continue;
+                for (int k = 0; k < p.size; ++k) {
+                    const double* s = &hs[(size_t)3 * (p.start + k)];
+                    const double ms = std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+                    if (ms > 0) for (int q = 0; q < 3; ++q) e[q] += std::fabs(s[q] / ms);
+                }
+            }
+            const double me = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+            if (me > 0) for (int q = 0; q < 3; ++q) h->sp.geomD[q] = (e[q] / me > 1e-6) ? -1 : 1;
+        }
+    }
+
+    // work-list capacities
+    h->capMixed = nC;
+    h->capNear = nC;
+    h->capWork = (int)std::min<long long>(nCF, std::max<long long>(1 << 20, nCF / 3));
+    h->nWords = cdiv(nC, 32);
+    h->nScanBlocks = cdiv(h->nWords, SV_SCAN_WORDS);
+}
+
+void allocFields(svof_handle* h)
+{
+    const size_t nC = h->nC, nF = h->nF, nBF = std::max(h->nBF, 1);
+    h->alphaBuf[0] = dalloc<double>(h, nC);
+    h->alphaBuf[1] = dalloc<double>(h, nC);
+    h->phi = dalloc<double>(h, nF);
+    h->alphaPhi = dalloc<double>(h, nF);
+    h->alphaBBuf[0] = dalloc<double>(h, nBF);
+    h->alphaBBuf[1] = dalloc<double>(h, nBF);
+    h->U = dalloc<double>(h, 3 * nC);
+    h->Ub = dalloc<double>(h, 3 * nBF);
+    h->Sp = dalloc<double>(h, nC);
+    h->Su = dalloc<double>(h, nC);
+    h->iN = dalloc<double>(h, 3 * nC);
+    h->iD = dalloc<double>(h, nC);
+    h->iC = dalloc<double>(h, 3 * nC);
+    h->iS = dalloc<double>(h, 3 * nC);
+    h->cellSlot = dalloc<int>(h, nC, false);
+    CK(cudaMemsetAsync(h->cellSlot, 0xff, nC * sizeof(int), h->stream));
+    h->mixedCells = dalloc<int>(h, h->capMixed);
+    h->cellStatus = dalloc<int>(h, h->capMixed);
+    h->Un0 = dalloc<double>(h, h->capMixed);
+    h->mixedBits = dalloc<unsigned int>(h, h->nWords + 1);
+    h->near1 = dalloc<unsigned int>(h, h->nWords + 1);
+    h->near2 = dalloc<unsigned int>(h, h->nWords + 1);
+    h->blockSums = dalloc<unsigned int>(h, h->nScanBlocks + 1);
+    h->near2List = dalloc<int>(h, h->capNear);
+    h->work = dalloc<int2>(h, h->capWork);
+    h->dVfGeo = dalloc<double>(h, nF);
+    h->dVf = dalloc<double>(h, nF);
+    h->corr = dalloc<double>(h, nF);
+    h->scratchF = dalloc<double>(h, nF);
+    h->corrBy = dalloc<int>(h, nF, false);
+    CK(cudaMemsetAsync(h->corrBy, 0xff, nF * sizeof(int), h->stream));
+    h->corrPos = dalloc<int>(h, nF);
+    h->oobList = dalloc<int>(h, h->capNear);
+    h->oobState = dalloc<unsigned char>(h, nC);
+    h->ctl = dalloc<Ctl>(h, 1);
+    h->partial = dalloc<double>(h, 1024);
+    CK(cudaMallocHost((void**)&h->hctl, sizeof(Ctl)));
+    CK(cudaMallocHost((void**)&h->hpartial, 1024 * sizeof(double)));
+    memset(h->hctl, 0, sizeof(Ctl));
+    h->events.resize(64);
+    for (EventPair& e : h->events) {
+        CK(cudaEventCreate(&e.a));
+        CK(cudaEventCreate(&e.b));
+    }
+}
+
+void harvestEvents(svof_handle* h, bool block)
+{
+    for (EventPair& e : h->events) {
+        if (!e.pending) continue;
+        if (block) CK(cudaEventSynchronize(e.b));
+        else if (cudaEventQuery(e.b) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e.a, e.b));
+        if (e.kind == 0) { h->reconTime += ms * 1e-3; h->lastReconMs = ms; }
+        else { h->advTime += ms * 1e-3; h->lastAdvMs = ms; }
+        e.pending = false;
+    }
+}
+EventPair& beginTimed(svof_handle* h, int kind)
+{
+    EventPair& e = h->events[h->evNext++ % h->events.size()];
+    if (e.pending) {
+        CK(cudaEventSynchronize(e.b));
+        harvestEvents(h, false);
+    }
+    e.kind = kind;
+    CK(cudaEventRecord(e.a, h->stream));
+    return e;
+}
+void endTimed(svof_handle* h, EventPair& e)
+{
+    CK(cudaEventRecord(e.b, h->stream));
+    e.pending = true;
+}
+
+__global__ void k_ctl_reset_advect(Ctl* ctl)
+{
+    ctl->nWork = 0;
+    ctl->nSweeps = 0;
+    ctl->nOob = 0;
+    ctl->nPending = 0;
+    ctl->minDense = ~0ull;
+    ctl->maxDense = 0ull;
+    for (int s = 0; s <= SV_MAX_SWEEPS; ++s) {
+        ctl->minNear[s] = ~0ull;
+        ctl->maxNear[s] = 0ull;
+    }
+}
+__global__ void k_ctl_reset_recon(Ctl* ctl) { ctl->nNear2 = 0; }
+
+void alphaBC(svof_handle* h)
+{
+    if (h->nBF > 0)
+        LAUNCH(h, k_alpha_bc, cdiv(h->nBF, 256), 256, h->md, h->dPatches, h->bPatch, h->alphaBuf[h->cur], h->phi, h->alphaBBuf[h->cb]);
+}
+
+void doReconstruct(svof_handle* h)
+{
+    const MeshDev& d = h->md;
+    cudaStream_t s = h->stream;
+    double* alpha = h->alphaBuf[h->cur];
+    const int g128 = sparseGrid(h, 128), g256 = sparseGrid(h, 256);
+    // A1: sparse zeroing of the previous interface data, mixed-cell list in ascending order
+    LAUNCH(h, k_clear_prev, g256, 256, h->mixedCells, h->ctl, h->iN, h->iD, h->iC, h->iS, h->cellSlot);
+    if (!h->bitsValid) LAUNCH(h, k_mixed_bits, cdiv(h->nC, 256), 256, alpha, h->nC, h->prm.mixed_cell_tol, h->mixedBits);
+    LAUNCH(h, k_count_bits, h->nScanBlocks, SV_SCAN_WORDS, h->mixedBits, h->nWords, h->blockSums);
+    LAUNCH(h, k_scan_blocks, 1, 1024, h->blockSums, h->nScanBlocks, h->ctl, h->capMixed);
+    LAUNCH(h, k_write_mixed, h->nScanBlocks, SV_SCAN_WORDS, h->mixedBits, h->nWords, h->blockSums, h->capMixed, h->mixedCells,
+           h->cellStatus, h->cellSlot);
+    CK(cudaMemsetAsync(h->near1, 0, sizeof(unsigned int) * h->nWords, s));
+    CK(cudaMemsetAsync(h->near2, 0, sizeof(unsigned int) * h->nWords, s));
+    LAUNCH(h, k_ctl_reset_recon, 1, 1, h->ctl);
+    LAUNCH(h, k_mark_near, g256, 256, d, h->mixedCells, h->ctl, h->near1, h->near2, h->near2List, h->capNear);
+    // A2: LS normals; A3-A5: plane positions
+    LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
+    GEO(h, plic, s, g128, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
+    h->bitsValid = false;  // consumed
+}
+
+void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
+{
+    const MeshDev& d = h->md;
+    const int g128 = sparseGrid(h, 128), g256 = sparseGrid(h, 256);
+    double* aOld = h->alphaBuf[h->cur];
+    double* aNew = h->alphaBuf[h->cur ^ 1];
+    LAUNCH(h, k_ctl_reset_advect, 1, 1, h->ctl);
+    // A7-A9: geometric fluxes on the downwind faces of cut cells
+    LAUNCH(h, k_un0_worklist, g128, 128, d, h->mixedCells, h->cellStatus, h->ctl, h->iN, h->iC, h->U, h->Ub, h->phi, h->Un0, h->work,
+           h->capWork);
+    GEO(h, faceFlux, h->stream, g128, d, h->work, h->ctl, h->mixedCells, h->iN, h->iD, h->Un0, h->phi, dt, h->dVfGeo);
+    // A6+A10(+A12): the streaming pass, then the same update for the near2 cells
+    LAUNCH(h, k_dense_update, cdiv(h->nC, 256), 256, d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits, dt, dSp,
+           dSu, h->sp, h->ctl);
+    LAUNCH(h, k_near_update, g128, 128, d, h->near2List, h->ctl, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->cellSlot, h->cellStatus, h->dVfGeo,
+           h->dVf, dt, dSp, dSu);
+    // A11: conservative bounding sweeps (device-side predicate: a sweep that is not needed exits at once)
+    for (int sidx = 0; sidx < h->sp.nAlphaBounds; ++sidx) {
+        LAUNCH(h, k_bound_find, g256, 256, d, h->near2List, h->near1, h->ctl, sidx, aNew, h->corr, h->corrBy, h->oobList, h->oobState);
+        LAUNCH(h, k_bound_wave, g128, 128, d, h->ctl, sidx, h->oobList, h->oobState, aNew, aOld, h->phi, h->dVf, h->corr, h->corrBy,
+               h->corrPos, dt, dSp, dSu);
+        LAUNCH(h, k_bound_wave, g128, 128, d, h->ctl, sidx, h->oobList, h->oobState, aNew, aOld, h->phi, h->dVf, h->corr, h->corrBy,
+               h->corrPos, dt, dSp, dSu);
+        LAUNCH(h, k_bound_drain, 1, 1024, d, h->ctl, sidx, h->oobList, h->oobState, aNew, aOld, h->phi, h->dVf, h->corr, h->corrBy,
+               h->corrPos, dt, dSp, dSu);
+        LAUNCH(h, k_bound_apply, g128, 128, d, h->near2List, h->ctl, sidx, aNew, h->dVf, h->corr, h->corrBy, h->corrPos, h->oobList,
+               h->oobState);
+        LAUNCH(h, k_bound_reset, g256, 256, h->ctl, h->oobList, h->oobState, h->corrBy, d);
+        LAUNCH(h, k_bound_reset_counts, 1, 1, h->ctl);
+    }
+    // A12: snap/clip + alphaPhi for near2; boundary values of the new field
+    LAUNCH(h, k_near_finalize, g128, 128, d, h->near2List, h->ctl, aNew, h->dVf, h->alphaPhi, h->mixedBits, dt, h->sp);
+    h->cur ^= 1;
+    h->cb ^= 1;  // keep the patch values alpha.oldTime() was advected with (for dVf materialisation)
+    alphaBC(h);
+    h->bitsValid = true;
+    h->advected = true;
+    h->lastDt = dt;
+}
+
+void fetchCtl(svof_handle* h)
+{
+    CK(cudaMemcpyAsync(h->hctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+}
+
+int fail(svof_handle* h, int code, const char* what)
+{
+    if (h) h->err = what;
+    return code;
+}
+
+#define API_BEGIN try {
+#define API_END(h)                                           \
+    }                                                        \
+    catch (const std::invalid_argument& e) { return fail(h, SVOF_ERR_INVALID_ARG, e.what()); } \
+    catch (const std::length_error& e) { return fail(h, SVOF_ERR_CAPACITY, e.what()); }        \
+    catch (const std::exception& e) { return fail(h, SVOF_ERR_CUDA, e.what()); }
+
+bool parseBool(const char* v, int32_t* out)
+{
+    static const char* T[] = {"true", "on", "yes", "y", "t", "1"};
+    static const char* F[] = {"false", "off", "no", "n", "f", "0", "none"};
+    for (const char* s : T) if (!strcmp(v, s)) { *out = 1; return true; }
+    for (const char* s : F) if (!strcmp(v, s)) { *out = 0; return true; }
+    return false;
+}
+
+int checkDeviceErr(svof_handle* h)
+{
+    fetchCtl(h);
+    if (h->hctl->err) {
+        char b[256];
+        snprintf(b, sizeof(b), "device capacity flag 0x%x (1 face verts, 2 cell faces, 4 cell points, 8 interface points, "
+                 "16 LS stencil, 32 work list)", h->hctl->err);
+        h->err = b;
+        return SVOF_ERR_CAPACITY;
+    }
+    return SVOF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int svof_params_default(svof_params* p)
+{
+    if (!p) return SVOF_ERR_INVALID_ARG;
+    memset(p, 0, sizeof(*p));
+    p->mixed_cell_tol = 1e-8;
+    p->snap_tol = 0.0;
+    p->rdf_tol = 1e-6;
+    p->rdf_rel_tol = 0.1;
+    p->n_alpha_bounds = 10;
+    p->clip = 1;
+    p->orientation_method = SVOF_ORIENT_ISO_ALPHA_GRAD;
+    p->rdf_iterations = 5;
+    return SVOF_OK;
+}
+
+int svof_params_set(svof_params* p, const char* key, const char* value)
+{
+    if (!p || !key || !value) return SVOF_ERR_INVALID_ARG;
+    std::string k(key), v(value);
+    while (!v.empty() && (v.back() == ';' || v.back() == ' ')) v.pop_back();
+    char* end = nullptr;
+    auto num = [&](double* out) {
+        *out = strtod(v.c_str(), &end);
+        return end != v.c_str() && *end == '\0';
+    };
+    double dv;
+    int32_t b;
+    if (k == "mixedCellTol") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; p->mixed_cell_tol = dv; p->mixed_cell_tol_set = 1; return SVOF_OK; }
+    if (k == "surfCellTol") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; if (!p->mixed_cell_tol_set) p->mixed_cell_tol = dv; return SVOF_OK; }
+    if (k == "isoFaceTol") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; p->iso_face_tol = dv; return SVOF_OK; }
+    if (k == "snapTol") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; p->snap_tol = dv; return SVOF_OK; }
+    if (k == "tol") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; p->rdf_tol = dv; return SVOF_OK; }
+    if (k == "relTol") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; p->rdf_rel_tol = dv; return SVOF_OK; }
+    if (k == "nAlphaBounds") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; p->n_alpha_bounds = (int32_t)dv; return SVOF_OK; }
+    if (k == "iterations") { if (!num(&dv)) return SVOF_ERR_INVALID_ARG; p->rdf_iterations = (int32_t)dv; return SVOF_OK; }
+    if (k == "clip") { if (!parseBool(v.c_str(), &b)) return SVOF_ERR_INVALID_ARG; p->clip = b; return SVOF_OK; }
+    if (k == "splitWarpedFace") { if (!parseBool(v.c_str(), &b)) return SVOF_ERR_INVALID_ARG; p->split_warped_face = b; return SVOF_OK; }
+    if (k == "mapAlphaField") { if (!parseBool(v.c_str(), &b)) return SVOF_ERR_INVALID_ARG; p->map_alpha_field = b; return SVOF_OK; }
+    if (k == "writePlicFields") { if (!parseBool(v.c_str(), &b)) return SVOF_ERR_INVALID_ARG; p->write_plic_fields = b; return SVOF_OK; }
+    if (k == "orientationMethod") {
+        if (v == "alphaGrad") p->orientation_method = SVOF_ORIENT_ALPHA_GRAD;
+        else if (v == "isoAlphaGrad" || v == "LS") p->orientation_method = SVOF_ORIENT_ISO_ALPHA_GRAD;
+        else if (v == "isoRDF" || v == "RDF") p->orientation_method = SVOF_ORIENT_ISO_RDF;
+        else return SVOF_ERR_BAD_CONFIG;
+        return SVOF_OK;
+    }
+    if (k == "nAlphaSubCycles" || k == "cAlpha" || k == "period" || k == "reverseTime" || k == "nAlphaCorr") return SVOF_OK;
+    return SVOF_ERR_INVALID_ARG;
+}
+
+int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_comm* comm, svof_handle** out)
+{
+    if (!mesh || !params || !out) { g_createError = "svof_create: null argument"; return SVOF_ERR_INVALID_ARG; }
+    if (comm && comm->world_size > 1) { g_createError = "decomposed runs: use svof_create on each rank with processor patches (not yet enabled)"; return SVOF_ERR_UNSUPPORTED; }
+    if (params->orientation_method != SVOF_ORIENT_ISO_ALPHA_GRAD) {
+        g_createError = "orientationMethod: only isoAlphaGrad/LS is implemented on the device (alphaGrad, isoRDF: SURVEY.md 8f)";
+        return SVOF_ERR_UNSUPPORTED;
+    }
+    if (params->n_alpha_bounds > SV_MAX_SWEEPS) { g_createError = "nAlphaBounds exceeds 32"; return SVOF_ERR_INVALID_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_createError = "no CUDA device: this library has no CPU path";
+        (void)cudaGetLastError();
+        return SVOF_ERR_CUDA;
+    }
+    svof_handle* h = new svof_handle;
+    int rc = SVOF_OK;
+    try {
+        h->device = (comm && comm->device >= 0) ? comm->device : ((comm ? comm->rank : 0) % ndev);
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, h->device));
+        h->sms = prop.multiProcessorCount;
+        h->prm = *params;
+        h->sp.mixedTol = params->mixed_cell_tol;
+        h->sp.snapTol = params->snap_tol;
+        h->sp.clip = params->clip;
+        h->sp.nAlphaBounds = params->n_alpha_bounds;
+        h->sp.split = params->split_warped_face;
+        buildMesh(h, *mesh);
+        allocFields(h);
+        CK(cudaStreamSynchronize(h->stream));
+    } catch (const std::invalid_argument& e) { g_createError = e.what(); rc = SVOF_ERR_BAD_MESH; }
+    catch (const std::length_error& e) { g_createError = e.what(); rc = SVOF_ERR_CAPACITY; }
+    catch (const std::exception& e) { g_createError = e.what(); rc = SVOF_ERR_CUDA; }
+    if (rc) {
+        svof_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return SVOF_OK;
+}
+
+int svof_destroy(svof_handle* h)
+{
+    if (!h) return SVOF_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->hctl) cudaFreeHost(h->hctl);
+    if (h->hpartial) cudaFreeHost(h->hpartial);
+    for (EventPair& e : h->events) {
+        if (e.a) cudaEventDestroy(e.a);
+        if (e.b) cudaEventDestroy(e.b);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SVOF_OK;
+}
+
+const char* svof_last_error(const svof_handle* h) { return h ? h->err.c_str() : g_createError.c_str(); }
+
+int svof_set_alpha(svof_handle* h, const double* alpha)
+{
+    if (!h || !alpha) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->alphaBuf[h->cur], alpha, sizeof(double) * h->nC, cudaMemcpyHostToDevice, h->stream));
+    alphaBC(h);
+    CK(cudaStreamSynchronize(h->stream));
+    h->haveAlpha = true;
+    h->bitsValid = false;
+    h->advected = false;
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_set_phi(svof_handle* h, const double* phi)
+{
+    if (!h || !phi) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->havePhi = true;
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_set_U(svof_handle* h, const double* U, const double* Ub)
+{
+    if (!h || !U) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->U, U, sizeof(double) * 3 * h->nC, cudaMemcpyHostToDevice, h->stream));
+    if (Ub && h->nBF) CK(cudaMemcpyAsync(h->Ub, Ub, sizeof(double) * 3 * h->nBF, cudaMemcpyHostToDevice, h->stream));
+    else if (h->nBF) CK(cudaMemsetAsync(h->Ub, 0, sizeof(double) * 3 * h->nBF, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->haveU = true;
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_set_phi_device(svof_handle* h, const void* dphi)
+{
+    if (!h || !dphi) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->phi, dphi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, h->stream));
+    h->havePhi = true;
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb)
+{
+    if (!h || !dU) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->U, dU, sizeof(double) * 3 * h->nC, cudaMemcpyDeviceToDevice, h->stream));
+    if (dUb && h->nBF) CK(cudaMemcpyAsync(h->Ub, dUb, sizeof(double) * 3 * h->nBF, cudaMemcpyDeviceToDevice, h->stream));
+    h->haveU = true;
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_reconstruct(svof_handle* h)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    if (!h->haveAlpha) return fail(h, SVOF_ERR_STATE, "svof_reconstruct: alpha not set");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    EventPair& e = beginTimed(h, 0);
+    doReconstruct(h);
+    endTimed(h, e);
+    CK(cudaGetLastError());
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
+{
+    if (!h || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
+    if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_advect: alpha/phi/U not set");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    const double *dSp = nullptr, *dSu = nullptr;
+    if (Sp) { CK(cudaMemcpyAsync(h->Sp, Sp, sizeof(double) * h->nC, cudaMemcpyHostToDevice, h->stream)); dSp = h->Sp; }
+    if (Su) { CK(cudaMemcpyAsync(h->Su, Su, sizeof(double) * h->nC, cudaMemcpyHostToDevice, h->stream)); dSu = h->Su; }
+    EventPair& e = beginTimed(h, 1);
+    doAdvect(h, dt, dSp, dSu);
+    endTimed(h, e);
+    CK(cudaGetLastError());
+    if (Sp || Su) CK(cudaStreamSynchronize(h->stream));  // caller's buffers may be pageable
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U, const double* Ub, double* alpha_out,
+                   double* alpha_phi_out)
+{
+    if (!h || !phi || !U || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
+    if (!h->haveAlpha) return fail(h, SVOF_ERR_STATE, "svof_step_host: alpha not set");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->U, U, sizeof(double) * 3 * h->nC, cudaMemcpyHostToDevice, h->stream));
+    if (Ub && h->nBF) CK(cudaMemcpyAsync(h->Ub, Ub, sizeof(double) * 3 * h->nBF, cudaMemcpyHostToDevice, h->stream));
+    h->havePhi = h->haveU = true;
+    EventPair& e0 = beginTimed(h, 0);
+    doReconstruct(h);
+    endTimed(h, e0);
+    EventPair& e1 = beginTimed(h, 1);
+    doAdvect(h, dt, nullptr, nullptr);
+    endTimed(h, e1);
+    if (alpha_out) CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, h->stream));
+    if (alpha_phi_out) CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return SVOF_OK;
+    API_END(h)
+}
+
+int64_t svof_get_field(svof_handle* h, int which, void* dst, int64_t capacity)
+{
+    if (!h || !dst) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    const int64_t nC = h->nC, nF = h->nF;
+    const void* src = nullptr;
+    int64_t n = 0;
+    size_t esz = 8;
+    switch (which) {
+        case SVOF_F_ALPHA: src = h->alphaBuf[h->cur]; n = nC; break;
+        case SVOF_F_ALPHA_PHI: src = h->alphaPhi; n = nF; break;
+        case SVOF_F_DVF: {
+            n = nF;
+            if (h->advected) {
+                LAUNCH(h, k_materialize_dvf, cdiv(nF, 256), 256, h->md, h->alphaBuf[h->cur ^ 1], h->alphaBBuf[h->cb ^ 1], h->phi, h->lastDt, h->near2,
+                       h->dVf, h->scratchF);
+            } else {
+                CK(cudaMemsetAsync(h->scratchF, 0, sizeof(double) * nF, h->stream));
+            }
+            src = h->scratchF;
+            break;
+        }
+        case SVOF_F_INTERFACE_N: src = h->iN; n = 3 * nC; break;
+        case SVOF_F_INTERFACE_D: src = h->iD; n = nC; break;
+        case SVOF_F_INTERFACE_C: src = h->iC; n = 3 * nC; break;
+        case SVOF_F_INTERFACE_S: src = h->iS; n = 3 * nC; break;
+        case SVOF_F_MIXED_CELLS: fetchCtl(h); src = h->mixedCells; n = h->hctl->nMixed; esz = 4; break;
+        case SVOF_F_CELL_STATUS: fetchCtl(h); src = h->cellStatus; n = h->hctl->nMixed; esz = 4; break;
+        case SVOF_F_FACE_FLATNESS: src = h->md.flat; n = nF; break;
+        case SVOF_F_CF: src = h->md.Cf; n = 3 * nF; break;
+        case SVOF_F_SF: src = h->md.Sf; n = 3 * nF; break;
+        case SVOF_F_C: src = h->md.C; n = 3 * nC; break;
+        case SVOF_F_V: src = h->md.V; n = nC; break;
+        case SVOF_F_ALPHA_BOUNDARY: src = h->alphaBBuf[h->cb]; n = h->nBF; break;
+        case SVOF_F_UN0: fetchCtl(h); src = h->Un0; n = h->hctl->nMixed; break;
+        default: return fail(h, SVOF_ERR_INVALID_ARG, "svof_get_field: unknown field");
+    }
+    if (capacity < n) return fail(h, SVOF_ERR_INVALID_ARG, "svof_get_field: destination too small");
+    if (n) CK(cudaMemcpyAsync(dst, src, (size_t)n * esz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return n;
+    API_END(h)
+}
+
+int svof_get_info(svof_handle* h, int which, double* out)
+{
+    if (!h || !out) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    auto sweepVals = [&](bool after, bool wantMin) {
+        fetchCtl(h);
+        const Ctl& c = *h->hctl;
+        const int s = after ? c.nSweeps : 0;
+        if (wantMin) return dunkey(std::min(c.minDense, c.minNear[s]));
+        return dunkey(std::max(c.maxDense, c.maxNear[s])) - 1.0;
+    };
+    switch (which) {
+        case SVOF_I_N_MIXED: fetchCtl(h); *out = h->hctl->nMixed; return SVOF_OK;
+        case SVOF_I_MIN_ALPHA_BEFORE: *out = sweepVals(false, true); return SVOF_OK;
+        case SVOF_I_MAX_ALPHA_M1_BEFORE: *out = sweepVals(false, false); return SVOF_OK;
+        case SVOF_I_MIN_ALPHA_AFTER: *out = sweepVals(true, true); return SVOF_OK;
+        case SVOF_I_MAX_ALPHA_M1_AFTER: *out = sweepVals(true, false); return SVOF_OK;
+        case SVOF_I_N_BOUND_SWEEPS: fetchCtl(h); *out = h->hctl->nSweeps; return SVOF_OK;
+        case SVOF_I_RECONSTRUCTION_TIME: harvestEvents(h, true); *out = h->reconTime; return SVOF_OK;
+        case SVOF_I_ADVECTION_TIME: harvestEvents(h, true); *out = h->advTime; return SVOF_OK;
+        case SVOF_I_ALPHA_MAPPING_TIME: *out = 0; return SVOF_OK;
+        case SVOF_I_VOLUME: {
+            LAUNCH(h, k_volume_partial, 1024, 256, h->alphaBuf[h->cur], h->md.V, h->nC, h->partial);
+            CK(cudaMemcpyAsync(h->hpartial, h->partial, 1024 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            // fixed pairwise tree on the host: deterministic
+            double buf[1024];
+            memcpy(buf, h->hpartial, sizeof(buf));
+            for (int o = 512; o > 0; o >>= 1)
+                for (int i = 0; i < o; ++i) buf[i] += buf[i + o];
+            *out = buf[0];
+            return SVOF_OK;
+        }
+        case SVOF_I_GPU_LAUNCHES: *out = (double)h->launches; return SVOF_OK;
+        case SVOF_I_FLATNESS_MIN: *out = h->flatMin; return SVOF_OK;
+        case SVOF_I_FLATNESS_MAX: *out = h->flatMax; return SVOF_OK;
+        case SVOF_I_FLATNESS_AVG: *out = h->flatAvg; return SVOF_OK;
+        case SVOF_I_DEVICE_BYTES: *out = (double)h->bytes; return SVOF_OK;
+        case SVOF_I_ERROR_FLAGS: fetchCtl(h); *out = h->hctl->err; return SVOF_OK;
+    }
+    return fail(h, SVOF_ERR_INVALID_ARG, "svof_get_info: unknown item");
+    API_END(h)
+}
+
+int svof_device_ptr(svof_handle* h, int which, void** dptr)
+{
+    if (!h || !dptr) return SVOF_ERR_INVALID_ARG;
+    switch (which) {
+        case SVOF_F_ALPHA: *dptr = h->alphaBuf[h->cur]; return SVOF_OK;
+        case SVOF_F_ALPHA_PHI: *dptr = h->alphaPhi; return SVOF_OK;
+        case SVOF_F_CF: *dptr = (void*)h->md.Cf; return SVOF_OK;
+        case SVOF_F_SF: *dptr = (void*)h->md.Sf; return SVOF_OK;
+        case SVOF_F_C: *dptr = (void*)h->md.C; return SVOF_OK;
+        case SVOF_F_V: *dptr = (void*)h->md.V; return SVOF_OK;
+        case SVOF_F_INTERFACE_N: *dptr = h->iN; return SVOF_OK;
+        case SVOF_F_INTERFACE_D: *dptr = h->iD; return SVOF_OK;
+        case SVOF_F_INTERFACE_C: *dptr = h->iC; return SVOF_OK;
+        case SVOF_F_INTERFACE_S: *dptr = h->iS; return SVOF_OK;
+    }
+    return fail(h, SVOF_ERR_INVALID_ARG, "svof_device_ptr: field not exposed");
+}
+
+int svof_device_touch(svof_handle* h, int which)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    if (which != SVOF_F_ALPHA) return fail(h, SVOF_ERR_INVALID_ARG, "svof_device_touch: only ALPHA is writable in place");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    alphaBC(h);
+    h->haveAlpha = true;
+    h->bitsValid = false;
+    h->advected = false;
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_synchronize(svof_handle* h)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    return checkDeviceErr(h);
+    API_END(h)
+}
+
+int svof_last_step_ms(svof_handle* h, double* r, double* a)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    harvestEvents(h, true);
+    if (r) *r = h->lastReconMs;
+    if (a) *a = h->lastAdvMs;
+    return SVOF_OK;
+    API_END(h)
+}
+
+// ---- geometry primitives ------------------------------------------------------------------------
+#define PRIM_PROLOGUE                      \
+    CK(cudaSetDevice(h->device));          \
+    std::vector<void*> tmp;                \
+    auto up = [&](const void* src, size_t bytes) { \
+        void* p = nullptr;                 \
+        CK(cudaMalloc(&p, std::max<size_t>(bytes, 8))); \
+        tmp.push_back(p);                  \
+        if (src) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, h->stream)); \
+        else CK(cudaMemsetAsync(p, 0, std::max<size_t>(bytes, 8), h->stream)); \
+        return p;                          \
+    };                                     \
+    auto down = [&](void* dstp, const void* srcp, size_t bytes) { CK(cudaMemcpyAsync(dstp, srcp, bytes, cudaMemcpyDeviceToHost, h->stream)); }; \
+    int* dErr = (int*)up(nullptr, sizeof(int)); \
+    int hErr = 0;
+#define PRIM_EPILOGUE                                  \
+    down(&hErr, dErr, sizeof(int));                    \
+    CK(cudaStreamSynchronize(h->stream));              \
+    for (void* p : tmp) cudaFree(p);                   \
+    CK(cudaGetLastError());                            \
+    if (hErr) return fail(h, SVOF_ERR_CAPACITY, "geometry primitive exceeded a compiled capacity"); \
+    return SVOF_OK;
+
+int svof_cut_faces(svof_handle* h, int32_t n_polys, int32_t n_verts, const double* pts, const double* normals, const double* dists,
+                   int32_t* status, double* centres, double* areas)
+{
+    if (!h || n_polys < 0 || n_verts < 3 || !pts || !normals || !dists || !status || !centres || !areas) return SVOF_ERR_INVALID_ARG;
+    if (n_verts > CapsPoly::MAXFV) return fail(h, SVOF_ERR_CAPACITY, "svof_cut_faces: more than 16 vertices");
+    API_BEGIN
+    PRIM_PROLOGUE
+    double* dp = (double*)up(pts, sizeof(double) * 3 * (size_t)n_polys * n_verts);
+    double* dn = (double*)up(normals, sizeof(double) * 3 * n_polys);
+    double* dd = (double*)up(dists, sizeof(double) * n_polys);
+    int* ds = (int*)up(nullptr, sizeof(int) * n_polys);
+    double* dc = (double*)up(nullptr, sizeof(double) * 3 * n_polys);
+    double* da = (double*)up(nullptr, sizeof(double) * 3 * n_polys);
+    if (n_polys) { GeoLaunch<CapsPoly>::cutFaces(h->stream, n_polys, n_verts, dp, dn, dd, ds, dc, da, dErr); h->launches++; }
+    down(status, ds, sizeof(int) * n_polys);
+    down(centres, dc, sizeof(double) * 3 * n_polys);
+    down(areas, da, sizeof(double) * 3 * n_polys);
+    PRIM_EPILOGUE
+    API_END(h)
+}
+
+int svof_cut_cells(svof_handle* h, int32_t n, const int32_t* cells, const double* normals, const double* dists, int32_t* status,
+                   double* vof, double* sub_volume, double* ic, double* ia)
+{
+    if (!h || n < 0 || !cells || !normals || !dists || !status || !vof || !sub_volume || !ic || !ia) return SVOF_ERR_INVALID_ARG;
+    for (int i = 0; i < n; ++i) if (cells[i] < 0 || cells[i] >= h->nC) return fail(h, SVOF_ERR_INVALID_ARG, "svof_cut_cells: cell out of range");
+    API_BEGIN
+    PRIM_PROLOGUE
+    int* dcell = (int*)up(cells, sizeof(int) * n);
+    double* dn = (double*)up(normals, sizeof(double) * 3 * n);
+    double* dd = (double*)up(dists, sizeof(double) * n);
+    int* ds = (int*)up(nullptr, sizeof(int) * n);
+    double* dv = (double*)up(nullptr, sizeof(double) * n);
+    double* dsv = (double*)up(nullptr, sizeof(double) * n);
+    double* dic = (double*)up(nullptr, sizeof(double) * 3 * n);
+    double* dia = (double*)up(nullptr, sizeof(double) * 3 * n);
+    if (n) {
+        // the non-split capacity variant of this mesh
+        const int v = (h->variant == 3) ? 2 : h->variant;
+        switch (v) {
+            case 0: GeoLaunch<CapsHex>::cutCells(h->stream, h->md, n, dcell, dn, dd, ds, dv, dsv, dic, dia, dErr); break;
+            case 1: GeoLaunch<CapsSmall>::cutCells(h->stream, h->md, n, dcell, dn, dd, ds, dv, dsv, dic, dia, dErr); break;
+            default: GeoLaunch<CapsPoly>::cutCells(h->stream, h->md, n, dcell, dn, dd, ds, dv, dsv, dic, dia, dErr); break;
+        }
+        h->launches++;
+    }
+    down(status, ds, sizeof(int) * n);
+    down(vof, dv, sizeof(double) * n);
+    down(sub_volume, dsv, sizeof(double) * n);
+    down(ic, dic, sizeof(double) * 3 * n);
+    down(ia, dia, sizeof(double) * 3 * n);
+    PRIM_EPILOGUE
+    API_END(h)
+}
+
+int svof_find_signed_distance(svof_handle* h, int32_t n, const int32_t* cells, const double* alphas, const double* normals,
+                              int32_t* status, double* dists, double* ic, double* ia)
+{
+    if (!h || n < 0 || !cells || !alphas || !normals || !status || !dists || !ic || !ia) return SVOF_ERR_INVALID_ARG;
+    for (int i = 0; i < n; ++i) if (cells[i] < 0 || cells[i] >= h->nC) return fail(h, SVOF_ERR_INVALID_ARG, "svof_find_signed_distance: cell out of range");
+    API_BEGIN
+    PRIM_PROLOGUE
+    int* dcell = (int*)up(cells, sizeof(int) * n);
+    double* dal = (double*)up(alphas, sizeof(double) * n);
+    double* dn = (double*)up(normals, sizeof(double) * 3 * n);
+    int* ds = (int*)up(nullptr, sizeof(int) * n);
+    double* dd = (double*)up(nullptr, sizeof(double) * n);
+    double* dic = (double*)up(nullptr, sizeof(double) * 3 * n);
+    double* dia = (double*)up(nullptr, sizeof(double) * 3 * n);
+    if (n) GEO(h, findDistance, h->stream, h->md, n, dcell, dal, dn, h->sp.split, ds, dd, dic, dia, dErr);
+    down(status, ds, sizeof(int) * n);
+    down(dists, dd, sizeof(double) * n);
+    down(ic, dic, sizeof(double) * 3 * n);
+    down(ia, dia, sizeof(double) * 3 * n);
+    PRIM_EPILOGUE
+    API_END(h)
+}
+
+int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const double* normals, const double* dists, const double* Un0,
+                     double dt, const double* phi, double* dVf)
+{
+    if (!h || n < 0 || !faces || !normals || !dists || !Un0 || !phi || !dVf) return SVOF_ERR_INVALID_ARG;
+    for (int i = 0; i < n; ++i) if (faces[i] < 0 || faces[i] >= h->nF) return fail(h, SVOF_ERR_INVALID_ARG, "svof_face_fluxes: face out of range");
+    API_BEGIN
+    PRIM_PROLOGUE
+    int* df = (int*)up(faces, sizeof(int) * n);
+    double* dn = (double*)up(normals, sizeof(double) * 3 * n);
+    double* dd = (double*)up(dists, sizeof(double) * n);
+    double* du = (double*)up(Un0, sizeof(double) * n);
+    double* dph = (double*)up(phi, sizeof(double) * n);
+    double* dout = (double*)up(nullptr, sizeof(double) * n);
+    if (n) GEO(h, faceFluxes, h->stream, h->md, n, df, dn, dd, du, dt, dph, dout, dErr);
+    down(dVf, dout, sizeof(double) * n);
+    PRIM_EPILOGUE
+    API_END(h)
+}
+
+}  // extern "C"

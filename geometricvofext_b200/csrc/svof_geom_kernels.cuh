@@ -1,0 +1,167 @@
+// svof_geom_kernels.cuh -- the kernels that depend on the compiled polyhedron capacity variant
+// (Caps<MAXFV, MAXCF, MAXCP>).  Each variant is instantiated in its own translation unit
+// (svof_inst.cu compiled with -DSV_VARIANT=n) so the variants build in parallel.
+#pragma once
+#include "svof_kernels.cuh"
+
+namespace svof {
+
+typedef Caps<4, 6, 8> CapsHex;         // hexahedra (blockMesh), flat faces
+typedef Caps<8, 16, 32> CapsSmall;     // tets/prisms/small polyhedra
+typedef Caps<16, 40, 72> CapsPoly;     // polyDualMesh cells (~14 faces, 24+ vertices)
+typedef Caps<16, 200, 128> CapsSplit;  // splitWarpedFace local triangulations
+
+// host-callable launchers, one explicit instantiation per variant
+template <class CP>
+struct GeoLaunch {
+    static void plic(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* alpha, const double* iN,
+                     int split, int* cellStatus, double* iD, double* iC, double* iS);
+    static void faceFlux(cudaStream_t st, int grid, MeshDev m, const int2* work, Ctl* ctl, const int* mixedCells, const double* iN,
+                         const double* iD, const double* Un0, const double* phi, double dt, double* dVfGeo);
+    static void cutFaces(cudaStream_t st, int nPolys, int nVerts, const double* pts, const double* normals, const double* dists,
+                         int* status, double* centres, double* areas, int* errOut);
+    static void cutCells(cudaStream_t st, MeshDev m, int n, const int* cells, const double* normals, const double* dists, int* status,
+                         double* vof, double* subVol, double* ic, double* ia, int* errOut);
+    static void findDistance(cudaStream_t st, MeshDev m, int n, const int* cells, const double* alphas, const double* normals,
+                             int split, int* status, double* dists, double* ic, double* ia, int* errOut);
+    static void faceFluxes(cudaStream_t st, MeshDev m, int n, const int* faces, const double* normals, const double* dists,
+                           const double* Un0, double dt, const double* phi, double* out, int* errOut);
+};
+
+#ifdef SV_VARIANT
+// A3-A5: plane positioning, thread per mixed cell
+template <class CP>
+__global__ void __launch_bounds__(128) k_plic(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
+                                              const double* iN, int split, int* cellStatus, double* iD, double* iC, double* iS)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = mixedCells[i];
+        int err = 0;
+        PlicOut po;
+        signedDistance<CP>(m, c, alpha[c], ld3(iN, c), split != 0, po, err);
+        cellStatus[i] = po.status;
+        if (po.wrote) {
+            iD[c] = po.D;
+            st3(iC, c, po.C);
+            st3(iS, c, po.S);
+        }
+        if (err) atomicOr(&ctl->err, err);
+    }
+}
+
+// A8+A9: thread per (cut cell, downwind face)
+template <class CP>
+__global__ void __launch_bounds__(128) k_face_flux(MeshDev m, const int2* work, Ctl* ctl, const int* mixedCells, const double* iN,
+                                                   const double* iD, const double* Un0, const double* __restrict__ phi, double dt,
+                                                   double* dVfGeo)
+{
+    int n = ctl->nWork;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int2 w = work[i];
+        const int c = mixedCells[w.x], f = w.y;
+        int err = 0;
+        dVfGeo[f] = faceFlux<CP>(m, f, ld3(iN, c), iD[c], Un0[w.x], dt, phi[f], m.magSf[f], err);
+        if (err) atomicOr(&ctl->err, err);
+    }
+}
+
+// ---- geometry primitives exposed through the C ABI (unit-test surface) -------------------------
+template <class CP>
+__global__ void k_cut_faces(int nPolys, int nVerts, const double* pts, const double* normals, const double* dists, int* status,
+                            double* centres, double* areas, int* errOut)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nPolys) return;
+    d3 fp[CP::MAXFV], c, a, ip[CP::MAXIP];
+    int nip, err = 0;
+    const int nv = nVerts > CP::MAXFV ? CP::MAXFV : nVerts;
+    for (int k = 0; k < nv; ++k) fp[k] = ld3(pts, (int64_t)i * nVerts + k);
+    status[i] = clipFace<CP>(fp, nv, ld3(normals, i), dists[i], c, a, ip, nip, err);
+    st3(centres, i, c);
+    st3(areas, i, a);
+    if (err || nVerts > CP::MAXFV) atomicOr(errOut, err | (nVerts > CP::MAXFV ? SVERR_FACE_VERTS : 0));
+}
+template <class CP>
+__global__ void k_cut_cells(MeshDev m, int n, const int* cells, const double* normals, const double* dists, int* status, double* vof,
+                            double* subVol, double* ic, double* ia, int* errOut)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SubCellOut sc;
+    int err = 0;
+    subCell<CP>(m, cells[i], ld3(normals, i), dists[i], false, sc, err);
+    status[i] = sc.status;
+    vof[i] = sc.VOF;
+    subVol[i] = sc.subVol;
+    st3(ic, i, sc.iC);
+    st3(ia, i, sc.iS);
+    if (err) atomicOr(errOut, err);
+}
+template <class CP>
+__global__ void k_find_distance(MeshDev m, int n, const int* cells, const double* alphas, const double* normals, int split,
+                                int* status, double* dists, double* ic, double* ia, int* errOut)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PlicOut po;
+    int err = 0;
+    signedDistance<CP>(m, cells[i], alphas[i], ld3(normals, i), split != 0, po, err);
+    status[i] = po.status;
+    dists[i] = po.D;
+    st3(ic, i, po.C);
+    st3(ia, i, po.S);
+    if (err) atomicOr(errOut, err);
+}
+template <class CP>
+__global__ void k_face_fluxes(MeshDev m, int n, const int* faces, const double* normals, const double* dists, const double* Un0,
+                              double dt, const double* phi, double* out, int* errOut)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int err = 0;
+    const int f = faces[i];
+    out[i] = faceFlux<CP>(m, f, ld3(normals, i), dists[i], Un0[i], dt, phi[i], m.magSf[f], err);
+    if (err) atomicOr(errOut, err);
+}
+
+
+template <class CP>
+void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* alpha, const double* iN,
+                         int split, int* cellStatus, double* iD, double* iC, double* iS)
+{
+    k_plic<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
+}
+template <class CP>
+void GeoLaunch<CP>::faceFlux(cudaStream_t st, int grid, MeshDev m, const int2* work, Ctl* ctl, const int* mixedCells, const double* iN,
+                             const double* iD, const double* Un0, const double* phi, double dt, double* dVfGeo)
+{
+    k_face_flux<CP><<<grid, 128, 0, st>>>(m, work, ctl, mixedCells, iN, iD, Un0, phi, dt, dVfGeo);
+}
+template <class CP>
+void GeoLaunch<CP>::cutFaces(cudaStream_t st, int nPolys, int nVerts, const double* pts, const double* normals, const double* dists,
+                             int* status, double* centres, double* areas, int* errOut)
+{
+    k_cut_faces<CP><<<(nPolys + 127) / 128, 128, 0, st>>>(nPolys, nVerts, pts, normals, dists, status, centres, areas, errOut);
+}
+template <class CP>
+void GeoLaunch<CP>::cutCells(cudaStream_t st, MeshDev m, int n, const int* cells, const double* normals, const double* dists,
+                             int* status, double* vof, double* subVol, double* ic, double* ia, int* errOut)
+{
+    k_cut_cells<CP><<<(n + 127) / 128, 128, 0, st>>>(m, n, cells, normals, dists, status, vof, subVol, ic, ia, errOut);
+}
+template <class CP>
+void GeoLaunch<CP>::findDistance(cudaStream_t st, MeshDev m, int n, const int* cells, const double* alphas, const double* normals,
+                                 int split, int* status, double* dists, double* ic, double* ia, int* errOut)
+{
+    k_find_distance<CP><<<(n + 127) / 128, 128, 0, st>>>(m, n, cells, alphas, normals, split, status, dists, ic, ia, errOut);
+}
+template <class CP>
+void GeoLaunch<CP>::faceFluxes(cudaStream_t st, MeshDev m, int n, const int* faces, const double* normals, const double* dists,
+                               const double* Un0, double dt, const double* phi, double* out, int* errOut)
+{
+    k_face_fluxes<CP><<<(n + 127) / 128, 128, 0, st>>>(m, n, faces, normals, dists, Un0, dt, phi, out, errOut);
+}
+#endif  // SV_VARIANT
+
+}  // namespace svof

@@ -1,0 +1,1060 @@
+// svof_kernels.cuh -- the CUDA kernels of the SimPLIC step (sm_100a, FP64, no tensor cores:
+// nothing on this path is a dense contraction).  Kernel map:
+//
+//   once per mesh   k_face_geom, k_cell_geom, k_flatness_tetbase        (K0)
+//   reconstruct()   k_clear_prev, k_mixed_bits, k_count_bits, k_scan_blocks, k_write_mixed,
+//                   k_mark_near, k_ls_normals (K2), k_plic<Caps> (K3)
+//   advect()        k_un0_worklist (K5), k_face_flux<Caps> (K6), k_dense_update (K7, THE
+//                   streaming kernel: the only pass over all cells/faces), k_near_update,
+//                   k_bound_find / k_bound_wave / k_bound_drain / k_bound_apply (K8),
+//                   k_near_finalize, k_alpha_bc (K9)
+//
+// Every list is built on the device and every launch has a size known on the host
+// (grid-stride over device-side counts), so a step needs no device->host round trip.
+#pragma once
+#include "svof_geom.cuh"
+
+namespace svof {
+
+#define SV_MAX_SWEEPS 32
+
+// device-resident control block (one per handle)
+struct Ctl {
+    int nMixed;       // mixedCells_.size()
+    int nMixedPrev;   // of the previous reconstruct (for sparse clearing)
+    int nNear2;       // |near2|
+    int nWork;        // (cut cell, downwind face) work items
+    int nOob;         // out-of-bounds cells of the current sweep
+    int nPending;     // ... not yet processed
+    int nSweeps;      // sweeps executed by the last advect
+    int err;          // SVERR_* flags
+    unsigned long long minDense, maxDense;                 // keys over cells outside near2
+    unsigned long long minNear[SV_MAX_SWEEPS + 1], maxNear[SV_MAX_SWEEPS + 1];  // over near2 after s sweeps
+};
+
+struct StepParams {
+    double mixedTol, snapTol;
+    int clip, nAlphaBounds, split;
+    int geomD[3];
+};
+
+__device__ __forceinline__ bool bitTest(const unsigned int* bits, int i) { return (bits[i >> 5] >> (i & 31)) & 1u; }
+
+#ifndef SV_VARIANT  // the capacity-independent kernels live in the main translation unit only
+// ============================================================================ K0 ====
+// primitiveMeshTools::faceCentresAndAreas (OF, recalled) -- thread per face
+__global__ void k_face_geom(MeshDev m, double* Cf, double* Sf, double* magSf, int haveGeom)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.nFaces) return;
+    if (!haveGeom) {
+        const int o = m.faceOff[f], n = m.faceOff[f + 1] - o;
+        d3 fc, fa;
+        if (n == 3) {
+            const d3 p0 = ld3(m.points, m.facePts[o]), p1 = ld3(m.points, m.facePts[o + 1]), p2 = ld3(m.points, m.facePts[o + 2]);
+            fc = (1.0 / 3.0) * (p0 + p1 + p2);
+            fa = 0.5 * cross(p1 - p0, p2 - p0);
+        } else {
+            d3 sumN = zero3(), sumAc = zero3();
+            double sumA = 0.0;
+            d3 fCentre = ld3(m.points, m.facePts[o]);
+            for (int pi = 1; pi < n; ++pi) fCentre += ld3(m.points, m.facePts[o + pi]);
+            fCentre /= double(n);
+            for (int pi = 0; pi < n; ++pi) {
+                const d3 nextPoint = ld3(m.points, m.facePts[o + ((pi == n - 1) ? 0 : pi + 1)]);
+                const d3 thisPoint = ld3(m.points, m.facePts[o + pi]);
+                const d3 c = thisPoint + nextPoint + fCentre;
+                const d3 nn = cross(nextPoint - thisPoint, fCentre - thisPoint);
+                const double a = mag(nn);
+                sumN += nn;
+                sumA += a;
+                sumAc += a * c;
+            }
+            if (sumA < SV_ROOTVSMALL) {
+                fc = fCentre;
+                fa = zero3();
+            } else {
+                fc = (1.0 / 3.0) * sumAc / sumA;
+                fa = 0.5 * sumN;
+            }
+        }
+        st3(Cf, f, fc);
+        st3(Sf, f, fa);
+    }
+    magSf[f] = mag(mk3(Sf[3 * (int64_t)f], Sf[3 * (int64_t)f + 1], Sf[3 * (int64_t)f + 2]));
+}
+
+// primitiveMeshTools::cellCentresAndVols (OF, recalled) -- thread per cell over the cells() row,
+// which visits owned faces (ascending) then neighbour-side faces (ascending): OF's own order.
+__global__ void k_cell_geom(MeshDev m, double* C, double* V)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.nCells) return;
+    const int c0 = m.cellOff[c], c1 = m.cellOff[c + 1];
+    d3 cEst = zero3();
+    for (int k = c0; k < c1; ++k) cEst += ld3(m.Cf, m.cellFaces[k]);
+    cEst /= double(c1 - c0);
+    d3 cc = zero3();
+    double vol = 0.0;
+    for (int k = c0; k < c1; ++k) {
+        const int f = m.cellFaces[k];
+        const d3 fc = ld3(m.Cf, f), fa = ld3(m.Sf, f);
+        const double pyr3Vol = (m.owner[f] == c) ? dot(fa, fc - cEst) : dot(fa, cEst - fc);
+        const d3 pc = (3.0 / 4.0) * fc + (1.0 / 4.0) * cEst;
+        cc += pyr3Vol * pc;
+        vol += pyr3Vol;
+    }
+    if (fabs(vol) > SV_VSMALL) cc /= vol; else cc = cEst;
+    st3(C, c, cc);
+    V[c] = vol * (1.0 / 3.0);
+}
+
+// reconstruction::updateFaceFlatness (reconstruction.C:408-440) + polyMesh::tetBasePtIs
+__device__ __forceinline__ double tetQuality(const d3& a, const d3& b, const d3& c, const d3& d)
+{
+    const double vol = (1.0 / 6.0) * dot(cross(b - a, c - a), d - a);
+    const d3 ea = b - a, eb = c - a, ec = d - a;
+    const double lambda = magSqr(ec) - dot(ea, ec);
+    const double mu = magSqr(eb) - dot(ea, eb);
+    const d3 ba = cross(eb, ea), ca = cross(ec, ea);
+    const d3 num = lambda * ba - mu * ca;
+    const double denom = dot(ec, ba);
+    double R = SV_GREAT;
+    if (fabs(denom) >= SV_ROOTVSMALL) R = mag(0.5 * (ea + num / denom));
+    const double Rm = dmin(R, SV_GREAT);
+    return vol / ((8.0 / (9.0 * sqrt(3.0))) * (Rm * (Rm * Rm)) + SV_ROOTVSMALL);
+}
+
+__global__ void k_flatness_tetbase(MeshDev m, double* flat, unsigned char* tetBase)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.nFaces) return;
+    const int o = m.faceOff[f], n = m.faceOff[f + 1] - o;
+    double fl = 1.0;
+    if (n > 3 && m.magSf[f] > SV_ROOTVSMALL) {
+        const d3 fc = ld3(m.Cf, f);
+        double sumA = 0.0;
+        for (int pi = 0; pi < n; ++pi) {
+            const d3 thisPoint = ld3(m.points, m.facePts[o + pi]);
+            const d3 nextPoint = ld3(m.points, m.facePts[o + ((pi + 1) % n)]);
+            sumA += mag(0.5 * cross(nextPoint - thisPoint, fc - thisPoint));
+        }
+        fl = m.magSf[f] / (sumA + SV_ROOTVSMALL);
+    }
+    flat[f] = fl;
+    // polyMeshTetDecomposition::findFaceBasePts, minTetQuality 1e-9
+    const bool internal = f < m.nIF;
+    const d3 oCc = ld3(m.C, m.owner[f]);
+    const d3 nCc = internal ? ld3(m.C, m.neighbour[f]) : zero3();
+    int found = -1;
+    for (int base = 0; base < n && found < 0; ++base) {
+        double minQ = SV_VGREAT;
+        const d3 pb = ld3(m.points, m.facePts[o + base]);
+        for (int t = 1; t < n - 1; ++t) {
+            const int ia = (t + base) % n, ib = (ia + 1) % n;
+            const d3 pa = ld3(m.points, m.facePts[o + ia]), pbb = ld3(m.points, m.facePts[o + ib]);
+            double q = tetQuality(oCc, pb, pa, pbb);
+            if (internal) q = dmin(q, tetQuality(nCc, pb, pbb, pa));
+            if (q < minQ) minQ = q;
+        }
+        if (minQ > 1e-9) found = base;
+    }
+    tetBase[f] = (unsigned char)((found < 0) ? 0 : found);
+}
+
+// ==================================================================== reconstruct ====
+// sparse replacement of the reference's dense zero-fill of interfaceN/D/C/S (reconstruction.C:636-641)
+__global__ void k_clear_prev(const int* mixedPrev, Ctl* ctl, double* iN, double* iD, double* iC, double* iS, int* cellSlot)
+{
+    const int n = ctl->nMixed;  // still the previous reconstruct's count and list
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = mixedPrev[i];
+        st3(iN, c, zero3());
+        st3(iC, c, zero3());
+        st3(iS, c, zero3());
+        iD[c] = 0.0;
+        cellSlot[c] = -1;
+    }
+}
+
+// A1 (reconstruction.C:665-672, reconstruction.H:281-288): one bit per cell, one coalesced word per warp
+__global__ void k_mixed_bits(const double* __restrict__ alpha, int nCells, double tol, unsigned int* bits)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    bool mixed = false;
+    if (c < nCells) {
+        const double a = alpha[c];
+        mixed = (tol < a) && (a < 1.0 - tol);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, mixed);
+    if ((threadIdx.x & 31) == 0 && c < nCells) bits[c >> 5] = w;
+}
+
+// ordered compaction of a bitmap into an ascending list (keeps mixedCells_ bit-exact in ORDER too)
+#define SV_SCAN_WORDS 1024  // words per block
+__global__ void k_count_bits(const unsigned int* bits, int nWords, unsigned int* blockSums)
+{
+    __shared__ unsigned int red[32];
+    const int w = blockIdx.x * SV_SCAN_WORDS + threadIdx.x;
+    unsigned int cnt = (w < nWords) ? __popc(bits[w]) : 0;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned int v = red[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) blockSums[blockIdx.x] = v;
+    }
+}
+__global__ void k_scan_blocks(unsigned int* blockSums, int nBlocks, Ctl* ctl, int capacity)
+{
+    // single CTA, exclusive scan in place; total -> ctl->nMixed
+    __shared__ unsigned int warpTot[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nBlocks; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const unsigned int v = (i < nBlocks) ? blockSums[i] : 0;
+        unsigned int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned int t = warpTot[threadIdx.x], ti = t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, ti, o);
+                if (threadIdx.x >= o) ti += u;
+            }
+            warpTot[threadIdx.x] = ti - t;  // exclusive
+        }
+        __syncthreads();
+        const unsigned int excl = carry + warpTot[threadIdx.x >> 5] + inc - v;
+        if (i < nBlocks) blockSums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int n = (int)carry;
+        if (n > capacity) {
+            atomicOr(&ctl->err, SVERR_LIST);
+            n = capacity;
+        }
+        ctl->nMixed = n;
+    }
+}
+__global__ void k_write_mixed(const unsigned int* bits, int nWords, const unsigned int* blockSums, int capacity,
+                              int* mixedCells, int* cellStatus, int* cellSlot)
+{
+    __shared__ unsigned int warpTot[32];
+    const int w = blockIdx.x * SV_SCAN_WORDS + threadIdx.x;
+    const unsigned int word = (w < nWords) ? bits[w] : 0;
+    const unsigned int v = __popc(word);
+    unsigned int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned int t = warpTot[threadIdx.x], ti = t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, ti, o);
+            if (threadIdx.x >= o) ti += u;
+        }
+        warpTot[threadIdx.x] = ti - t;
+    }
+    __syncthreads();
+    unsigned int pos = blockSums[blockIdx.x] + warpTot[threadIdx.x >> 5] + inc - v;
+    unsigned int rem = word;
+    while (rem) {
+        const int b = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const int c = (w << 5) + b;
+        if ((int)pos < capacity) {
+            mixedCells[pos] = c;
+            cellStatus[pos] = -100;  // reconstruction.C:670
+            cellSlot[c] = (int)pos;
+        }
+        ++pos;
+    }
+}
+
+// near1 = mixed U face-neighbours (== needBounding of advectionTemplates.C:138-141 via
+// advection.C:54-82); near2 = near1 U face-neighbours (cells a bounding correction can touch).
+// Bits are set with atomicOr; the thread that flips a near2 bit appends the cell to the list,
+// so the list is a duplicate-free SET (its order is irrelevant: every consumer is per-cell).
+__device__ __forceinline__ void markNear2(int c, unsigned int* near2, int* near2List, Ctl* ctl, int cap)
+{
+    const unsigned int bit = 1u << (c & 31);
+    const unsigned int old = atomicOr(&near2[c >> 5], bit);
+    if (!(old & bit)) {
+        const int pos = atomicAdd(&ctl->nNear2, 1);
+        if (pos < cap) near2List[pos] = c; else atomicOr(&ctl->err, SVERR_LIST);
+    }
+}
+__global__ void k_mark_near(MeshDev m, const int* mixedCells, Ctl* ctl, unsigned int* near1, unsigned int* near2,
+                            int* near2List, int cap)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = mixedCells[i];
+        atomicOr(&near1[c >> 5], 1u << (c & 31));
+        markNear2(c, near2, near2List, ctl, cap);
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int y = m.cellAsc[k].y;
+            if (y < 0) continue;
+            atomicOr(&near1[y >> 5], 1u << (y & 31));
+            markNear2(y, near2, near2List, ctl, cap);
+            for (int q = m.cellOff[y]; q < m.cellOff[y + 1]; ++q) {
+                const int z = m.cellAsc[q].y;
+                if (z >= 0) markNear2(z, near2, near2List, ctl, cap);
+            }
+        }
+    }
+}
+
+// A2: reconstruction::calcInterfaceNFromIsoAlphaGrad (reconstruction.C:85-141), thread per mixed
+// cell.  Stencil = the cell, then every cell sharing a vertex (ascending label), then the valid
+// boundary faces at its vertices (ascending): zoneCPCStencil membership with a pinned order.
+// The dense normalisation pass of :138 collapses to the mixed cells (0/(0+SMALL) = 0 elsewhere).
+#define SV_MAXST 160
+#define SV_MAXSB 64
+__device__ __forceinline__ bool sortedInsert(int* a, int& n, int cap, int v)
+{
+    int j = n - 1;
+    while (j >= 0 && a[j] > v) --j;
+    if (j >= 0 && a[j] == v) return true;
+    if (n >= cap) return false;
+    for (int q = n - 1; q > j; --q) a[q + 1] = a[q];
+    a[j + 1] = v;
+    ++n;
+    return true;
+}
+__global__ void __launch_bounds__(128) k_ls_normals(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
+                                                    const double* __restrict__ alphaB, StepParams sp, double* iN)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int celli = mixedCells[i];
+        int st[SV_MAXST], sb[SV_MAXSB];
+        int ns = 0, nb = 0, err = 0;
+        for (int k = m.cellPtOff[celli]; k < m.cellPtOff[celli + 1]; ++k) {
+            const int p = m.cellPts[k];
+            for (int j = m.ptCellOff[p]; j < m.ptCellOff[p + 1]; ++j) {
+                const int c = m.ptCells[j];
+                if (c != celli && !sortedInsert(st, ns, SV_MAXST, c)) err |= SVERR_STENCIL;
+            }
+            for (int j = m.ptBFOff[p]; j < m.ptBFOff[p + 1]; ++j) {
+                const int bf = m.ptBFaces[j];
+                if (m.bKind[bf] == 0 && !sortedInsert(sb, nb, SV_MAXSB, bf)) err |= SVERR_STENCIL;
+            }
+        }
+        if (err) atomicOr(&ctl->err, err);
+        int dims[3], nDims = 0;
+        for (int d = 0; d < 3; ++d)
+            if (sp.geomD[d] == 1) dims[nDims++] = d;
+        const int nTerms = 1 + nDims;
+        double A[4][4], src[4];
+        for (int r = 0; r < 4; ++r) {
+            src[r] = 0.0;
+            for (int q = 0; q < 4; ++q) A[r][q] = 0.0;
+        }
+        const d3 Ci = ld3(m.C, celli);
+        for (int s = -1; s < ns + nb; ++s) {
+            d3 pos;
+            double val;
+            if (s < 0) {
+                pos = Ci;
+                val = alpha[celli];
+            } else if (s < ns) {
+                pos = ld3(m.C, st[s]);
+                val = alpha[st[s]];
+            } else {
+                const int bf = sb[s - ns];
+                pos = ld3(m.Cf, m.nIF + bf);
+                val = alphaB[bf];
+            }
+            pos -= Ci;
+            const double comp[3] = {pos.x, pos.y, pos.z};
+            double terms[4];
+            terms[0] = 1.0;
+            for (int d = 0; d < nDims; ++d) terms[d + 1] = comp[dims[d]];
+            for (int r = 0; r < nTerms; ++r) {
+                src[r] += terms[r] * val;
+                for (int q = 0; q < nTerms; ++q) A[r][q] += terms[r] * terms[q];
+            }
+        }
+        luSolve4(A, src, nTerms);
+        double g[3] = {0.0, 0.0, 0.0};
+        for (int d = 0; d < nDims; ++d) g[dims[d]] = src[d + 1];
+        d3 nn = -mk3(g[0], g[1], g[2]);
+        nn /= (mag(nn) + SV_SMALL);
+        st3(iN, celli, nn);
+    }
+}
+
+// ========================================================================= advect ====
+// volPointInterpolation evaluated lazily at one point (OF, recalled)
+__device__ d3 pointU(const MeshDev& m, int p, const double* __restrict__ U, const double* __restrict__ Ub)
+{
+    const d3 pt = ld3(m.points, p);
+    d3 val = zero3();
+    if (!m.isPatchPoint[p]) {
+        const int j0 = m.ptCellOff[p], j1 = m.ptCellOff[p + 1];
+        double sumW = 0.0;
+        for (int j = j0; j < j1; ++j) sumW += 1.0 / mag(pt - ld3(m.C, m.ptCells[j]));
+        for (int j = j0; j < j1; ++j) {
+            const int c = m.ptCells[j];
+            const double pw = (1.0 / mag(pt - ld3(m.C, c))) / sumW;
+            val += pw * ld3(U, c);
+        }
+        return val;
+    }
+    const int j0 = m.ptBFOff[p], j1 = m.ptBFOff[p + 1];
+    double sumW = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const int bf = m.ptBFaces[j];
+        if (m.bKind[bf] == 0) sumW += 1.0 / mag(pt - ld3(m.Cf, m.nIF + bf));
+    }
+    for (int j = j0; j < j1; ++j) {
+        const int bf = m.ptBFaces[j];
+        if (m.bKind[bf] != 0) continue;
+        const double pw = (1.0 / mag(pt - ld3(m.Cf, m.nIF + bf))) / sumW;
+        val += pw * ld3(Ub, bf);
+    }
+    return val;
+}
+
+// tetrahedron::pointToBarycentric (OF, recalled); a = cell centre
+__device__ __forceinline__ double pointToBarycentric(const d3& a, const d3& b, const d3& c, const d3& d, const d3& pt, double* bary)
+{
+    const d3 v0 = a - d, v1 = b - d, v2 = c - d;
+    const double xx = v0.x, xy = v1.x, xz = v2.x, yx = v0.y, yy = v1.y, yz = v2.y, zx = v0.z, zy = v1.z, zz = v2.z;
+    const double detT = (xx * yy * zz + xy * yz * zx + xz * yx * zy - xx * yz * zy - xy * yx * zz - xz * yy * zx);
+    if (fabs(detT) < SV_SMALL) {
+        bary[0] = bary[1] = bary[2] = bary[3] = 0.25;
+        return detT;
+    }
+    const double ixx = (yy * zz - zy * yz) / detT, ixy = (xz * zy - xy * zz) / detT, ixz = (xy * yz - xz * yy) / detT;
+    const double iyx = (zx * yz - yx * zz) / detT, iyy = (xx * zz - xz * zx) / detT, iyz = (yx * xz - xx * yz) / detT;
+    const double izx = (yx * zy - yy * zx) / detT, izy = (xy * zx - xx * zy) / detT, izz = (xx * yy - yx * xy) / detT;
+    const d3 r = pt - d;
+    const double rx = ixx * r.x + ixy * r.y + ixz * r.z;
+    const double ry = iyx * r.x + iyy * r.y + iyz * r.z;
+    const double rz = izx * r.x + izy * r.y + izz * r.z;
+    bary[0] = rx;
+    bary[1] = ry;
+    bary[2] = rz;
+    bary[3] = 1 - (rx + ry + rz);
+    return detT;
+}
+
+__device__ __forceinline__ void tetTri(const MeshDev& m, int f, int tetPt, int celli, int* tri)
+{
+    const int o = m.faceOff[f], n = m.faceOff[f + 1] - o;
+    const int base = m.tetBase[f];
+    int facePtI = (tetPt + base) % n;
+    int faceOtherPtI = (facePtI + 1) % n;
+    if (m.owner[f] != celli) {
+        const int t = facePtI;
+        facePtI = faceOtherPtI;
+        faceOtherPtI = t;
+    }
+    tri[0] = m.facePts[o + base];
+    tri[1] = m.facePts[o + facePtI];
+    tri[2] = m.facePts[o + faceOtherPtI];
+}
+
+// interpolationCellPoint<vector>::interpolate(position, celli) (OF, recalled)
+__device__ d3 interpolateU(const MeshDev& m, const d3& position, int celli, const double* __restrict__ U,
+                           const double* __restrict__ Ub)
+{
+    const double tol = SV_SMALL;
+    const double cellVolume = m.V[celli];
+    const d3 cc = ld3(m.C, celli);
+    double w[4];
+    int tri[3];
+    bool found = false;
+    const int c0 = m.cellOff[celli], c1 = m.cellOff[celli + 1];
+    for (int k = c0; k < c1 && !found; ++k) {
+        const int f = m.cellFaces[k];
+        const int nv = m.faceOff[f + 1] - m.faceOff[f];
+        for (int tetPt = 1; tetPt < nv - 1 && !found; ++tetPt) {
+            tetTri(m, f, tetPt, celli, tri);
+            const double det = pointToBarycentric(cc, ld3(m.points, tri[0]), ld3(m.points, tri[1]), ld3(m.points, tri[2]), position, w);
+            if (fabs(det / cellVolume) > tol) {
+                const double u = w[0], v = w[1], ww = w[2];
+                if ((u + tol > 0) && (v + tol > 0) && (ww + tol > 0) && (u + v + ww < 1 + tol)) found = true;
+            }
+        }
+    }
+    if (!found) {  // least-violated tet (the interface centre lies inside its cell; safety net)
+        double best = SV_VGREAT;
+        int bt[3] = {0, 0, 0};
+        double bw[4] = {0.25, 0.25, 0.25, 0.25};
+        for (int k = c0; k < c1; ++k) {
+            const int f = m.cellFaces[k];
+            const int nv = m.faceOff[f + 1] - m.faceOff[f];
+            for (int tetPt = 1; tetPt < nv - 1; ++tetPt) {
+                int t3[3];
+                double tw[4];
+                tetTri(m, f, tetPt, celli, t3);
+                pointToBarycentric(cc, ld3(m.points, t3[0]), ld3(m.points, t3[1]), ld3(m.points, t3[2]), position, tw);
+                double viol = 0;
+                for (int q = 0; q < 4; ++q) viol += (tw[q] < 0) ? -tw[q] : 0;
+                if (viol < best) {
+                    best = viol;
+                    for (int q = 0; q < 3; ++q) bt[q] = t3[q];
+                    for (int q = 0; q < 4; ++q) bw[q] = tw[q];
+                }
+            }
+        }
+        for (int q = 0; q < 3; ++q) tri[q] = bt[q];
+        for (int q = 0; q < 4; ++q) w[q] = bw[q];
+    }
+    d3 t = ld3(U, celli) * w[0];
+    t += pointU(m, tri[0], U, Ub) * w[1];
+    t += pointU(m, tri[1], U, Ub) * w[2];
+    t += pointU(m, tri[2], U, Ub) * w[3];
+    return t;
+}
+
+// A7 first half (advection.C:112-175): interface speed per cut cell + the compacted work list of
+// (cut cell, downwind face) pairs.  Each face has exactly one upwind cell, so the list is
+// duplicate free and the flux kernel's writes are conflict free.
+__global__ void __launch_bounds__(128) k_un0_worklist(MeshDev m, const int* mixedCells, const int* cellStatus, Ctl* ctl,
+                                                      const double* iN, const double* iC, const double* __restrict__ U,
+                                                      const double* __restrict__ Ub, const double* __restrict__ phi,
+                                                      double* Un0, int2* work, int capWork)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (cellStatus[i] != 0) {
+            Un0[i] = 0.0;
+            continue;
+        }
+        const int c = mixedCells[i];
+        const d3 nn = ld3(iN, c);
+        Un0[i] = dot(interpolateU(m, ld3(iC, c), c, U, Ub), nn);
+        int cnt = 0;
+        int loc[64];
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int f = m.cellFaces[k];
+            bool down;
+            if (f < m.nIF) down = (m.owner[f] == c) ? (phi[f] >= 0.0) : (phi[f] < 0.0);
+            else down = (m.bKind[f - m.nIF] != 1) && (phi[f] >= 0.0);  // advection.C:192-197
+            if (down) {
+                if (cnt < 64) loc[cnt++] = f; else atomicOr(&ctl->err, SVERR_CELL_FACES);
+            }
+        }
+        if (cnt) {
+            const int pos = atomicAdd(&ctl->nWork, cnt);
+            for (int q = 0; q < cnt; ++q) {
+                if (pos + q < capWork) work[pos + q] = make_int2(i, loc[q]); else atomicOr(&ctl->err, SVERR_LIST);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void blockMinMax(double mn, double mx, unsigned long long* gmin, unsigned long long* gmax)
+{
+    __shared__ unsigned long long smn[32], smx[32];
+    unsigned long long kmn = dkey(mn), kmx = dkey(mx);
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long a = __shfl_down_sync(0xffffffffu, kmn, o);
+        const unsigned long long b = __shfl_down_sync(0xffffffffu, kmx, o);
+        kmn = (a < kmn) ? a : kmn;
+        kmx = (b > kmx) ? b : kmx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        smn[threadIdx.x >> 5] = kmn;
+        smx[threadIdx.x >> 5] = kmx;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        kmn = (threadIdx.x < nw) ? smn[threadIdx.x] : ~0ull;
+        kmx = (threadIdx.x < nw) ? smx[threadIdx.x] : 0ull;
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long a = __shfl_down_sync(0xffffffffu, kmn, o);
+            const unsigned long long b = __shfl_down_sync(0xffffffffu, kmx, o);
+            kmn = (a < kmn) ? a : kmn;
+            kmx = (b > kmx) ? b : kmx;
+        }
+        if (threadIdx.x == 0) {
+            atomicMin(gmin, kmn);
+            atomicMax(gmax, kmx);
+        }
+    }
+}
+
+// advection.C:291-308, applied per cell
+__device__ __forceinline__ double snapClip(double a, double snapTol, int clip)
+{
+    if (snapTol > 0.0) a = a * pos0(a - snapTol) * neg0(a - (1.0 - snapTol)) + pos0(a - (1.0 - snapTol));
+    if (clip) a = dmin(1.0, dmax(0.0, a));
+    return a;
+}
+
+// upwind face transport of one face seen from cell c (advectionTemplates.C:371), boundary incl.
+__device__ __forceinline__ bool upwindDVf(const MeshDev& m, int c, int f, bool flip, int other, double ph,
+                                          const double* __restrict__ aOld, const double* __restrict__ alphaB, double dt, double& dvf)
+{
+    if (other >= 0) {
+        const int own = flip ? other : c, nei = flip ? c : other;
+        const double aUp = (ph >= 0) ? aOld[own] : aOld[nei];
+        dvf = (ph * aUp) * dt;
+        return true;
+    }
+    const int bf = -1 - other;
+    const unsigned char kind = m.bKind[bf];
+    if (kind == 1) return false;  // empty patch: no field
+    double ab = alphaB[bf];
+    if (kind == 2) ab = (ph >= 0) ? aOld[c] : ab;  // processor: upwind between the two sides
+    dvf = (ph * ab) * dt;
+    return true;
+}
+
+// A6 + A10 + A12 fused: THE streaming pass (K7).  Thread per cell; a cell gathers its faces in
+// ascending face order through the cell->face CSR (deterministic segmented reduction, no atomics,
+// same summation order as fvc::surfaceIntegrate), recomputes the upwind transport of each face on
+// the fly (dVf is never materialised), writes alpha_new and, for the faces it owns, alphaPhi.
+// Cells in near2 are left to the sparse kernels.  Also emits the next step's mixed-cell bitmap.
+__global__ void __launch_bounds__(256) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                                      const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                                      double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
+                                                      unsigned int* __restrict__ mixedNext, double dt, const double* __restrict__ Sp,
+                                                      const double* __restrict__ Su, StepParams sp, Ctl* ctl)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    bool mixed = false;
+    if (c < m.nCells && !bitTest(near2, c)) {
+        const double rDt = 1.0 / dt;
+        const int k0 = __ldg(m.cellOff + c), k1 = __ldg(m.cellOff + c + 1);
+        double sum = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const int2 e = __ldg(m.cellAsc + k);
+            const int f = e.x & 0x7fffffff;
+            const bool flip = e.x < 0;
+            double dvf;
+            if (!upwindDVf(m, c, f, flip, e.y, __ldg(phi + f), aOld, alphaB, dt, dvf)) continue;
+            if (!flip) {
+                sum += dvf;
+                alphaPhi[f] = dvf / dt;
+            } else {
+                sum -= dvf;
+            }
+        }
+        const double ivf = sum / __ldg(m.V + c);
+        double num = aOld[c] * rDt;
+        if (Su) num = num + Su[c];
+        num = num - ivf * rDt;
+        double a = num / (Sp ? (rDt - Sp[c]) : rDt);
+        mn = a;
+        mx = a;
+        a = snapClip(a, sp.snapTol, sp.clip);
+        aNew[c] = a;
+        mixed = (sp.mixedTol < a) && (a < 1.0 - sp.mixedTol);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, mixed);
+    if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
+    blockMinMax(mn, mx, &ctl->minDense, &ctl->maxDense);
+}
+
+// true transport of face f seen from cell c: the geometric value where the face is downwind of a
+// cut cell (advection.C:134-166,185-217), else the upwind value
+__device__ __forceinline__ bool faceDVf(const MeshDev& m, int c, int f, bool flip, int other, double ph,
+                                        const double* __restrict__ aOld, const double* __restrict__ alphaB, double dt,
+                                        const int* __restrict__ cellSlot, const int* __restrict__ cellStatus,
+                                        const double* __restrict__ dVfGeo, double& dvf)
+{
+    int up;
+    if (other >= 0) {
+        const int own = flip ? other : c, nei = flip ? c : other;
+        up = (ph >= 0) ? own : nei;
+    } else {
+        if (m.bKind[-1 - other] == 1) return false;
+        up = (ph >= 0) ? c : -1;
+    }
+    if (up >= 0) {
+        const int slot = cellSlot[up];
+        if (slot >= 0 && cellStatus[slot] == 0) {
+            dvf = dVfGeo[f];
+            return true;
+        }
+    }
+    return upwindDVf(m, c, f, flip, other, ph, aOld, alphaB, dt, dvf);
+}
+
+// A10 for the near2 cells (same expression and order as k_dense_update) + dVf scratch for bounding
+__global__ void __launch_bounds__(128) k_near_update(MeshDev m, const int* near2List, Ctl* ctl, const double* __restrict__ aOld,
+                                                     double* aNew, const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                                     const int* cellSlot, const int* cellStatus, const double* dVfGeo, double* dVf,
+                                                     double dt, const double* Sp, const double* Su)
+{
+    const int n = ctl->nNear2;
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = near2List[i];
+        const double rDt = 1.0 / dt;
+        double sum = 0.0;
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int2 e = m.cellAsc[k];
+            const int f = e.x & 0x7fffffff;
+            const bool flip = e.x < 0;
+            double dvf;
+            if (!faceDVf(m, c, f, flip, e.y, phi[f], aOld, alphaB, dt, cellSlot, cellStatus, dVfGeo, dvf)) continue;
+            dVf[f] = dvf;  // both sides store the identical value
+            if (!flip) sum += dvf; else sum -= dvf;
+        }
+        const double ivf = sum / m.V[c];
+        double num = aOld[c] * rDt;
+        if (Su) num = num + Su[c];
+        num = num - ivf * rDt;
+        const double a = num / (Sp ? (rDt - Sp[c]) : rDt);
+        aNew[c] = a;
+        mn = dmin(mn, a);
+        mx = dmax(mx, a);
+    }
+    blockMinMax(mn, mx, &ctl->minNear[0], &ctl->maxNear[0]);
+}
+
+// ---- A11: limitFlux / boundFlux (advectionTemplates.C:118-349) -----------------------------------
+__device__ __forceinline__ bool needSweep(const Ctl* ctl, int s)
+{
+    const unsigned long long kmn = (ctl->minDense < ctl->minNear[s]) ? ctl->minDense : ctl->minNear[s];
+    const unsigned long long kmx = (ctl->maxDense > ctl->maxNear[s]) ? ctl->maxDense : ctl->maxNear[s];
+    const double maxAlphaMinus1 = dunkey(kmx) - 1.0, minAlpha = dunkey(kmn);
+    return (maxAlphaMinus1 > SV_ATOL || minAlpha < -SV_ATOL);
+}
+
+__device__ __forceinline__ bool faceActive(const MeshDev& m, int f) { return f < m.nIF || m.bKind[f - m.nIF] != 1; }
+
+// sweep s, step 1: reset the correction scratch on the faces of needBounding cells and list the
+// cells that violate the bounds (advectionTemplates.C:243-245)
+__global__ void k_bound_find(MeshDev m, const int* near2List, const unsigned int* near1, Ctl* ctl, int s, const double* alpha,
+                             double* corr, int* corrBy, int* oobList, unsigned char* oobState)
+{
+    if (!needSweep(ctl, s)) return;
+    const int n = ctl->nNear2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = near2List[i];
+        if (!bitTest(near1, c)) continue;
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int f = m.cellFaces[k];
+            corr[f] = 0.0;
+            corrBy[f] = -1;
+        }
+        const double a = alpha[c];
+        if (a < -SV_ATOL || a > 1.0 + SV_ATOL) {
+            oobState[c] = 1;
+            const int pos = atomicAdd(&ctl->nOob, 1);
+            oobList[pos] = c;
+            atomicAdd(&ctl->nPending, 1);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->nSweeps = s + 1;
+}
+
+// body of boundFlux for one cell (advectionTemplates.C:245-346)
+__device__ void boundCell(const MeshDev& m, int celli, const double* alpha, const double* aOld, const double* __restrict__ phi,
+                          const double* dVf, double* corr, int* corrBy, int* corrPos, double dt, const double* Sp,
+                          const double* Su)
+{
+    const double rDeltaT = 1.0 / dt;
+    const double Vi = m.V[celli];
+    const int c0 = m.cellOff[celli], c1 = m.cellOff[celli + 1];
+    const double a0 = alpha[celli];
+    double alphaOvershoot = pos0(a0 - 1.0) * (a0 - 1.0) + neg0(a0) * a0;
+    double fluidToPassOn = alphaOvershoot * Vi;
+    int nFacesToPassFluidThrough = 1;
+    bool firstLoop = true;
+    int nRecorded = 0;
+    for (int iter = 0; iter < 10; ++iter) {
+        if (fabs(alphaOvershoot) < SV_ATOL || nFacesToPassFluidThrough == 0) break;
+        // pass 1 over the downwind faces (setDownwindFaces, advection.C:224-256): dVftot
+        double dVftot = 0;
+        nFacesToPassFluidThrough = 0;
+        for (int k = c0; k < c1; ++k) {
+            const int f = m.cellFaces[k];
+            const double phif = faceActive(m, f) ? phi[f] : 0.0;
+            const bool down = (m.owner[f] == celli) ? (phif >= 0) : (phif < 0);
+            if (!down) continue;
+            const double dVff = (faceActive(m, f) ? dVf[f] : 0.0) + (faceActive(m, f) ? corr[f] : 0.0);
+            const double maxExtra = fabs(pos0(fluidToPassOn) * phif * dt - dVff);
+            if (maxExtra / Vi > SV_ATOL) dVftot += fabs(phif * dt);
+        }
+        // pass 2: distribute.  Eligibility is re-evaluated from the values of pass 1: a face's own
+        // corr entry is only modified after its test, exactly as in the two loops of the reference
+        // (facesToPassFluidThrough is fixed before any correction of this iteration is written).
+        double room[64];
+        int nEl = 0;
+        for (int k = c0; k < c1; ++k) {
+            const int f = m.cellFaces[k];
+            const double phif = faceActive(m, f) ? phi[f] : 0.0;
+            const bool down = (m.owner[f] == celli) ? (phif >= 0) : (phif < 0);
+            double r = -1.0;
+            if (down) {
+                const double dVff = (faceActive(m, f) ? dVf[f] : 0.0) + (faceActive(m, f) ? corr[f] : 0.0);
+                const double maxExtra = fabs(pos0(fluidToPassOn) * phif * dt - dVff);
+                if (maxExtra / Vi > SV_ATOL) r = maxExtra;
+            }
+            if (nEl < 64) room[nEl++] = r;
+        }
+        int q = 0;
+        for (int k = c0; k < c1; ++k, ++q) {
+            if (q >= 64 || room[q] < 0.0) continue;
+            const int f = m.cellFaces[k];
+            const double phif = phi[f];
+            double through = fabs(fluidToPassOn) * fabs(phif * dt) / dVftot;
+            nFacesToPassFluidThrough += int(pos0(room[q] - through));
+            through = dmin(through, room[q]);
+            double dVff = corr[f];
+            dVff += sgn(phif) * sgn(fluidToPassOn) * through;
+            corr[f] = dVff;
+            if (firstLoop) {
+                corrBy[f] = celli;
+                corrPos[f] = nRecorded++;
+            }
+        }
+        firstLoop = false;
+        double nf = 0.0, nc = 0.0;  // netFlux(dVf_), netFlux(dVfCorrectionValues)  (advection.C:259-288)
+        for (int k = c0; k < c1; ++k) {
+            const int f = m.cellFaces[k];
+            const double a = faceActive(m, f) ? dVf[f] : 0.0, b = faceActive(m, f) ? corr[f] : 0.0;
+            if (m.owner[f] == celli) {
+                nf += a;
+                nc += b;
+            } else {
+                nf -= a;
+                nc -= b;
+            }
+        }
+        const double SuI = Su ? Su[celli] : 0.0, SpI = Sp ? Sp[celli] : 0.0;
+        const double alpha1New = (aOld[celli] * rDeltaT + SuI - nf / Vi * rDeltaT - nc / Vi * rDeltaT) / (rDeltaT - SpI);
+        alphaOvershoot = pos0(alpha1New - 1.0) * (alpha1New - 1.0) + neg0(alpha1New) * alpha1New;
+        fluidToPassOn = alphaOvershoot * Vi;
+    }
+}
+
+// A cell may run once every LOWER-index face-neighbour that is also out of bounds has finished:
+// that reproduces the ascending-index Gauss-Seidel sweep of the reference (SURVEY 8a' item 15).
+__device__ __forceinline__ bool boundReady(const MeshDev& m, int c, const volatile unsigned char* oobState)
+{
+    for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+        const int y = m.cellAsc[k].y;
+        if (y >= 0 && y < c && oobState[y] == 1) return false;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_bound_wave(MeshDev m, Ctl* ctl, int s, const int* oobList, unsigned char* oobState,
+                                                    const double* alpha, const double* aOld, const double* phi, const double* dVf,
+                                                    double* corr, int* corrBy, int* corrPos, double dt, const double* Sp,
+                                                    const double* Su)
+{
+    if (ctl->nSweeps != s + 1 || ctl->nPending == 0) return;
+    const int n = ctl->nOob;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = oobList[i];
+        if (oobState[c] != 1) continue;
+        if (!boundReady(m, c, oobState)) continue;
+        boundCell(m, c, alpha, aOld, phi, dVf, corr, corrBy, corrPos, dt, Sp, Su);
+        __threadfence();
+        ((volatile unsigned char*)oobState)[c] = 2;
+        atomicSub(&ctl->nPending, 1);
+    }
+}
+
+// single CTA: drains whatever dependency chains the wave launches left
+__global__ void __launch_bounds__(1024) k_bound_drain(MeshDev m, Ctl* ctl, int s, const int* oobList, unsigned char* oobState,
+                                                      const double* alpha, const double* aOld, const double* phi, const double* dVf,
+                                                      double* corr, int* corrBy, int* corrPos, double dt, const double* Sp,
+                                                      const double* Su)
+{
+    if (ctl->nSweeps != s + 1) return;
+    const int n = ctl->nOob;
+    for (int guard = 0; guard < (1 << 20); ++guard) {
+        if (((volatile Ctl*)ctl)->nPending == 0) break;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int c = oobList[i];
+            if (oobState[c] != 1) continue;
+            if (!boundReady(m, c, oobState)) continue;
+            boundCell(m, c, alpha, aOld, phi, dVf, corr, corrBy, corrPos, dt, Sp, Su);
+            __threadfence();
+            ((volatile unsigned char*)oobState)[c] = 2;
+            atomicSub(&ctl->nPending, 1);
+        }
+        __threadfence();
+        __syncthreads();
+    }
+}
+
+// sweep s, last step (advectionTemplates.C:164-192,207-208): apply each recorded correction once
+// to alpha[own]/alpha[nei]/dVf, in the order of the reference's correctedFaces list
+// (= ascending corrector cell, then position in its first-iteration face list).
+__global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, const int* near2List, Ctl* ctl, int s, double* alpha, double* dVf,
+                                                     const double* corr, const int* corrBy, const int* corrPos, const int* oobList,
+                                                     unsigned char* oobState)
+{
+    const bool swept = (ctl->nSweeps == s + 1);
+    const int n = ctl->nNear2;
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = near2List[i];
+        double a = alpha[c];
+        if (swept) {
+            int fl[64];
+            long long key[64];
+            int nf = 0;
+            for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+                const int f = m.cellFaces[k];
+                if (!faceActive(m, f)) continue;
+                // corrBy is only meaningful on faces of needBounding cells (reset in k_bound_find)
+                const int by = corrBy[f];
+                if (by < 0) continue;
+                const int other = (m.owner[f] == c) ? (f < m.nIF ? m.neighbour[f] : -1) : m.owner[f];
+                if (by != c && by != other) continue;  // stale entry of an earlier step
+                if (nf < 64) {
+                    fl[nf] = f;
+                    key[nf] = ((long long)by << 20) | (long long)corrPos[f];
+                    nf++;
+                }
+            }
+            for (int x = 1; x < nf; ++x) {  // insertion sort by key
+                const long long kx = key[x];
+                const int fx = fl[x];
+                int y = x - 1;
+                while (y >= 0 && key[y] > kx) {
+                    key[y + 1] = key[y];
+                    fl[y + 1] = fl[y];
+                    --y;
+                }
+                key[y + 1] = kx;
+                fl[y + 1] = fx;
+            }
+            const double Vc = m.V[c];
+            for (int x = 0; x < nf; ++x) {
+                const int f = fl[x];
+                if (m.owner[f] == c) {
+                    a -= corr[f] / Vc;
+                    dVf[f] = dVf[f] + corr[f];  // setFaceValue(dVf_, facei, corrVf): done once, by the owner
+                } else {
+                    a += corr[f] / Vc;
+                }
+            }
+            alpha[c] = a;
+        }
+        mn = dmin(mn, a);
+        mx = dmax(mx, a);
+    }
+    blockMinMax(mn, mx, &ctl->minNear[s + 1], &ctl->maxNear[s + 1]);
+}
+
+// reset the per-sweep scratch (stream-ordered after k_bound_apply)
+__global__ void k_bound_reset(Ctl* ctl, const int* oobList, unsigned char* oobState, int* corrBy, MeshDev m)
+{
+    const int n = ctl->nOob;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = oobList[i];
+        oobState[c] = 0;
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) corrBy[m.cellFaces[k]] = -1;
+    }
+}
+__global__ void k_bound_reset_counts(Ctl* ctl)
+{
+    ctl->nOob = 0;
+    ctl->nPending = 0;
+}
+
+// A12 for the near2 cells + alphaPhi on the faces they own + their bits of the next mixed bitmap
+__global__ void __launch_bounds__(128) k_near_finalize(MeshDev m, const int* near2List, Ctl* ctl, double* alpha, const double* dVf,
+                                                       double* alphaPhi, unsigned int* mixedNext, double dt, StepParams sp)
+{
+    const int n = ctl->nNear2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = near2List[i];
+        const double a = snapClip(alpha[c], sp.snapTol, sp.clip);
+        alpha[c] = a;
+        if ((sp.mixedTol < a) && (a < 1.0 - sp.mixedTol)) atomicOr(&mixedNext[c >> 5], 1u << (c & 31));
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int f = m.cellFaces[k];
+            if (m.owner[f] == c && faceActive(m, f)) alphaPhi[f] = dVf[f] / dt;  // advectionTemplates.C:417
+        }
+    }
+}
+
+// volScalarField::correctBoundaryConditions for zeroGradient / fixedValue / inletOutlet -- thread per boundary face
+struct PatchDev {
+    int start, size, kind, bc;
+    double value;
+};
+__global__ void k_alpha_bc(MeshDev m, const PatchDev* patches, const int* bPatch, const double* __restrict__ alpha,
+                           const double* __restrict__ phi, double* alphaB)
+{
+    const int bf = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bf >= m.nBF) return;
+    const PatchDev p = patches[bPatch[bf]];
+    if (p.kind == 2) return;  // processor: filled by the halo exchange
+    double v = 0.0;
+    if (p.kind == 0) {
+        const int f = m.nIF + bf;
+        const double internal = alpha[m.owner[f]];
+        if (p.bc == 1) v = p.value;
+        else if (p.bc == 2) {
+            const double vf = 1.0 - pos0(phi[f]);
+            v = vf * p.value + (1.0 - vf) * internal;
+        } else v = internal;
+    }
+    alphaB[bf] = v;
+}
+
+// ---- on-demand outputs ---------------------------------------------------------------------
+// dVf_ as the reference holds it after advect(): alphaPhi*dt is NOT bitwise dVf, so it is rebuilt:
+// upwind transport (from alpha.oldTime) everywhere, the stored scratch on faces of near2 cells.
+__global__ void k_materialize_dvf(MeshDev m, const double* aOld, const double* alphaB, const double* phi, double dt,
+                                  const unsigned int* near2, const double* dVfScratch, double* out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= m.nFaces) return;
+    const int own = m.owner[f];
+    const int nei = (f < m.nIF) ? m.neighbour[f] : -1;
+    if (!faceActive(m, f)) {
+        out[f] = 0.0;
+        return;
+    }
+    if (bitTest(near2, own) || (nei >= 0 && bitTest(near2, nei))) {
+        out[f] = dVfScratch[f];
+        return;
+    }
+    double dvf = 0.0;
+    upwindDVf(m, own, f, false, (nei >= 0) ? nei : (-1 - (f - m.nIF)), phi[f], aOld, alphaB, dt, dvf);
+    out[f] = dvf;
+}
+
+// deterministic sum(alpha*V): fixed-shape tree (block partials, then one block)
+__global__ void k_volume_partial(const double* alpha, const double* V, int n, double* partial)
+{
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += alpha[i] * V[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+#endif  // !SV_VARIANT
+
+}  // namespace svof

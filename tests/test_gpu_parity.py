@@ -1,0 +1,175 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances are BASELINE.json's: interface-cell set and cut-face topology
+bit-exact, alpha within 1e-12 absolute per step, volume conserved to 1e-13 relative.
+In practice the two agree BITWISE (same operation order, no FMA contraction); the asserts
+state the contractual tolerance and the bitwise result is reported."""
+import numpy as np
+import pytest
+
+from common import LEVEQUE_CONTROLS, SolveVofEqu, capi, exact_sphere_alpha, fields, meshmod
+
+pytestmark = pytest.mark.gpu
+
+ATOL_ALPHA = 1e-12
+
+
+def _pair(m, controls, oracle, product):
+    return SolveVofEqu(m, controls, lib=oracle), SolveVofEqu(m, controls, lib=product)
+
+
+def _setup_leveque(m, so, sg, t=0.0, dt=None, alpha0=None):
+    a0 = exact_sphere_alpha(m) if alpha0 is None else alpha0
+    C, Cf, Sf = so.field(capi.F_C), so.field(capi.F_CF), so.field(capi.F_SF)
+    U0, phi0 = fields.leveque_velocity(C), fields.face_flux(Cf, Sf)
+    for s in (so, sg):
+        s.setAlpha(a0)
+    return a0, U0, phi0
+
+
+def test_mesh_geometry_matches(oracle, product):
+    m = meshmod.hex_block(12)
+    so, sg = _pair(m, LEVEQUE_CONTROLS, oracle, product)
+    for f in (capi.F_CF, capi.F_SF, capi.F_C, capi.F_V, capi.F_FACE_FLATNESS):
+        a, b = so.field(f), sg.field(f)
+        assert np.array_equal(a, b), "mesh field %d differs: max %g" % (f, np.abs(a - b).max())
+    for i in (capi.I_FLATNESS_MIN, capi.I_FLATNESS_MAX):
+        assert so.info(i) == sg.info(i)
+
+
+@pytest.mark.parametrize("N", [16, 32])
+def test_reconstruct_parity(oracle, product, N):
+    m = meshmod.hex_block(N)
+    so, sg = _pair(m, LEVEQUE_CONTROLS, oracle, product)
+    _setup_leveque(m, so, sg)
+    so.reconstruct()
+    sg.reconstruct()
+    mo, mg = so.mixedCells(), sg.mixedCells()
+    assert np.array_equal(mo, mg), "interface-cell list must be bit-exact (and in the same order)"
+    assert np.array_equal(so.cellStatus(), sg.cellStatus())
+    for name, f in (("N", capi.F_INTERFACE_N), ("D", capi.F_INTERFACE_D), ("C", capi.F_INTERFACE_C), ("S", capi.F_INTERFACE_S)):
+        a, b = so.field(f), sg.field(f)
+        assert np.abs(a - b).max() <= 1e-13, "interface%s differs by %g" % (name, np.abs(a - b).max())
+        assert np.array_equal(a, b), "interface%s not bitwise equal (max %g)" % (name, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("N,steps", [(16, 12), (32, 8)])
+def test_step_parity_leveque(oracle, product, N, steps):
+    m = meshmod.hex_block(N)
+    so, sg = _pair(m, LEVEQUE_CONTROLS, oracle, product)
+    a0, U0, phi0 = _setup_leveque(m, so, sg)
+    dt = 0.5 / N / 2.0
+    t = 0.0
+    v0 = sg.volume()
+    for k in range(steps):
+        t += dt
+        f = fields.u_factor(t, dt, 6.0)
+        for s in (so, sg):
+            s.setPhi(phi0 * f)
+            s.setU(U0 * f)
+            s.reconstruct()
+            s.advect(dt)
+        ao, ag = so.alpha(), sg.alpha()
+        assert np.array_equal(so.mixedCells(), sg.mixedCells()), "step %d: interface-cell set differs" % k
+        assert np.array_equal(so.cellStatus(), sg.cellStatus()), "step %d: cut status differs" % k
+        d = np.abs(ao - ag).max()
+        assert d <= ATOL_ALPHA, "step %d: alpha differs by %g" % (k, d)
+        assert np.array_equal(ao, ag), "step %d: alpha not bitwise equal (max %g)" % (k, d)
+        assert np.array_equal(so.field(capi.F_UN0), sg.field(capi.F_UN0))
+        assert np.array_equal(so.alphaPhi(), sg.alphaPhi()), "step %d: alphaPhi differs" % k
+        assert np.array_equal(so.field(capi.F_DVF), sg.field(capi.F_DVF)), "step %d: dVf differs" % k
+        assert so.info(capi.I_N_BOUND_SWEEPS) == sg.info(capi.I_N_BOUND_SWEEPS)
+        for i in (capi.I_MIN_ALPHA_BEFORE, capi.I_MAX_ALPHA_M1_BEFORE, capi.I_MIN_ALPHA_AFTER, capi.I_MAX_ALPHA_M1_AFTER):
+            assert so.info(i) == sg.info(i), "info %d differs: %r vs %r" % (i, so.info(i), sg.info(i))
+        assert abs(sg.volume() - v0) <= 1e-13 * abs(v0), "volume not conserved"
+        assert abs(sg.volume() - so.volume()) <= 1e-13 * abs(v0)
+    assert sg.info(capi.I_ERROR_FLAGS) == 0
+
+
+def test_step_parity_clip_snap_sources(oracle, product):
+    """damBreak-style controls (clip true, snapTol 1e-12, mixedCellTol 1e-10, nAlphaBounds 5:
+    tutorials/solvers/interPlicFoam/damBreakWithObstacle/system/fvSolution) and non-zero Sp/Su
+    (interPlicPhaseChangeFoam/alphaSuSp.H:14-15)."""
+    N = 16
+    m = meshmod.hex_block(N)
+    ctl = dict(LEVEQUE_CONTROLS, clip=True, snapTol=1e-12, mixedCellTol=1e-10, nAlphaBounds=5)
+    so, sg = _pair(m, ctl, oracle, product)
+    a0, U0, phi0 = _setup_leveque(m, so, sg)
+    rng = np.random.default_rng(7)
+    Sp = -0.3 * rng.random(m.n_cells)
+    Su = 0.05 * rng.random(m.n_cells) * (a0 > 0)
+    dt = 0.01
+    for k in range(6):
+        for s in (so, sg):
+            s.setPhi(phi0)
+            s.setU(U0)
+            s.reconstruct()
+            s.advect(dt, Sp=Sp, Su=Su)
+        ao, ag = so.alpha(), sg.alpha()
+        assert np.array_equal(so.mixedCells(), sg.mixedCells())
+        assert np.abs(ao - ag).max() <= ATOL_ALPHA
+        assert np.array_equal(ao, ag)
+        assert ag.min() >= 0.0 and ag.max() <= 1.0
+        assert np.array_equal(so.field(capi.F_ALPHA_BOUNDARY), sg.field(capi.F_ALPHA_BOUNDARY))
+
+
+def test_primitives_parity(oracle, product):
+    N = 8
+    m = meshmod.hex_block(N)
+    so, sg = _pair(m, LEVEQUE_CONTROLS, oracle, product)
+    rng = np.random.default_rng(3)
+    n = 4000
+    h = 1.0 / N
+    # polygons: random quads/pentagons near the unit square, random planes
+    for nv in (3, 4, 5, 7):
+        ang = np.sort(rng.uniform(0, 2 * np.pi, size=(n, nv)), axis=1)
+        r = rng.uniform(0.5, 1.0, size=(n, nv))
+        pts = np.stack([r * np.cos(ang), r * np.sin(ang), 0.05 * rng.normal(size=(n, nv))], axis=2)
+        nrm = rng.normal(size=(n, 3))
+        nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        D = rng.uniform(-0.8, 0.8, n)
+        D[:50] = -(nrm[:50] * pts[:50, 0]).sum(1)  # plane exactly through a vertex
+        ro, rg = so.cutFaces(pts, nrm, D), sg.cutFaces(pts, nrm, D)
+        for a, b in zip(ro, rg):
+            assert np.array_equal(a, b)
+    cells = rng.integers(0, m.n_cells, n).astype(np.int32)
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    nrm[:100] = np.eye(3)[rng.integers(0, 3, 100)]  # axis-aligned: planes through faces/vertices
+    C = so.field(capi.F_C)[cells]
+    D = -(nrm * (C + rng.uniform(-0.7 * h, 0.7 * h, size=(n, 3)))).sum(1)
+    for a, b in zip(so.cutCells(cells, nrm, D), sg.cutCells(cells, nrm, D)):
+        assert np.array_equal(a, b)
+    al = rng.uniform(1e-8, 1 - 1e-8, n)
+    al[:20] = 10.0 ** rng.uniform(-8, -3, 20)
+    for a, b in zip(so.findSignedDistance(cells, al, nrm), sg.findSignedDistance(cells, al, nrm)):
+        assert np.array_equal(a, b)
+    faces = rng.integers(0, m.n_faces, n).astype(np.int32)
+    Cf = so.field(capi.F_CF)[faces]
+    D = -(nrm * (Cf + rng.uniform(-0.6 * h, 0.6 * h, size=(n, 3)))).sum(1)
+    Un0 = rng.uniform(-2, 2, n)
+    Un0[:30] = 0.0
+    phi = rng.uniform(-1, 1, n) * h * h
+    assert np.array_equal(so.faceFluxes(faces, nrm, D, Un0, 0.3 * h, phi), sg.faceFluxes(faces, nrm, D, Un0, 0.3 * h, phi))
+
+
+def test_step_host_matches_split_calls(oracle, product):
+    N = 16
+    m = meshmod.hex_block(N)
+    s1 = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=product)
+    s2 = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=product)
+    a0 = exact_sphere_alpha(m)
+    C, Cf, Sf = s1.field(capi.F_C), s1.field(capi.F_CF), s1.field(capi.F_SF)
+    U0, phi0 = fields.leveque_velocity(C), fields.face_flux(Cf, Sf)
+    s1.setAlpha(a0)
+    s2.setAlpha(a0)
+    out = np.empty(m.n_cells)
+    aphi = np.empty(m.n_faces)
+    for k in range(3):
+        s1.setPhi(phi0)
+        s1.setU(U0)
+        s1.reconstruct()
+        s1.advect(0.01)
+        s2.step_host(0.01, phi0, U0, None, out, aphi)
+        assert np.array_equal(s1.alpha(), out)
+        assert np.array_equal(s1.alphaPhi(), aphi)
+    assert s1.info(capi.I_GPU_LAUNCHES) > 0
