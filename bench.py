@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- SimPLIC alpha-advection throughput (BASELINE.json metric) on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  the reference algorithm on the host cores
+
+A "step" = one solveVofEqu::reconstruct() + advect() over the whole mesh (the two calls the
+reference driver times, plicVof.H:37-52).  Workload at N=1: BASELINE.json configs[1], the
+3-D LeVeque deformation test, sphere r=0.15 in the unit cube, 256^3 hexes, FP64, controls of
+tutorials/test/plicVofAdvectionFoam/system/fvSolution, fixed dt = 0.2/N (Co ~ 0.5).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from geometricvofext_b200 import capi, fields, mesh as meshmod  # noqa: E402
+from geometricvofext_b200.solver import SolveVofEqu  # noqa: E402
+
+CONTROLS = {"nAlphaBounds": 3, "snapTol": 0, "clip": False, "mixedCellTol": 1e-8, "orientationMethod": "LS",
+            "splitWarpedFace": False}
+METRIC = "alpha-advection cell-updates/sec"
+UNIT = "cell-updates/s"
+PERIOD = 6.0
+
+
+def b_alg(m):
+    """Algorithmic bytes of one step (SURVEY.md 8d / BASELINE.md): 24 nC + 16 nF + 4 (2 nIF + nBF)."""
+    nC, nF, nIF = m.n_cells, m.n_faces, m.n_internal_faces
+    return 24 * nC + 16 * nF + 4 * (2 * nIF + (nF - nIF))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(n, lo=None, hi=None, proc_nbr=None, cut_as_wall=False):
+    m = meshmod.hex_block(n, lo=lo or (0, 0, 0), hi=hi, proc_nbr=proc_nbr, cut_as_wall=cut_as_wall)
+    a0 = fields.sphere_alpha_quadrature(m)
+    return m, a0
+
+
+def velocity_fields(s, t, dt):
+    C_, Cf, Sf = s.field(capi.F_C), s.field(capi.F_CF), s.field(capi.F_SF)
+    f = fields.u_factor(t, dt, PERIOD)
+    U = fields.leveque_velocity(C_) * f
+    phi = fields.face_flux(Cf, Sf) * f
+    return U, phi
+
+
+def cpu_oracle_rate(m, a0, U, phi, dt, steps):
+    """The CPU restatement of the reference algorithm, timed on this box's host (1 core)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build as oracle_build
+    lib = capi.load(oracle_build.build_oracle())
+    so = SolveVofEqu(m, CONTROLS, lib=lib)
+    so.setAlpha(a0)
+    so.setPhi(phi)
+    so.setU(U)
+    so.reconstruct()   # warm-up (page faults, first-touch)
+    so.advect(dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        so.reconstruct()
+        so.advect(dt)
+    el = time.perf_counter() - t0
+    rate = m.n_cells * steps / el
+    so.close()
+    return rate, el
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 or world > 1:
+        from geometricvofext_b200 import multigpu
+        return multigpu.bench(args, CONTROLS, METRIC, UNIT)
+    n = args.n
+    t_setup = time.perf_counter()
+    m, a0 = build_case(n)
+    s = SolveVofEqu(m, CONTROLS)
+    dt = 0.2 / n
+    U, phi = velocity_fields(s, dt, dt)
+    Ub = np.zeros((s.nBF, 3))
+    s.setAlpha(a0)
+    s.setPhi(phi)
+    s.setU(U, Ub)
+    s.synchronize()
+    setup_s = time.perf_counter() - t_setup
+
+    lib, h = s.lib, s._h
+    # ---- device-resident leg: inputs already in HBM ------------------------------------------
+    for _ in range(args.warmup):
+        s.reconstruct()
+        s.advect(dt)
+    s.synchronize()
+    l0, d0, dn0 = s.info(capi.I_GPU_LAUNCHES), s.info(capi.I_DENSE_KERNEL_MS), s.info(capi.I_DENSE_KERNEL_LAUNCHES)
+    clocks = ClockSampler()
+    clocks.start()
+    lib.svof_mark(h, 0)
+    for _ in range(args.steps):
+        s.reconstruct()
+        s.advect(dt)
+    lib.svof_mark(h, 1)
+    ms = C.c_double()
+    lib.svof_elapsed_ms(h, 0, 1, C.byref(ms))
+    s.synchronize()
+    clk = clocks.stop()
+    total_ms = ms.value
+    launches = int(s.info(capi.I_GPU_LAUNCHES) - l0)
+    dense_ms = (s.info(capi.I_DENSE_KERNEL_MS) - d0) / max(1.0, s.info(capi.I_DENSE_KERNEL_LAUNCHES) - dn0)
+    value = m.n_cells * args.steps / (total_ms * 1e-3)
+    n_mixed, n_near = int(s.info(capi.I_N_MIXED)), int(s.info(capi.I_N_NEAR))
+    recon_s, adv_s = s.reconstructionTime(), s.advectionTime()
+
+    # ---- end-to-end leg: host buffers in, results out, every step ------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    phi_h, U_h, Ub_h = capi.pinned_array(lib, (s.nF,)), capi.pinned_array(lib, (s.nC, 3)), capi.pinned_array(lib, (max(s.nBF, 1), 3))
+    a_out, ap_out = capi.pinned_array(lib, (s.nC,)), capi.pinned_array(lib, (s.nF,))
+    phi_h[:] = phi
+    U_h[:] = U
+    Ub_h[:] = 0
+    s.step_host(dt, phi_h, U_h, Ub_h, a_out, ap_out)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.step_host(dt, phi_h, U_h, Ub_h, a_out, ap_out)
+    e2e_s = time.perf_counter() - t0
+    e2e_val = m.n_cells * e2e_steps / e2e_s
+    h2d = 8 * (s.nF + 3 * s.nC + 3 * s.nBF)
+    d2h = 8 * (s.nC + s.nF)
+
+    # ---- roofline of the dominant (streaming) kernel ------------------------------------------
+    peak, peak_src = measured_peak()
+    B = b_alg(m)
+    achieved = B / (dense_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_dense_update_dram_bytes_per_launch_%d" % n)
+        except Exception:
+            traffic = None
+
+    # ---- CPU baseline: the oracle on the same workload, bounded sample ---------------------------
+    cpu = None
+    if not args.no_cpu:
+        cs = max(1, args.cpu_steps)
+        rate, el = cpu_oracle_rate(m, a0, U, phi, dt, cs)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "same %d^3 workload and fields, %d steps (%.1f s) of the single-threaded CPU restatement "
+                         "of the reference algorithm (oracle/), OpenFOAM itself is not installable here" % (n, cs, el)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LeVeque 3-D deformation, sphere r=0.15, %d^3 hex blockMesh (BASELINE.json configs[1])" % n,
+                   "cells": m.n_cells, "faces": m.n_faces, "dt": dt, "controls": CONTROLS, "mixed_cells": n_mixed,
+                   "near_cells": n_near, "l2": "inputs larger than L2 (%.2f GB of fields+connectivity per step)" % (B / 1e9),
+                   "timing": "CUDA events on the handle's stream around %d steps" % args.steps,
+                   "reconstruct_ms": 1e3 * recon_s / (args.steps + args.warmup + e2e_steps + 1),
+                   "advect_ms": 1e3 * adv_s / (args.steps + args.warmup + e2e_steps + 1), "setup_s": setup_s},
+        "clocks": clk,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "k_dense_update", "kernel_ms": dense_ms,
+                     "algorithmic_bytes_per_launch": B, "peak_source": peak_src,
+                     "step_frac": (B / (total_ms / args.steps * 1e-3) / 1e9) / peak},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def _ref_worker(args_tuple):
+    n, lo, hi, dt, steps, warm = args_tuple
+    m, a0 = build_case(n, lo=lo, hi=hi, cut_as_wall=True)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import build as oracle_build
+    lib = capi.load(oracle_build.build_oracle())
+    so = SolveVofEqu(m, CONTROLS, lib=lib)
+    U, phi = velocity_fields(so, dt, dt)
+    so.setAlpha(a0)
+    so.setPhi(phi)
+    so.setU(U)
+    for _ in range(warm):
+        so.reconstruct()
+        so.advect(dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        so.reconstruct()
+        so.advect(dt)
+    return m.n_cells, time.perf_counter() - t0
+
+
+def run_reference(args):
+    """The reference's own CPU algorithm for the path on the box's host cores.  OpenFOAM v2312 cannot be
+    built here (no wmake/MPI), so this is the oracle port, run the way the reference runs in parallel:
+    P sub-domains (z-slabs of the same mesh), one single-threaded process each, no halo exchange
+    (cut faces are treated as walls, which only removes communication cost from the CPU side)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    n = args.n
+    P = max(1, min(os.cpu_count() or 1, args.ref_procs or (os.cpu_count() or 1), n))
+    # the whole mesh, one z-slab per process (a smaller sample mesh only on request)
+    ns = args.ref_n or n
+    dt = 0.2 / ns
+    bounds = [(ns * p) // P for p in range(P + 1)]
+    steps = max(1, args.steps)
+    jobs = [(ns, (0, 0, bounds[p]), (ns, ns, bounds[p + 1]), dt, steps, max(1, min(args.warmup, 1))) for p in range(P)]
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(P) as pool:
+        res = pool.map(_ref_worker, jobs)
+    wall = time.perf_counter() - t0
+    cells = sum(r[0] for r in res)
+    tmax = max(r[1] for r in res)
+    value = cells * steps / tmax
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tmax / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LeVeque 3-D deformation, sphere r=0.15, %d^3 hex blockMesh (BASELINE.json configs[1])" % n,
+                   "sample_mesh": "%d^3 in %d z-slabs" % (ns, P), "dt": dt, "controls": CONTROLS, "wall_s": wall},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port",
+                         "sample": "%d^3 LeVeque mesh split into %d z-slab sub-domains, one single-threaded process each "
+                                   "(CPU restatement of the reference algorithm; OpenFOAM v2312/MPI not installable here), "
+                                   "%d steps, slowest rank %.1f s" % (ns, P, steps, tmax)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("SVOF_BENCH_N", "256")))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-procs", type=int, default=0)
+    ap.add_argument("--ref-n", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

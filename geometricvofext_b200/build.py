@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
                 raise RuntimeError("nvcc failed for %s" % name)
     objs = [os.path.join(OBJ, name + ".o") for name, _, _ in UNITS]
     if force or jobs or _stale(OUT, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-o", OUT] + objs
+        cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-Xlinker", "-Bsymbolic", "-o", OUT] + objs
         subprocess.check_call(cmd)
     return OUT
 

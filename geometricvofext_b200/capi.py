@@ -25,7 +25,8 @@ BC_ZERO_GRADIENT, BC_FIXED_VALUE, BC_INLET_OUTLET = 0, 1, 2
 # svof_info
 (I_N_MIXED, I_MIN_ALPHA_BEFORE, I_MAX_ALPHA_M1_BEFORE, I_MIN_ALPHA_AFTER, I_MAX_ALPHA_M1_AFTER, I_N_BOUND_SWEEPS,
  I_RECONSTRUCTION_TIME, I_ADVECTION_TIME, I_ALPHA_MAPPING_TIME, I_VOLUME, I_GPU_LAUNCHES, I_FLATNESS_MIN,
- I_FLATNESS_MAX, I_FLATNESS_AVG, I_DEVICE_BYTES, I_ERROR_FLAGS) = range(16)
+ I_FLATNESS_MAX, I_FLATNESS_AVG, I_DEVICE_BYTES, I_ERROR_FLAGS, I_DENSE_KERNEL_MS, I_DENSE_KERNEL_LAUNCHES,
+ I_N_NEAR) = range(19)
 
 
 class SvofPatch(C.Structure):
@@ -74,7 +75,11 @@ SYMBOLS = [
     ("svof_set_phi_device", C.c_int, [_H, C.c_void_p]),
     ("svof_set_U_device", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("svof_synchronize", C.c_int, [_H]),
+    ("svof_mark", C.c_int, [_H, C.c_int]),
+    ("svof_elapsed_ms", C.c_int, [_H, C.c_int, C.c_int, c_double_p]),
     ("svof_last_step_ms", C.c_int, [_H, c_double_p, c_double_p]),
+    ("svof_host_alloc", C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    ("svof_host_free", C.c_int, [C.c_void_p]),
     ("svof_cut_faces", C.c_int, [_H, C.c_int32, C.c_int32, c_double_p, c_double_p, c_double_p, c_int32_p,
                                  c_double_p, c_double_p]),
     ("svof_cut_cells", C.c_int, [_H, C.c_int32, c_int32_p, c_double_p, c_double_p, c_int32_p, c_double_p,
@@ -99,7 +104,8 @@ def load(path):
     if not os.path.exists(path):
         raise FileNotFoundError(
             "%s not found: build it first (python -c 'import __graft_entry__ as g; g.build()')" % path)
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # RTLD_LOCAL: the product and the test oracle export the same svof_* names
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     for name, res, args in SYMBOLS:
         fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
         fn.restype = res
@@ -136,3 +142,19 @@ def f64(a, shape=None):
 
 def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def pinned_array(lib, shape, dtype=np.float64):
+    """numpy array over page-locked host memory from svof_host_alloc (lives for the process)."""
+    count = int(np.prod(shape))
+    n = max(count * np.dtype(dtype).itemsize, 8)
+    p = C.c_void_p()
+    rc = lib.svof_host_alloc(n, C.byref(p))
+    if rc:
+        raise SvofError(rc, "svof_host_alloc(%d)" % n)
+    buf = (C.c_char * n).from_address(p.value)
+    _PINNED_KEEP.append((buf, p))
+    return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+
+_PINNED_KEEP = []

@@ -36,7 +36,11 @@ struct EventPair {
 
 struct svof_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // main stream: copies, sparse kernels, timing events
+    cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
+    cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr;
+    bool inputsAfterNear = false, freshRecon = false;
+    int advectCount = 0;
     int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
     std::vector<svof_patch> patches;
     svof_params prm;
@@ -59,8 +63,9 @@ struct svof_handle {
     int* near2List = nullptr;
     int2* work = nullptr;
     int capWork = 0, capMixed = 0, capNear = 0, nWords = 0, nScanBlocks = 0;
-    double *dVfGeo = nullptr, *dVf = nullptr, *corr = nullptr, *scratchF = nullptr;
-    int *corrBy = nullptr, *corrPos = nullptr, *oobList = nullptr;
+    double *dVfGeo = nullptr, *dVf = nullptr, *scratchF = nullptr;
+    BoundScratch bs;
+    int *oobList[2] = {nullptr, nullptr}, *affList = nullptr, *pendList = nullptr;
     unsigned char* oobState = nullptr;
     Ctl* ctl = nullptr;
     Ctl* hctl = nullptr;  // pinned mirror
@@ -75,6 +80,9 @@ struct svof_handle {
     double reconTime = 0, advTime = 0, lastReconMs = 0, lastAdvMs = 0;
     double flatMin = 1, flatMax = 1, flatAvg = 1;
     std::vector<EventPair> events;
+    cudaEvent_t marks[8] = {nullptr};
+    double denseMs = 0;
+    long long denseLaunches = 0;
     size_t evNext = 0;
     int sms = 148;
 };
@@ -398,19 +406,28 @@ void allocFields(svof_handle* h)
     h->work = dalloc<int2>(h, h->capWork);
     h->dVfGeo = dalloc<double>(h, nF);
     h->dVf = dalloc<double>(h, nF);
-    h->corr = dalloc<double>(h, nF);
     h->scratchF = dalloc<double>(h, nF);
-    h->corrBy = dalloc<int>(h, nF, false);
-    CK(cudaMemsetAsync(h->corrBy, 0xff, nF * sizeof(int), h->stream));
-    h->corrPos = dalloc<int>(h, nF);
-    h->oobList = dalloc<int>(h, h->capNear);
+    h->bs.corr = dalloc<double>(h, nF);
+    h->bs.tagV = dalloc<int>(h, nF);
+    h->bs.tagR = dalloc<int>(h, nF);
+    h->bs.corrBy = dalloc<int>(h, nF);
+    h->bs.corrPos = dalloc<int>(h, nF);
+    h->bs.affStamp = dalloc<int>(h, nC);
+    h->oobList[0] = dalloc<int>(h, h->capNear);
+    h->oobList[1] = dalloc<int>(h, h->capNear);
+    h->affList = dalloc<int>(h, h->capNear);
+    h->pendList = dalloc<int>(h, h->capNear);
     h->oobState = dalloc<unsigned char>(h, nC);
     h->ctl = dalloc<Ctl>(h, 1);
     h->partial = dalloc<double>(h, 1024);
     CK(cudaMallocHost((void**)&h->hctl, sizeof(Ctl)));
     CK(cudaMallocHost((void**)&h->hpartial, 1024 * sizeof(double)));
     memset(h->hctl, 0, sizeof(Ctl));
-    h->events.resize(64);
+    for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->marks[i]));
+    CK(cudaEventCreateWithFlags(&h->evNear, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evDense, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evInputs, cudaEventDisableTiming));
+    h->events.resize(96);
     for (EventPair& e : h->events) {
         CK(cudaEventCreate(&e.a));
         CK(cudaEventCreate(&e.b));
@@ -426,9 +443,26 @@ void harvestEvents(svof_handle* h, bool block)
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, e.a, e.b));
         if (e.kind == 0) { h->reconTime += ms * 1e-3; h->lastReconMs = ms; }
-        else { h->advTime += ms * 1e-3; h->lastAdvMs = ms; }
+        else if (e.kind == 1) { h->advTime += ms * 1e-3; h->lastAdvMs = ms; }
+        else { h->denseMs += ms; h->denseLaunches++; }
         e.pending = false;
     }
+}
+EventPair& beginTimedOn(svof_handle* h, int kind, cudaStream_t st)
+{
+    EventPair& e = h->events[h->evNext++ % h->events.size()];
+    if (e.pending) {
+        CK(cudaEventSynchronize(e.b));
+        harvestEvents(h, false);
+    }
+    e.kind = kind;
+    CK(cudaEventRecord(e.a, st));
+    return e;
+}
+void endTimedOn(svof_handle* h, EventPair& e, cudaStream_t st)
+{
+    CK(cudaEventRecord(e.b, st));
+    e.pending = true;
 }
 EventPair& beginTimed(svof_handle* h, int kind)
 {
@@ -450,17 +484,24 @@ void endTimed(svof_handle* h, EventPair& e)
 __global__ void k_ctl_reset_advect(Ctl* ctl)
 {
     ctl->nWork = 0;
-    ctl->nSweeps = 0;
-    ctl->nOob = 0;
-    ctl->nPending = 0;
+    ctl->nOob[0] = ctl->nOob[1] = 0;
+    for (int s = 0; s <= SV_MAX_SWEEPS; ++s) ctl->nPend[s] = ctl->nAff[s] = ctl->nearOob[s] = 0;
+    ctl->minNear0 = ctl->minNearF = ~0ull;
+    ctl->maxNear0 = ctl->maxNearF = 0ull;
+}
+// everything the streaming kernel touches is reset BEFORE the near bitmaps are published (evNear)
+__global__ void k_ctl_reset_recon(Ctl* ctl)
+{
+    ctl->nNear2 = 0;
     ctl->minDense = ~0ull;
     ctl->maxDense = 0ull;
-    for (int s = 0; s <= SV_MAX_SWEEPS; ++s) {
-        ctl->minNear[s] = ~0ull;
-        ctl->maxNear[s] = 0ull;
-    }
 }
-__global__ void k_ctl_reset_recon(Ctl* ctl) { ctl->nNear2 = 0; }
+
+__global__ void k_ctl_reset_dense(Ctl* ctl)
+{
+    ctl->minDense = ~0ull;
+    ctl->maxDense = 0ull;
+}
 
 void alphaBC(svof_handle* h)
 {
@@ -485,6 +526,9 @@ void doReconstruct(svof_handle* h)
     CK(cudaMemsetAsync(h->near2, 0, sizeof(unsigned int) * h->nWords, s));
     LAUNCH(h, k_ctl_reset_recon, 1, 1, h->ctl);
     LAUNCH(h, k_mark_near, g256, 256, d, h->mixedCells, h->ctl, h->near1, h->near2, h->near2List, h->capNear);
+    CK(cudaEventRecord(h->evNear, s));  // the streaming kernel of the coming advect() may start from here
+    h->inputsAfterNear = false;
+    h->freshRecon = true;
     // A2: LS normals; A3-A5: plane positions
     LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
     GEO(h, plic, s, g128, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
@@ -494,41 +538,66 @@ void doReconstruct(svof_handle* h)
 void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
 {
     const MeshDev& d = h->md;
-    const int g128 = sparseGrid(h, 128), g256 = sparseGrid(h, 256);
+    const int g128 = sparseGrid(h, 128);
     double* aOld = h->alphaBuf[h->cur];
     double* aNew = h->alphaBuf[h->cur ^ 1];
+    const double rDt = 1.0 / dt;
+    cudaStream_t sS = h->stream, sD = h->streamD;
+
+    // ---- streaming kernel on its own stream: depends only on alpha.oldTime, phi and the near2 bitmap,
+    //      so it overlaps the tail of reconstruct() and the whole sparse chain below
+    if (!h->freshRecon) LAUNCH(h, k_ctl_reset_dense, 1, 1, h->ctl);  // advect() without a new reconstruct()
+    if (h->inputsAfterNear || dSp || dSu || !h->freshRecon) {
+        CK(cudaEventRecord(h->evInputs, sS));
+        CK(cudaStreamWaitEvent(sD, h->evInputs, 0));
+    } else {
+        CK(cudaStreamWaitEvent(sD, h->evNear, 0));
+    }
+    EventPair& ed = beginTimedOn(h, 2, sD);
+    k_dense_update<<<cdiv(h->nC, 256), 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
+                                                      dt, rDt, dSp, dSu, h->sp, h->ctl);
+    h->launches++;
+    endTimedOn(h, ed, sD);
+    CK(cudaEventRecord(h->evDense, sD));
+
+    // ---- sparse chain
     LAUNCH(h, k_ctl_reset_advect, 1, 1, h->ctl);
     // A7-A9: geometric fluxes on the downwind faces of cut cells
     LAUNCH(h, k_un0_worklist, g128, 128, d, h->mixedCells, h->cellStatus, h->ctl, h->iN, h->iC, h->U, h->Ub, h->phi, h->Un0, h->work,
            h->capWork);
-    GEO(h, faceFlux, h->stream, g128, d, h->work, h->ctl, h->mixedCells, h->iN, h->iD, h->Un0, h->phi, dt, h->dVfGeo);
-    // A6+A10(+A12): the streaming pass, then the same update for the near2 cells
-    LAUNCH(h, k_dense_update, cdiv(h->nC, 256), 256, d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits, dt, dSp,
-           dSu, h->sp, h->ctl);
-    LAUNCH(h, k_near_update, g128, 128, d, h->near2List, h->ctl, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->cellSlot, h->cellStatus, h->dVfGeo,
-           h->dVf, dt, dSp, dSu);
-    // A11: conservative bounding sweeps (device-side predicate: a sweep that is not needed exits at once)
+    GEO(h, faceFlux, sS, g128, d, h->work, h->ctl, h->mixedCells, h->iN, h->iD, h->Un0, h->phi, dt, h->dVfGeo);
+    // A10 for the near2 cells
+    LAUNCH(h, k_near_update, g128, 128, d, h->near2List, h->near1, h->ctl, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->cellSlot,
+           h->cellStatus, h->dVfGeo, h->dVf, dt, rDt, dSp, dSu, h->oobList[0], h->oobState);
+    // A11: conservative bounding sweeps, each proportional to the number of out-of-bounds cells
+    const int gB = std::max(1, h->sms / 2);
     for (int sidx = 0; sidx < h->sp.nAlphaBounds; ++sidx) {
-        LAUNCH(h, k_bound_find, g256, 256, d, h->near2List, h->near1, h->ctl, sidx, aNew, h->corr, h->corrBy, h->oobList, h->oobState);
-        LAUNCH(h, k_bound_wave, g128, 128, d, h->ctl, sidx, h->oobList, h->oobState, aNew, aOld, h->phi, h->dVf, h->corr, h->corrBy,
-               h->corrPos, dt, dSp, dSu);
-        LAUNCH(h, k_bound_wave, g128, 128, d, h->ctl, sidx, h->oobList, h->oobState, aNew, aOld, h->phi, h->dVf, h->corr, h->corrBy,
-               h->corrPos, dt, dSp, dSu);
-        LAUNCH(h, k_bound_drain, 1, 1024, d, h->ctl, sidx, h->oobList, h->oobState, aNew, aOld, h->phi, h->dVf, h->corr, h->corrBy,
-               h->corrPos, dt, dSp, dSu);
-        LAUNCH(h, k_bound_apply, g128, 128, d, h->near2List, h->ctl, sidx, aNew, h->dVf, h->corr, h->corrBy, h->corrPos, h->oobList,
+        const int tag = h->advectCount * (SV_MAX_SWEEPS + 1) + sidx + 1;
+        LAUNCH(h, k_bound_wave, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, h->bs,
+               h->affList, h->pendList, dt, rDt, dSp, dSu);
+        LAUNCH(h, k_bound_drain, 1, 1024, d, h->ctl, sidx, tag, h->pendList, h->oobState, aNew, aOld, h->phi, h->dVf, h->bs, dt, rDt, dSp,
+               dSu);
+        LAUNCH(h, k_bound_apply, gB, 128, d, h->ctl, sidx, tag, h->affList, h->near1, aNew, h->dVf, h->bs, h->oobList[(sidx + 1) & 1],
                h->oobState);
-        LAUNCH(h, k_bound_reset, g256, 256, h->ctl, h->oobList, h->oobState, h->corrBy, d);
-        LAUNCH(h, k_bound_reset_counts, 1, 1, h->ctl);
+        LAUNCH(h, k_bound_flip, 1, 1, h->ctl, sidx);
     }
+    // join: the finalize kernel ORs into the bitmap words the streaming kernel wrote
+    CK(cudaStreamWaitEvent(sS, h->evDense, 0));
     // A12: snap/clip + alphaPhi for near2; boundary values of the new field
-    LAUNCH(h, k_near_finalize, g128, 128, d, h->near2List, h->ctl, aNew, h->dVf, h->alphaPhi, h->mixedBits, dt, h->sp);
+    LAUNCH(h, k_near_finalize, g128, 128, d, h->near2List, h->ctl, aNew, h->dVf, h->alphaPhi, h->mixedBits, dt, h->sp, h->oobState);
     h->cur ^= 1;
     h->cb ^= 1;  // keep the patch values alpha.oldTime() was advected with (for dVf materialisation)
     alphaBC(h);
     h->bitsValid = true;
     h->advected = true;
+    h->freshRecon = false;
     h->lastDt = dt;
+    if (++h->advectCount >= (1 << 25)) {  // tags would wrap: clear the tag arrays
+        CK(cudaMemsetAsync(h->bs.tagV, 0, sizeof(int) * h->nF, sS));
+        CK(cudaMemsetAsync(h->bs.tagR, 0, sizeof(int) * h->nF, sS));
+        CK(cudaMemsetAsync(h->bs.affStamp, 0, sizeof(int) * h->nC, sS));
+        h->advectCount = 0;
+    }
 }
 
 void fetchCtl(svof_handle* h)
@@ -647,6 +716,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         h->device = (comm && comm->device >= 0) ? comm->device : ((comm ? comm->rank : 0) % ndev);
         CK(cudaSetDevice(h->device));
         CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->streamD, cudaStreamNonBlocking));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
@@ -675,6 +745,7 @@ int svof_destroy(svof_handle* h)
     if (!h) return SVOF_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->streamD) cudaStreamSynchronize(h->streamD);
     for (void* p : h->allocs) cudaFree(p);
     if (h->hctl) cudaFreeHost(h->hctl);
     if (h->hpartial) cudaFreeHost(h->hpartial);
@@ -682,7 +753,12 @@ int svof_destroy(svof_handle* h)
         if (e.a) cudaEventDestroy(e.a);
         if (e.b) cudaEventDestroy(e.b);
     }
+    for (int i = 0; i < 8; ++i) if (h->marks[i]) cudaEventDestroy(h->marks[i]);
+    if (h->evNear) cudaEventDestroy(h->evNear);
+    if (h->evDense) cudaEventDestroy(h->evDense);
+    if (h->evInputs) cudaEventDestroy(h->evInputs);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->streamD) cudaStreamDestroy(h->streamD);
     delete h;
     return SVOF_OK;
 }
@@ -737,6 +813,7 @@ int svof_set_phi_device(svof_handle* h, const void* dphi)
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->phi, dphi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, h->stream));
     h->havePhi = true;
+    h->inputsAfterNear = true;
     return SVOF_OK;
     API_END(h)
 }
@@ -860,12 +937,22 @@ int svof_get_info(svof_handle* h, int which, double* out)
     if (!h || !out) return SVOF_ERR_INVALID_ARG;
     API_BEGIN
     CK(cudaSetDevice(h->device));
+    // number of sweeps the reference's loop executes = leading sweeps whose loop condition holds
+    // (advectionTemplates.C:144-198); derived from the recorded min/max and out-of-bounds counts
+    auto nSweeps = [&]() {
+        fetchCtl(h);
+        const Ctl& c = *h->hctl;
+        const bool denseOob = (c.maxDense != 0ull || c.minDense != ~0ull) &&
+                              (((dunkey(c.maxDense) - 1.0) > SV_ATOL) || (dunkey(c.minDense) < -SV_ATOL));
+        int n = 0;
+        while (n < h->sp.nAlphaBounds && (denseOob || c.nearOob[n] > 0)) ++n;
+        return n;
+    };
     auto sweepVals = [&](bool after, bool wantMin) {
         fetchCtl(h);
         const Ctl& c = *h->hctl;
-        const int s = after ? c.nSweeps : 0;
-        if (wantMin) return dunkey(std::min(c.minDense, c.minNear[s]));
-        return dunkey(std::max(c.maxDense, c.maxNear[s])) - 1.0;
+        if (wantMin) return dunkey(std::min(c.minDense, after ? c.minNearF : c.minNear0));
+        return dunkey(std::max(c.maxDense, after ? c.maxNearF : c.maxNear0)) - 1.0;
     };
     switch (which) {
         case SVOF_I_N_MIXED: fetchCtl(h); *out = h->hctl->nMixed; return SVOF_OK;
@@ -873,7 +960,7 @@ int svof_get_info(svof_handle* h, int which, double* out)
         case SVOF_I_MAX_ALPHA_M1_BEFORE: *out = sweepVals(false, false); return SVOF_OK;
         case SVOF_I_MIN_ALPHA_AFTER: *out = sweepVals(true, true); return SVOF_OK;
         case SVOF_I_MAX_ALPHA_M1_AFTER: *out = sweepVals(true, false); return SVOF_OK;
-        case SVOF_I_N_BOUND_SWEEPS: fetchCtl(h); *out = h->hctl->nSweeps; return SVOF_OK;
+        case SVOF_I_N_BOUND_SWEEPS: *out = nSweeps(); return SVOF_OK;
         case SVOF_I_RECONSTRUCTION_TIME: harvestEvents(h, true); *out = h->reconTime; return SVOF_OK;
         case SVOF_I_ADVECTION_TIME: harvestEvents(h, true); *out = h->advTime; return SVOF_OK;
         case SVOF_I_ALPHA_MAPPING_TIME: *out = 0; return SVOF_OK;
@@ -895,6 +982,9 @@ int svof_get_info(svof_handle* h, int which, double* out)
         case SVOF_I_FLATNESS_AVG: *out = h->flatAvg; return SVOF_OK;
         case SVOF_I_DEVICE_BYTES: *out = (double)h->bytes; return SVOF_OK;
         case SVOF_I_ERROR_FLAGS: fetchCtl(h); *out = h->hctl->err; return SVOF_OK;
+        case SVOF_I_DENSE_KERNEL_MS: harvestEvents(h, true); *out = h->denseMs; return SVOF_OK;
+        case SVOF_I_DENSE_KERNEL_LAUNCHES: harvestEvents(h, true); *out = (double)h->denseLaunches; return SVOF_OK;
+        case SVOF_I_N_NEAR: fetchCtl(h); *out = h->hctl->nNear2; return SVOF_OK;
     }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_get_info: unknown item");
     API_END(h)
@@ -937,9 +1027,33 @@ int svof_synchronize(svof_handle* h)
     if (!h) return SVOF_ERR_INVALID_ARG;
     API_BEGIN
     CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->streamD));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     return checkDeviceErr(h);
+    API_END(h)
+}
+
+int svof_mark(svof_handle* h, int slot)
+{
+    if (!h || slot < 0 || slot > 7) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->marks[slot], h->stream));
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_elapsed_ms(svof_handle* h, int a, int b, double* ms)
+{
+    if (!h || !ms || a < 0 || a > 7 || b < 0 || b > 7) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->marks[b]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, h->marks[a], h->marks[b]));
+    *ms = f;
+    return SVOF_OK;
     API_END(h)
 }
 
@@ -953,6 +1067,26 @@ int svof_last_step_ms(svof_handle* h, double* r, double* a)
     if (a) *a = h->lastAdvMs;
     return SVOF_OK;
     API_END(h)
+}
+
+int svof_host_alloc(int64_t bytes, void** out)
+{
+    if (!out || bytes <= 0) return SVOF_ERR_INVALID_ARG;
+    if (cudaMallocHost(out, (size_t)bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        g_createError = "cudaMallocHost failed";
+        return SVOF_ERR_CUDA;
+    }
+    return SVOF_OK;
+}
+
+int svof_host_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return SVOF_ERR_CUDA;
+    }
+    return SVOF_OK;
 }
 
 // ---- geometry primitives ------------------------------------------------------------------------

@@ -20,16 +20,18 @@ namespace svof {
 
 // device-resident control block (one per handle)
 struct Ctl {
-    int nMixed;       // mixedCells_.size()
-    int nMixedPrev;   // of the previous reconstruct (for sparse clearing)
-    int nNear2;       // |near2|
-    int nWork;        // (cut cell, downwind face) work items
-    int nOob;         // out-of-bounds cells of the current sweep
-    int nPending;     // ... not yet processed
-    int nSweeps;      // sweeps executed by the last advect
-    int err;          // SVERR_* flags
-    unsigned long long minDense, maxDense;                 // keys over cells outside near2
-    unsigned long long minNear[SV_MAX_SWEEPS + 1], maxNear[SV_MAX_SWEEPS + 1];  // over near2 after s sweeps
+    int nMixed;   // mixedCells_.size()
+    int nNear2;   // |near2|
+    int nWork;    // (cut cell, downwind face) work items
+    int err;      // SVERR_* flags
+    int nOob[2];  // out-of-bounds lists (double buffered between sweeps)
+    int nPend[SV_MAX_SWEEPS + 1];    // cells the wave launch of sweep s deferred
+    int nAff[SV_MAX_SWEEPS + 1];     // cells touched by the corrections of sweep s
+    int nearOob[SV_MAX_SWEEPS + 1];  // # near2 cells violating the limitFlux loop condition after s sweeps
+    int pad_;
+    unsigned long long minDense, maxDense;  // keys over the cells outside near2 (streaming kernel)
+    unsigned long long minNear0, maxNear0;  // over near2 before bounding
+    unsigned long long minNearF, maxNearF;  // over near2 after bounding (before snap/clip)
 };
 
 struct StepParams {
@@ -629,14 +631,14 @@ __device__ __forceinline__ bool upwindDVf(const MeshDev& m, int c, int f, bool f
 __global__ void __launch_bounds__(256) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
                                                       const double* __restrict__ phi, const double* __restrict__ alphaB,
                                                       double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
-                                                      unsigned int* __restrict__ mixedNext, double dt, const double* __restrict__ Sp,
-                                                      const double* __restrict__ Su, StepParams sp, Ctl* ctl)
+                                                      unsigned int* __restrict__ mixedNext, double dt, double rDt,
+                                                      const double* __restrict__ Sp, const double* __restrict__ Su, StepParams sp,
+                                                      Ctl* ctl)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     double mn = SV_VGREAT, mx = -SV_VGREAT;
     bool mixed = false;
     if (c < m.nCells && !bitTest(near2, c)) {
-        const double rDt = 1.0 / dt;
         const int k0 = __ldg(m.cellOff + c), k1 = __ldg(m.cellOff + c + 1);
         double sum = 0.0;
         for (int k = k0; k < k1; ++k) {
@@ -693,17 +695,25 @@ __device__ __forceinline__ bool faceDVf(const MeshDev& m, int c, int f, bool fli
     return upwindDVf(m, c, f, flip, other, ph, aOld, alphaB, dt, dvf);
 }
 
+// the two out-of-bounds tests of the reference are NOT the same expression:
+//   limitFlux loop condition (advectionTemplates.C:146): max(alpha) - 1 > aTol || min(alpha) < -aTol
+//   boundFlux eligibility     (advectionTemplates.C:245): alpha < -aTol || alpha > 1 + aTol
+__device__ __forceinline__ bool oobGlobal(double a) { return ((a - 1.0) > SV_ATOL) || (a < -SV_ATOL); }
+__device__ __forceinline__ bool oobBound(double a) { return (a < -SV_ATOL) || (a > 1.0 + SV_ATOL); }
+
 // A10 for the near2 cells (same expression and order as k_dense_update) + dVf scratch for bounding
-__global__ void __launch_bounds__(128) k_near_update(MeshDev m, const int* near2List, Ctl* ctl, const double* __restrict__ aOld,
-                                                     double* aNew, const double* __restrict__ phi, const double* __restrict__ alphaB,
-                                                     const int* cellSlot, const int* cellStatus, const double* dVfGeo, double* dVf,
-                                                     double dt, const double* Sp, const double* Su)
+// + the out-of-bounds list of the first bounding sweep.
+__global__ void __launch_bounds__(128) k_near_update(MeshDev m, const int* near2List, const unsigned int* near1, Ctl* ctl,
+                                                     const double* __restrict__ aOld, double* aNew, const double* __restrict__ phi,
+                                                     const double* __restrict__ alphaB, const int* cellSlot, const int* cellStatus,
+                                                     const double* dVfGeo, double* dVf, double dt, double rDt, const double* Sp,
+                                                     const double* Su, int* oobList0, unsigned char* oobState)
 {
     const int n = ctl->nNear2;
     double mn = SV_VGREAT, mx = -SV_VGREAT;
+    int nOobG = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = near2List[i];
-        const double rDt = 1.0 / dt;
         double sum = 0.0;
         for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
             const int2 e = m.cellAsc[k];
@@ -722,53 +732,41 @@ __global__ void __launch_bounds__(128) k_near_update(MeshDev m, const int* near2
         aNew[c] = a;
         mn = dmin(mn, a);
         mx = dmax(mx, a);
+        if (oobGlobal(a)) nOobG++;
+        if (oobBound(a) && bitTest(near1, c)) {  // needBounding = near1 (advectionTemplates.C:138-141)
+            oobState[c] = 1;
+            oobList0[atomicAdd(&ctl->nOob[0], 1)] = c;
+        }
     }
-    blockMinMax(mn, mx, &ctl->minNear[0], &ctl->maxNear[0]);
+    if (nOobG) atomicAdd(&ctl->nearOob[0], nOobG);
+    blockMinMax(mn, mx, &ctl->minNear0, &ctl->maxNear0);
 }
 
 // ---- A11: limitFlux / boundFlux (advectionTemplates.C:118-349) -----------------------------------
-__device__ __forceinline__ bool needSweep(const Ctl* ctl, int s)
-{
-    const unsigned long long kmn = (ctl->minDense < ctl->minNear[s]) ? ctl->minDense : ctl->minNear[s];
-    const unsigned long long kmx = (ctl->maxDense > ctl->maxNear[s]) ? ctl->maxDense : ctl->maxNear[s];
-    const double maxAlphaMinus1 = dunkey(kmx) - 1.0, minAlpha = dunkey(kmn);
-    return (maxAlphaMinus1 > SV_ATOL || minAlpha < -SV_ATOL);
-}
+// Work is proportional to the number of out-of-bounds cells, not to the mesh:
+//   sweep 0 starts from the list k_near_update built; sweep s+1 from the list k_bound_apply(s) built
+//   (a cell can only go/stay out of bounds where a correction touched it).
+// The sweeps do not depend on the streaming kernel: if the global loop condition holds only because
+// of cells outside needBounding the reference's sweep is a no-op too, so the sweeps run
+// unconditionally and "number of sweeps executed" is derived afterwards from the recorded counts.
+// Scratch arrays are validated by a per-sweep tag instead of being cleared.
+struct BoundScratch {
+    double* corr;   // dVfCorrectionValues, valid where tagV == tag
+    int* tagV;
+    int* tagR;      // == tag where the face was recorded in correctedFaces (first inner iteration)
+    int* corrBy;    // ... by which cell
+    int* corrPos;   // ... at which position of that cell's list
+    int* affStamp;  // per cell: == tag once the cell is in the affected list
+};
 
 __device__ __forceinline__ bool faceActive(const MeshDev& m, int f) { return f < m.nIF || m.bKind[f - m.nIF] != 1; }
-
-// sweep s, step 1: reset the correction scratch on the faces of needBounding cells and list the
-// cells that violate the bounds (advectionTemplates.C:243-245)
-__global__ void k_bound_find(MeshDev m, const int* near2List, const unsigned int* near1, Ctl* ctl, int s, const double* alpha,
-                             double* corr, int* corrBy, int* oobList, unsigned char* oobState)
-{
-    if (!needSweep(ctl, s)) return;
-    const int n = ctl->nNear2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int c = near2List[i];
-        if (!bitTest(near1, c)) continue;
-        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
-            const int f = m.cellFaces[k];
-            corr[f] = 0.0;
-            corrBy[f] = -1;
-        }
-        const double a = alpha[c];
-        if (a < -SV_ATOL || a > 1.0 + SV_ATOL) {
-            oobState[c] = 1;
-            const int pos = atomicAdd(&ctl->nOob, 1);
-            oobList[pos] = c;
-            atomicAdd(&ctl->nPending, 1);
-        }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->nSweeps = s + 1;
-}
+__device__ __forceinline__ double corrVal(const BoundScratch& b, int f, int tag) { return (b.tagV[f] == tag) ? b.corr[f] : 0.0; }
 
 // body of boundFlux for one cell (advectionTemplates.C:245-346)
 __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, const double* aOld, const double* __restrict__ phi,
-                          const double* dVf, double* corr, int* corrBy, int* corrPos, double dt, const double* Sp,
+                          const double* dVf, const BoundScratch& b, int tag, double dt, double rDeltaT, const double* Sp,
                           const double* Su)
 {
-    const double rDeltaT = 1.0 / dt;
     const double Vi = m.V[celli];
     const int c0 = m.cellOff[celli], c1 = m.cellOff[celli + 1];
     const double a0 = alpha[celli];
@@ -779,36 +777,30 @@ __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, cons
     int nRecorded = 0;
     for (int iter = 0; iter < 10; ++iter) {
         if (fabs(alphaOvershoot) < SV_ATOL || nFacesToPassFluidThrough == 0) break;
-        // pass 1 over the downwind faces (setDownwindFaces, advection.C:224-256): dVftot
+        // downwind faces (setDownwindFaces, advection.C:224-256) with room: facesToPassFluidThrough.
+        // Eligibility and dVftot are fixed BEFORE any correction of this iteration is written,
+        // exactly as in the two loops of the reference.
+        double room[64];
         double dVftot = 0;
         nFacesToPassFluidThrough = 0;
-        for (int k = c0; k < c1; ++k) {
+        int q = 0;
+        for (int k = c0; k < c1; ++k, ++q) {
             const int f = m.cellFaces[k];
-            const double phif = faceActive(m, f) ? phi[f] : 0.0;
-            const bool down = (m.owner[f] == celli) ? (phif >= 0) : (phif < 0);
-            if (!down) continue;
-            const double dVff = (faceActive(m, f) ? dVf[f] : 0.0) + (faceActive(m, f) ? corr[f] : 0.0);
-            const double maxExtra = fabs(pos0(fluidToPassOn) * phif * dt - dVff);
-            if (maxExtra / Vi > SV_ATOL) dVftot += fabs(phif * dt);
-        }
-        // pass 2: distribute.  Eligibility is re-evaluated from the values of pass 1: a face's own
-        // corr entry is only modified after its test, exactly as in the two loops of the reference
-        // (facesToPassFluidThrough is fixed before any correction of this iteration is written).
-        double room[64];
-        int nEl = 0;
-        for (int k = c0; k < c1; ++k) {
-            const int f = m.cellFaces[k];
-            const double phif = faceActive(m, f) ? phi[f] : 0.0;
+            const bool act = faceActive(m, f);
+            const double phif = act ? phi[f] : 0.0;
             const bool down = (m.owner[f] == celli) ? (phif >= 0) : (phif < 0);
             double r = -1.0;
             if (down) {
-                const double dVff = (faceActive(m, f) ? dVf[f] : 0.0) + (faceActive(m, f) ? corr[f] : 0.0);
+                const double dVff = (act ? dVf[f] : 0.0) + (act ? corrVal(b, f, tag) : 0.0);
                 const double maxExtra = fabs(pos0(fluidToPassOn) * phif * dt - dVff);
-                if (maxExtra / Vi > SV_ATOL) r = maxExtra;
+                if (maxExtra / Vi > SV_ATOL) {
+                    r = maxExtra;
+                    dVftot += fabs(phif * dt);
+                }
             }
-            if (nEl < 64) room[nEl++] = r;
+            if (q < 64) room[q] = r;
         }
-        int q = 0;
+        q = 0;
         for (int k = c0; k < c1; ++k, ++q) {
             if (q >= 64 || room[q] < 0.0) continue;
             const int f = m.cellFaces[k];
@@ -816,25 +808,41 @@ __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, cons
             double through = fabs(fluidToPassOn) * fabs(phif * dt) / dVftot;
             nFacesToPassFluidThrough += int(pos0(room[q] - through));
             through = dmin(through, room[q]);
-            double dVff = corr[f];
+            double dVff = corrVal(b, f, tag);
             dVff += sgn(phif) * sgn(fluidToPassOn) * through;
-            corr[f] = dVff;
+            b.corr[f] = dVff;
+            b.tagV[f] = tag;
             if (firstLoop) {
-                corrBy[f] = celli;
-                corrPos[f] = nRecorded++;
+                b.corrBy[f] = celli;
+                b.corrPos[f] = nRecorded++;
+                b.tagR[f] = tag;
             }
         }
         firstLoop = false;
         double nf = 0.0, nc = 0.0;  // netFlux(dVf_), netFlux(dVfCorrectionValues)  (advection.C:259-288)
         for (int k = c0; k < c1; ++k) {
             const int f = m.cellFaces[k];
-            const double a = faceActive(m, f) ? dVf[f] : 0.0, b = faceActive(m, f) ? corr[f] : 0.0;
-            if (m.owner[f] == celli) {
-                nf += a;
-                nc += b;
+            const bool act = faceActive(m, f);
+            const bool isOwn = (m.owner[f] == celli);
+            double bv = act ? corrVal(b, f, tag) : 0.0;
+            if (act) {
+                // a correction on a face that is downwind of the OTHER cell was written by that cell;
+                // in the reference's ascending sweep this cell has only seen it if the writer has a
+                // lower index (higher-index cells may already have run here: mask them out)
+                const double phif = phi[f];
+                const bool down = isOwn ? (phif >= 0) : (phif < 0);
+                if (!down) {
+                    const int other = isOwn ? ((f < m.nIF) ? m.neighbour[f] : -1) : m.owner[f];
+                    if (other > celli) bv = 0.0;
+                }
+            }
+            const double av = act ? dVf[f] : 0.0;
+            if (isOwn) {
+                nf += av;
+                nc += bv;
             } else {
-                nf -= a;
-                nc -= b;
+                nf -= av;
+                nc -= bv;
             }
         }
         const double SuI = Su ? Su[celli] : 0.0, SpI = Sp ? Sp[celli] : 0.0;
@@ -844,152 +852,171 @@ __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, cons
     }
 }
 
-// A cell may run once every LOWER-index face-neighbour that is also out of bounds has finished:
-// that reproduces the ascending-index Gauss-Seidel sweep of the reference (SURVEY 8a' item 15).
-__device__ __forceinline__ bool boundReady(const MeshDev& m, int c, const volatile unsigned char* oobState)
+// The reference sweeps the cells in ascending index (Gauss-Seidel, SURVEY 8a' item 15).  A cell only
+// ever READS corrections written by another cell on the faces that are DOWNWIND of that other cell,
+// so cell c must wait exactly for the lower-index out-of-bounds neighbours that are upwind of it
+// across the shared face; everything else commutes.
+__device__ __forceinline__ bool boundReady(const MeshDev& m, int c, const double* __restrict__ phi,
+                                           const volatile unsigned char* oobState)
 {
     for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
-        const int y = m.cellAsc[k].y;
-        if (y >= 0 && y < c && oobState[y] == 1) return false;
+        const int2 e = m.cellAsc[k];
+        const int y = e.y;
+        if (y < 0 || y >= c) continue;
+        if (oobState[y] != 1) continue;
+        const bool flip = e.x < 0;                      // c is the neighbour side of this face
+        const double ph = phi[e.x & 0x7fffffff];
+        const bool yIsUpwind = flip ? (ph >= 0) : (ph < 0);  // owner is upwind iff phi >= 0
+        if (yIsUpwind) return false;
     }
     return true;
 }
 
-__global__ void __launch_bounds__(128) k_bound_wave(MeshDev m, Ctl* ctl, int s, const int* oobList, unsigned char* oobState,
-                                                    const double* alpha, const double* aOld, const double* phi, const double* dVf,
-                                                    double* corr, int* corrBy, int* corrPos, double dt, const double* Sp,
-                                                    const double* Su)
+__device__ __forceinline__ void markAffected(int c, const BoundScratch& b, int tag, int* affList, int* nAff)
 {
-    if (ctl->nSweeps != s + 1 || ctl->nPending == 0) return;
-    const int n = ctl->nOob;
+    if (atomicExch(&b.affStamp[c], tag) != tag) affList[atomicAdd(nAff, 1)] = c;
+}
+
+__global__ void __launch_bounds__(128) k_bound_wave(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList, unsigned char* oobState,
+                                                    const double* alpha, const double* aOld, const double* phi, const double* dVf,
+                                                    BoundScratch b, int* affList, int* pendList, double dt, double rDt,
+                                                    const double* Sp, const double* Su)
+{
+    const int n = ctl->nOob[s & 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = oobList[i];
-        if (oobState[c] != 1) continue;
-        if (!boundReady(m, c, oobState)) continue;
-        boundCell(m, c, alpha, aOld, phi, dVf, corr, corrBy, corrPos, dt, Sp, Su);
-        __threadfence();
-        ((volatile unsigned char*)oobState)[c] = 2;
-        atomicSub(&ctl->nPending, 1);
-    }
-}
-
-// single CTA: drains whatever dependency chains the wave launches left
-__global__ void __launch_bounds__(1024) k_bound_drain(MeshDev m, Ctl* ctl, int s, const int* oobList, unsigned char* oobState,
-                                                      const double* alpha, const double* aOld, const double* phi, const double* dVf,
-                                                      double* corr, int* corrBy, int* corrPos, double dt, const double* Sp,
-                                                      const double* Su)
-{
-    if (ctl->nSweeps != s + 1) return;
-    const int n = ctl->nOob;
-    for (int guard = 0; guard < (1 << 20); ++guard) {
-        if (((volatile Ctl*)ctl)->nPending == 0) break;
-        __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int c = oobList[i];
-            if (oobState[c] != 1) continue;
-            if (!boundReady(m, c, oobState)) continue;
-            boundCell(m, c, alpha, aOld, phi, dVf, corr, corrBy, corrPos, dt, Sp, Su);
+        markAffected(c, b, tag, affList, &ctl->nAff[s]);
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int y = m.cellAsc[k].y;
+            if (y >= 0) markAffected(y, b, tag, affList, &ctl->nAff[s]);
+        }
+        if (boundReady(m, c, phi, oobState)) {
+            boundCell(m, c, alpha, aOld, phi, dVf, b, tag, dt, rDt, Sp, Su);
             __threadfence();
             ((volatile unsigned char*)oobState)[c] = 2;
-            atomicSub(&ctl->nPending, 1);
+        } else {
+            pendList[atomicAdd(&ctl->nPend[s], 1)] = c;
         }
-        __threadfence();
-        __syncthreads();
     }
 }
 
-// sweep s, last step (advectionTemplates.C:164-192,207-208): apply each recorded correction once
-// to alpha[own]/alpha[nei]/dVf, in the order of the reference's correctedFaces list
-// (= ascending corrector cell, then position in its first-iteration face list).
-__global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, const int* near2List, Ctl* ctl, int s, double* alpha, double* dVf,
-                                                     const double* corr, const int* corrBy, const int* corrPos, const int* oobList,
+// single CTA: walks the dependency chains the wave launch deferred (a few % of the cells)
+__global__ void __launch_bounds__(1024) k_bound_drain(MeshDev m, Ctl* ctl, int s, int tag, const int* pendList, unsigned char* oobState,
+                                                      const double* alpha, const double* aOld, const double* phi, const double* dVf,
+                                                      BoundScratch b, double dt, double rDt, const double* Sp, const double* Su)
+{
+    const int n = ctl->nPend[s];
+    if (n == 0) return;
+    __shared__ int remaining;
+    for (int guard = 0; guard < (1 << 22); ++guard) {
+        if (threadIdx.x == 0) remaining = 0;
+        __syncthreads();
+        int mine = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int c = pendList[i];
+            if (((volatile unsigned char*)oobState)[c] != 1) continue;
+            if (boundReady(m, c, phi, oobState)) {
+                boundCell(m, c, alpha, aOld, phi, dVf, b, tag, dt, rDt, Sp, Su);
+                __threadfence();
+                ((volatile unsigned char*)oobState)[c] = 2;
+            } else {
+                mine++;
+            }
+        }
+        if (mine) atomicAdd(&remaining, mine);
+        __syncthreads();
+        const int r = remaining;
+        __syncthreads();
+        if (r == 0) break;
+    }
+}
+
+// sweep s, last step (advectionTemplates.C:164-192,207-208): apply each recorded correction once to
+// alpha[own]/alpha[nei]/dVf, in the order of the reference's correctedFaces list (= ascending
+// corrector cell, then position in its first-iteration face list); then build the next sweep's list.
+__global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s, int tag, const int* affList, const unsigned int* near1,
+                                                     double* alpha, double* dVf, BoundScratch b, int* oobListNext,
                                                      unsigned char* oobState)
 {
-    const bool swept = (ctl->nSweeps == s + 1);
+    const int n = ctl->nAff[s];
+    int delta = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = affList[i];
+        double a = alpha[c];
+        const bool was = oobGlobal(a);
+        int fl[64];
+        long long key[64];
+        int nf = 0;
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int f = m.cellFaces[k];
+            if (!faceActive(m, f) || b.tagR[f] != tag) continue;
+            if (nf < 64) {
+                fl[nf] = f;
+                key[nf] = ((long long)b.corrBy[f] << 20) | (long long)b.corrPos[f];
+                nf++;
+            }
+        }
+        for (int x = 1; x < nf; ++x) {  // insertion sort by key
+            const long long kx = key[x];
+            const int fx = fl[x];
+            int y = x - 1;
+            while (y >= 0 && key[y] > kx) {
+                key[y + 1] = key[y];
+                fl[y + 1] = fl[y];
+                --y;
+            }
+            key[y + 1] = kx;
+            fl[y + 1] = fx;
+        }
+        const double Vc = m.V[c];
+        for (int x = 0; x < nf; ++x) {
+            const int f = fl[x];
+            const double cv = b.corr[f];
+            if (m.owner[f] == c) {
+                a -= cv / Vc;
+                dVf[f] = dVf[f] + cv;  // setFaceValue(dVf_, facei, corrVf): once, by the owner
+            } else {
+                a += cv / Vc;
+            }
+        }
+        alpha[c] = a;
+        delta += int(oobGlobal(a)) - int(was);
+        if (oobBound(a) && bitTest(near1, c)) {
+            oobState[c] = 1;
+            oobListNext[atomicAdd(&ctl->nOob[(s + 1) & 1], 1)] = c;
+        } else {
+            oobState[c] = 0;
+        }
+    }
+    if (delta) atomicAdd(&ctl->nearOob[s + 1], delta);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->nearOob[s + 1], ctl->nearOob[s]);
+}
+
+// between sweeps: the list sweep s consumed becomes the (empty) output list of sweep s+1
+__global__ void k_bound_flip(Ctl* ctl, int s) { ctl->nOob[s & 1] = 0; }
+
+// A12 for the near2 cells + alphaPhi on the faces they own + their bits of the next mixed bitmap
+__global__ void __launch_bounds__(128) k_near_finalize(MeshDev m, const int* near2List, Ctl* ctl, double* alpha, const double* dVf,
+                                                       double* alphaPhi, unsigned int* mixedNext, double dt, StepParams sp,
+                                                       unsigned char* oobState)
+{
     const int n = ctl->nNear2;
     double mn = SV_VGREAT, mx = -SV_VGREAT;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = near2List[i];
-        double a = alpha[c];
-        if (swept) {
-            int fl[64];
-            long long key[64];
-            int nf = 0;
-            for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
-                const int f = m.cellFaces[k];
-                if (!faceActive(m, f)) continue;
-                // corrBy is only meaningful on faces of needBounding cells (reset in k_bound_find)
-                const int by = corrBy[f];
-                if (by < 0) continue;
-                const int other = (m.owner[f] == c) ? (f < m.nIF ? m.neighbour[f] : -1) : m.owner[f];
-                if (by != c && by != other) continue;  // stale entry of an earlier step
-                if (nf < 64) {
-                    fl[nf] = f;
-                    key[nf] = ((long long)by << 20) | (long long)corrPos[f];
-                    nf++;
-                }
-            }
-            for (int x = 1; x < nf; ++x) {  // insertion sort by key
-                const long long kx = key[x];
-                const int fx = fl[x];
-                int y = x - 1;
-                while (y >= 0 && key[y] > kx) {
-                    key[y + 1] = key[y];
-                    fl[y + 1] = fl[y];
-                    --y;
-                }
-                key[y + 1] = kx;
-                fl[y + 1] = fx;
-            }
-            const double Vc = m.V[c];
-            for (int x = 0; x < nf; ++x) {
-                const int f = fl[x];
-                if (m.owner[f] == c) {
-                    a -= corr[f] / Vc;
-                    dVf[f] = dVf[f] + corr[f];  // setFaceValue(dVf_, facei, corrVf): done once, by the owner
-                } else {
-                    a += corr[f] / Vc;
-                }
-            }
-            alpha[c] = a;
-        }
-        mn = dmin(mn, a);
-        mx = dmax(mx, a);
-    }
-    blockMinMax(mn, mx, &ctl->minNear[s + 1], &ctl->maxNear[s + 1]);
-}
-
-// reset the per-sweep scratch (stream-ordered after k_bound_apply)
-__global__ void k_bound_reset(Ctl* ctl, const int* oobList, unsigned char* oobState, int* corrBy, MeshDev m)
-{
-    const int n = ctl->nOob;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int c = oobList[i];
-        oobState[c] = 0;
-        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) corrBy[m.cellFaces[k]] = -1;
-    }
-}
-__global__ void k_bound_reset_counts(Ctl* ctl)
-{
-    ctl->nOob = 0;
-    ctl->nPending = 0;
-}
-
-// A12 for the near2 cells + alphaPhi on the faces they own + their bits of the next mixed bitmap
-__global__ void __launch_bounds__(128) k_near_finalize(MeshDev m, const int* near2List, Ctl* ctl, double* alpha, const double* dVf,
-                                                       double* alphaPhi, unsigned int* mixedNext, double dt, StepParams sp)
-{
-    const int n = ctl->nNear2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int c = near2List[i];
-        const double a = snapClip(alpha[c], sp.snapTol, sp.clip);
+        const double a0 = alpha[c];
+        mn = dmin(mn, a0);  // "After conservative bounding" (advectionTemplates.C:207-212), before snap/clip
+        mx = dmax(mx, a0);
+        const double a = snapClip(a0, sp.snapTol, sp.clip);
         alpha[c] = a;
+        oobState[c] = 0;
         if ((sp.mixedTol < a) && (a < 1.0 - sp.mixedTol)) atomicOr(&mixedNext[c >> 5], 1u << (c & 31));
         for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
             const int f = m.cellFaces[k];
             if (m.owner[f] == c && faceActive(m, f)) alphaPhi[f] = dVf[f] / dt;  // advectionTemplates.C:417
         }
     }
+    blockMinMax(mn, mx, &ctl->minNearF, &ctl->maxNearF);
 }
 
 // volScalarField::correctBoundaryConditions for zeroGradient / fixedValue / inletOutlet -- thread per boundary face

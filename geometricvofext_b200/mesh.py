@@ -84,13 +84,15 @@ class PolyMesh:
 _HEX_PATCHES = [("top", 2, 1), ("left", 1, 0), ("back", 0, 0), ("right", 1, 1), ("bottom", 2, 0), ("front", 0, 1)]
 
 
-def hex_block(n, lo=(0, 0, 0), hi=None, length=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), proc_nbr=None):
+def hex_block(n, lo=(0, 0, 0), hi=None, length=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), proc_nbr=None,
+              cut_as_wall=False):
     """Uniform hex mesh of cells [lo,hi) out of a global n=(Nx,Ny,Nz) box.
 
     Natural cell order c = i + nx*j + nx*ny*k, upper-triangular face order (what
     blockMesh emits).  `proc_nbr` maps (axis, side) -> neighbour rank for sides
     that are cut by a decomposition; those become processor patches listed after
     the six physical patches (zero-sized where the side is not physical).
+    `cut_as_wall` closes cut sides with the physical patch instead (stand-alone sub-domain).
     """
     N = np.array(n if np.ndim(n) else (n, n, n), dtype=np.int64)
     lo = np.array(lo, dtype=np.int64)
@@ -165,7 +167,7 @@ def hex_block(n, lo=(0, 0, 0), hi=None, length=(1.0, 1.0, 1.0), origin=(0.0, 0.0
     b_fpts, b_own, patches = [], [], []
     start = n_if
     for name, axis, side in _HEX_PATCHES:
-        physical = (lo[axis] == 0) if side == 0 else (hi[axis] == N[axis])
+        physical = cut_as_wall or ((lo[axis] == 0) if side == 0 else (hi[axis] == N[axis]))
         if physical and (axis, side) not in proc_nbr:
             f, o = side_faces(axis, side)
         else:

@@ -228,6 +228,9 @@ typedef enum {
     SVOF_I_FLATNESS_MIN = 11, SVOF_I_FLATNESS_MAX = 12, SVOF_I_FLATNESS_AVG = 13,
     SVOF_I_DEVICE_BYTES = 14,
     SVOF_I_ERROR_FLAGS = 15,     /* device-side capacity flags, 0 = clean         */
+    SVOF_I_DENSE_KERNEL_MS = 16, /* cumulative device ms of the streaming kernel  */
+    SVOF_I_DENSE_KERNEL_LAUNCHES = 17,
+    SVOF_I_N_NEAR = 18,          /* |mixed U 2 face-neighbour layers| (sparse set) */
     SVOF_I_COUNT_
 } svof_info;
 
@@ -246,9 +249,19 @@ int svof_set_phi_device(svof_handle* h, const void* dphi);
 int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
 /* Block until all device work queued by this handle has finished. */
 int svof_synchronize(svof_handle* h);
+/* CUDA-event stopwatch on the handle's own stream (the stream every kernel of
+ * this handle is launched on): svof_mark records event `slot` (0..7) there,
+ * svof_elapsed_ms synchronises on slot b and returns b - a in ms. */
+int svof_mark(svof_handle* h, int slot);
+int svof_elapsed_ms(svof_handle* h, int slot_a, int slot_b, double* ms);
 /* Elapsed device time (ms, CUDA events on the handle's own stream) of the
  * most recent svof_reconstruct + svof_advect pair. */
 int svof_last_step_ms(svof_handle* h, double* reconstruct_ms, double* advect_ms);
+
+/* Page-locked host memory for the caller's field storage (what the OpenFOAM
+ * adapter pins so svof_step_host's copies run at full PCIe rate). */
+int svof_host_alloc(int64_t bytes, void** out);
+int svof_host_free(void* p);
 
 /* ---- geometry primitives (unit-test / utility surface) -------------------- */
 /* These expose the L1 geometry kernels of the reference on caller-supplied

@@ -33,7 +33,7 @@ def build_oracle(force=False):
     if force or _stale(ORACLE_SO, srcs):
         os.makedirs(os.path.dirname(ORACLE_SO), exist_ok=True)
         cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
-               "-Wall", "-o", ORACLE_SO, srcs[0]]
+               "-Wl,-Bsymbolic", "-Wall", "-o", ORACLE_SO, srcs[0]]
         subprocess.check_call(cmd)
     return ORACLE_SO
 

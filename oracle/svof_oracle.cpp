@@ -24,6 +24,7 @@ struct svof_handle {
     Solver s;
     std::string err;
     double lastReconMs = 0, lastAdvectMs = 0;
+    double marks[8] = {0};
 };
 
 static thread_local std::string g_create_error = "";
@@ -263,6 +264,9 @@ int svof_get_info(svof_handle* h, int which, double* out)
         case SVOF_I_FLATNESS_AVG: *out = s.mesh.flatAvg; return SVOF_OK;
         case SVOF_I_DEVICE_BYTES: *out = 0; return SVOF_OK;
         case SVOF_I_ERROR_FLAGS: *out = 0; return SVOF_OK;
+        case SVOF_I_DENSE_KERNEL_MS: *out = 0; return SVOF_OK;
+        case SVOF_I_DENSE_KERNEL_LAUNCHES: *out = 0; return SVOF_OK;
+        case SVOF_I_N_NEAR: *out = 0; return SVOF_OK;
     }
     return SVOF_ERR_INVALID_ARG;
 }
@@ -272,11 +276,35 @@ int svof_device_touch(svof_handle*, int) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_phi_device(svof_handle*, const void*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_U_device(svof_handle*, const void*, const void*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_synchronize(svof_handle*) { return SVOF_OK; }
+int svof_mark(svof_handle* h, int slot)
+{
+    if (!h || slot < 0 || slot > 7) return SVOF_ERR_INVALID_ARG;
+    h->marks[slot] = nowSec();
+    return SVOF_OK;
+}
+int svof_elapsed_ms(svof_handle* h, int a, int b, double* ms)
+{
+    if (!h || !ms || a < 0 || a > 7 || b < 0 || b > 7) return SVOF_ERR_INVALID_ARG;
+    *ms = (h->marks[b] - h->marks[a]) * 1e3;
+    return SVOF_OK;
+}
 int svof_last_step_ms(svof_handle* h, double* r, double* a)
 {
     if (!h) return SVOF_ERR_INVALID_ARG;
     if (r) *r = h->lastReconMs;
     if (a) *a = h->lastAdvectMs;
+    return SVOF_OK;
+}
+
+int svof_host_alloc(int64_t bytes, void** out)
+{
+    if (!out || bytes <= 0) return SVOF_ERR_INVALID_ARG;
+    *out = std::malloc(size_t(bytes));
+    return *out ? SVOF_OK : SVOF_ERR_INVALID_ARG;
+}
+int svof_host_free(void* p)
+{
+    std::free(p);
     return SVOF_OK;
 }
 
