@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -40,6 +41,7 @@ struct svof_handle {
     cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
     cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr;
     bool inputsAfterNear = false, freshRecon = false;
+    bool overlap = false;  // SVOF_OVERLAP=1: run the streaming kernel on its own stream, concurrently with the sparse chain
     int advectCount = 0;
     int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
     std::vector<svof_patch> patches;
@@ -85,6 +87,11 @@ struct svof_handle {
     long long denseLaunches = 0;
     size_t evNext = 0;
     int sms = 148;
+    // SVOF_PROFILE=1: CUDA events around every launch, table printed by svof_destroy
+    bool prof = false;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> profRecs;
+    std::map<std::string, std::pair<double, long>> profAcc;
 };
 
 namespace {
@@ -121,23 +128,65 @@ T* dupload(svof_handle* h, const T* src, size_t n)
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline int sparseGrid(svof_handle* h, int threads) { return h->sms * (1024 / threads > 0 ? 1024 / threads : 1); }
 
+void profBegin(svof_handle* h, const char* name, cudaStream_t st);
+void profEnd(svof_handle* h, cudaStream_t st);
 #define LAUNCH(h, kern, grid, block, ...)                        \
     do {                                                         \
+        if ((h)->prof) profBegin(h, #kern, (h)->stream);         \
         kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);  \
+        if ((h)->prof) profEnd(h, (h)->stream);                  \
         (h)->launches++;                                         \
     } while (0)
 
 // dispatch a capacity-variant launcher (explicitly instantiated in svof_inst.cu)
 #define GEO(h, fn, ...)                                               \
     do {                                                              \
+        if ((h)->prof) profBegin(h, #fn, (h)->stream);                \
         switch ((h)->variant) {                                       \
             case 0: GeoLaunch<CapsHex>::fn(__VA_ARGS__); break;       \
             case 1: GeoLaunch<CapsSmall>::fn(__VA_ARGS__); break;     \
             case 2: GeoLaunch<CapsPoly>::fn(__VA_ARGS__); break;      \
             default: GeoLaunch<CapsSplit>::fn(__VA_ARGS__); break;    \
         }                                                             \
+        if ((h)->prof) profEnd(h, (h)->stream);                       \
         (h)->launches++;                                              \
     } while (0)
+
+void profFlush(svof_handle* h)
+{
+    for (auto& r : h->profRecs) {
+        cudaEventSynchronize(r.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& acc = h->profAcc[r.name];
+        acc.first += ms;
+        acc.second++;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->profRecs.clear();
+}
+void profBegin(svof_handle* h, const char* name, cudaStream_t st)
+{
+    if (h->profRecs.size() > 4000) profFlush(h);
+    svof_handle::ProfRec r;
+    r.name = name;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    h->profRecs.push_back(r);
+}
+void profEnd(svof_handle* h, cudaStream_t st) { cudaEventRecord(h->profRecs.back().b, st); }
+void profPrint(svof_handle* h)
+{
+    profFlush(h);
+    double tot = 0;
+    for (auto& kv : h->profAcc) tot += kv.second.first;
+    fprintf(stderr, "[svof profile] in-situ event timing per launch site (ms total / launches / us each)\n");
+    for (auto& kv : h->profAcc)
+        fprintf(stderr, "  %-24s %10.3f ms %8ld  %9.2f us  %5.1f%%\n", kv.first.c_str(), kv.second.first, kv.second.second,
+                1e3 * kv.second.first / std::max(1L, kv.second.second), 100.0 * kv.second.first / std::max(tot, 1e-30));
+}
 
 void buildMesh(svof_handle* h, const svof_mesh& m)
 {
@@ -542,23 +591,27 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     double* aOld = h->alphaBuf[h->cur];
     double* aNew = h->alphaBuf[h->cur ^ 1];
     const double rDt = 1.0 / dt;
-    cudaStream_t sS = h->stream, sD = h->streamD;
+    cudaStream_t sS = h->stream, sD = h->overlap ? h->streamD : h->stream;
 
     // ---- streaming kernel on its own stream: depends only on alpha.oldTime, phi and the near2 bitmap,
     //      so it overlaps the tail of reconstruct() and the whole sparse chain below
     if (!h->freshRecon) LAUNCH(h, k_ctl_reset_dense, 1, 1, h->ctl);  // advect() without a new reconstruct()
-    if (h->inputsAfterNear || dSp || dSu || !h->freshRecon) {
-        CK(cudaEventRecord(h->evInputs, sS));
-        CK(cudaStreamWaitEvent(sD, h->evInputs, 0));
-    } else {
-        CK(cudaStreamWaitEvent(sD, h->evNear, 0));
+    if (h->overlap) {
+        if (h->inputsAfterNear || dSp || dSu || !h->freshRecon) {
+            CK(cudaEventRecord(h->evInputs, sS));
+            CK(cudaStreamWaitEvent(sD, h->evInputs, 0));
+        } else {
+            CK(cudaStreamWaitEvent(sD, h->evNear, 0));
+        }
     }
+    if (h->prof) profBegin(h, "k_dense_update", sD);
     EventPair& ed = beginTimedOn(h, 2, sD);
     k_dense_update<<<cdiv(h->nC, 256), 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
                                                       dt, rDt, dSp, dSu, h->sp, h->ctl);
     h->launches++;
     endTimedOn(h, ed, sD);
-    CK(cudaEventRecord(h->evDense, sD));
+    if (h->prof) profEnd(h, sD);
+    if (h->overlap) CK(cudaEventRecord(h->evDense, sD));
 
     // ---- sparse chain
     LAUNCH(h, k_ctl_reset_advect, 1, 1, h->ctl);
@@ -582,7 +635,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         LAUNCH(h, k_bound_flip, 1, 1, h->ctl, sidx);
     }
     // join: the finalize kernel ORs into the bitmap words the streaming kernel wrote
-    CK(cudaStreamWaitEvent(sS, h->evDense, 0));
+    if (h->overlap) CK(cudaStreamWaitEvent(sS, h->evDense, 0));
     // A12: snap/clip + alphaPhi for near2; boundary values of the new field
     LAUNCH(h, k_near_finalize, g128, 128, d, h->near2List, h->ctl, aNew, h->dVf, h->alphaPhi, h->mixedBits, dt, h->sp, h->oobState);
     h->cur ^= 1;
@@ -715,11 +768,16 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
     try {
         h->device = (comm && comm->device >= 0) ? comm->device : ((comm ? comm->rank : 0) % ndev);
         CK(cudaSetDevice(h->device));
-        CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&h->streamD, cudaStreamNonBlocking));
+        // the sparse chain is the latency-critical one: give its CTAs priority over the streaming kernel's
+        int prLo = 0, prHi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+        CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prHi));
+        CK(cudaStreamCreateWithPriority(&h->streamD, cudaStreamNonBlocking, prLo));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
+        h->overlap = getenv("SVOF_OVERLAP") && atoi(getenv("SVOF_OVERLAP")) > 0;
+        h->prof = getenv("SVOF_PROFILE") && atoi(getenv("SVOF_PROFILE")) > 0;
         h->prm = *params;
         h->sp.mixedTol = params->mixed_cell_tol;
         h->sp.snapTol = params->snap_tol;
@@ -744,6 +802,7 @@ int svof_destroy(svof_handle* h)
 {
     if (!h) return SVOF_OK;
     cudaSetDevice(h->device);
+    if (h->prof) profPrint(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->streamD) cudaStreamSynchronize(h->streamD);
     for (void* p : h->allocs) cudaFree(p);

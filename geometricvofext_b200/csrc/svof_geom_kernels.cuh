@@ -3,6 +3,7 @@
 // (svof_inst.cu compiled with -DSV_VARIANT=n) so the variants build in parallel.
 #pragma once
 #include "svof_kernels.cuh"
+#include "svof_plic_group.cuh"
 
 namespace svof {
 
@@ -130,7 +131,21 @@ template <class CP>
 void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* alpha, const double* iN,
                          int split, int* cellStatus, double* iD, double* iC, double* iS)
 {
-    k_plic<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
+    // lane-cooperative kernel (8 lanes per cell) whenever the per-cell staging area fits shared memory
+    const size_t perCell = sizeof(GCellShared<CP>);
+    int threads = 128;
+    while (threads > 32 && perCell * (threads / SV_G) > 100 * 1024) threads >>= 1;
+    const size_t smem = perCell * (threads / SV_G);
+    if (smem <= 200 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_plic_group<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+            configured = true;
+        }
+        k_plic_group<CP><<<grid, threads, smem, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
+    } else {
+        k_plic<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
+    }
 }
 template <class CP>
 void GeoLaunch<CP>::faceFlux(cudaStream_t st, int grid, MeshDev m, const int2* work, Ctl* ctl, const int* mixedCells, const double* iN,

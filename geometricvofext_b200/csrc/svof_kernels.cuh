@@ -623,12 +623,49 @@ __device__ __forceinline__ bool upwindDVf(const MeshDev& m, int c, int f, bool f
     return true;
 }
 
+// exact-division shortcuts: x/y == x bitwise when x is +-0 (y finite, non-zero); most of a VOF
+// domain is exactly empty, so the FP64 divides (~30 SASS instructions each) are skipped there
+__device__ __forceinline__ double divz(double x, double y) { return (x == 0.0) ? x : x / y; }
+
+// warp min/max of doubles through their order-preserving keys with 4 REDUX instead of 20 SHFL
+__device__ __forceinline__ unsigned long long warpMaxKey(unsigned long long k)
+{
+    const unsigned int hi = (unsigned int)(k >> 32);
+    const unsigned int mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned int lo = (hi == mhi) ? (unsigned int)k : 0u;
+    const unsigned int mlo = __reduce_max_sync(0xffffffffu, lo);
+    return ((unsigned long long)mhi << 32) | mlo;
+}
+__device__ __forceinline__ unsigned long long warpMinKey(unsigned long long k) { return ~warpMaxKey(~k); }
+
+__device__ __forceinline__ void blockMinMaxFast(double mn, double mx, unsigned long long* gmin, unsigned long long* gmax)
+{
+    __shared__ unsigned long long smn[32], smx[32];
+    const unsigned long long kmn = warpMinKey(dkey(mn)), kmx = warpMaxKey(dkey(mx));
+    if ((threadIdx.x & 31) == 0) {
+        smn[threadIdx.x >> 5] = kmn;
+        smx[threadIdx.x >> 5] = kmx;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int nw = (blockDim.x + 31) >> 5;
+        const unsigned long long a = warpMinKey((threadIdx.x < nw) ? smn[threadIdx.x] : ~0ull);
+        const unsigned long long b = warpMaxKey((threadIdx.x < nw) ? smx[threadIdx.x] : 0ull);
+        if (threadIdx.x == 0) {
+            atomicMin(gmin, a);
+            atomicMax(gmax, b);
+        }
+    }
+}
+
 // A6 + A10 + A12 fused: THE streaming pass (K7).  Thread per cell; a cell gathers its faces in
 // ascending face order through the cell->face CSR (deterministic segmented reduction, no atomics,
 // same summation order as fvc::surfaceIntegrate), recomputes the upwind transport of each face on
 // the fly (dVf is never materialised), writes alpha_new and, for the faces it owns, alphaPhi.
 // Cells in near2 are left to the sparse kernels.  Also emits the next step's mixed-cell bitmap.
-__global__ void __launch_bounds__(256) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
+// (A sliced-ELL row layout with batched loads was tried in round 1: it coalesces the row loads but
+// loses the L1 reuse of the 48-byte rows and needs 71 registers; measured 1.05 ms vs 0.58 ms.)
+__global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
                                                       const double* __restrict__ phi, const double* __restrict__ alphaB,
                                                       double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
                                                       unsigned int* __restrict__ mixedNext, double dt, double rDt,
@@ -640,25 +677,38 @@ __global__ void __launch_bounds__(256) k_dense_update(MeshDev m, const double* _
     bool mixed = false;
     if (c < m.nCells && !bitTest(near2, c)) {
         const int k0 = __ldg(m.cellOff + c), k1 = __ldg(m.cellOff + c + 1);
+        const double aC = __ldg(aOld + c);
         double sum = 0.0;
         for (int k = k0; k < k1; ++k) {
             const int2 e = __ldg(m.cellAsc + k);
             const int f = e.x & 0x7fffffff;
             const bool flip = e.x < 0;
-            double dvf;
-            if (!upwindDVf(m, c, f, flip, e.y, __ldg(phi + f), aOld, alphaB, dt, dvf)) continue;
+            const double ph = __ldg(phi + f);
+            double aUp;
+            if (e.y >= 0) {
+                // upwind cell: owner if phi >= 0 else neighbour; this cell's own value is in a register
+                const bool selfUp = flip ? (ph < 0) : (ph >= 0);
+                aUp = selfUp ? aC : __ldg(aOld + e.y);
+            } else {
+                const int bf = -1 - e.y;
+                const unsigned char kind = __ldg(m.bKind + bf);
+                if (kind == 1) continue;  // empty patch: no field
+                aUp = __ldg(alphaB + bf);
+                if (kind == 2 && ph >= 0) aUp = aC;  // processor: upwind between the two sides
+            }
+            const double dvf = (ph * aUp) * dt;
             if (!flip) {
                 sum += dvf;
-                alphaPhi[f] = dvf / dt;
+                alphaPhi[f] = divz(dvf, dt);
             } else {
                 sum -= dvf;
             }
         }
-        const double ivf = sum / __ldg(m.V + c);
-        double num = aOld[c] * rDt;
+        const double ivf = divz(sum, __ldg(m.V + c));
+        double num = aC * rDt;
         if (Su) num = num + Su[c];
         num = num - ivf * rDt;
-        double a = num / (Sp ? (rDt - Sp[c]) : rDt);
+        double a = divz(num, (Sp ? (rDt - Sp[c]) : rDt));
         mn = a;
         mx = a;
         a = snapClip(a, sp.snapTol, sp.clip);
@@ -667,7 +717,7 @@ __global__ void __launch_bounds__(256) k_dense_update(MeshDev m, const double* _
     }
     const unsigned int w = __ballot_sync(0xffffffffu, mixed);
     if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
-    blockMinMax(mn, mx, &ctl->minDense, &ctl->maxDense);
+    blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
 }
 
 // true transport of face f seen from cell c: the geometric value where the face is downwind of a
@@ -762,93 +812,107 @@ struct BoundScratch {
 __device__ __forceinline__ bool faceActive(const MeshDev& m, int f) { return f < m.nIF || m.bKind[f - m.nIF] != 1; }
 __device__ __forceinline__ double corrVal(const BoundScratch& b, int f, int tag) { return (b.tagV[f] == tag) ? b.corr[f] : 0.0; }
 
-// body of boundFlux for one cell (advectionTemplates.C:245-346)
+// body of boundFlux for one cell (advectionTemplates.C:245-346).  The cell's faces are loaded once
+// into thread-local arrays (a sequential chain of dependent L2 loads per inner iteration was the
+// whole cost of this kernel); corrections are written back at the end -- a face is only ever
+// corrected by its upwind cell, so the local copy is exact.
+#define SV_MAXBF 64
 __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, const double* aOld, const double* __restrict__ phi,
                           const double* dVf, const BoundScratch& b, int tag, double dt, double rDeltaT, const double* Sp,
                           const double* Su)
 {
     const double Vi = m.V[celli];
-    const int c0 = m.cellOff[celli], c1 = m.cellOff[celli + 1];
+    const int c0 = m.cellOff[celli];
+    int nf = m.cellOff[celli + 1] - c0;
+    if (nf > SV_MAXBF) nf = SV_MAXBF;
+    int fId[SV_MAXBF];
+    double fPhi[SV_MAXBF], fDvf[SV_MAXBF], fCorr[SV_MAXBF], room[SV_MAXBF];
+    unsigned long long ownMask = 0, downMask = 0, modMask = 0, recMask = 0;
+    int recPos[SV_MAXBF];
+    for (int q = 0; q < nf; ++q) {
+        const int f = m.cellFaces[c0 + q];
+        const bool act = faceActive(m, f);
+        const bool isOwn = (m.owner[f] == celli);
+        const double ph = act ? phi[f] : 0.0;          // faceValue(phi_, facei)
+        const bool down = isOwn ? (ph >= 0) : (ph < 0);  // setDownwindFaces, advection.C:242-252
+        double cr = act ? corrVal(b, f, tag) : 0.0;
+        if (act && !down) {
+            // written by the cell on the other side; in the ascending sweep of the reference this
+            // cell has only seen it if the writer has a lower index
+            const int other = isOwn ? ((f < m.nIF) ? m.neighbour[f] : -1) : m.owner[f];
+            if (other > celli) cr = 0.0;
+        }
+        fId[q] = f;
+        fPhi[q] = ph;
+        fDvf[q] = act ? dVf[f] : 0.0;
+        fCorr[q] = cr;
+        if (isOwn) ownMask |= 1ull << q;
+        if (down) downMask |= 1ull << q;
+    }
     const double a0 = alpha[celli];
     double alphaOvershoot = pos0(a0 - 1.0) * (a0 - 1.0) + neg0(a0) * a0;
     double fluidToPassOn = alphaOvershoot * Vi;
     int nFacesToPassFluidThrough = 1;
     bool firstLoop = true;
     int nRecorded = 0;
+    const double SuI = Su ? Su[celli] : 0.0, SpI = Sp ? Sp[celli] : 0.0;
+    const double aOldI = aOld[celli];
     for (int iter = 0; iter < 10; ++iter) {
         if (fabs(alphaOvershoot) < SV_ATOL || nFacesToPassFluidThrough == 0) break;
-        // downwind faces (setDownwindFaces, advection.C:224-256) with room: facesToPassFluidThrough.
-        // Eligibility and dVftot are fixed BEFORE any correction of this iteration is written,
-        // exactly as in the two loops of the reference.
-        double room[64];
+        // facesToPassFluidThrough / dVfmax / dVftot: fixed before any correction of this iteration
         double dVftot = 0;
         nFacesToPassFluidThrough = 0;
-        int q = 0;
-        for (int k = c0; k < c1; ++k, ++q) {
-            const int f = m.cellFaces[k];
-            const bool act = faceActive(m, f);
-            const double phif = act ? phi[f] : 0.0;
-            const bool down = (m.owner[f] == celli) ? (phif >= 0) : (phif < 0);
+        for (int q = 0; q < nf; ++q) {
             double r = -1.0;
-            if (down) {
-                const double dVff = (act ? dVf[f] : 0.0) + (act ? corrVal(b, f, tag) : 0.0);
-                const double maxExtra = fabs(pos0(fluidToPassOn) * phif * dt - dVff);
+            if ((downMask >> q) & 1ull) {
+                const double dVff = fDvf[q] + fCorr[q];
+                const double maxExtra = fabs(pos0(fluidToPassOn) * fPhi[q] * dt - dVff);
                 if (maxExtra / Vi > SV_ATOL) {
                     r = maxExtra;
-                    dVftot += fabs(phif * dt);
+                    dVftot += fabs(fPhi[q] * dt);
                 }
             }
-            if (q < 64) room[q] = r;
+            room[q] = r;
         }
-        q = 0;
-        for (int k = c0; k < c1; ++k, ++q) {
-            if (q >= 64 || room[q] < 0.0) continue;
-            const int f = m.cellFaces[k];
-            const double phif = phi[f];
-            double through = fabs(fluidToPassOn) * fabs(phif * dt) / dVftot;
+        for (int q = 0; q < nf; ++q) {
+            if (room[q] < 0.0) continue;
+            double through = fabs(fluidToPassOn) * fabs(fPhi[q] * dt) / dVftot;
             nFacesToPassFluidThrough += int(pos0(room[q] - through));
             through = dmin(through, room[q]);
-            double dVff = corrVal(b, f, tag);
-            dVff += sgn(phif) * sgn(fluidToPassOn) * through;
-            b.corr[f] = dVff;
-            b.tagV[f] = tag;
+            double dVff = fCorr[q];
+            dVff += sgn(fPhi[q]) * sgn(fluidToPassOn) * through;
+            fCorr[q] = dVff;
+            modMask |= 1ull << q;
             if (firstLoop) {
-                b.corrBy[f] = celli;
-                b.corrPos[f] = nRecorded++;
-                b.tagR[f] = tag;
+                recMask |= 1ull << q;
+                recPos[q] = nRecorded++;
             }
         }
         firstLoop = false;
-        double nf = 0.0, nc = 0.0;  // netFlux(dVf_), netFlux(dVfCorrectionValues)  (advection.C:259-288)
-        for (int k = c0; k < c1; ++k) {
-            const int f = m.cellFaces[k];
-            const bool act = faceActive(m, f);
-            const bool isOwn = (m.owner[f] == celli);
-            double bv = act ? corrVal(b, f, tag) : 0.0;
-            if (act) {
-                // a correction on a face that is downwind of the OTHER cell was written by that cell;
-                // in the reference's ascending sweep this cell has only seen it if the writer has a
-                // lower index (higher-index cells may already have run here: mask them out)
-                const double phif = phi[f];
-                const bool down = isOwn ? (phif >= 0) : (phif < 0);
-                if (!down) {
-                    const int other = isOwn ? ((f < m.nIF) ? m.neighbour[f] : -1) : m.owner[f];
-                    if (other > celli) bv = 0.0;
-                }
-            }
-            const double av = act ? dVf[f] : 0.0;
-            if (isOwn) {
-                nf += av;
-                nc += bv;
+        double nfl = 0.0, nc = 0.0;  // netFlux(dVf_), netFlux(dVfCorrectionValues)  (advection.C:259-288)
+        for (int q = 0; q < nf; ++q) {
+            if ((ownMask >> q) & 1ull) {
+                nfl += fDvf[q];
+                nc += fCorr[q];
             } else {
-                nf -= av;
-                nc -= bv;
+                nfl -= fDvf[q];
+                nc -= fCorr[q];
             }
         }
-        const double SuI = Su ? Su[celli] : 0.0, SpI = Sp ? Sp[celli] : 0.0;
-        const double alpha1New = (aOld[celli] * rDeltaT + SuI - nf / Vi * rDeltaT - nc / Vi * rDeltaT) / (rDeltaT - SpI);
+        const double alpha1New = (aOldI * rDeltaT + SuI - nfl / Vi * rDeltaT - nc / Vi * rDeltaT) / (rDeltaT - SpI);
         alphaOvershoot = pos0(alpha1New - 1.0) * (alpha1New - 1.0) + neg0(alpha1New) * alpha1New;
         fluidToPassOn = alphaOvershoot * Vi;
+    }
+    for (int q = 0; q < nf; ++q) {
+        if (!((modMask >> q) & 1ull)) continue;
+        const int f = fId[q];
+        b.corr[f] = fCorr[q];
+        b.tagV[f] = tag;
+        if ((recMask >> q) & 1ull) {
+            b.corrBy[f] = celli;
+            b.corrPos[f] = recPos[q];
+            b.tagR[f] = tag;
+        }
     }
 }
 

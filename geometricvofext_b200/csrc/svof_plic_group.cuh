@@ -1,0 +1,461 @@
+// svof_plic_group.cuh -- plane positioning (cutCell::findSignedDistance, cutCell.C:611-799) with
+// a group of G=8 lanes per mixed cell instead of one thread per cell.
+//
+// Why: at 256^3 only ~3e4 cells are mixed, i.e. one thread per cell fills <10% of a B200 and each
+// thread walks ~35 polygon clips back to back (measured 0.50 ms, FP64 pipe 12% busy, 6 warps/SM).
+// Here the faces of a cell are clipped concurrently by the lanes of its group (a hex keeps one face
+// per lane entirely in registers, together with the plane-independent parts: n.p per vertex and the
+// whole-face centre/area used for submerged faces), and only the ORDERED reductions the reference
+// performs sequentially (interface polygon, pyramid volumes: cutCell.C:37-137) are done by the group
+// leader, from shared memory, in the reference's order -- so results stay bitwise identical to the
+// one-thread version (and to the oracle).
+//
+// Shared memory per cell (polyhedron staged once per cell):
+//   FaceRes res[MAXCF]  sub-face centre/area/status/interface points of each (local) face
+//   SegRes  seg[MAXCF]  per-face interface segments (a*c, n, a) once the polygon centre is known
+//   vd[MAXCP]           sorted vertex distances;  lf[MAXCF] local face list (splitWarpedFace)
+#pragma once
+#include "svof_geom.cuh"
+
+namespace svof {
+
+template <class CP>
+struct GFaceRes {
+    d3 c, a;             // sub-face centre / area vector (status 0 or -1)
+    d3 ip[CP::MAXIP];    // interface points (status 0)
+    int st, nip;
+};
+template <class CP>
+struct GSegRes {
+    d3 ac[CP::MAXIP - 1];  // a * (p0 + p1 + fC)
+    d3 nn[CP::MAXIP - 1];  // (p1 - p0) ^ (fC - p0)
+    double a[CP::MAXIP - 1];
+};
+template <class CP>
+struct GCellShared {
+    GFaceRes<CP> res[CP::MAXCF];
+    GSegRes<CP> seg[CP::MAXCF];
+    double pv[CP::MAXCF];   // pyramid 3*volumes of the sub-faces
+    double vd[CP::MAXCP];
+    int lfFace[CP::MAXCF];  // local face -> mesh face
+    short lfTri[CP::MAXCF]; // local face -> triangle index of a split warped face, or -1
+    // broadcast slots
+    double D;
+    d3 fC, cEst, iC, iS;
+    int nLocal, active, cutAny, nPts;
+};
+
+// one local face of the (possibly split) polyhedron into fp[]; returns vertex count
+template <class CP>
+__device__ __forceinline__ int loadLocalFace(const MeshDev& m, int cell, int f, int tri, bool split, d3* fp, int& err)
+{
+    int nv = loadFace<CP>(m, f, fp, err);
+    if (!split) return nv;
+    const bool own = (__ldg(m.owner + f) == cell);
+    if (tri < 0) {
+        if (!own) reversePoly(fp, nv);
+        return nv;
+    }
+    const int pn = (tri + 1 == nv) ? 0 : tri + 1;
+    const d3 a = fp[tri], b = fp[pn];
+    fp[0] = ld3(m.Cf, f);
+    fp[1] = own ? a : b;
+    fp[2] = own ? b : a;
+    return 3;
+}
+
+// clip with cached n.p (bitwise the same sums as clipFace: dot(fp[i], n) + D)
+template <class CP>
+__device__ __forceinline__ int clipFaceCached(const d3* fp, const double* pn, int nv, double D, const d3& fullC, const d3& fullA,
+                                              d3& centre, d3& area, d3* ip, int& nip, int& err)
+{
+    double s[CP::MAXFV];
+    int nSub = 0, first = -1;
+#pragma unroll
+    for (int i = 0; i < CP::MAXFV; ++i) {
+        if (i < nv) {
+            double si = pn[i] + D;
+            if (fabs(si) < SV_TSMALL) si += sgn(si) * SV_TSMALL;
+            s[i] = si;
+            if (si < 0.0) {
+                nSub++;
+                if (first < 0) first = i;
+            }
+        }
+    }
+    nip = 0;
+    if (nSub == nv) {
+        centre = fullC;
+        area = fullA;
+        return -1;
+    }
+    if (nSub == 0) {
+        centre = zero3();
+        area = zero3();
+        return 1;
+    }
+    d3 sp[2 * CP::MAXFV];
+    int np = 0;
+    int cur = first;
+    for (int i = 0; i < nv; ++i) {
+        const int nxt = (cur + 1 == nv) ? 0 : cur + 1;
+        if (s[cur] < 0) sp[np++] = fp[cur];
+        if ((s[cur] * s[nxt]) < 0) {
+            const double w = s[cur] / (s[cur] - s[nxt]);
+            const d3 cp = fp[cur] + w * (fp[nxt] - fp[cur]);
+            sp[np++] = cp;
+            if (nip < CP::MAXIP) ip[nip] = cp; else err |= SVERR_IFACE_POINTS;
+            nip++;
+        }
+        cur = nxt;
+    }
+    if (nip > CP::MAXIP) nip = CP::MAXIP;
+    if (np >= 3) {
+        subFaceCentreAndArea(sp, np, centre, area);
+        return 0;
+    }
+    centre = fullC;
+    area = fullA;
+    return -1;
+}
+
+#define SV_G 8  // lanes per cell
+
+template <class CP>
+__global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
+                                                    const double* iN, int split, int* cellStatus, double* iD, double* iC, double* iS)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    GCellShared<CP>* shAll = reinterpret_cast<GCellShared<CP>*>(smemRaw);
+    const int groupsPerBlock = blockDim.x / SV_G;
+    const int gid = threadIdx.x / SV_G, lane = threadIdx.x % SV_G;
+    GCellShared<CP>& sh = shAll[gid];
+    const bool leader = (lane == 0);
+    const int nMixed = ctl->nMixed;
+    const bool splitB = split != 0;
+    int err = 0;
+
+    for (int base = blockIdx.x * groupsPerBlock; base < nMixed; base += gridDim.x * groupsPerBlock) {
+        const int i = base + gid;
+        const bool valid = i < nMixed;
+        const int cell = valid ? mixedCells[i] : 0;
+        const double alphaI = valid ? alpha[cell] : 0.5;
+        const d3 n = valid ? ld3(iN, cell) : mk3(1.0, 0.0, 0.0);
+        const double Vcell = __ldg(m.V + cell);
+        const bool degenerate = mag(n) < SV_TSMALL;  // cutCell.C:625-628
+
+        // ---- stage the polyhedron: local face list, sorted vertex distances ------------------
+        if (leader && !valid) {
+            sh.nLocal = 0;
+            sh.nPts = 0;
+        }
+        if (leader && valid) {
+            int nl = 0;
+            const int c0 = __ldg(m.cellOff + cell), c1 = __ldg(m.cellOff + cell + 1);
+            for (int k = c0; k < c1; ++k) {
+                const int f = __ldg(m.cellFaces + k);
+                if (splitB && !(__ldg(m.flat + f) > (1.0 - SV_TSMALL))) {
+                    const int nv = __ldg(m.faceOff + f + 1) - __ldg(m.faceOff + f);
+                    for (int t = 0; t < nv; ++t) {
+                        if (nl < CP::MAXCF) {
+                            sh.lfFace[nl] = f;
+                            sh.lfTri[nl] = (short)t;
+                            nl++;
+                        } else err |= SVERR_CELL_FACES;
+                    }
+                } else {
+                    if (nl < CP::MAXCF) {
+                        sh.lfFace[nl] = f;
+                        sh.lfTri[nl] = -1;
+                        nl++;
+                    } else err |= SVERR_CELL_FACES;
+                }
+            }
+            sh.nLocal = nl;
+            // vertex distances, descending (values only: ties are indistinguishable, cutCell.C:664-670)
+            int nP = 0;
+            const int p0 = __ldg(m.cellPtOff + cell), p1 = __ldg(m.cellPtOff + cell + 1);
+            for (int k = p0; k < p1; ++k) {
+                if (nP < CP::MAXCP) sh.vd[nP++] = -dot(n, ld3(m.points, __ldg(m.cellPts + k)));
+                else err |= SVERR_CELL_POINTS;
+            }
+            if (splitB) {
+                for (int k = c0; k < c1; ++k) {
+                    const int f = __ldg(m.cellFaces + k);
+                    if (!(__ldg(m.flat + f) > (1.0 - SV_TSMALL))) {
+                        if (nP < CP::MAXCP) sh.vd[nP++] = -dot(n, ld3(m.Cf, f));
+                        else err |= SVERR_CELL_POINTS;
+                    }
+                }
+            }
+            sortDescending(sh.vd, nP);
+            sh.nPts = nP;
+        }
+        __syncwarp();
+        const int nLocal = sh.nLocal;
+        const int nP = sh.nPts;
+        const bool cached = nLocal <= SV_G;
+
+        // ---- plane-independent per-face data of this lane's face (when one face per lane) -----
+        d3 fpC[CP::MAXFV];
+        double pnC[CP::MAXFV];
+        d3 fullC = zero3(), fullA = zero3();
+        int nvC = 0;
+        if (cached && lane < nLocal) {
+            nvC = loadLocalFace<CP>(m, cell, sh.lfFace[lane], sh.lfTri[lane], splitB, fpC, err);
+#pragma unroll
+            for (int q = 0; q < CP::MAXFV; ++q)
+                if (q < nvC) pnC[q] = dot(fpC[q], n);
+            fullC = faceCentreOF(fpC, nvC);
+            fullA = faceAreaNormalOF(fpC, nvC);
+        }
+
+        // ---- leader's search state (cutCell.C:682-719) ----------------------------------------
+        double lowDistance = 0, upDistance = 0, lowAlpha = 0.0, upAlpha = 1.0;
+        int lowLabel = 0, upLabel = nP - 1;
+        double midLabel = 0, aOneThird = 0, deltaDistance = 0, curD = 0;
+        int phase = 0;  // 0 bracketing, 1 collapsed bracket, 2 one third, 3 two thirds, 4 final
+        int outStatus = 0;
+        bool wrote = false, done = !valid;
+        if (leader && valid) {
+            lowDistance = sh.vd[0];
+            upDistance = sh.vd[nP - 1];
+            if (degenerate) {
+                outStatus = int(sgn(0.5 - alphaI));
+                done = true;
+            } else if ((upLabel - lowLabel) > 1) {
+                midLabel = round(0.5 * (upLabel + lowLabel));
+                curD = sh.vd[int(midLabel)];
+                phase = 0;
+            } else if (fabs(lowDistance - upDistance) < SV_TSMALL) {
+                curD = 0.5 * (lowDistance + upDistance);
+                phase = 1;
+            } else {
+                deltaDistance = (upDistance - lowDistance) / 3.0;
+                curD = lowDistance + deltaDistance;
+                phase = 2;
+            }
+            sh.D = curD;
+        }
+        if (leader) sh.active = done ? 0 : 1;
+        __syncwarp();
+
+        // ---- evaluation loop: one calcSubCell (cutCell.C:343-542) per iteration ----------------
+        while (__any_sync(0xffffffffu, sh.active != 0)) {
+            const bool act = sh.active != 0;
+            const double D = sh.D;
+            // A. clip the faces of this lane
+            if (act) {
+                for (int k = lane; k < nLocal; k += SV_G) {
+                    GFaceRes<CP>& r = sh.res[k];
+                    d3 c, a, ipl[CP::MAXIP];
+                    int nip, st;
+                    if (cached) {
+                        st = clipFaceCached<CP>(fpC, pnC, nvC, D, fullC, fullA, c, a, ipl, nip, err);
+                    } else {
+                        d3 fp[CP::MAXFV];
+                        const int nv = loadLocalFace<CP>(m, cell, sh.lfFace[k], sh.lfTri[k], splitB, fp, err);
+                        st = clipFace<CP>(fp, nv, n, D, c, a, ipl, nip, err);
+                    }
+                    r.st = st;
+                    r.nip = nip;
+                    r.c = c;
+                    r.a = a;
+                    for (int q = 0; q < nip; ++q) r.ip[q] = ipl[q];
+                }
+            }
+            __syncwarp();
+            // B. leader: classification + interface polygon centre (cutCell.C:37-54)
+            bool fullySubmerged = true, fullyEmpty = true;
+            int nSubmergedFaces = 0, nCut = 0;
+            if (act && leader) {
+                d3 fC = zero3();
+                int nEp = 0;
+                for (int k = 0; k < nLocal; ++k) {
+                    const int st = sh.res[k].st;
+                    if (st == 0) {
+                        fullySubmerged = false;
+                        fullyEmpty = false;
+                        nCut++;
+                        const int nip = sh.res[k].nip;
+                        for (int q = 0; q < nip; ++q) {
+                            fC += sh.res[k].ip[q];
+                            nEp++;
+                        }
+                    } else if (st == -1) {
+                        fullyEmpty = false;
+                        nSubmergedFaces++;
+                        nCut++;
+                    } else {
+                        fullySubmerged = false;
+                    }
+                }
+                if (nEp > 0) fC /= double(nEp);
+                sh.fC = fC;
+                sh.cutAny = (!fullySubmerged && !fullyEmpty) ? 1 : 0;
+            }
+            __syncwarp();
+            // C. lanes: interface segments of their cut faces (cutCell.C:60-79, the per-segment part)
+            if (act && sh.cutAny) {
+                const d3 fC = sh.fC;
+                for (int k = lane; k < nLocal; k += SV_G) {
+                    const GFaceRes<CP>& r = sh.res[k];
+                    if (r.st != 0) continue;
+                    for (int pi = 0; pi < r.nip - 1; ++pi) {
+                        const d3 p0 = r.ip[pi], nx = r.ip[pi + 1];
+                        const d3 c = p0 + nx + fC;
+                        const d3 nn = cross(nx - p0, fC - p0);
+                        const double a = mag(nn);
+                        sh.seg[k].nn[pi] = nn;
+                        sh.seg[k].a[pi] = a;
+                        sh.seg[k].ac[pi] = a * c;
+                    }
+                }
+            }
+            __syncwarp();
+            // D. leader: ordered accumulation, interface centre/area, cEst (cutCell.C:56-99,110)
+            int status = 0;
+            double VOF = 0.0;
+            bool needVolume = false;
+            d3 iCl = zero3(), iSl = zero3();
+            if (act && leader) {
+                if (sh.cutAny) {
+                    d3 sumN = zero3(), sumAc = zero3();
+                    double sumA = 0.0;
+                    for (int k = 0; k < nLocal; ++k) {
+                        if (sh.res[k].st != 0) continue;
+                        for (int pi = 0; pi < sh.res[k].nip - 1; ++pi) {
+                            const d3 nn = sh.seg[k].nn[pi];
+                            sumN += sgn(dot(nn, sumN)) * nn;
+                            sumA += sh.seg[k].a[pi];
+                            sumAc += sh.seg[k].ac[pi];
+                        }
+                    }
+                    if (sumA < SV_ROOTVSMALL) {
+                        iCl = sh.fC;
+                        iSl = zero3();
+                    } else {
+                        iCl = (1.0 / 3.0) * sumAc / sumA;
+                        iSl = 0.5 * sumN;
+                    }
+                    if (dot(iSl, iCl - zero3()) < 0.0) iSl = iSl * (-1.0);  // vs the origin: SURVEY 8a' item 24
+                    if (mag(iSl) < SV_TSMALL) {
+                        if (nSubmergedFaces == 0) {
+                            status = 1;
+                            VOF = 0.0;
+                        } else {
+                            status = -1;
+                            VOF = 1.0;
+                        }
+                    } else {
+                        status = 0;
+                        needVolume = true;
+                        d3 cEst = zero3();
+                        for (int k = 0; k < nLocal; ++k)
+                            if (sh.res[k].st <= 0) cEst += sh.res[k].c;
+                        cEst += iCl;
+                        cEst /= double(nCut + 1);
+                        sh.cEst = cEst;
+                    }
+                } else if (fullyEmpty) {
+                    status = 1;
+                    VOF = 0.0;
+                } else {
+                    status = -1;
+                    VOF = 1.0;
+                }
+                sh.cutAny = needVolume ? 1 : 0;
+            }
+            __syncwarp();
+            // E. lanes: pyramid volumes of their sub-faces (cutCell.C:116-123)
+            if (act && sh.cutAny) {
+                const d3 cEst = sh.cEst;
+                for (int k = lane; k < nLocal; k += SV_G) {
+                    const GFaceRes<CP>& r = sh.res[k];
+                    if (r.st <= 0) sh.pv[k] = dmax(fabs(dot(r.a, r.c - cEst)), SV_VSMALL);
+                }
+            }
+            __syncwarp();
+            // F. leader: ordered volume sum, then advance the search (cutCell.C:691-799)
+            if (act && leader) {
+                if (needVolume) {
+                    double vol = 0.0;
+                    for (int k = 0; k < nLocal; ++k)
+                        if (sh.res[k].st <= 0) vol += sh.pv[k];
+                    vol += dmax(fabs(dot(iSl, iCl - sh.cEst)), SV_VSMALL);
+                    vol /= 3.0;
+                    VOF = vol / Vcell;
+                }
+                bool finish = false;
+                if (phase == 0) {
+                    const double midAlpha = VOF;
+                    if (fabs(midAlpha - alphaI) < SV_TSMALL) {
+                        finish = true;
+                    } else {
+                        if (midAlpha > alphaI) {
+                            upLabel = int(midLabel);
+                            upDistance = curD;
+                            upAlpha = midAlpha;
+                        } else {
+                            lowLabel = int(midLabel);
+                            lowDistance = curD;
+                            lowAlpha = midAlpha;
+                        }
+                        if ((upLabel - lowLabel) > 1) {
+                            midLabel = round(0.5 * (upLabel + lowLabel));
+                            curD = sh.vd[int(midLabel)];
+                        } else if (fabs(lowDistance - upDistance) < SV_TSMALL) {
+                            curD = 0.5 * (lowDistance + upDistance);
+                            phase = 1;
+                        } else {
+                            deltaDistance = (upDistance - lowDistance) / 3.0;
+                            curD = lowDistance + deltaDistance;
+                            phase = 2;
+                        }
+                    }
+                } else if (phase == 1 || phase == 4) {
+                    finish = true;
+                } else if (phase == 2) {
+                    aOneThird = VOF - lowAlpha;
+                    curD = lowDistance + 2.0 * deltaDistance;
+                    phase = 3;
+                } else {  // phase 3: cubic + Newton (cutCell.C:744-789)
+                    const double alphaPrismatoid = upAlpha - lowAlpha;
+                    const double alphaOneThird = aOneThird;
+                    const double alphaTwoThirds = VOF - lowAlpha;
+                    const double a = 13.5 * alphaOneThird - 13.5 * alphaTwoThirds + 4.5 * alphaPrismatoid;
+                    const double b = -22.5 * alphaOneThird + 18.0 * alphaTwoThirds - 4.5 * alphaPrismatoid;
+                    const double c = 9.0 * alphaOneThird - 4.5 * alphaTwoThirds + 1.0 * alphaPrismatoid;
+                    const double d = lowAlpha - alphaI;
+                    double lambda = 0.5;
+                    for (int iter = 0; iter < 100; ++iter) {
+                        const double func = a * (lambda * (lambda * lambda)) + b * (lambda * lambda) + c * lambda + d;
+                        const double funcPrime = 3.0 * a * (lambda * lambda) + 2.0 * b * lambda + c;
+                        const double lambdaNew = lambda - (func / funcPrime);
+                        if (fabs(lambdaNew - lambda) < SV_TSMALL) break;
+                        lambda = lambdaNew;
+                    }
+                    curD = lowDistance - lambda * (lowDistance - upDistance);
+                    phase = 4;
+                }
+                if (finish) {
+                    outStatus = status;
+                    wrote = true;
+                    iD[cell] = curD;
+                    st3(iC, cell, iCl);
+                    st3(iS, cell, iSl);
+                    sh.active = 0;
+                } else {
+                    sh.D = curD;
+                }
+            }
+            __syncwarp();
+        }
+        if (leader && valid) cellStatus[i] = outStatus;
+        (void)wrote;
+        __syncwarp();
+    }
+    if (err) atomicOr(&ctl->err, err);
+}
+
+}  // namespace svof
