@@ -296,12 +296,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("SVOF_BENCH_N", "256")))
+    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("SVOF_BENCH_N", "256")),
+                    help="cells per axis (per GPU block when --gpus > 1)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ref-procs", type=int, default=0)
-    ap.add_argument("--ref-n", type=int, default=0)
+    ap.add_argument("--ref-size", dest="ref_n", type=int, default=0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

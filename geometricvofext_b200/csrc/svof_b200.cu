@@ -177,9 +177,17 @@ void profBegin(svof_handle* h, const char* name, cudaStream_t st)
     h->profRecs.push_back(r);
 }
 void profEnd(svof_handle* h, cudaStream_t st) { cudaEventRecord(h->profRecs.back().b, st); }
+void fetchCtl(svof_handle* h);
 void profPrint(svof_handle* h)
 {
     profFlush(h);
+    fetchCtl(h);
+    {
+        const Ctl& c = *h->hctl;
+        fprintf(stderr, "[svof profile] last step: nMixed %d nNear2 %d nWork %d | sweep: nAff %d %d %d nPend %d %d %d nearOob %d %d %d %d nOob(left) %d %d\n",
+                c.nMixed, c.nNear2, c.nWork, c.nAff[0], c.nAff[1], c.nAff[2], c.nPend[0], c.nPend[1], c.nPend[2], c.nearOob[0],
+                c.nearOob[1], c.nearOob[2], c.nearOob[3], c.nOob[0], c.nOob[1]);
+    }
     double tot = 0;
     for (auto& kv : h->profAcc) tot += kv.second.first;
     fprintf(stderr, "[svof profile] in-situ event timing per launch site (ms total / launches / us each)\n");
