@@ -1,0 +1,224 @@
+"""Known-answer tests of the CPU oracle (the reference stores no per-cell SimPLIC
+output, so the oracle is pinned on analytic answers of the algorithm statements + golden fields)."""
+import numpy as np
+import pytest
+
+from common import LEVEQUE_CONTROLS, SolveVofEqu, capi, fields, meshmod, oracle_lib
+
+
+@pytest.fixture(scope="module")
+def s8():
+    s = SolveVofEqu(meshmod.hex_block(8), LEVEQUE_CONTROLS, lib=oracle_lib())
+    yield s
+    s.close()
+
+
+def test_hex_mesh_geometry(s8):
+    m = s8.mesh
+    assert (m.n_cells, m.n_internal_faces, m.n_faces) == (512, 3 * 8 * 8 * 7, 3 * 8 * 8 * 9)
+    V, C_, Sf = s8.field(capi.F_V), s8.field(capi.F_C), s8.field(capi.F_SF)
+    assert np.allclose(V, 1 / 512, rtol=0, atol=1e-18)
+    assert np.allclose(C_[0], [1 / 16] * 3, atol=1e-16) and np.allclose(C_[-1], [15 / 16] * 3, atol=1e-16)
+    assert np.allclose(np.linalg.norm(Sf, axis=1), 1 / 64, atol=1e-17)
+    # owner-outward orientation: boundary face normals point out of the unit cube
+    Cf = s8.field(capi.F_CF)[m.n_internal_faces:]
+    assert np.all(((Cf - 0.5) * Sf[m.n_internal_faces:]).sum(1) > 0)
+    assert np.array_equal(s8.faceFlatness(), np.ones(m.n_faces))
+    # upper-triangular face order (what blockMesh/renumberMesh produce)
+    own, nei = m.owner[:m.n_internal_faces], m.neighbour
+    assert np.all(own < nei) and np.all(np.diff(own) >= 0)
+
+
+def test_clip_unit_square():
+    s = SolveVofEqu(meshmod.hex_block(2), LEVEQUE_CONTROLS, lib=oracle_lib())
+    sq = np.array([[[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]]], dtype=float)
+    # plane x = 0.25: submerged side is n.x + D < 0
+    st, c, a = s.cutFaces(sq, [[1, 0, 0]], [-0.25])
+    assert st[0] == 0 and np.allclose(a[0], [0, 0, 0.25]) and np.allclose(c[0], [0.125, 0.5, 0])
+    # diagonal cut x + y = 1 -> triangle of area 1/2 (minus the 1e-14 lift of the two on-plane vertices)
+    n = np.array([[1, 1, 0]]) / np.sqrt(2)
+    st, c, a = s.cutFaces(sq, n, [-1 / np.sqrt(2)])
+    assert st[0] == 0 and abs(a[0, 2] - 0.5) < 1e-13 and np.allclose(c[0], [1 / 3, 1 / 3, 0])
+    # fully submerged / fully empty
+    assert s.cutFaces(sq, [[1, 0, 0]], [-2.0])[0][0] == -1 and s.cutFaces(sq, [[1, 0, 0]], [1.0])[0][0] == 1
+    # on-plane vertices count as dry (cutFace.C:159-165): the plane x = 0 touches two vertices only -> empty
+    assert s.cutFaces(sq, [[1, 0, 0]], [0.0])[0][0] == 1
+    # ... and the plane x = 1 leaves two dry vertices -> still a cut with the whole area
+    st, c, a = s.cutFaces(sq, [[1, 0, 0]], [-1.0])
+    assert st[0] == 0 and abs(a[0, 2] - 1.0) < 1e-13
+
+
+def test_plane_position_axis_aligned(s8):
+    # n = (1,0,0): D = -(x0 + alpha h)   
+    cells = np.array([0, 100, 300, 511], dtype=np.int32)
+    C_ = s8.field(capi.F_C)[cells]
+    h = 1 / 8
+    for al in (0.1, 0.5, 0.9, 1e-6):
+        st, D, ic, ia = s8.findSignedDistance(cells, np.full(4, al), np.tile([1.0, 0, 0], (4, 1)))
+        assert np.all(st == 0)
+        assert np.allclose(D, -(C_[:, 0] - h / 2 + al * h), rtol=0, atol=2e-14)  # Newton stops at |dlambda| < 1e-14
+        assert np.allclose(np.abs(ia[:, 0]), h * h, atol=1e-15)
+
+
+def test_plane_position_diagonal_known_volumes(s8):
+    # n = (1,1,1)/sqrt(3) through a cube: alpha = 1/6 when the plane passes through the three neighbours
+    # of the wet corner, 1/2 through the centre, 5/6 symmetric
+    h = 1 / 8
+    n = np.ones(3) / np.sqrt(3)
+    cell = np.array([73], dtype=np.int32)
+    c0 = s8.field(capi.F_C)[73] - h / 2
+    for al, dist in ((1 / 6, h), (0.5, 1.5 * h), (5 / 6, 2 * h)):
+        st, D, ic, ia = s8.findSignedDistance(cell, [al], [n])
+        # plane n.x + D = 0 at distance `dist`/sqrt(3)*sqrt(3).. i.e. x+y+z = c0.sum() + dist
+        assert abs(-D[0] * np.sqrt(3) - (c0.sum() + dist)) < 2e-14
+
+
+def test_volume_fraction_round_trip(s8):
+    rng = np.random.default_rng(0)
+    n = 500
+    cells = rng.integers(0, 512, n).astype(np.int32)
+    nrm = rng.normal(size=(n, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    al = rng.uniform(1e-6, 1 - 1e-6, n)
+    st, D, ic, ia = s8.findSignedDistance(cells, al, nrm)
+    st2, vof, sv, ic2, ia2 = s8.cutCells(cells, nrm, D)
+    assert np.all(st == 0) and np.all(st2 == 0)
+    assert np.abs(vof - al).max() < 5e-12      # SURVEY 8a' item 25: ~6e-13 round-off of the positioning itself
+    assert np.allclose(ic, ic2, atol=0) and np.allclose(ia, ia2, atol=0)
+    # the interface polygon lies in the plane and its area vector is parallel to n
+    assert np.abs((nrm * ic).sum(1) + D).max() < 1e-14
+    assert np.abs(np.abs((ia * nrm).sum(1)) - np.linalg.norm(ia, axis=1)).max() < 1e-15
+
+
+def test_sub_cell_volume_is_exactly_cubic_between_vertices(s8):
+    # between two consecutive vertex distances V(D) is a cubic: 3-point fit reproduces a 4th sample
+    cell = np.array([200], dtype=np.int32)
+    n = np.array([0.3, 0.5, 0.8])
+    n /= np.linalg.norm(n)
+    P = s8.mesh.points[s8.mesh.face_points.reshape(-1, 4)[s8.mesh.n_internal_faces]]  # any face: just for scale
+    C_ = s8.field(capi.F_C)[200]
+    h = 1 / 8
+    verts = C_ + h * (np.array([[i, j, k] for i in (0, 1) for j in (0, 1) for k in (0, 1)]) - 0.5)
+    d = np.sort(-(verts @ n))
+    lo, hi = d[3], d[4]
+    xs = lo + (hi - lo) * np.array([0.0, 0.25, 0.5, 0.75, 1.0])
+    vof = s8.cutCells(np.repeat(cell, 5), np.tile(n, (5, 1)), xs)[1]
+    coef = np.polyfit(xs[[0, 1, 2, 4]], vof[[0, 1, 2, 4]], 3)
+    assert abs(np.polyval(coef, xs[3]) - vof[3]) < 1e-12
+
+
+def test_time_integrated_flux_closed_forms(s8):
+    m = s8.mesh
+    # an internal x-face (normal +x) of area h^2; interface plane moving along +y sweeps it linearly
+    f = 0
+    Cf, Sf = s8.field(capi.F_CF)[f], s8.field(capi.F_SF)[f]
+    assert np.allclose(Sf, [1 / 64, 0, 0])
+    h = 1 / 8
+    y0 = Cf[1] - h / 2
+    n = np.array([[0.0, 1.0, 0.0]])
+    phi = np.array([0.3 * h * h])
+    dt = 0.1
+    # plane y = y0 + 0.25 h at t=0 moving with Un0 so that it reaches y0 + 0.75 h at dt: mean wet fraction 0.5
+    Un0 = np.array([0.5 * h / dt])
+    D = np.array([-(y0 + 0.25 * h)])
+    dv = s8.faceFluxes([f], n, D, Un0, dt, phi)
+    assert abs(dv[0] - phi[0] * dt * 0.5) < 1e-17
+    # stationary interface: phi dt A_sub / A
+    dv = s8.faceFluxes([f], n, D, [0.0], dt, phi)
+    assert abs(dv[0] - phi[0] * dt * 0.25) < 1e-17
+    # interface already past the face and moving on: full (Un0 > 0) ...
+    dv = s8.faceFluxes([f], n, [-(y0 + 2 * h)], Un0, dt, phi)
+    assert abs(dv[0] - phi[0] * dt) < 1e-18
+    # ... plane below the face moving towards it but not arriving: empty
+    dv = s8.faceFluxes([f], n, [-(y0 - 2 * h)], Un0, dt, phi)
+    assert dv[0] == 0.0
+    # |phi| <= 1e-14 returns 0 (cutFace.C:275-278)
+    assert s8.faceFluxes([f], n, D, Un0, dt, [1e-15])[0] == 0.0
+
+
+def test_time_integrated_flux_vs_quadrature(s8):
+    rng = np.random.default_rng(1)
+    m = s8.mesh
+    nt = 300
+    faces = rng.integers(0, m.n_internal_faces, nt).astype(np.int32)
+    Cf, Sf = s8.field(capi.F_CF), s8.field(capi.F_SF)
+    n = rng.normal(size=(nt, 3))
+    n /= np.linalg.norm(n, axis=1)[:, None]
+    h = 1 / 8
+    D = -(n * (Cf[faces] + rng.uniform(-0.6 * h, 0.6 * h, size=(nt, 3)))).sum(1)
+    Un0 = rng.uniform(-2, 2, nt)
+    dt = 0.3 * h
+    phi = rng.uniform(-1, 1, nt) * h * h
+    got = s8.faceFluxes(faces, n, D, Un0, dt, phi)
+    pts = m.points[m.face_points.reshape(-1, 4)[faces]]
+    K = 2000
+    acc = np.zeros(nt)
+    for tau in (np.arange(K) + 0.5) / K * dt:
+        acc += np.linalg.norm(s8.cutFaces(pts, n, D - tau * Un0)[2], axis=1)
+    ref = phi / np.linalg.norm(Sf[faces], axis=1) * acc * dt / K
+    assert (np.abs(got - ref) / (np.abs(phi) * dt)).max() < 1e-6   # midpoint-rule accuracy of the check itself
+
+
+def test_plane_advection_is_nearly_exact():
+    """A planar interface translated by a uniform velocity: LS normals are within a degree and the
+    geometric fluxes keep alpha within 1e-3 of the exact plane/cell volumes."""
+    N = 24
+    m = meshmod.hex_block(N)
+    s = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=oracle_lib())
+    nrm = np.array([0.6, 0.5, 0.62])
+    nrm /= np.linalg.norm(nrm)
+
+    def plane_alpha(p0):
+        return s.cutCells(np.arange(m.n_cells), np.tile(nrm, (m.n_cells, 1)), np.full(m.n_cells, -nrm @ p0))[1]
+
+    p0 = np.array([0.4, 0.4, 0.4])
+    vel = np.array([1.0, 0.7, 0.4])
+    C_, Cf, Sf = s.field(capi.F_C), s.field(capi.F_CF), s.field(capi.F_SF)
+    s.setAlpha(plane_alpha(p0))
+    s.setPhi(Sf @ vel)
+    s.setU(np.tile(vel, (m.n_cells, 1)), np.tile(vel, (m.n_boundary_faces, 1)))
+    dt = 0.25 / 2.1 / N
+    inner = np.all((C_ > 0.3) & (C_ < 0.7), axis=1)
+    for i in range(10):
+        s.reconstruct()
+        s.advect(dt)
+    err = np.abs(s.alpha() - plane_alpha(p0 + vel * dt * 10))[inner]
+    assert err.max() < 2e-3
+
+
+def test_conservation_and_boundedness_leveque():
+    N = 24
+    m = meshmod.hex_block(N)
+    s = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=oracle_lib())
+    a0 = fields.sphere_alpha_quadrature(m)
+    drv = fields.AdvectionDriver(s, fixed_dt=0.25 / N)
+    s.setAlpha(a0)
+    v0 = s.volume()
+    for i in range(12):
+        drv.step()
+        assert abs(s.volume() - v0) <= 1e-13 * v0          # total volume conserved to 1e-13 relative
+        assert s.info(capi.I_MIN_ALPHA_AFTER) > -1e-6 and s.info(capi.I_MAX_ALPHA_M1_AFTER) < 1e-6
+        # bounding never makes things worse
+        assert s.info(capi.I_MAX_ALPHA_M1_AFTER) <= max(s.info(capi.I_MAX_ALPHA_M1_BEFORE), 1e-13) + 1e-15
+    assert 0 < s.info(capi.I_N_MIXED) < m.n_cells
+    # mixed-cell list is ascending and matches the definition (reconstruction.H:281-288)
+    drv.s.reconstruct()
+    a = s.alpha()
+    assert np.array_equal(s.mixedCells(), np.nonzero((a > 1e-8) & (a < 1 - 1e-8))[0])
+
+
+def test_snap_and_clip_semantics():
+    N = 12
+    m = meshmod.hex_block(N)
+    ctl = dict(LEVEQUE_CONTROLS, clip=True, snapTol=1e-3)
+    s = SolveVofEqu(m, ctl, lib=oracle_lib())
+    a0 = fields.sphere_alpha_quadrature(m)
+    drv = fields.AdvectionDriver(s, fixed_dt=0.2 / N)
+    s.setAlpha(a0)
+    for i in range(5):
+        drv.step()
+    a = s.alpha()
+    assert a.min() >= 0.0 and a.max() <= 1.0
+    assert not np.any((a > 0) & (a < 1e-3)) and not np.any((a < 1) & (a > 1 - 1e-3))
+    # alphaPhi stays conservative even though alpha was snapped (SURVEY 8a' item 18): it is dVf/dt
+    assert np.array_equal(s.alphaPhi(), s.field(capi.F_DVF) / drv.dt)
