@@ -636,7 +636,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         const int tag = h->advectCount * (SV_MAX_SWEEPS + 1) + sidx + 1;
         LAUNCH(h, k_bound_wave, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, h->bs,
                h->affList, h->pendList, dt, rDt, dSp, dSu);
-        LAUNCH(h, k_bound_drain, 1, 1024, d, h->ctl, sidx, tag, h->pendList, h->oobState, aNew, aOld, h->phi, h->dVf, h->bs, dt, rDt, dSp,
+        LAUNCH(h, k_bound_drain, 1, 256, d, h->ctl, sidx, tag, h->pendList, h->oobState, aNew, aOld, h->phi, h->dVf, h->bs, dt, rDt, dSp,
                dSu);
         LAUNCH(h, k_bound_apply, gB, 128, d, h->ctl, sidx, tag, h->affList, h->near1, aNew, h->dVf, h->bs, h->oobList[(sidx + 1) & 1],
                h->oobState);

@@ -133,7 +133,7 @@ void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedC
 {
     // lane-cooperative kernel (8 lanes per cell) whenever the per-cell staging area fits shared memory
     const size_t perCell = sizeof(GCellShared<CP>);
-    int threads = 128;
+    int threads = 256;  // 32 cells x 8 lanes: the leader phases then fill one whole warp
     while (threads > 32 && perCell * (threads / SV_G) > 100 * 1024) threads >>= 1;
     const size_t smem = perCell * (threads / SV_G);
     if (smem <= 200 * 1024) {

@@ -812,51 +812,111 @@ struct BoundScratch {
 __device__ __forceinline__ bool faceActive(const MeshDev& m, int f) { return f < m.nIF || m.bKind[f - m.nIF] != 1; }
 __device__ __forceinline__ double corrVal(const BoundScratch& b, int f, int tag) { return (b.tagV[f] == tag) ? b.corr[f] : 0.0; }
 
-// body of boundFlux for one cell (advectionTemplates.C:245-346).  The cell's faces are loaded once
-// into thread-local arrays (a sequential chain of dependent L2 loads per inner iteration was the
-// whole cost of this kernel); corrections are written back at the end -- a face is only ever
-// corrected by its upwind cell, so the local copy is exact.
+// ---- one cell of boundFlux (advectionTemplates.C:245-346) ---------------------------------------
+// These kernels are pure latency: a few thousand threads, each a chain of dependent gathers.  The
+// cell's faces are therefore fetched in unrolled batches of 8 (row -> 8 faces -> 8x6 independent
+// gathers -> local arrays), i.e. ~4 memory round trips per cell instead of ~10 per face per inner
+// iteration, and the inner iterations then run on thread-local data only.  Corrections are written
+// back at the end: a face is only ever corrected by its upwind cell, so the local copy is exact.
 #define SV_MAXBF 64
-__device__ void boundCell(const MeshDev& m, int celli, const double* alpha, const double* aOld, const double* __restrict__ phi,
-                          const double* dVf, const BoundScratch& b, int tag, double dt, double rDeltaT, const double* Sp,
-                          const double* Su)
+struct CellBound {
+    int nf;
+    int fId[SV_MAXBF], other[SV_MAXBF];
+    double fPhi[SV_MAXBF], fDvf[SV_MAXBF], fCorr[SV_MAXBF];
+    unsigned long long ownMask, downMask;
+};
+
+__device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const double* __restrict__ phi, const double* dVf,
+                                              const BoundScratch& b, int tag, CellBound& cb)
 {
-    const double Vi = m.V[celli];
     const int c0 = m.cellOff[celli];
     int nf = m.cellOff[celli + 1] - c0;
     if (nf > SV_MAXBF) nf = SV_MAXBF;
-    int fId[SV_MAXBF];
-    double fPhi[SV_MAXBF], fDvf[SV_MAXBF], fCorr[SV_MAXBF], room[SV_MAXBF];
-    unsigned long long ownMask = 0, downMask = 0, modMask = 0, recMask = 0;
-    int recPos[SV_MAXBF];
-    for (int q = 0; q < nf; ++q) {
-        const int f = m.cellFaces[c0 + q];
-        const bool act = faceActive(m, f);
-        const bool isOwn = (m.owner[f] == celli);
-        const double ph = act ? phi[f] : 0.0;          // faceValue(phi_, facei)
-        const bool down = isOwn ? (ph >= 0) : (ph < 0);  // setDownwindFaces, advection.C:242-252
-        double cr = act ? corrVal(b, f, tag) : 0.0;
-        if (act && !down) {
-            // written by the cell on the other side; in the ascending sweep of the reference this
-            // cell has only seen it if the writer has a lower index
-            const int other = isOwn ? ((f < m.nIF) ? m.neighbour[f] : -1) : m.owner[f];
-            if (other > celli) cr = 0.0;
+    cb.nf = nf;
+    cb.ownMask = cb.downMask = 0ull;
+    for (int q0 = 0; q0 < nf; q0 += 8) {
+        int ff[8], ow[8], nb[8], tg[8];
+        double ph[8], dv[8], cr[8];
+        unsigned char bk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ff[j] = (q0 + j < nf) ? m.cellFaces[c0 + q0 + j] : -1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            ow[j] = 0; nb[j] = -1; tg[j] = 0; ph[j] = 0.0; dv[j] = 0.0; cr[j] = 0.0; bk[j] = 0;
+            if (ff[j] >= 0) {
+                const int f = ff[j];
+                ow[j] = m.owner[f];
+                ph[j] = phi[f];
+                dv[j] = dVf[f];
+                tg[j] = b.tagV[f];
+                cr[j] = b.corr[f];
+                if (f < m.nIF) nb[j] = m.neighbour[f]; else bk[j] = m.bKind[f - m.nIF];
+            }
         }
-        fId[q] = f;
-        fPhi[q] = ph;
-        fDvf[q] = act ? dVf[f] : 0.0;
-        fCorr[q] = cr;
-        if (isOwn) ownMask |= 1ull << q;
-        if (down) downMask |= 1ull << q;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (ff[j] < 0) continue;
+            const int q = q0 + j;
+            const bool act = (bk[j] != 1);                     // faceValue(): empty patches read as zero
+            const bool isOwn = (ow[j] == celli);
+            const double p = act ? ph[j] : 0.0;
+            const bool down = isOwn ? (p >= 0) : (p < 0);      // setDownwindFaces, advection.C:242-252
+            const int oth = isOwn ? nb[j] : ow[j];
+            double c = (act && tg[j] == tag) ? cr[j] : 0.0;
+            // a correction on a face that is downwind of the OTHER cell was written by that cell; in the
+            // ascending sweep of the reference this cell has only seen it if the writer has a lower index
+            if (act && !down && oth > celli) c = 0.0;
+            cb.fId[q] = ff[j];
+            cb.other[q] = act ? oth : -1;
+            cb.fPhi[q] = p;
+            cb.fDvf[q] = act ? dv[j] : 0.0;
+            cb.fCorr[q] = c;
+            if (isOwn) cb.ownMask |= 1ull << q;
+            if (down) cb.downMask |= 1ull << q;
+        }
     }
+}
+
+// The reference sweeps the cells in ascending index (Gauss-Seidel, SURVEY 8a' item 15).  A cell only
+// ever READS corrections written by another cell on the faces that are DOWNWIND of that other cell,
+// so cell c must wait exactly for the lower-index out-of-bounds neighbours that are upwind of it
+// across the shared face; everything else commutes (reads of higher-index writers are masked above).
+__device__ __forceinline__ bool boundReady(const CellBound& cb, int celli, const volatile unsigned char* oobState)
+{
+    bool ready = true;
+    for (int q0 = 0; q0 < cb.nf; q0 += 8) {
+        unsigned char st[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            st[j] = 0;
+            const int q = q0 + j;
+            if (q < cb.nf) {
+                const int y = cb.other[q];
+                if (y >= 0 && y < celli && !((cb.downMask >> q) & 1ull)) st[j] = oobState[y];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ready = ready && (st[j] != 1);
+    }
+    return ready;
+}
+
+__device__ void boundCell(const MeshDev& m, int celli, CellBound& cb, const double* alpha, const double* aOld,
+                          const BoundScratch& b, int tag, double dt, double rDeltaT, const double* Sp, const double* Su)
+{
+    const double Vi = m.V[celli];
+    const int nf = cb.nf;
+    double room[SV_MAXBF];
+    int recPos[SV_MAXBF];
+    unsigned long long modMask = 0, recMask = 0;
     const double a0 = alpha[celli];
+    const double SuI = Su ? Su[celli] : 0.0, SpI = Sp ? Sp[celli] : 0.0;
+    const double aOldI = aOld[celli];
     double alphaOvershoot = pos0(a0 - 1.0) * (a0 - 1.0) + neg0(a0) * a0;
     double fluidToPassOn = alphaOvershoot * Vi;
     int nFacesToPassFluidThrough = 1;
     bool firstLoop = true;
     int nRecorded = 0;
-    const double SuI = Su ? Su[celli] : 0.0, SpI = Sp ? Sp[celli] : 0.0;
-    const double aOldI = aOld[celli];
     for (int iter = 0; iter < 10; ++iter) {
         if (fabs(alphaOvershoot) < SV_ATOL || nFacesToPassFluidThrough == 0) break;
         // facesToPassFluidThrough / dVfmax / dVftot: fixed before any correction of this iteration
@@ -864,24 +924,24 @@ __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, cons
         nFacesToPassFluidThrough = 0;
         for (int q = 0; q < nf; ++q) {
             double r = -1.0;
-            if ((downMask >> q) & 1ull) {
-                const double dVff = fDvf[q] + fCorr[q];
-                const double maxExtra = fabs(pos0(fluidToPassOn) * fPhi[q] * dt - dVff);
+            if ((cb.downMask >> q) & 1ull) {
+                const double dVff = cb.fDvf[q] + cb.fCorr[q];
+                const double maxExtra = fabs(pos0(fluidToPassOn) * cb.fPhi[q] * dt - dVff);
                 if (maxExtra / Vi > SV_ATOL) {
                     r = maxExtra;
-                    dVftot += fabs(fPhi[q] * dt);
+                    dVftot += fabs(cb.fPhi[q] * dt);
                 }
             }
             room[q] = r;
         }
         for (int q = 0; q < nf; ++q) {
             if (room[q] < 0.0) continue;
-            double through = fabs(fluidToPassOn) * fabs(fPhi[q] * dt) / dVftot;
+            double through = fabs(fluidToPassOn) * fabs(cb.fPhi[q] * dt) / dVftot;
             nFacesToPassFluidThrough += int(pos0(room[q] - through));
             through = dmin(through, room[q]);
-            double dVff = fCorr[q];
-            dVff += sgn(fPhi[q]) * sgn(fluidToPassOn) * through;
-            fCorr[q] = dVff;
+            double dVff = cb.fCorr[q];
+            dVff += sgn(cb.fPhi[q]) * sgn(fluidToPassOn) * through;
+            cb.fCorr[q] = dVff;
             modMask |= 1ull << q;
             if (firstLoop) {
                 recMask |= 1ull << q;
@@ -891,12 +951,12 @@ __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, cons
         firstLoop = false;
         double nfl = 0.0, nc = 0.0;  // netFlux(dVf_), netFlux(dVfCorrectionValues)  (advection.C:259-288)
         for (int q = 0; q < nf; ++q) {
-            if ((ownMask >> q) & 1ull) {
-                nfl += fDvf[q];
-                nc += fCorr[q];
+            if ((cb.ownMask >> q) & 1ull) {
+                nfl += cb.fDvf[q];
+                nc += cb.fCorr[q];
             } else {
-                nfl -= fDvf[q];
-                nc -= fCorr[q];
+                nfl -= cb.fDvf[q];
+                nc -= cb.fCorr[q];
             }
         }
         const double alpha1New = (aOldI * rDeltaT + SuI - nfl / Vi * rDeltaT - nc / Vi * rDeltaT) / (rDeltaT - SpI);
@@ -905,8 +965,8 @@ __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, cons
     }
     for (int q = 0; q < nf; ++q) {
         if (!((modMask >> q) & 1ull)) continue;
-        const int f = fId[q];
-        b.corr[f] = fCorr[q];
+        const int f = cb.fId[q];
+        b.corr[f] = cb.fCorr[q];
         b.tagV[f] = tag;
         if ((recMask >> q) & 1ull) {
             b.corrBy[f] = celli;
@@ -914,31 +974,6 @@ __device__ void boundCell(const MeshDev& m, int celli, const double* alpha, cons
             b.tagR[f] = tag;
         }
     }
-}
-
-// The reference sweeps the cells in ascending index (Gauss-Seidel, SURVEY 8a' item 15).  A cell only
-// ever READS corrections written by another cell on the faces that are DOWNWIND of that other cell,
-// so cell c must wait exactly for the lower-index out-of-bounds neighbours that are upwind of it
-// across the shared face; everything else commutes.
-__device__ __forceinline__ bool boundReady(const MeshDev& m, int c, const double* __restrict__ phi,
-                                           const volatile unsigned char* oobState)
-{
-    for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
-        const int2 e = m.cellAsc[k];
-        const int y = e.y;
-        if (y < 0 || y >= c) continue;
-        if (oobState[y] != 1) continue;
-        const bool flip = e.x < 0;                      // c is the neighbour side of this face
-        const double ph = phi[e.x & 0x7fffffff];
-        const bool yIsUpwind = flip ? (ph >= 0) : (ph < 0);  // owner is upwind iff phi >= 0
-        if (yIsUpwind) return false;
-    }
-    return true;
-}
-
-__device__ __forceinline__ void markAffected(int c, const BoundScratch& b, int tag, int* affList, int* nAff)
-{
-    if (atomicExch(&b.affStamp[c], tag) != tag) affList[atomicAdd(nAff, 1)] = c;
 }
 
 __global__ void __launch_bounds__(128) k_bound_wave(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList, unsigned char* oobState,
@@ -949,13 +984,31 @@ __global__ void __launch_bounds__(128) k_bound_wave(MeshDev m, Ctl* ctl, int s, 
     const int n = ctl->nOob[s & 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = oobList[i];
-        markAffected(c, b, tag, affList, &ctl->nAff[s]);
-        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
-            const int y = m.cellAsc[k].y;
-            if (y >= 0) markAffected(y, b, tag, affList, &ctl->nAff[s]);
+        CellBound cb;
+        loadCellBound(m, c, phi, dVf, b, tag, cb);
+        // affected set = this cell + its face neighbours (the cells the corrections can change);
+        // all stamps are exchanged first, then ONE counter atomic reserves the list slots
+        int newIds[SV_MAXBF + 1];
+        int nNew = 0;
+        if (atomicExch(&b.affStamp[c], tag) != tag) newIds[nNew++] = c;
+        for (int q0 = 0; q0 < cb.nf; q0 += 8) {
+            int old[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                old[j] = tag;
+                const int q = q0 + j;
+                if (q < cb.nf && cb.other[q] >= 0) old[j] = atomicExch(&b.affStamp[cb.other[q]], tag);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (old[j] != tag) newIds[nNew++] = cb.other[q0 + j];
         }
-        if (boundReady(m, c, phi, oobState)) {
-            boundCell(m, c, alpha, aOld, phi, dVf, b, tag, dt, rDt, Sp, Su);
+        if (nNew) {
+            const int pos = atomicAdd(&ctl->nAff[s], nNew);
+            for (int j = 0; j < nNew; ++j) affList[pos + j] = newIds[j];
+        }
+        if (boundReady(cb, c, oobState)) {
+            boundCell(m, c, cb, alpha, aOld, b, tag, dt, rDt, Sp, Su);
             __threadfence();
             ((volatile unsigned char*)oobState)[c] = 2;
         } else {
@@ -964,8 +1017,9 @@ __global__ void __launch_bounds__(128) k_bound_wave(MeshDev m, Ctl* ctl, int s, 
     }
 }
 
-// single CTA: walks the dependency chains the wave launch deferred (a few % of the cells)
-__global__ void __launch_bounds__(1024) k_bound_drain(MeshDev m, Ctl* ctl, int s, int tag, const int* pendList, unsigned char* oobState,
+// single CTA: walks the dependency chains the wave launch deferred (a few % of the cells).
+// Each thread keeps its deferred cells' data in local memory and only re-polls the neighbour states.
+__global__ void __launch_bounds__(256) k_bound_drain(MeshDev m, Ctl* ctl, int s, int tag, const int* pendList, unsigned char* oobState,
                                                       const double* alpha, const double* aOld, const double* phi, const double* dVf,
                                                       BoundScratch b, double dt, double rDt, const double* Sp, const double* Su)
 {
@@ -979,8 +1033,11 @@ __global__ void __launch_bounds__(1024) k_bound_drain(MeshDev m, Ctl* ctl, int s
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int c = pendList[i];
             if (((volatile unsigned char*)oobState)[c] != 1) continue;
-            if (boundReady(m, c, phi, oobState)) {
-                boundCell(m, c, alpha, aOld, phi, dVf, b, tag, dt, rDt, Sp, Su);
+            CellBound cb;
+            loadCellBound(m, c, phi, dVf, b, tag, cb);
+            if (boundReady(cb, c, oobState)) {
+                // the corrections of the cells this one waited for are visible now: reload and process
+                boundCell(m, c, cb, alpha, aOld, b, tag, dt, rDt, Sp, Su);
                 __threadfence();
                 ((volatile unsigned char*)oobState)[c] = 2;
             } else {
@@ -1008,39 +1065,65 @@ __global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s,
         const int c = affList[i];
         double a = alpha[c];
         const bool was = oobGlobal(a);
-        int fl[64];
-        long long key[64];
+        const int c0 = m.cellOff[c];
+        int nfc = m.cellOff[c + 1] - c0;
+        if (nfc > SV_MAXBF) nfc = SV_MAXBF;
+        int fl[SV_MAXBF];
+        long long key[SV_MAXBF];
+        double cvv[SV_MAXBF];
+        unsigned long long ownM = 0;
         int nf = 0;
-        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
-            const int f = m.cellFaces[k];
-            if (!faceActive(m, f) || b.tagR[f] != tag) continue;
-            if (nf < 64) {
-                fl[nf] = f;
-                key[nf] = ((long long)b.corrBy[f] << 20) | (long long)b.corrPos[f];
+        for (int q0 = 0; q0 < nfc; q0 += 8) {
+            int ff[8], tr[8], by[8], ps[8], ow[8];
+            double cv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ff[j] = (q0 + j < nfc) ? m.cellFaces[c0 + q0 + j] : -1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                tr[j] = 0; by[j] = 0; ps[j] = 0; ow[j] = 0; cv[j] = 0.0;
+                if (ff[j] >= 0) {
+                    tr[j] = b.tagR[ff[j]];
+                    by[j] = b.corrBy[ff[j]];
+                    ps[j] = b.corrPos[ff[j]];
+                    cv[j] = b.corr[ff[j]];
+                    ow[j] = m.owner[ff[j]];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (ff[j] < 0 || tr[j] != tag) continue;  // empty-patch faces are never recorded
+                fl[nf] = ff[j];
+                key[nf] = ((long long)by[j] << 20) | (long long)ps[j];
+                cvv[nf] = cv[j];
+                if (ow[j] == c) ownM |= 1ull << nf;
                 nf++;
             }
         }
         for (int x = 1; x < nf; ++x) {  // insertion sort by key
             const long long kx = key[x];
             const int fx = fl[x];
+            const double vx = cvv[x];
+            const bool ox = (ownM >> x) & 1ull;
             int y = x - 1;
             while (y >= 0 && key[y] > kx) {
                 key[y + 1] = key[y];
                 fl[y + 1] = fl[y];
+                cvv[y + 1] = cvv[y];
+                ownM = (ownM & ~(1ull << (y + 1))) | (((ownM >> y) & 1ull) << (y + 1));
                 --y;
             }
             key[y + 1] = kx;
             fl[y + 1] = fx;
+            cvv[y + 1] = vx;
+            ownM = (ownM & ~(1ull << (y + 1))) | ((unsigned long long)ox << (y + 1));
         }
         const double Vc = m.V[c];
         for (int x = 0; x < nf; ++x) {
-            const int f = fl[x];
-            const double cv = b.corr[f];
-            if (m.owner[f] == c) {
-                a -= cv / Vc;
-                dVf[f] = dVf[f] + cv;  // setFaceValue(dVf_, facei, corrVf): once, by the owner
+            if ((ownM >> x) & 1ull) {
+                a -= cvv[x] / Vc;
+                dVf[fl[x]] = dVf[fl[x]] + cvv[x];  // setFaceValue(dVf_, facei, corrVf): once, by the owner
             } else {
-                a += cv / Vc;
+                a += cvv[x] / Vc;
             }
         }
         alpha[c] = a;

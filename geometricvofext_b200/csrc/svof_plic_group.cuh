@@ -121,141 +121,143 @@ __device__ __forceinline__ int clipFaceCached(const d3* fp, const double* pn, in
 
 #define SV_G 8  // lanes per cell
 
+// CTA = cpb cells x 8 lanes.  Face phases (A, C, E): thread t works for cell t/8, lane t%8.
+// Leader phases (staging, B, D, F): the first cpb threads, one per cell (thread t <-> cell t), so the
+// sequential reductions of 32 cells run on 32 lanes of ONE warp instead of 1 lane in each of 8 warps
+// (measured on the first version: 9 of 32 lanes active on average, 10.8k warp-instructions per
+// evaluation; the leader phases dominated).
 template <class CP>
-__global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
+__global__ void __launch_bounds__(256) k_plic_group(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
                                                     const double* iN, int split, int* cellStatus, double* iD, double* iC, double* iS)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     GCellShared<CP>* shAll = reinterpret_cast<GCellShared<CP>*>(smemRaw);
-    const int groupsPerBlock = blockDim.x / SV_G;
-    const int gid = threadIdx.x / SV_G, lane = threadIdx.x % SV_G;
-    GCellShared<CP>& sh = shAll[gid];
-    const bool leader = (lane == 0);
+    const int cpb = blockDim.x / SV_G;  // cells per block
+    const int gidF = threadIdx.x / SV_G, lane = threadIdx.x % SV_G;
+    const bool leader = (threadIdx.x < cpb);
+    GCellShared<CP>& shF = shAll[gidF];                      // the cell this thread clips faces for
+    GCellShared<CP>& shL = shAll[leader ? threadIdx.x : 0];  // the cell this thread leads (if leader)
     const int nMixed = ctl->nMixed;
     const bool splitB = split != 0;
     int err = 0;
 
-    for (int base = blockIdx.x * groupsPerBlock; base < nMixed; base += gridDim.x * groupsPerBlock) {
-        const int i = base + gid;
-        const bool valid = i < nMixed;
-        const int cell = valid ? mixedCells[i] : 0;
-        const double alphaI = valid ? alpha[cell] : 0.5;
-        const d3 n = valid ? ld3(iN, cell) : mk3(1.0, 0.0, 0.0);
-        const double Vcell = __ldg(m.V + cell);
-        const bool degenerate = mag(n) < SV_TSMALL;  // cutCell.C:625-628
-
-        // ---- stage the polyhedron: local face list, sorted vertex distances ------------------
-        if (leader && !valid) {
-            sh.nLocal = 0;
-            sh.nPts = 0;
-        }
-        if (leader && valid) {
-            int nl = 0;
-            const int c0 = __ldg(m.cellOff + cell), c1 = __ldg(m.cellOff + cell + 1);
-            for (int k = c0; k < c1; ++k) {
-                const int f = __ldg(m.cellFaces + k);
-                if (splitB && !(__ldg(m.flat + f) > (1.0 - SV_TSMALL))) {
-                    const int nv = __ldg(m.faceOff + f + 1) - __ldg(m.faceOff + f);
-                    for (int t = 0; t < nv; ++t) {
+    for (int base = blockIdx.x * cpb; base < nMixed; base += gridDim.x * cpb) {
+        // ---- leader role: stage the polyhedron (local face list, sorted vertex distances), init the search
+        const int iL = base + threadIdx.x;
+        const bool validL = leader && iL < nMixed;
+        const int cellL = validL ? mixedCells[iL] : 0;
+        const double alphaI = validL ? alpha[cellL] : 0.5;
+        const d3 nL = validL ? ld3(iN, cellL) : mk3(1.0, 0.0, 0.0);
+        const double Vcell = validL ? __ldg(m.V + cellL) : 1.0;
+        double lowDistance = 0, upDistance = 0, lowAlpha = 0.0, upAlpha = 1.0;
+        int lowLabel = 0, upLabel = 0;
+        double midLabel = 0, aOneThird = 0, deltaDistance = 0, curD = 0;
+        int phase = 0;  // 0 bracketing, 1 collapsed bracket, 2 one third, 3 two thirds, 4 final
+        int outStatus = 0;
+        if (leader) {
+            int nl = 0, nP = 0;
+            if (validL) {
+                const int c0 = __ldg(m.cellOff + cellL), c1 = __ldg(m.cellOff + cellL + 1);
+                for (int k = c0; k < c1; ++k) {
+                    const int f = __ldg(m.cellFaces + k);
+                    if (splitB && !(__ldg(m.flat + f) > (1.0 - SV_TSMALL))) {
+                        const int nv = __ldg(m.faceOff + f + 1) - __ldg(m.faceOff + f);
+                        for (int t = 0; t < nv; ++t) {
+                            if (nl < CP::MAXCF) {
+                                shL.lfFace[nl] = f;
+                                shL.lfTri[nl] = (short)t;
+                                nl++;
+                            } else err |= SVERR_CELL_FACES;
+                        }
+                    } else {
                         if (nl < CP::MAXCF) {
-                            sh.lfFace[nl] = f;
-                            sh.lfTri[nl] = (short)t;
+                            shL.lfFace[nl] = f;
+                            shL.lfTri[nl] = -1;
                             nl++;
                         } else err |= SVERR_CELL_FACES;
                     }
-                } else {
-                    if (nl < CP::MAXCF) {
-                        sh.lfFace[nl] = f;
-                        sh.lfTri[nl] = -1;
-                        nl++;
-                    } else err |= SVERR_CELL_FACES;
                 }
-            }
-            sh.nLocal = nl;
-            // vertex distances, descending (values only: ties are indistinguishable, cutCell.C:664-670)
-            int nP = 0;
-            const int p0 = __ldg(m.cellPtOff + cell), p1 = __ldg(m.cellPtOff + cell + 1);
-            for (int k = p0; k < p1; ++k) {
-                if (nP < CP::MAXCP) sh.vd[nP++] = -dot(n, ld3(m.points, __ldg(m.cellPts + k)));
-                else err |= SVERR_CELL_POINTS;
-            }
-            if (splitB) {
-                for (int k = c0; k < c1; ++k) {
-                    const int f = __ldg(m.cellFaces + k);
-                    if (!(__ldg(m.flat + f) > (1.0 - SV_TSMALL))) {
-                        if (nP < CP::MAXCP) sh.vd[nP++] = -dot(n, ld3(m.Cf, f));
-                        else err |= SVERR_CELL_POINTS;
+                // vertex distances, descending (values only: ties are indistinguishable, cutCell.C:664-670)
+                const int p0 = __ldg(m.cellPtOff + cellL), p1 = __ldg(m.cellPtOff + cellL + 1);
+                for (int k = p0; k < p1; ++k) {
+                    if (nP < CP::MAXCP) shL.vd[nP++] = -dot(nL, ld3(m.points, __ldg(m.cellPts + k)));
+                    else err |= SVERR_CELL_POINTS;
+                }
+                if (splitB) {
+                    for (int k = c0; k < c1; ++k) {
+                        const int f = __ldg(m.cellFaces + k);
+                        if (!(__ldg(m.flat + f) > (1.0 - SV_TSMALL))) {
+                            if (nP < CP::MAXCP) shL.vd[nP++] = -dot(nL, ld3(m.Cf, f));
+                            else err |= SVERR_CELL_POINTS;
+                        }
                     }
                 }
+                sortDescending(shL.vd, nP);
             }
-            sortDescending(sh.vd, nP);
-            sh.nPts = nP;
+            shL.nLocal = nl;
+            shL.nPts = nP;
+            // search state (cutCell.C:682-719)
+            bool done = !validL;
+            if (validL) {
+                upLabel = nP - 1;
+                lowDistance = shL.vd[0];
+                upDistance = shL.vd[nP - 1];
+                if (mag(nL) < SV_TSMALL) {  // cutCell.C:625-628: D/C/S stay untouched
+                    outStatus = int(sgn(0.5 - alphaI));
+                    done = true;
+                } else if ((upLabel - lowLabel) > 1) {
+                    midLabel = round(0.5 * (upLabel + lowLabel));
+                    curD = shL.vd[int(midLabel)];
+                    phase = 0;
+                } else if (fabs(lowDistance - upDistance) < SV_TSMALL) {
+                    curD = 0.5 * (lowDistance + upDistance);
+                    phase = 1;
+                } else {
+                    deltaDistance = (upDistance - lowDistance) / 3.0;
+                    curD = lowDistance + deltaDistance;
+                    phase = 2;
+                }
+                shL.D = curD;
+            }
+            shL.active = done ? 0 : 1;
         }
-        __syncwarp();
-        const int nLocal = sh.nLocal;
-        const int nP = sh.nPts;
-        const bool cached = nLocal <= SV_G;
+        __syncthreads();
 
-        // ---- plane-independent per-face data of this lane's face (when one face per lane) -----
+        // ---- face role: plane-independent data of this lane's face (when one face per lane) -----------
+        const int iF = base + gidF;
+        const bool validF = iF < nMixed;
+        const int cellF = validF ? mixedCells[iF] : 0;
+        const d3 nF = validF ? ld3(iN, cellF) : mk3(1.0, 0.0, 0.0);
+        const int nLocal = shF.nLocal;
+        const bool cached = nLocal <= SV_G;
         d3 fpC[CP::MAXFV];
         double pnC[CP::MAXFV];
         d3 fullC = zero3(), fullA = zero3();
         int nvC = 0;
-        if (cached && lane < nLocal) {
-            nvC = loadLocalFace<CP>(m, cell, sh.lfFace[lane], sh.lfTri[lane], splitB, fpC, err);
+        if (validF && shF.active && cached && lane < nLocal) {
+            nvC = loadLocalFace<CP>(m, cellF, shF.lfFace[lane], shF.lfTri[lane], splitB, fpC, err);
 #pragma unroll
             for (int q = 0; q < CP::MAXFV; ++q)
-                if (q < nvC) pnC[q] = dot(fpC[q], n);
+                if (q < nvC) pnC[q] = dot(fpC[q], nF);
             fullC = faceCentreOF(fpC, nvC);
             fullA = faceAreaNormalOF(fpC, nvC);
         }
 
-        // ---- leader's search state (cutCell.C:682-719) ----------------------------------------
-        double lowDistance = 0, upDistance = 0, lowAlpha = 0.0, upAlpha = 1.0;
-        int lowLabel = 0, upLabel = nP - 1;
-        double midLabel = 0, aOneThird = 0, deltaDistance = 0, curD = 0;
-        int phase = 0;  // 0 bracketing, 1 collapsed bracket, 2 one third, 3 two thirds, 4 final
-        int outStatus = 0;
-        bool wrote = false, done = !valid;
-        if (leader && valid) {
-            lowDistance = sh.vd[0];
-            upDistance = sh.vd[nP - 1];
-            if (degenerate) {
-                outStatus = int(sgn(0.5 - alphaI));
-                done = true;
-            } else if ((upLabel - lowLabel) > 1) {
-                midLabel = round(0.5 * (upLabel + lowLabel));
-                curD = sh.vd[int(midLabel)];
-                phase = 0;
-            } else if (fabs(lowDistance - upDistance) < SV_TSMALL) {
-                curD = 0.5 * (lowDistance + upDistance);
-                phase = 1;
-            } else {
-                deltaDistance = (upDistance - lowDistance) / 3.0;
-                curD = lowDistance + deltaDistance;
-                phase = 2;
-            }
-            sh.D = curD;
-        }
-        if (leader) sh.active = done ? 0 : 1;
-        __syncwarp();
-
-        // ---- evaluation loop: one calcSubCell (cutCell.C:343-542) per iteration ----------------
-        while (__any_sync(0xffffffffu, sh.active != 0)) {
-            const bool act = sh.active != 0;
-            const double D = sh.D;
+        // ---- evaluation loop: one calcSubCell (cutCell.C:343-542) per iteration ----------------------
+        while (__syncthreads_or(leader ? shL.active : 0)) {
             // A. clip the faces of this lane
-            if (act) {
+            if (shF.active) {
+                const double D = shF.D;
                 for (int k = lane; k < nLocal; k += SV_G) {
-                    GFaceRes<CP>& r = sh.res[k];
+                    GFaceRes<CP>& r = shF.res[k];
                     d3 c, a, ipl[CP::MAXIP];
                     int nip, st;
                     if (cached) {
                         st = clipFaceCached<CP>(fpC, pnC, nvC, D, fullC, fullA, c, a, ipl, nip, err);
                     } else {
                         d3 fp[CP::MAXFV];
-                        const int nv = loadLocalFace<CP>(m, cell, sh.lfFace[k], sh.lfTri[k], splitB, fp, err);
-                        st = clipFace<CP>(fp, nv, n, D, c, a, ipl, nip, err);
+                        const int nv = loadLocalFace<CP>(m, cellF, shF.lfFace[k], shF.lfTri[k], splitB, fp, err);
+                        st = clipFace<CP>(fp, nv, nF, D, c, a, ipl, nip, err);
                     }
                     r.st = st;
                     r.nip = nip;
@@ -264,22 +266,24 @@ __global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedC
                     for (int q = 0; q < nip; ++q) r.ip[q] = ipl[q];
                 }
             }
-            __syncwarp();
-            // B. leader: classification + interface polygon centre (cutCell.C:37-54)
+            __syncthreads();
+            // B. leaders: classification + interface polygon centre (cutCell.C:37-54)
+            const bool act = leader && shL.active;
+            const int nLoc = leader ? shL.nLocal : 0;
             bool fullySubmerged = true, fullyEmpty = true;
             int nSubmergedFaces = 0, nCut = 0;
-            if (act && leader) {
+            if (act) {
                 d3 fC = zero3();
                 int nEp = 0;
-                for (int k = 0; k < nLocal; ++k) {
-                    const int st = sh.res[k].st;
+                for (int k = 0; k < nLoc; ++k) {
+                    const int st = shL.res[k].st;
                     if (st == 0) {
                         fullySubmerged = false;
                         fullyEmpty = false;
                         nCut++;
-                        const int nip = sh.res[k].nip;
+                        const int nip = shL.res[k].nip;
                         for (int q = 0; q < nip; ++q) {
-                            fC += sh.res[k].ip[q];
+                            fC += shL.res[k].ip[q];
                             nEp++;
                         }
                     } else if (st == -1) {
@@ -291,48 +295,48 @@ __global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedC
                     }
                 }
                 if (nEp > 0) fC /= double(nEp);
-                sh.fC = fC;
-                sh.cutAny = (!fullySubmerged && !fullyEmpty) ? 1 : 0;
+                shL.fC = fC;
+                shL.cutAny = (!fullySubmerged && !fullyEmpty) ? 1 : 0;
             }
-            __syncwarp();
+            __syncthreads();
             // C. lanes: interface segments of their cut faces (cutCell.C:60-79, the per-segment part)
-            if (act && sh.cutAny) {
-                const d3 fC = sh.fC;
+            if (shF.active && shF.cutAny) {
+                const d3 fC = shF.fC;
                 for (int k = lane; k < nLocal; k += SV_G) {
-                    const GFaceRes<CP>& r = sh.res[k];
+                    const GFaceRes<CP>& r = shF.res[k];
                     if (r.st != 0) continue;
                     for (int pi = 0; pi < r.nip - 1; ++pi) {
                         const d3 p0 = r.ip[pi], nx = r.ip[pi + 1];
                         const d3 c = p0 + nx + fC;
                         const d3 nn = cross(nx - p0, fC - p0);
                         const double a = mag(nn);
-                        sh.seg[k].nn[pi] = nn;
-                        sh.seg[k].a[pi] = a;
-                        sh.seg[k].ac[pi] = a * c;
+                        shF.seg[k].nn[pi] = nn;
+                        shF.seg[k].a[pi] = a;
+                        shF.seg[k].ac[pi] = a * c;
                     }
                 }
             }
-            __syncwarp();
-            // D. leader: ordered accumulation, interface centre/area, cEst (cutCell.C:56-99,110)
+            __syncthreads();
+            // D. leaders: ordered accumulation, interface centre/area, cEst (cutCell.C:56-99,110)
             int status = 0;
             double VOF = 0.0;
             bool needVolume = false;
             d3 iCl = zero3(), iSl = zero3();
-            if (act && leader) {
-                if (sh.cutAny) {
+            if (act) {
+                if (shL.cutAny) {
                     d3 sumN = zero3(), sumAc = zero3();
                     double sumA = 0.0;
-                    for (int k = 0; k < nLocal; ++k) {
-                        if (sh.res[k].st != 0) continue;
-                        for (int pi = 0; pi < sh.res[k].nip - 1; ++pi) {
-                            const d3 nn = sh.seg[k].nn[pi];
+                    for (int k = 0; k < nLoc; ++k) {
+                        if (shL.res[k].st != 0) continue;
+                        for (int pi = 0; pi < shL.res[k].nip - 1; ++pi) {
+                            const d3 nn = shL.seg[k].nn[pi];
                             sumN += sgn(dot(nn, sumN)) * nn;
-                            sumA += sh.seg[k].a[pi];
-                            sumAc += sh.seg[k].ac[pi];
+                            sumA += shL.seg[k].a[pi];
+                            sumAc += shL.seg[k].ac[pi];
                         }
                     }
                     if (sumA < SV_ROOTVSMALL) {
-                        iCl = sh.fC;
+                        iCl = shL.fC;
                         iSl = zero3();
                     } else {
                         iCl = (1.0 / 3.0) * sumAc / sumA;
@@ -351,11 +355,11 @@ __global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedC
                         status = 0;
                         needVolume = true;
                         d3 cEst = zero3();
-                        for (int k = 0; k < nLocal; ++k)
-                            if (sh.res[k].st <= 0) cEst += sh.res[k].c;
+                        for (int k = 0; k < nLoc; ++k)
+                            if (shL.res[k].st <= 0) cEst += shL.res[k].c;
                         cEst += iCl;
                         cEst /= double(nCut + 1);
-                        sh.cEst = cEst;
+                        shL.cEst = cEst;
                     }
                 } else if (fullyEmpty) {
                     status = 1;
@@ -364,25 +368,25 @@ __global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedC
                     status = -1;
                     VOF = 1.0;
                 }
-                sh.cutAny = needVolume ? 1 : 0;
+                shL.cutAny = needVolume ? 1 : 0;
             }
-            __syncwarp();
+            __syncthreads();
             // E. lanes: pyramid volumes of their sub-faces (cutCell.C:116-123)
-            if (act && sh.cutAny) {
-                const d3 cEst = sh.cEst;
+            if (shF.active && shF.cutAny) {
+                const d3 cEst = shF.cEst;
                 for (int k = lane; k < nLocal; k += SV_G) {
-                    const GFaceRes<CP>& r = sh.res[k];
-                    if (r.st <= 0) sh.pv[k] = dmax(fabs(dot(r.a, r.c - cEst)), SV_VSMALL);
+                    const GFaceRes<CP>& r = shF.res[k];
+                    if (r.st <= 0) shF.pv[k] = dmax(fabs(dot(r.a, r.c - cEst)), SV_VSMALL);
                 }
             }
-            __syncwarp();
-            // F. leader: ordered volume sum, then advance the search (cutCell.C:691-799)
-            if (act && leader) {
+            __syncthreads();
+            // F. leaders: ordered volume sum, then advance the search (cutCell.C:691-799)
+            if (act) {
                 if (needVolume) {
                     double vol = 0.0;
-                    for (int k = 0; k < nLocal; ++k)
-                        if (sh.res[k].st <= 0) vol += sh.pv[k];
-                    vol += dmax(fabs(dot(iSl, iCl - sh.cEst)), SV_VSMALL);
+                    for (int k = 0; k < nLoc; ++k)
+                        if (shL.res[k].st <= 0) vol += shL.pv[k];
+                    vol += dmax(fabs(dot(iSl, iCl - shL.cEst)), SV_VSMALL);
                     vol /= 3.0;
                     VOF = vol / Vcell;
                 }
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedC
                         }
                         if ((upLabel - lowLabel) > 1) {
                             midLabel = round(0.5 * (upLabel + lowLabel));
-                            curD = sh.vd[int(midLabel)];
+                            curD = shL.vd[int(midLabel)];
                         } else if (fabs(lowDistance - upDistance) < SV_TSMALL) {
                             curD = 0.5 * (lowDistance + upDistance);
                             phase = 1;
@@ -440,20 +444,18 @@ __global__ void __launch_bounds__(128) k_plic_group(MeshDev m, const int* mixedC
                 }
                 if (finish) {
                     outStatus = status;
-                    wrote = true;
-                    iD[cell] = curD;
-                    st3(iC, cell, iCl);
-                    st3(iS, cell, iSl);
-                    sh.active = 0;
+                    iD[cellL] = curD;
+                    st3(iC, cellL, iCl);
+                    st3(iS, cellL, iSl);
+                    shL.active = 0;
                 } else {
-                    sh.D = curD;
+                    shL.D = curD;
                 }
             }
-            __syncwarp();
+            // (the __syncthreads_or of the loop condition is the barrier after F)
         }
-        if (leader && valid) cellStatus[i] = outStatus;
-        (void)wrote;
-        __syncwarp();
+        if (validL) cellStatus[iL] = outStatus;
+        __syncthreads();
     }
     if (err) atomicOr(&ctl->err, err);
 }
