@@ -41,7 +41,7 @@ struct svof_handle {
     cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
     cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr;
     bool inputsAfterNear = false, freshRecon = false;
-    bool overlap = false;  // SVOF_OVERLAP=1: run the streaming kernel on its own stream, concurrently with the sparse chain
+    bool overlap = true;   // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=0 / svof_set_option to disable)
     int advectCount = 0;
     int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
     std::vector<svof_patch> patches;
@@ -784,7 +784,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
-        h->overlap = getenv("SVOF_OVERLAP") && atoi(getenv("SVOF_OVERLAP")) > 0;
+        h->overlap = !(getenv("SVOF_OVERLAP") && atoi(getenv("SVOF_OVERLAP")) == 0);  // default on
         h->prof = getenv("SVOF_PROFILE") && atoi(getenv("SVOF_PROFILE")) > 0;
         h->prm = *params;
         h->sp.mixedTol = params->mixed_cell_tol;
@@ -1086,6 +1086,19 @@ int svof_device_touch(svof_handle* h, int which)
     h->bitsValid = false;
     h->advected = false;
     return SVOF_OK;
+    API_END(h)
+}
+
+int svof_set_option(svof_handle* h, const char* name, int value)
+{
+    if (!h || !name) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->streamD));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!strcmp(name, "overlap")) { h->overlap = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
+    return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");
     API_END(h)
 }
 

@@ -208,3 +208,135 @@ def cell_centres_hex(mesh):
     C3[..., 1] = cy[None, :, None]
     C3[..., 2] = cz[:, None, None]
     return C3.reshape(-1, 3)
+
+
+# ---------------------------------------------------------------------------------------------
+# general polyhedral meshes (the arbitrary-polyhedron PLIC path)
+# ---------------------------------------------------------------------------------------------
+def perturb_points(mesh, amplitude=0.15, seed=0):
+    """Jitter the INTERIOR points of a hex_block mesh by `amplitude` x cell size: every interior
+    face becomes a warped (non-planar) quad -> face flatness < 1, the warped branch of
+    timeIntegratedFaceFlux (cutFace.C:312-347) and splitWarpedFace (cutCell.C:140-236)."""
+    rng = np.random.default_rng(seed)
+    h = np.array(mesh.meta["h"])
+    lo = np.array(mesh.meta["origin"])
+    hi = lo + np.array(mesh.meta["length"])
+    pts = mesh.points.copy()
+    interior = np.all((pts > lo + 1e-12) & (pts < hi - 1e-12), axis=1)
+    pts[interior] += amplitude * h * rng.uniform(-1.0, 1.0, size=(int(interior.sum()), 3))
+    out = PolyMesh(points=pts, face_offsets=mesh.face_offsets, face_points=mesh.face_points, owner=mesh.owner,
+                   neighbour=mesh.neighbour, patches=list(mesh.patches), n_cells=mesh.n_cells,
+                   cell_global=mesh.cell_global, meta=dict(mesh.meta, kind="perturbed_hex"))
+    return out
+
+
+def build_polymesh(points, cells, patch_of=None, patch_names=("walls",)):
+    """Assemble an OpenFOAM-ordered polyMesh from cells given as lists of outward-oriented faces.
+
+    Internal faces come out in upper-triangular order (sorted by owner, then neighbour, oriented
+    owner -> neighbour); boundary faces are grouped into patches by `patch_of(face_centre) -> index`.
+    """
+    face_map = {}
+    for c, faces in enumerate(cells):
+        for f in faces:
+            key = tuple(sorted(f))
+            if key in face_map:
+                face_map[key][2] = c
+            else:
+                face_map[key] = [c, list(f), -1]
+    internal = [(o, n, v) for (o, v, n) in face_map.values() if n >= 0]
+    internal.sort(key=lambda t: (t[0], t[1]))
+    boundary = [(o, v) for (o, v, n) in face_map.values() if n < 0]
+    pts = np.asarray(points, dtype=np.float64)
+    npatch = len(patch_names)
+    groups = [[] for _ in range(npatch)]
+    for o, v in boundary:
+        pi = 0 if patch_of is None else int(patch_of(pts[v].mean(axis=0)))
+        groups[pi].append((o, v))
+    for g in groups:
+        g.sort(key=lambda t: t[0])
+    owner = [t[0] for t in internal]
+    neighbour = [t[1] for t in internal]
+    fverts = [t[2] for t in internal]
+    patches = []
+    start = len(internal)
+    for name, g in zip(patch_names, groups):
+        patches.append(Patch(name, start, len(g)))
+        owner += [t[0] for t in g]
+        fverts += [t[1] for t in g]
+        start += len(g)
+    off = np.zeros(len(fverts) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(v) for v in fverts])
+    return PolyMesh(points=pts, face_offsets=off, face_points=np.concatenate(fverts).astype(np.int32),
+                    owner=np.array(owner, dtype=np.int32), neighbour=np.array(neighbour, dtype=np.int32),
+                    patches=patches, n_cells=len(cells), meta={"kind": "poly"})
+
+
+def prism_mesh(n):
+    """Unit cube of n^3 hexes, each split into two triangular prisms along the x-y diagonal:
+    triangular and quadrilateral faces, 5-face / 6-point cells."""
+    g = np.linspace(0.0, 1.0, n + 1)
+    P = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+
+    def pid(i, j, k):
+        return (i * (n + 1) + j) * (n + 1) + k
+
+    cells = []
+    for k in range(n):
+        for j in range(n):
+            for i in range(n):
+                a, b, c, d = pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)
+                e, f, g_, h = pid(i, j, k + 1), pid(i + 1, j, k + 1), pid(i + 1, j + 1, k + 1), pid(i, j + 1, k + 1)
+                # prism 1: triangle a-b-c (bottom) / e-f-g (top);  prism 2: a-c-d / e-g-h
+                cells.append([[a, c, b], [e, f, g_], [a, b, f, e], [b, c, g_, f], [c, a, e, g_]])
+                cells.append([[a, d, c], [e, g_, h], [a, c, g_, e], [c, d, h, g_], [d, a, e, h]])
+    return build_polymesh(P, cells)
+
+
+def refined_interface_mesh(n):
+    """2:1 refinement interface (what dynamicRefineFvMesh produces in the reference's AMR cases): the half
+    x < 0.5 is meshed with n^3/2 coarse hexes, the half x > 0.5 with 8x finer ones; the coarse cells on the
+    interface are genuine polyhedra (9 faces, 13 points, four coplanar quads on one side)."""
+    assert n % 2 == 0
+    H, hf = 1.0 / n, 0.5 / n
+    pts, index = [], {}
+
+    def P(x, y, z):
+        key = (int(round(x / hf)), int(round(y / hf)), int(round(z / hf)))
+        if key not in index:
+            index[key] = len(pts)
+            pts.append((key[0] * hf, key[1] * hf, key[2] * hf))
+        return index[key]
+
+    def hex_faces(x0, y0, z0, s, split_xplus=False):
+        x1, y1, z1 = x0 + s, y0 + s, z0 + s
+        f = [[P(x0, y0, z0), P(x0, y0, z1), P(x0, y1, z1), P(x0, y1, z0)],      # x-
+             [P(x0, y0, z0), P(x1, y0, z0), P(x1, y0, z1), P(x0, y0, z1)],      # y-
+             [P(x0, y1, z0), P(x0, y1, z1), P(x1, y1, z1), P(x1, y1, z0)],      # y+
+             [P(x0, y0, z0), P(x0, y1, z0), P(x1, y1, z0), P(x1, y0, z0)],      # z-
+             [P(x0, y0, z1), P(x1, y0, z1), P(x1, y1, z1), P(x0, y1, z1)]]      # z+
+        if not split_xplus:
+            f.append([P(x1, y0, z0), P(x1, y1, z0), P(x1, y1, z1), P(x1, y0, z1)])
+        else:
+            ym, zm = y0 + s / 2, z0 + s / 2
+            for (ya, yb) in ((y0, ym), (ym, y1)):
+                for (za, zb) in ((z0, zm), (zm, z1)):
+                    f.append([P(x1, ya, za), P(x1, yb, za), P(x1, yb, zb), P(x1, ya, zb)])
+            # the neighbouring coarse faces sharing the split edges need the mid-edge points too
+            f[1] = [P(x0, y0, z0), P(x1, y0, z0), P(x1, y0, zm), P(x1, y0, z1), P(x0, y0, z1)]
+            f[2] = [P(x0, y1, z0), P(x0, y1, z1), P(x1, y1, z1), P(x1, y1, zm), P(x1, y1, z0)]
+            f[3] = [P(x0, y0, z0), P(x0, y1, z0), P(x1, y1, z0), P(x1, ym, z0), P(x1, y0, z0)]
+            f[4] = [P(x0, y0, z1), P(x1, y0, z1), P(x1, ym, z1), P(x1, y1, z1), P(x0, y1, z1)]
+        return f
+
+    cells = []
+    nc = n // 2
+    for k in range(n):
+        for j in range(n):
+            for i in range(nc):
+                cells.append(hex_faces(i * H, j * H, k * H, H, split_xplus=(i == nc - 1)))
+    for k in range(2 * n):
+        for j in range(2 * n):
+            for i in range(n, 2 * n):
+                cells.append(hex_faces(i * hf, j * hf, k * hf, hf))
+    return build_polymesh(np.array(pts), cells)

@@ -192,6 +192,9 @@ class SolveVofEqu:
         """gSum(alpha*V) as printed by the reference driver (plicVof.H:44-46)."""
         return self.info(capi.I_VOLUME)
 
+    def setOption(self, name, value):
+        self._chk(self.lib.svof_set_option(self._h, name.encode(), int(value)))
+
     def synchronize(self):
         self._chk(self.lib.svof_synchronize(self._h))
 

@@ -247,6 +247,9 @@ int svof_device_touch(svof_handle* h, int which);
  * device-to-device (CUDA library only). */
 int svof_set_phi_device(svof_handle* h, const void* dphi);
 int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
+/* Runtime switches: "overlap" (0/1: run the streaming kernel on a second stream concurrently with
+ * the sparse interface chain), "profile" (0/1: CUDA events around every launch, printed at destroy). */
+int svof_set_option(svof_handle* h, const char* name, int value);
 /* Block until all device work queued by this handle has finished. */
 int svof_synchronize(svof_handle* h);
 /* CUDA-event stopwatch on the handle's own stream (the stream every kernel of
