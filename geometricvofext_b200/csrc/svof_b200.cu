@@ -67,11 +67,14 @@ struct svof_handle {
     int capWork = 0, capMixed = 0, capNear = 0, nWords = 0, nScanBlocks = 0;
     double *dVfGeo = nullptr, *dVf = nullptr, *scratchF = nullptr;
     BoundScratch bs;
-    int *oobList[2] = {nullptr, nullptr}, *affList = nullptr, *pendList = nullptr;
+    int *oobList[2] = {nullptr, nullptr}, *affList = nullptr, *depInit = nullptr, *depLeft = nullptr;
     unsigned char* oobState = nullptr;
     Ctl* ctl = nullptr;
     Ctl* hctl = nullptr;  // pinned mirror
     PatchDev* dPatches = nullptr;
+    DenseStage dstage;
+    size_t dstageSmem = 0;
+    bool useStaged = false;
     int* bPatch = nullptr;
     double* partial = nullptr;
     double* hpartial = nullptr;
@@ -272,6 +275,29 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
             }
         }
     }
+    // staging plan of the streaming kernel: per 256-cell CTA, the contiguous range of internal faces its cells own
+    // (internal faces are ordered by owner in any OpenFOAM mesh) and the shared-memory capacities
+    std::vector<int> ctaFace;
+    int maxRowSlab = 0, maxPhiSlab = 0;
+    {
+        bool ownerSorted = true;
+        for (int f = 1; f < nIF; ++f) ownerSorted &= (own[f - 1] <= own[f]);
+        const int nCta = (nC + 255) / 256;
+        if (ownerSorted) {
+            ctaFace.resize(nCta + 1);
+            int f = 0;
+            for (int b = 0; b <= nCta; ++b) {
+                const int cFirst = std::min(b * 256, nC);
+                while (f < nIF && own[f] < cFirst) ++f;
+                ctaFace[b] = f;
+            }
+        }
+        for (int b = 0; b < nCta; ++b) {
+            const int cA = b * 256, cB = std::min(nC, cA + 256);
+            maxRowSlab = std::max(maxRowSlab, cellOff[cB] - (cellOff[cA] & ~1));
+            if (ownerSorted) maxPhiSlab = std::max(maxPhiSlab, ctaFace[b + 1] - (ctaFace[b] & ~1));
+        }
+    }
     // cellPoints ascending; pointCells ascending
     std::vector<int> cellPtOff(nC + 1, 0), cellPts;
     cellPts.reserve((size_t)nC * 8);
@@ -355,6 +381,8 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
     d.neighbour = dupload(h, nei, (size_t)nIF);
     d.cellOff = dupload(h, cellOff.data(), cellOff.size());
     d.cellFaces = dupload(h, cellFaces.data(), cellFaces.size());
+    cellAsc.push_back(make_int2(0, -1));  // slack: the staged streaming kernel copies rows in 16-byte requests
+    cellAsc.push_back(make_int2(0, -1));
     d.cellAsc = dupload(h, cellAsc.data(), cellAsc.size());
     d.cellPtOff = dupload(h, cellPtOff.data(), cellPtOff.size());
     d.cellPts = dupload(h, cellPts.data(), cellPts.size());
@@ -365,6 +393,13 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
     d.bKind = dupload(h, bKind.data(), bKind.size());
     d.isPatchPoint = dupload(h, isPatchPoint.data(), isPatchPoint.size());
     h->dPatches = dupload(h, pd.data(), pd.size());
+    h->dstage.ctaFace = ctaFace.empty() ? nullptr : dupload(h, ctaFace.data(), ctaFace.size());
+    h->dstage.rowCap = (std::min(maxRowSlab + 2, 4096) + 1) & ~1;   // <= 32 KB of rows per CTA, even
+    h->dstage.phiCap = (std::min(maxPhiSlab + 2, 1536) + 1) & ~1;   // <= 12 KB of phi per CTA
+    h->dstageSmem = (size_t)(h->dstage.rowCap + 2) * 8 + (size_t)(h->dstage.phiCap + 2) * 8;
+    // measured (profiles/r1l_*): 0.431 ms for the CSR kernel vs 0.556 ms staged -> staged is opt-in (SVOF_DENSE_STAGED=1)
+    h->useStaged = getenv("SVOF_DENSE_STAGED") && atoi(getenv("SVOF_DENSE_STAGED")) > 0;
+    CK(cudaFuncSetAttribute(k_dense_update_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dstageSmem));
     h->bPatch = dupload(h, bPatch.data(), bPatch.size());
 
     double* Cf = dalloc<double>(h, (size_t)3 * nF);
@@ -438,7 +473,7 @@ void allocFields(svof_handle* h)
     const size_t nC = h->nC, nF = h->nF, nBF = std::max(h->nBF, 1);
     h->alphaBuf[0] = dalloc<double>(h, nC);
     h->alphaBuf[1] = dalloc<double>(h, nC);
-    h->phi = dalloc<double>(h, nF);
+    h->phi = dalloc<double>(h, nF + 2);  // +2: the staged streaming kernel may read one 16-byte request past nIF
     h->alphaPhi = dalloc<double>(h, nF);
     h->alphaBBuf[0] = dalloc<double>(h, nBF);
     h->alphaBBuf[1] = dalloc<double>(h, nBF);
@@ -473,7 +508,8 @@ void allocFields(svof_handle* h)
     h->oobList[0] = dalloc<int>(h, h->capNear);
     h->oobList[1] = dalloc<int>(h, h->capNear);
     h->affList = dalloc<int>(h, h->capNear);
-    h->pendList = dalloc<int>(h, h->capNear);
+    h->depInit = dalloc<int>(h, nC);
+    h->depLeft = dalloc<int>(h, nC);
     h->oobState = dalloc<unsigned char>(h, nC);
     h->ctl = dalloc<Ctl>(h, 1);
     h->partial = dalloc<double>(h, 1024);
@@ -614,8 +650,13 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     }
     if (h->prof) profBegin(h, "k_dense_update", sD);
     EventPair& ed = beginTimedOn(h, 2, sD);
-    k_dense_update<<<cdiv(h->nC, 256), 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
-                                                      dt, rDt, dSp, dSu, h->sp, h->ctl);
+    if (h->useStaged)
+        k_dense_update_staged<<<cdiv(h->nC, 256), 256, h->dstageSmem, sD>>>(d, h->dstage, aOld, aNew, h->phi, h->alphaBBuf[h->cb],
+                                                                             h->alphaPhi, h->near2, h->mixedBits, dt, rDt, dSp, dSu,
+                                                                             h->sp, h->ctl);
+    else
+        k_dense_update<<<cdiv(h->nC, 256), 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
+                                                          dt, rDt, dSp, dSu, h->sp, h->ctl);
     h->launches++;
     endTimedOn(h, ed, sD);
     if (h->prof) profEnd(h, sD);
@@ -634,10 +675,10 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     const int gB = std::max(1, h->sms / 2);
     for (int sidx = 0; sidx < h->sp.nAlphaBounds; ++sidx) {
         const int tag = h->advectCount * (SV_MAX_SWEEPS + 1) + sidx + 1;
-        LAUNCH(h, k_bound_wave, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, h->bs,
-               h->affList, h->pendList, dt, rDt, dSp, dSu);
-        LAUNCH(h, k_bound_drain, 1, 256, d, h->ctl, sidx, tag, h->pendList, h->oobState, aNew, aOld, h->phi, h->dVf, h->bs, dt, rDt, dSp,
-               dSu);
+        LAUNCH(h, k_bound_deps, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, h->phi, h->bs, h->depInit, h->depLeft,
+               h->affList);
+        LAUNCH(h, k_bound_run, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, h->bs,
+               h->depInit, h->depLeft, dt, rDt, dSp, dSu);
         LAUNCH(h, k_bound_apply, gB, 128, d, h->ctl, sidx, tag, h->affList, h->near1, aNew, h->dVf, h->bs, h->oobList[(sidx + 1) & 1],
                h->oobState);
         LAUNCH(h, k_bound_flip, 1, 1, h->ctl, sidx);

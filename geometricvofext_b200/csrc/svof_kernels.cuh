@@ -25,7 +25,7 @@ struct Ctl {
     int nWork;    // (cut cell, downwind face) work items
     int err;      // SVERR_* flags
     int nOob[2];  // out-of-bounds lists (double buffered between sweeps)
-    int nPend[SV_MAX_SWEEPS + 1];    // cells the wave launch of sweep s deferred
+    int nPend[SV_MAX_SWEEPS + 1];    // (unused)
     int nAff[SV_MAX_SWEEPS + 1];     // cells touched by the corrections of sweep s
     int nearOob[SV_MAX_SWEEPS + 1];  // # near2 cells violating the limitFlux loop condition after s sweeps
     int pad_;
@@ -625,7 +625,14 @@ __device__ __forceinline__ bool upwindDVf(const MeshDev& m, int c, int f, bool f
 
 // exact-division shortcuts: x/y == x bitwise when x is +-0 (y finite, non-zero); most of a VOF
 // domain is exactly empty, so the FP64 divides (~30 SASS instructions each) are skipped there
-__device__ __forceinline__ double divz(double x, double y) { return (x == 0.0) ? x : x / y; }
+// The branch is made WARP-UNIFORM with a vote: nvcc if-converts a plain `x == 0 ? x : x / y` into an
+// unconditional divide + select (measured: 5 divide subroutine calls per warp, 40% of all instructions
+// of the streaming kernel, in a domain that is 98.6% empty).
+__device__ __forceinline__ double divz(double x, double y)
+{
+    if (__any_sync(__activemask(), x != 0.0)) x = (x == 0.0) ? x : x / y;
+    return x;
+}
 
 // warp min/max of doubles through their order-preserving keys with 4 REDUX instead of 20 SHFL
 __device__ __forceinline__ unsigned long long warpMaxKey(unsigned long long k)
@@ -717,6 +724,112 @@ __global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double
     }
     const unsigned int w = __ballot_sync(0xffffffffu, mixed);
     if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
+    blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
+}
+
+// K7, staged variant: the same arithmetic as k_dense_update, but the CTA first copies (cp.async, 16-byte
+// requests, no registers) its contiguous slab of cell->face rows and the phi values of the faces its cells
+// OWN (contiguous too: OpenFOAM orders internal faces by owner) into shared memory.  That turns the two
+// biggest gathers (48 B/cell of rows read with a 48-byte stride, 12 B/cell... of owned phi with a 24-byte
+// stride) into fully coalesced bulk copies with ~20 KB in flight per CTA, instead of one dependent
+// chain of three loads per face per thread.
+struct DenseStage {
+    const int* ctaFace;   // [nCta+1] first owned INTERNAL face of the first cell of each CTA (nullptr: no phi staging)
+    int rowCap;           // int2 entries of row storage in shared memory
+    int phiCap;           // doubles of phi storage
+};
+
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
+{
+    const unsigned int sa = (unsigned int)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cpAsyncWaitAll() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(256, 6) k_dense_update_staged(MeshDev m, DenseStage ds, const double* __restrict__ aOld,
+                                                                double* __restrict__ aNew, const double* __restrict__ phi,
+                                                                const double* __restrict__ alphaB, double* __restrict__ alphaPhi,
+                                                                const unsigned int* __restrict__ near2, unsigned int* __restrict__ mixedNext,
+                                                                double dt, double rDt, const double* __restrict__ Sp,
+                                                                const double* __restrict__ Su, StepParams sp, Ctl* ctl)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    int2* rows = reinterpret_cast<int2*>(dsm);                                   // [rowCap]  (+2 for alignment slack)
+    double* sphi = reinterpret_cast<double*>(dsm + (size_t)(ds.rowCap + 2) * 8);  // [phiCap]  (+2)
+    const int c0 = blockIdx.x * blockDim.x;
+    const int c = c0 + threadIdx.x;
+    const int cEnd = min(c0 + (int)blockDim.x, m.nCells);
+    // slab of rows [rowBeg, rowEnd) and owned internal faces [fBeg, fEnd)
+    const int rowBeg = __ldg(m.cellOff + c0), rowEnd = __ldg(m.cellOff + cEnd);
+    const int rowBegA = rowBeg & ~1;  // 16-byte aligned start (int2 = 8 B)
+    const int nRow16 = (rowEnd - rowBegA + 1) >> 1;
+    const bool rowsStaged = (rowEnd - rowBegA) <= ds.rowCap;
+    if (rowsStaged) {
+        for (int i = threadIdx.x; i < nRow16; i += blockDim.x) cpAsync16(rows + 2 * i, m.cellAsc + rowBegA + 2 * i);
+    }
+    int fBeg = 0, fEnd = 0, fBegA = 0;
+    bool phiStaged = false;
+    if (ds.ctaFace) {
+        fBeg = __ldg(ds.ctaFace + blockIdx.x);
+        fEnd = __ldg(ds.ctaFace + blockIdx.x + 1);
+        fBegA = fBeg & ~1;
+        phiStaged = (fEnd - fBegA) <= ds.phiCap;
+        if (phiStaged) {
+            const int n16 = (fEnd - fBegA + 1) >> 1;
+            // the tail request may read one double past fEnd: phi has nF >= nIF + ... entries and is allocated with slack
+            for (int i = threadIdx.x; i < n16; i += blockDim.x) cpAsync16(sphi + 2 * i, phi + fBegA + 2 * i);
+        }
+    }
+    // independent loads while the copies are in flight
+    const bool inRange = c < m.nCells;
+    const bool work = inRange && !bitTest(near2, c);
+    const int k0 = inRange ? __ldg(m.cellOff + c) : 0, k1 = inRange ? __ldg(m.cellOff + c + 1) : 0;
+    const double aC = inRange ? __ldg(aOld + c) : 0.0;
+    const double Vc = inRange ? __ldg(m.V + c) : 1.0;
+    cpAsyncWaitAll();
+    __syncthreads();
+
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    bool mixed = false;
+    if (work) {
+        double sum = 0.0;
+        for (int k = k0; k < k1; ++k) {
+            const int2 e = rowsStaged ? rows[k - rowBegA] : __ldg(m.cellAsc + k);
+            const int f = e.x & 0x7fffffff;
+            const bool flip = e.x < 0;
+            const double ph = (phiStaged && f >= fBeg && f < fEnd) ? sphi[f - fBegA] : __ldg(phi + f);
+            double aUp;
+            if (e.y >= 0) {
+                const bool selfUp = flip ? (ph < 0) : (ph >= 0);
+                aUp = selfUp ? aC : __ldg(aOld + e.y);
+            } else {
+                const int bf = -1 - e.y;
+                const unsigned char kind = __ldg(m.bKind + bf);
+                if (kind == 1) continue;  // empty patch: no field
+                aUp = __ldg(alphaB + bf);
+                if (kind == 2 && ph >= 0) aUp = aC;  // processor: upwind between the two sides
+            }
+            const double dvf = (ph * aUp) * dt;
+            if (!flip) {
+                sum += dvf;
+                alphaPhi[f] = divz(dvf, dt);
+            } else {
+                sum -= dvf;
+            }
+        }
+        const double ivf = divz(sum, Vc);
+        double num = aC * rDt;
+        if (Su) num = num + Su[c];
+        num = num - ivf * rDt;
+        double a = divz(num, (Sp ? (rDt - Sp[c]) : rDt));
+        mn = a;
+        mx = a;
+        a = snapClip(a, sp.snapTol, sp.clip);
+        aNew[c] = a;
+        mixed = (sp.mixedTol < a) && (a < 1.0 - sp.mixedTol);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, mixed);
+    if ((threadIdx.x & 31) == 0 && inRange) mixedNext[c >> 5] = w;
     blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
 }
 
@@ -848,8 +961,8 @@ __device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const
                 ow[j] = m.owner[f];
                 ph[j] = phi[f];
                 dv[j] = dVf[f];
-                tg[j] = b.tagV[f];
-                cr[j] = b.corr[f];
+                tg[j] = __ldcg(b.tagV + f);  // L2 reads: written by other SMs during this kernel
+                cr[j] = __ldcg(b.corr + f);
                 if (f < m.nIF) nb[j] = m.neighbour[f]; else bk[j] = m.bKind[f - m.nIF];
             }
         }
@@ -875,30 +988,6 @@ __device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const
             if (down) cb.downMask |= 1ull << q;
         }
     }
-}
-
-// The reference sweeps the cells in ascending index (Gauss-Seidel, SURVEY 8a' item 15).  A cell only
-// ever READS corrections written by another cell on the faces that are DOWNWIND of that other cell,
-// so cell c must wait exactly for the lower-index out-of-bounds neighbours that are upwind of it
-// across the shared face; everything else commutes (reads of higher-index writers are masked above).
-__device__ __forceinline__ bool boundReady(const CellBound& cb, int celli, const volatile unsigned char* oobState)
-{
-    bool ready = true;
-    for (int q0 = 0; q0 < cb.nf; q0 += 8) {
-        unsigned char st[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            st[j] = 0;
-            const int q = q0 + j;
-            if (q < cb.nf) {
-                const int y = cb.other[q];
-                if (y >= 0 && y < celli && !((cb.downMask >> q) & 1ull)) st[j] = oobState[y];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ready = ready && (st[j] != 1);
-    }
-    return ready;
 }
 
 __device__ void boundCell(const MeshDev& m, int celli, CellBound& cb, const double* alpha, const double* aOld,
@@ -976,79 +1065,100 @@ __device__ void boundCell(const MeshDev& m, int celli, CellBound& cb, const doub
     }
 }
 
-__global__ void __launch_bounds__(128) k_bound_wave(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList, unsigned char* oobState,
-                                                    const double* alpha, const double* aOld, const double* phi, const double* dVf,
-                                                    BoundScratch b, int* affList, int* pendList, double dt, double rDt,
-                                                    const double* Sp, const double* Su)
+// The reference sweeps the cells in ascending index (Gauss-Seidel, SURVEY 8a' item 15).  A cell only
+// ever READS corrections written by another cell on the faces that are DOWNWIND of that other cell,
+// so cell y depends exactly on the lower-index out-of-bounds neighbours that are upwind of it across
+// the shared face; everything else commutes (reads of higher-index writers are masked in
+// loadCellBound).  The sweep is therefore a DAG executed by dependency counting:
+//   k_bound_deps : per out-of-bounds cell, count its predecessors (and mark the affected set)
+//   k_bound_run  : roots start at once; whoever finishes the last predecessor of a cell runs that
+//                  cell next (continuation passing) -- no polling, no single-CTA drain loop.
+__global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList,
+                                                    const unsigned char* oobState, const double* __restrict__ phi, BoundScratch b,
+                                                    int* depInit, int* depLeft, int* affList)
 {
     const int n = ctl->nOob[s & 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = oobList[i];
-        CellBound cb;
-        loadCellBound(m, c, phi, dVf, b, tag, cb);
-        // affected set = this cell + its face neighbours (the cells the corrections can change);
-        // all stamps are exchanged first, then ONE counter atomic reserves the list slots
+        const int k0 = m.cellOff[c];
+        int nf = m.cellOff[c + 1] - k0;
+        if (nf > SV_MAXBF) nf = SV_MAXBF;
         int newIds[SV_MAXBF + 1];
-        int nNew = 0;
+        int nNew = 0, deps = 0;
         if (atomicExch(&b.affStamp[c], tag) != tag) newIds[nNew++] = c;
-        for (int q0 = 0; q0 < cb.nf; q0 += 8) {
+        for (int q0 = 0; q0 < nf; q0 += 8) {
+            int2 e[8];
+            double ph[8];
+            unsigned char st[8];
             int old[8];
 #pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = (q0 + j < nf) ? m.cellAsc[k0 + q0 + j] : make_int2(0, -1);
+#pragma unroll
             for (int j = 0; j < 8; ++j) {
-                old[j] = tag;
-                const int q = q0 + j;
-                if (q < cb.nf && cb.other[q] >= 0) old[j] = atomicExch(&b.affStamp[cb.other[q]], tag);
+                ph[j] = 0.0; st[j] = 0; old[j] = tag;
+                if (e[j].y >= 0) {
+                    ph[j] = phi[e[j].x & 0x7fffffff];
+                    st[j] = oobState[e[j].y];
+                    old[j] = atomicExch(&b.affStamp[e[j].y], tag);  // affected set = cell + face neighbours
+                }
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (old[j] != tag) newIds[nNew++] = cb.other[q0 + j];
+            for (int j = 0; j < 8; ++j) {
+                if (e[j].y < 0) continue;
+                if (old[j] != tag) newIds[nNew++] = e[j].y;
+                const bool flip = e[j].x < 0;  // c is the neighbour side of this face
+                const bool yIsUpwind = flip ? (ph[j] >= 0) : (ph[j] < 0);  // owner is upwind iff phi >= 0
+                if (e[j].y < c && st[j] == 1 && yIsUpwind) deps++;
+            }
         }
+        depInit[c] = deps;
+        depLeft[c] = deps;
         if (nNew) {
             const int pos = atomicAdd(&ctl->nAff[s], nNew);
             for (int j = 0; j < nNew; ++j) affList[pos + j] = newIds[j];
         }
-        if (boundReady(cb, c, oobState)) {
-            boundCell(m, c, cb, alpha, aOld, b, tag, dt, rDt, Sp, Su);
-            __threadfence();
-            ((volatile unsigned char*)oobState)[c] = 2;
-        } else {
-            pendList[atomicAdd(&ctl->nPend[s], 1)] = c;
-        }
     }
 }
 
-// single CTA: walks the dependency chains the wave launch deferred (a few % of the cells).
-// Each thread keeps its deferred cells' data in local memory and only re-polls the neighbour states.
-__global__ void __launch_bounds__(256) k_bound_drain(MeshDev m, Ctl* ctl, int s, int tag, const int* pendList, unsigned char* oobState,
-                                                      const double* alpha, const double* aOld, const double* phi, const double* dVf,
-                                                      BoundScratch b, double dt, double rDt, const double* Sp, const double* Su)
+#define SV_BSTACK 192
+__global__ void __launch_bounds__(128) k_bound_run(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList,
+                                                   const unsigned char* oobState, const double* alpha, const double* aOld,
+                                                   const double* phi, const double* dVf, BoundScratch b, const int* depInit,
+                                                   int* depLeft, double dt, double rDt, const double* Sp, const double* Su)
 {
-    const int n = ctl->nPend[s];
-    if (n == 0) return;
-    __shared__ int remaining;
-    for (int guard = 0; guard < (1 << 22); ++guard) {
-        if (threadIdx.x == 0) remaining = 0;
-        __syncthreads();
-        int mine = 0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int c = pendList[i];
-            if (((volatile unsigned char*)oobState)[c] != 1) continue;
+    const int n = ctl->nOob[s & 1];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int c = oobList[i];
+        if (depInit[c] != 0) continue;  // released later by whoever finishes its last predecessor
+        int stack[SV_BSTACK];
+        int sp = 0;
+        for (;;) {
             CellBound cb;
             loadCellBound(m, c, phi, dVf, b, tag, cb);
-            if (boundReady(cb, c, oobState)) {
-                // the corrections of the cells this one waited for are visible now: reload and process
-                boundCell(m, c, cb, alpha, aOld, b, tag, dt, rDt, Sp, Su);
-                __threadfence();
-                ((volatile unsigned char*)oobState)[c] = 2;
-            } else {
-                mine++;
+            boundCell(m, c, cb, alpha, aOld, b, tag, dt, rDt, Sp, Su);
+            __threadfence();  // corrections visible before any successor is released
+            // successors: higher-index out-of-bounds neighbours across the faces that are downwind of c
+            for (int q0 = 0; q0 < cb.nf; q0 += 8) {
+                unsigned char st[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    st[j] = 0;
+                    const int q = q0 + j;
+                    if (q < cb.nf && cb.other[q] > c && ((cb.downMask >> q) & 1ull)) st[j] = oobState[cb.other[q]];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (st[j] != 1) continue;
+                    const int y = cb.other[q0 + j];
+                    if (atomicSub(&depLeft[y], 1) == 1) {  // last predecessor: run y next on this thread
+                        if (sp < SV_BSTACK) stack[sp++] = y; else atomicOr(&ctl->err, SVERR_LIST);
+                    }
+                }
             }
+            if (sp == 0) break;
+            c = stack[--sp];
+            __threadfence();  // acquire side of the release above
         }
-        if (mine) atomicAdd(&remaining, mine);
-        __syncthreads();
-        const int r = remaining;
-        __syncthreads();
-        if (r == 0) break;
     }
 }
 
