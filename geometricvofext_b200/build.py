@@ -23,7 +23,8 @@ OUT = os.path.join(HERE, "lib", "libsvof_b200.so")
 OBJ = os.path.join(HERE, "lib", "obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC"] + \
+             (["-DSV_BOUND_STATS"] if os.environ.get("SVOF_BOUND_STATS") else [])
 
 UNITS = [("svof_b200", "svof_b200.cu", [])] + \
         [("svof_inst%d" % v, "svof_inst.cu", ["-DSV_VARIANT=%d" % v]) for v in range(4)]

@@ -49,6 +49,7 @@ struct svof_handle {
     StepParams sp;
     MeshDev md;
     int variant = 0;
+    int maxCF = 0;
     std::vector<void*> allocs;
     size_t bytes = 0;
     std::string err;
@@ -67,7 +68,9 @@ struct svof_handle {
     int capWork = 0, capMixed = 0, capNear = 0, nWords = 0, nScanBlocks = 0;
     double *dVfGeo = nullptr, *dVf = nullptr, *scratchF = nullptr;
     BoundScratch bs;
-    int *oobList[2] = {nullptr, nullptr}, *affList = nullptr, *depInit = nullptr, *depLeft = nullptr;
+    int *oobList[2] = {nullptr, nullptr}, *affList = nullptr, *depInit = nullptr, *depLeft = nullptr, *oobIdx = nullptr;
+    void* boundRecs = nullptr;
+    int capRec = 0;
     unsigned char* oobState = nullptr;
     Ctl* ctl = nullptr;
     Ctl* hctl = nullptr;  // pinned mirror
@@ -184,6 +187,15 @@ void fetchCtl(svof_handle* h);
 void profPrint(svof_handle* h)
 {
     profFlush(h);
+#ifdef SV_BOUND_STATS
+    {
+        unsigned long long d[8];
+        cudaMemcpyFromSymbol(d, g_dbg, sizeof(d));
+        fprintf(stderr, "[svof bound stats] cells %llu inner-iterations %llu (%.2f/cell) cycles: load %.0f compute %.0f release %.0f per cell; max chain per thread %llu\n",
+                d[0], d[1], (double)d[1] / std::max(1ull, d[0]), (double)d[2] / std::max(1ull, d[0]), (double)d[3] / std::max(1ull, d[0]),
+                (double)d[5] / std::max(1ull, d[0]), d[4]);
+    }
+#endif
     fetchCtl(h);
     {
         const Ctl& c = *h->hctl;
@@ -370,6 +382,7 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
         throw std::length_error(b);
     }
     if (maxCF > 64) throw std::length_error("cells with more than 64 faces are not supported");
+    h->maxCF = maxCF;
 
     // upload
     MeshDev& d = h->md;
@@ -510,6 +523,12 @@ void allocFields(svof_handle* h)
     h->affList = dalloc<int>(h, h->capNear);
     h->depInit = dalloc<int>(h, nC);
     h->depLeft = dalloc<int>(h, nC);
+    h->oobIdx = dalloc<int>(h, nC);
+    {
+        const size_t recBytes = (h->maxCF <= 8) ? sizeof(CellBound<8>) : (h->maxCF <= 16) ? sizeof(CellBound<16>) : sizeof(CellBound<64>);
+        h->capRec = (int)std::min<size_t>(nC, std::max<size_t>(65536, nC / 16));
+        h->boundRecs = dalloc<unsigned char>(h, recBytes * (size_t)h->capRec, false);
+    }
     h->oobState = dalloc<unsigned char>(h, nC);
     h->ctl = dalloc<Ctl>(h, 1);
     h->partial = dalloc<double>(h, 1024);
@@ -675,12 +694,18 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     const int gB = std::max(1, h->sms / 2);
     for (int sidx = 0; sidx < h->sp.nAlphaBounds; ++sidx) {
         const int tag = h->advectCount * (SV_MAX_SWEEPS + 1) + sidx + 1;
-        LAUNCH(h, k_bound_deps, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, h->phi, h->bs, h->depInit, h->depLeft,
-               h->affList);
-        LAUNCH(h, k_bound_run, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, h->bs,
-               h->depInit, h->depLeft, dt, rDt, dSp, dSu);
-        LAUNCH(h, k_bound_apply, gB, 128, d, h->ctl, sidx, tag, h->affList, h->near1, aNew, h->dVf, h->bs, h->oobList[(sidx + 1) & 1],
-               h->oobState);
+#define BOUND_SWEEP(MB)                                                                                                       \
+    do {                                                                                                                     \
+        LAUNCH(h, k_bound_deps<MB>, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, \
+               dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList);           \
+        LAUNCH(h, k_bound_run<MB>, 2 * gB, 64, h->ctl, sidx, tag, h->oobList[sidx & 1], h->bs, h->depInit, h->depLeft, h->oobIdx, \
+               (const CellBound<MB>*)h->boundRecs, h->capRec, dt, rDt);                                                      \
+        LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, tag, h->affList, h->near1, aNew, h->dVf, h->bs,               \
+               h->oobList[(sidx + 1) & 1], h->oobState);                                                                     \
+    } while (0)
+        if (h->maxCF <= 8) BOUND_SWEEP(8);
+        else if (h->maxCF <= 16) BOUND_SWEEP(16);
+        else BOUND_SWEEP(64);
         LAUNCH(h, k_bound_flip, 1, 1, h->ctl, sidx);
     }
     // join: the finalize kernel ORs into the bitmap words the streaming kernel wrote

@@ -32,6 +32,7 @@ struct Ctl {
     unsigned long long minDense, maxDense;  // keys over the cells outside near2 (streaming kernel)
     unsigned long long minNear0, maxNear0;  // over near2 before bounding
     unsigned long long minNearF, maxNearF;  // over near2 after bounding (before snap/clip)
+    unsigned long long dbg[8];              // SV_BOUND_STATS instrumentation
 };
 
 struct StepParams {
@@ -913,6 +914,9 @@ __global__ void __launch_bounds__(128) k_near_update(MeshDev m, const int* near2
 // of cells outside needBounding the reference's sweep is a no-op too, so the sweeps run
 // unconditionally and "number of sweeps executed" is derived afterwards from the recorded counts.
 // Scratch arrays are validated by a per-sweep tag instead of being cleared.
+#ifdef SV_BOUND_STATS
+__device__ unsigned long long g_dbg[8];
+#endif
 struct BoundScratch {
     double* corr;   // dVfCorrectionValues, valid where tagV == tag
     int* tagV;
@@ -931,22 +935,32 @@ __device__ __forceinline__ double corrVal(const BoundScratch& b, int f, int tag)
 // gathers -> local arrays), i.e. ~4 memory round trips per cell instead of ~10 per face per inner
 // iteration, and the inner iterations then run on thread-local data only.  Corrections are written
 // back at the end: a face is only ever corrected by its upwind cell, so the local copy is exact.
-#define SV_MAXBF 64
-struct CellBound {
-    int nf;
-    int fId[SV_MAXBF], other[SV_MAXBF];
+// MAXBF (faces per cell the bounding kernels keep in thread-local arrays) is a template parameter chosen from
+// the mesh: with 64 the 3.6 KB/thread of local memory thrashed L1 (measured 25k cycles per cell for ONE
+// inner iteration); a hex mesh uses 8.
+// CellBound doubles as the per-out-of-bounds-cell RECORD that k_bound_deps (parallel over all cells)
+// writes to global memory, so that the latency-critical chain walk of k_bound_run costs one contiguous
+// record read per cell instead of three dependent gathers.
+template <int SV_MAXBF>
+struct __align__(16) CellBound {
     double fPhi[SV_MAXBF], fDvf[SV_MAXBF], fCorr[SV_MAXBF];
+    double V, alpha, aOld, Sp, Su;
     unsigned long long ownMask, downMask;
+    unsigned long long predMask;  // faces whose other cell is a predecessor (lower index, out of bounds, upwind of this cell)
+    unsigned long long succMask;  // faces whose other cell is a successor   (higher index, out of bounds, this cell upwind)
+    int fId[SV_MAXBF], other[SV_MAXBF];
+    int nf, pad_;
 };
 
+template <int SV_MAXBF>
 __device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const double* __restrict__ phi, const double* dVf,
-                                              const BoundScratch& b, int tag, CellBound& cb)
+                                              const BoundScratch& b, int tag, CellBound<SV_MAXBF>& cb)
 {
     const int c0 = m.cellOff[celli];
     int nf = m.cellOff[celli + 1] - c0;
     if (nf > SV_MAXBF) nf = SV_MAXBF;
     cb.nf = nf;
-    cb.ownMask = cb.downMask = 0ull;
+    cb.ownMask = cb.downMask = cb.predMask = cb.succMask = 0ull;
     for (int q0 = 0; q0 < nf; q0 += 8) {
         int ff[8], ow[8], nb[8], tg[8];
         double ph[8], dv[8], cr[8];
@@ -990,17 +1004,17 @@ __device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const
     }
 }
 
-__device__ void boundCell(const MeshDev& m, int celli, CellBound& cb, const double* alpha, const double* aOld,
-                          const BoundScratch& b, int tag, double dt, double rDeltaT, const double* Sp, const double* Su)
+template <int SV_MAXBF>
+__device__ void boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch& b, int tag, double dt, double rDeltaT)
 {
-    const double Vi = m.V[celli];
+    const double Vi = cb.V;
     const int nf = cb.nf;
     double room[SV_MAXBF];
     int recPos[SV_MAXBF];
     unsigned long long modMask = 0, recMask = 0;
-    const double a0 = alpha[celli];
-    const double SuI = Su ? Su[celli] : 0.0, SpI = Sp ? Sp[celli] : 0.0;
-    const double aOldI = aOld[celli];
+    const double a0 = cb.alpha;
+    const double SuI = cb.Su, SpI = cb.Sp;
+    const double aOldI = cb.aOld;
     double alphaOvershoot = pos0(a0 - 1.0) * (a0 - 1.0) + neg0(a0) * a0;
     double fluidToPassOn = alphaOvershoot * Vi;
     int nFacesToPassFluidThrough = 1;
@@ -1008,6 +1022,9 @@ __device__ void boundCell(const MeshDev& m, int celli, CellBound& cb, const doub
     int nRecorded = 0;
     for (int iter = 0; iter < 10; ++iter) {
         if (fabs(alphaOvershoot) < SV_ATOL || nFacesToPassFluidThrough == 0) break;
+#ifdef SV_BOUND_STATS
+        atomicAdd(&g_dbg[1], 1ull);
+#endif
         // facesToPassFluidThrough / dVfmax / dVftot: fixed before any correction of this iteration
         double dVftot = 0;
         nFacesToPassFluidThrough = 0;
@@ -1073,46 +1090,54 @@ __device__ void boundCell(const MeshDev& m, int celli, CellBound& cb, const doub
 //   k_bound_deps : per out-of-bounds cell, count its predecessors (and mark the affected set)
 //   k_bound_run  : roots start at once; whoever finishes the last predecessor of a cell runs that
 //                  cell next (continuation passing) -- no polling, no single-CTA drain loop.
+template <int SV_MAXBF>
 __global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList,
-                                                    const unsigned char* oobState, const double* __restrict__ phi, BoundScratch b,
-                                                    int* depInit, int* depLeft, int* affList)
+                                                    const unsigned char* oobState, const double* alpha, const double* aOld,
+                                                    const double* __restrict__ phi, const double* dVf, const double* Sp,
+                                                    const double* Su, BoundScratch b, int* depInit, int* depLeft, int* oobIdx,
+                                                    CellBound<SV_MAXBF>* recs, int capRec, int* affList)
 {
     const int n = ctl->nOob[s & 1];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = oobList[i];
-        const int k0 = m.cellOff[c];
-        int nf = m.cellOff[c + 1] - k0;
-        if (nf > SV_MAXBF) nf = SV_MAXBF;
+        CellBound<SV_MAXBF> cb;
+        loadCellBound(m, c, phi, dVf, b, tag, cb);  // corrections of this sweep do not exist yet: fCorr == 0
+        cb.V = m.V[c];
+        cb.alpha = alpha[c];
+        cb.aOld = aOld[c];
+        cb.Sp = Sp ? Sp[c] : 0.0;
+        cb.Su = Su ? Su[c] : 0.0;
         int newIds[SV_MAXBF + 1];
         int nNew = 0, deps = 0;
         if (atomicExch(&b.affStamp[c], tag) != tag) newIds[nNew++] = c;
-        for (int q0 = 0; q0 < nf; q0 += 8) {
-            int2 e[8];
-            double ph[8];
+        for (int q0 = 0; q0 < cb.nf; q0 += 8) {
             unsigned char st[8];
             int old[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) e[j] = (q0 + j < nf) ? m.cellAsc[k0 + q0 + j] : make_int2(0, -1);
-#pragma unroll
             for (int j = 0; j < 8; ++j) {
-                ph[j] = 0.0; st[j] = 0; old[j] = tag;
-                if (e[j].y >= 0) {
-                    ph[j] = phi[e[j].x & 0x7fffffff];
-                    st[j] = oobState[e[j].y];
-                    old[j] = atomicExch(&b.affStamp[e[j].y], tag);  // affected set = cell + face neighbours
+                st[j] = 0; old[j] = tag;
+                const int q = q0 + j;
+                if (q < cb.nf && cb.other[q] >= 0) {
+                    st[j] = oobState[cb.other[q]];
+                    old[j] = atomicExch(&b.affStamp[cb.other[q]], tag);  // affected set = cell + face neighbours
                 }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (e[j].y < 0) continue;
-                if (old[j] != tag) newIds[nNew++] = e[j].y;
-                const bool flip = e[j].x < 0;  // c is the neighbour side of this face
-                const bool yIsUpwind = flip ? (ph[j] >= 0) : (ph[j] < 0);  // owner is upwind iff phi >= 0
-                if (e[j].y < c && st[j] == 1 && yIsUpwind) deps++;
+                const int q = q0 + j;
+                if (q >= cb.nf || cb.other[q] < 0) continue;
+                const int y = cb.other[q];
+                if (old[j] != tag) newIds[nNew++] = y;
+                if (st[j] != 1) continue;
+                const bool down = (cb.downMask >> q) & 1ull;
+                if (y < c && !down) { cb.predMask |= 1ull << q; deps++; }
+                if (y > c && down) cb.succMask |= 1ull << q;
             }
         }
         depInit[c] = deps;
         depLeft[c] = deps;
+        oobIdx[c] = i;
+        if (i < capRec) recs[i] = cb; else atomicOr(&ctl->err, SVERR_LIST);
         if (nNew) {
             const int pos = atomicAdd(&ctl->nAff[s], nNew);
             for (int j = 0; j < nNew; ++j) affList[pos + j] = newIds[j];
@@ -1120,43 +1145,56 @@ __global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, 
     }
 }
 
-#define SV_BSTACK 192
-__global__ void __launch_bounds__(128) k_bound_run(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList,
-                                                   const unsigned char* oobState, const double* alpha, const double* aOld,
-                                                   const double* phi, const double* dVf, BoundScratch b, const int* depInit,
-                                                   int* depLeft, double dt, double rDt, const double* Sp, const double* Su)
+#define SV_BSTACK 64
+template <int SV_MAXBF>
+__global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, const int* oobList, BoundScratch b, const int* depInit,
+                                                  int* depLeft, const int* oobIdx, const CellBound<SV_MAXBF>* recs, int capRec,
+                                                  double dt, double rDt)
 {
-    const int n = ctl->nOob[s & 1];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        int c = oobList[i];
+    const int n = min(ctl->nOob[s & 1], capRec);
+    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+        int c = oobList[i0];
         if (depInit[c] != 0) continue;  // released later by whoever finishes its last predecessor
+        int i = i0;
         int stack[SV_BSTACK];
         int sp = 0;
         for (;;) {
-            CellBound cb;
-            loadCellBound(m, c, phi, dVf, b, tag, cb);
-            boundCell(m, c, cb, alpha, aOld, b, tag, dt, rDt, Sp, Su);
-            __threadfence();  // corrections visible before any successor is released
-            // successors: higher-index out-of-bounds neighbours across the faces that are downwind of c
-            for (int q0 = 0; q0 < cb.nf; q0 += 8) {
-                unsigned char st[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    st[j] = 0;
-                    const int q = q0 + j;
-                    if (q < cb.nf && cb.other[q] > c && ((cb.downMask >> q) & 1ull)) st[j] = oobState[cb.other[q]];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (st[j] != 1) continue;
-                    const int y = cb.other[q0 + j];
+#ifdef SV_BOUND_STATS
+            const long long t0 = clock64();
+#endif
+            CellBound<SV_MAXBF> cb = recs[i];
+            // corrections its predecessors wrote (they are complete: this cell was released by the last of them)
+            for (unsigned long long pm = cb.predMask; pm; pm &= pm - 1) {
+                const int q = __ffsll((long long)pm) - 1;
+                const int f = cb.fId[q];
+                cb.fCorr[q] = (__ldcg(b.tagV + f) == tag) ? __ldcg(b.corr + f) : 0.0;
+            }
+#ifdef SV_BOUND_STATS
+            const long long t1 = clock64();
+#endif
+            boundCell(c, cb, b, tag, dt, rDt);
+#ifdef SV_BOUND_STATS
+            const long long t2 = clock64();
+            atomicAdd(&g_dbg[0], 1ull);
+            atomicAdd(&g_dbg[2], (unsigned long long)(t1 - t0));
+            atomicAdd(&g_dbg[3], (unsigned long long)(t2 - t1));
+#endif
+            if (cb.succMask) {
+                __threadfence();  // corrections visible before any successor is released
+                for (unsigned long long sm = cb.succMask; sm; sm &= sm - 1) {
+                    const int q = __ffsll((long long)sm) - 1;
+                    const int y = cb.other[q];
                     if (atomicSub(&depLeft[y], 1) == 1) {  // last predecessor: run y next on this thread
                         if (sp < SV_BSTACK) stack[sp++] = y; else atomicOr(&ctl->err, SVERR_LIST);
                     }
                 }
             }
+#ifdef SV_BOUND_STATS
+            atomicAdd(&g_dbg[5], (unsigned long long)(clock64() - t2));
+#endif
             if (sp == 0) break;
             c = stack[--sp];
+            i = oobIdx[c];
             __threadfence();  // acquire side of the release above
         }
     }
@@ -1165,6 +1203,7 @@ __global__ void __launch_bounds__(128) k_bound_run(MeshDev m, Ctl* ctl, int s, i
 // sweep s, last step (advectionTemplates.C:164-192,207-208): apply each recorded correction once to
 // alpha[own]/alpha[nei]/dVf, in the order of the reference's correctedFaces list (= ascending
 // corrector cell, then position in its first-iteration face list); then build the next sweep's list.
+template <int SV_MAXBF>
 __global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s, int tag, const int* affList, const unsigned int* near1,
                                                      double* alpha, double* dVf, BoundScratch b, int* oobListNext,
                                                      unsigned char* oobState)
