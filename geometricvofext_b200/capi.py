@@ -75,6 +75,7 @@ SYMBOLS = [
     ("svof_set_phi_device", C.c_int, [_H, C.c_void_p]),
     ("svof_set_U_device", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("svof_set_option", C.c_int, [_H, C.c_char_p, C.c_int]),
+    ("svof_get_stream", C.c_int, [_H, C.POINTER(C.c_void_p)]),
     ("svof_synchronize", C.c_int, [_H]),
     ("svof_mark", C.c_int, [_H, C.c_int]),
     ("svof_elapsed_ms", C.c_int, [_H, C.c_int, C.c_int, c_double_p]),

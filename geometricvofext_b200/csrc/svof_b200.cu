@@ -1168,6 +1168,13 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     API_END(h)
 }
 
+int svof_get_stream(svof_handle* h, void** stream)
+{
+    if (!h || !stream) return SVOF_ERR_INVALID_ARG;
+    *stream = (void*)h->stream;
+    return SVOF_OK;
+}
+
 int svof_synchronize(svof_handle* h)
 {
     if (!h) return SVOF_ERR_INVALID_ARG;

@@ -130,6 +130,9 @@ class DecomposedSolveVofEqu:
             self.send_idx = {r: torch.as_tensor(v, device=dev) for r, v in self.plan["send"].items()}
             self.recv_idx = {r: torch.as_tensor(v, device=dev) for r, v in self.plan["recv"].items()}
             self.recv_buf = {r: torch.empty(v.numel(), dtype=torch.float64, device=dev) for r, v in self.recv_idx.items()}
+            st = C.c_void_p()
+            self.s._chk(self.s.lib.svof_get_stream(self.s._h, C.byref(st)))
+            self.ext_stream = torch.cuda.ExternalStream(st.value, device=dev)
         self.halo_bytes = 8 * sum(len(v) for v in self.plan["recv"].values())
 
     # -- halo exchange: alpha of halo cells <- owning rank ---------------------------------------
@@ -138,32 +141,26 @@ class DecomposedSolveVofEqu:
         if self.world == 1:
             return
         if self.on_gpu:
+            # Fully stream-ordered: gather -> NCCL send/recv -> scatter are enqueued on the solver's own CUDA
+            # stream (wrapped as a torch ExternalStream), so the step needs no host synchronisation.
             torch = self.torch
-            dbg = os.environ.get("SVOF_MG_DEBUG")
-            t0 = time.perf_counter()
-            self.s.synchronize()
-            t1 = time.perf_counter()
             p = C.c_void_p()
             self.s._chk(self.s.lib.svof_device_ptr(self.s._h, capi.F_ALPHA, C.byref(p)))
-            a = torch.as_tensor(_DevArr(p.value, self.s.nC), device=torch.device("cuda", self.device))
-            ops, keep = [], []
-            for r, idx in self.send_idx.items():
-                buf = a.index_select(0, idx)
-                keep.append(buf)
-                ops.append(dist.P2POp(dist.isend, buf, r))
-            for r, buf in self.recv_buf.items():
-                ops.append(dist.P2POp(dist.irecv, buf, r))
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-            for r, idx in self.recv_idx.items():
-                a.index_copy_(0, idx, self.recv_buf[r])
-            t2 = time.perf_counter()
-            torch.cuda.current_stream(self.device).synchronize()
-            t3 = time.perf_counter()
+            with torch.cuda.stream(self.ext_stream):
+                a = torch.as_tensor(_DevArr(p.value, self.s.nC), device=torch.device("cuda", self.device))
+                ops, keep = [], []
+                for r, idx in self.send_idx.items():
+                    buf = a.index_select(0, idx)
+                    keep.append(buf)
+                    ops.append(dist.P2POp(dist.isend, buf, r))
+                for r, buf in self.recv_buf.items():
+                    ops.append(dist.P2POp(dist.irecv, buf, r))
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()          # stream-level wait (no host block) for NCCL work
+                for r, idx in self.recv_idx.items():
+                    a.index_copy_(0, idx, self.recv_buf[r])
+                self._keep = keep     # buffers stay alive until the next exchange
             self.s._chk(self.s.lib.svof_device_touch(self.s._h, capi.F_ALPHA))
-            if dbg and self.rank == 0:
-                print("[mg] wait-own-stream %.3f ms, enqueue+nccl %.3f ms, torch sync %.3f ms" %
-                      (1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2)), file=sys.stderr)
         else:
             import torch
             a = self.s.alpha()

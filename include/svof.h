@@ -250,6 +250,9 @@ int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
 /* Runtime switches: "overlap" (0/1: run the streaming kernel on a second stream concurrently with
  * the sparse interface chain), "profile" (0/1: CUDA events around every launch, printed at destroy). */
 int svof_set_option(svof_handle* h, const char* name, int value);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this handle is ordered on, so a caller that
+ * lives on the GPU (halo exchange in multigpu.py) can enqueue its own work in order without a host sync. */
+int svof_get_stream(svof_handle* h, void** stream);
 /* Block until all device work queued by this handle has finished. */
 int svof_synchronize(svof_handle* h);
 /* CUDA-event stopwatch on the handle's own stream (the stream every kernel of

@@ -276,6 +276,7 @@ int svof_device_touch(svof_handle*, int) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_phi_device(svof_handle*, const void*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_U_device(svof_handle*, const void*, const void*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_option(svof_handle* h, const char* name, int) { return (h && name) ? SVOF_OK : SVOF_ERR_INVALID_ARG; }
+int svof_get_stream(svof_handle*, void**) { return SVOF_ERR_UNSUPPORTED; }
 int svof_synchronize(svof_handle*) { return SVOF_OK; }
 int svof_mark(svof_handle* h, int slot)
 {
