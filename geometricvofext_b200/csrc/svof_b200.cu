@@ -698,7 +698,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     do {                                                                                                                     \
         LAUNCH(h, k_bound_deps<MB>, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, \
                dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList);           \
-        LAUNCH(h, k_bound_run<MB>, 2 * gB, 64, h->ctl, sidx, tag, h->oobList[sidx & 1], h->bs, h->depInit, h->depLeft, h->oobIdx, \
+        LAUNCH(h, k_bound_run<MB>, 2 * gB, 64, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx, \
                (const CellBound<MB>*)h->boundRecs, h->capRec, dt, rDt);                                                      \
         LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, tag, h->affList, h->near1, aNew, h->dVf, h->bs,               \
                h->oobList[(sidx + 1) & 1], h->oobState);                                                                     \

@@ -1005,8 +1005,9 @@ __device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const
 }
 
 template <int SV_MAXBF>
-__device__ void boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch& b, int tag, double dt, double rDeltaT)
+__device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch& b, int tag, double dt, double rDeltaT)
 {
+    bool hadRoom = false;
     const double Vi = cb.V;
     const int nf = cb.nf;
     double room[SV_MAXBF];
@@ -1049,6 +1050,7 @@ __device__ void boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
             dVff += sgn(cb.fPhi[q]) * sgn(fluidToPassOn) * through;
             cb.fCorr[q] = dVff;
             modMask |= 1ull << q;
+            hadRoom = true;
             if (firstLoop) {
                 recMask |= 1ull << q;
                 recPos[q] = nRecorded++;
@@ -1080,6 +1082,7 @@ __device__ void boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
             b.tagR[f] = tag;
         }
     }
+    return hadRoom;
 }
 
 // The reference sweeps the cells in ascending index (Gauss-Seidel, SURVEY 8a' item 15).  A cell only
@@ -1147,7 +1150,8 @@ __global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, 
 
 #define SV_BSTACK 64
 template <int SV_MAXBF>
-__global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, const int* oobList, BoundScratch b, const int* depInit,
+__global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, const int* oobList, unsigned char* oobState, BoundScratch b,
+                                                  const int* depInit,
                                                   int* depLeft, const int* oobIdx, const CellBound<SV_MAXBF>* recs, int capRec,
                                                   double dt, double rDt)
 {
@@ -1172,7 +1176,10 @@ __global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, cons
 #ifdef SV_BOUND_STATS
             const long long t1 = clock64();
 #endif
-            boundCell(c, cb, b, tag, dt, rDt);
+            // A cell whose first inner iteration finds no downwind face with room writes nothing, and will write
+            // nothing in later sweeps either until a neighbour's correction changes its alpha (its downwind faces are
+            // only ever corrected by itself): mark it dormant so later sweeps skip it (exactly the reference's result).
+            if (!boundCell(c, cb, b, tag, dt, rDt)) oobState[c] = 3;
 #ifdef SV_BOUND_STATS
             const long long t2 = clock64();
             atomicAdd(&g_dbg[0], 1ull);
@@ -1278,8 +1285,10 @@ __global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s,
         alpha[c] = a;
         delta += int(oobGlobal(a)) - int(was);
         if (oobBound(a) && bitTest(near1, c)) {
-            oobState[c] = 1;
-            oobListNext[atomicAdd(&ctl->nOob[(s + 1) & 1], 1)] = c;
+            if (!(oobState[c] == 3 && nf == 0)) {  // dormant cells (no room, alpha unchanged) stay off the next list
+                oobState[c] = 1;
+                oobListNext[atomicAdd(&ctl->nOob[(s + 1) & 1], 1)] = c;
+            }
         } else {
             oobState[c] = 0;
         }
