@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -153,6 +153,8 @@ def run_ours(args):
         s.reconstruct()
         s.advect(dt)
     s.synchronize()
+    clocks = ClockSampler()
+    clocks.start()          # sampled over every timed leg below (roofline, device-resident, end-to-end)
     d0, dn0 = s.info(capi.I_DENSE_KERNEL_MS), s.info(capi.I_DENSE_KERNEL_LAUNCHES)
     lib.svof_mark(h, 2)
     for _ in range(args.steps):
@@ -170,8 +172,6 @@ def run_ours(args):
         s.advect(dt)
     s.synchronize()
     l0 = s.info(capi.I_GPU_LAUNCHES)
-    clocks = ClockSampler()
-    clocks.start()
     lib.svof_mark(h, 0)
     for _ in range(args.steps):
         s.reconstruct()
@@ -180,7 +180,6 @@ def run_ours(args):
     ms = C.c_double()
     lib.svof_elapsed_ms(h, 0, 1, C.byref(ms))
     s.synchronize()
-    clk = clocks.stop()
     total_ms = ms.value
     launches = int(s.info(capi.I_GPU_LAUNCHES) - l0)
     value = m.n_cells * args.steps / (total_ms * 1e-3)
@@ -199,9 +198,10 @@ def run_ours(args):
     for _ in range(e2e_steps):
         s.step_host(dt, phi_h, U_h, Ub_h, a_out, ap_out)
     e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
     e2e_val = m.n_cells * e2e_steps / e2e_s
-    h2d = 8 * (s.nF + 3 * s.nC + 3 * s.nBF)
-    d2h = 8 * (s.nC + s.nF)
+    h2d = int(s.info(capi.I_H2D_BYTES))   # bytes the library actually copied in the last step (sparse_io: only the rows of U
+    d2h = int(s.info(capi.I_D2H_BYTES))   # the interpolation reads go in; alpha/alphaPhi come back as bitwise deltas)
 
     # ---- roofline of the dominant (streaming) kernel ------------------------------------------
     peak, peak_src = measured_peak()
@@ -236,7 +236,10 @@ def run_ours(args):
                    "advect_ms": 1e3 * adv_s / (args.steps + args.warmup + e2e_steps + 1), "setup_s": setup_s},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "full_field_bytes_per_step": {"h2d": 8 * (s.nF + 3 * s.nC + 3 * s.nBF), "d2h": 8 * (s.nC + s.nF)},
+                "note": "svof_step_host with pinned host buffers for phi, U, Ub in and alpha, alphaPhi out; the caller's output buffers hold "
+                        "the complete new fields after every call"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_dense_update", "kernel_ms": dense_ms,

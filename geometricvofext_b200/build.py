@@ -24,7 +24,8 @@ OBJ = os.path.join(HERE, "lib", "obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC"] + \
-             (["-DSV_BOUND_STATS"] if os.environ.get("SVOF_BOUND_STATS") else [])
+             (["-DSV_BOUND_STATS"] if os.environ.get("SVOF_BOUND_STATS") else []) + \
+             (["-DSV_DENSE_UNROLL=" + os.environ["SVOF_DENSE_UNROLL"]] if os.environ.get("SVOF_DENSE_UNROLL") else [])
 
 UNITS = [("svof_b200", "svof_b200.cu", [])] + \
         [("svof_inst%d" % v, "svof_inst.cu", ["-DSV_VARIANT=%d" % v]) for v in range(4)]
@@ -61,7 +62,7 @@ def build(force=False, verbose=False):
                 raise RuntimeError("nvcc failed for %s" % name)
     objs = [os.path.join(OBJ, name + ".o") for name, _, _ in UNITS]
     if force or jobs or _stale(OUT, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-Xlinker", "-Bsymbolic", "-o", OUT] + objs
+        cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-Xlinker", "-Bsymbolic", "-Xcompiler", "-pthread", "-o", OUT] + objs
         subprocess.check_call(cmd)
     return OUT
 

@@ -16,6 +16,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/svof.h"
@@ -39,7 +40,7 @@ struct svof_handle {
     int device = 0;
     cudaStream_t stream = nullptr;   // main stream: copies, sparse kernels, timing events
     cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
-    cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr;
+    cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr, evCopy = nullptr;
     bool inputsAfterNear = false, freshRecon = false;
     bool overlap = true;   // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=0 / svof_set_option to disable)
     int advectCount = 0;
@@ -75,6 +76,19 @@ struct svof_handle {
     Ctl* ctl = nullptr;
     Ctl* hctl = nullptr;  // pinned mirror
     PatchDev* dPatches = nullptr;
+    // end-to-end transfer reduction (svof_step_host)
+    bool sparseIO = true;            // "sparse_io" option
+    unsigned int* uBits = nullptr;
+    int *uList = nullptr, *hUList = nullptr;
+    double *uPacked = nullptr, *hUPacked = nullptr;
+    int capU = 0;
+    double* alphaPhiPrev = nullptr;  // what the caller's alphaPhi buffer holds
+    int *dIdx = nullptr, *hIdx = nullptr;
+    double *dVal = nullptr, *hVal = nullptr;
+    int capDelta = 0;
+    const double* hostAlphaSynced = nullptr;     // caller buffers known to hold the previous step's results
+    const double* hostAlphaPhiSynced = nullptr;
+    long long h2dBytes = 0, d2hBytes = 0;        // bytes actually moved by the last svof_step_host
     DenseStage dstage;
     size_t dstageSmem = 0;
     bool useStaged = false;
@@ -531,6 +545,18 @@ void allocFields(svof_handle* h)
     }
     h->oobState = dalloc<unsigned char>(h, nC);
     h->ctl = dalloc<Ctl>(h, 1);
+    h->uBits = dalloc<unsigned int>(h, h->nWords + 1);
+    h->capU = (int)std::min<size_t>(nC, std::max<size_t>(1 << 20, nC / 8));
+    h->uList = dalloc<int>(h, h->capU);
+    h->uPacked = dalloc<double>(h, 3 * (size_t)h->capU);
+    h->alphaPhiPrev = dalloc<double>(h, nF);
+    h->capDelta = (int)std::min<size_t>(nF, std::max<size_t>(1 << 20, nF / 6));
+    h->dIdx = dalloc<int>(h, h->capDelta);
+    h->dVal = dalloc<double>(h, h->capDelta);
+    CK(cudaMallocHost((void**)&h->hUList, sizeof(int) * h->capU));
+    CK(cudaMallocHost((void**)&h->hUPacked, sizeof(double) * 3 * (size_t)h->capU));
+    CK(cudaMallocHost((void**)&h->hIdx, sizeof(int) * h->capDelta));
+    CK(cudaMallocHost((void**)&h->hVal, sizeof(double) * h->capDelta));
     h->partial = dalloc<double>(h, 1024);
     CK(cudaMallocHost((void**)&h->hctl, sizeof(Ctl)));
     CK(cudaMallocHost((void**)&h->hpartial, 1024 * sizeof(double)));
@@ -539,6 +565,7 @@ void allocFields(svof_handle* h)
     CK(cudaEventCreateWithFlags(&h->evNear, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evDense, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evInputs, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evCopy, cudaEventDisableTiming));
     h->events.resize(96);
     for (EventPair& e : h->events) {
         CK(cudaEventCreate(&e.a));
@@ -882,6 +909,10 @@ int svof_destroy(svof_handle* h)
     for (void* p : h->allocs) cudaFree(p);
     if (h->hctl) cudaFreeHost(h->hctl);
     if (h->hpartial) cudaFreeHost(h->hpartial);
+    if (h->hUList) cudaFreeHost(h->hUList);
+    if (h->hUPacked) cudaFreeHost(h->hUPacked);
+    if (h->hIdx) cudaFreeHost(h->hIdx);
+    if (h->hVal) cudaFreeHost(h->hVal);
     for (EventPair& e : h->events) {
         if (e.a) cudaEventDestroy(e.a);
         if (e.b) cudaEventDestroy(e.b);
@@ -890,6 +921,7 @@ int svof_destroy(svof_handle* h)
     if (h->evNear) cudaEventDestroy(h->evNear);
     if (h->evDense) cudaEventDestroy(h->evDense);
     if (h->evInputs) cudaEventDestroy(h->evInputs);
+    if (h->evCopy) cudaEventDestroy(h->evCopy);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->streamD) cudaStreamDestroy(h->streamD);
     delete h;
@@ -909,6 +941,7 @@ int svof_set_alpha(svof_handle* h, const double* alpha)
     h->haveAlpha = true;
     h->bitsValid = false;
     h->advected = false;
+    h->hostAlphaSynced = nullptr;
     return SVOF_OK;
     API_END(h)
 }
@@ -989,11 +1022,45 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
     EventPair& e = beginTimed(h, 1);
     doAdvect(h, dt, dSp, dSu);
     endTimed(h, e);
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;  // the caller's buffers no longer mirror the device
     CK(cudaGetLastError());
     if (Sp || Su) CK(cudaStreamSynchronize(h->stream));  // caller's buffers may be pageable
     return SVOF_OK;
     API_END(h)
 }
+
+namespace {
+// (index, value) read-back of the entries of `cur` that differ bitwise from what the host buffer holds
+bool deltaReadback(svof_handle* h, const double* cur, double* prevDev, const double* refDev, long long n, int* counter, double* hostOut)
+{
+    CK(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
+    LAUNCH(h, k_delta, cdiv(n, 256), 256, cur, prevDev, refDev, n, counter, h->dIdx, h->dVal, h->capDelta);
+    int cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, counter, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->d2hBytes += sizeof(int);
+    if (cnt > h->capDelta) return false;  // too many changes: the caller falls back to a full copy
+    if (cnt) {
+        CK(cudaMemcpyAsync(h->hIdx, h->dIdx, sizeof(int) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->hVal, h->dVal, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->d2hBytes += 12LL * cnt;
+        // scatter into the caller's buffer; a few host threads (random writes into a field-sized array)
+        const int nT = cnt > (1 << 16) ? 8 : 1;
+        auto work = [&](int t) {
+            const int lo = (int)((long long)cnt * t / nT), hi = (int)((long long)cnt * (t + 1) / nT);
+            for (int i = lo; i < hi; ++i) hostOut[h->hIdx[i]] = h->hVal[i];
+        };
+        if (nT == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nT; ++t) th.emplace_back(work, t);
+            for (auto& x : th) x.join();
+        }
+    }
+    return true;
+}
+}  // namespace
 
 int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U, const double* Ub, double* alpha_out,
                    double* alpha_phi_out)
@@ -1002,19 +1069,85 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     if (!h->haveAlpha) return fail(h, SVOF_ERR_STATE, "svof_step_host: alpha not set");
     API_BEGIN
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->U, U, sizeof(double) * 3 * h->nC, cudaMemcpyHostToDevice, h->stream));
-    if (Ub && h->nBF) CK(cudaMemcpyAsync(h->Ub, Ub, sizeof(double) * 3 * h->nBF, cudaMemcpyHostToDevice, h->stream));
-    h->havePhi = h->haveU = true;
+    cudaStream_t st = h->stream;
+    h->h2dBytes = h->d2hBytes = 0;
+    // phi (the one field that has to cross PCIe in full) goes up on the second stream while reconstruct() and the
+    // sparse-U round trip run on the main one
+    CK(cudaEventRecord(h->evInputs, st));
+    CK(cudaStreamWaitEvent(h->streamD, h->evInputs, 0));  // previous step's readers of phi/Ub are done
+    CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
+    h->h2dBytes += 8LL * h->nF;
+    if (Ub && h->nBF) {
+        CK(cudaMemcpyAsync(h->Ub, Ub, sizeof(double) * 3 * h->nBF, cudaMemcpyHostToDevice, h->streamD));
+        h->h2dBytes += 24LL * h->nBF;
+    }
+    CK(cudaEventRecord(h->evCopy, h->streamD));
+    h->havePhi = true;
     EventPair& e0 = beginTimed(h, 0);
     doReconstruct(h);
     endTimed(h, e0);
+    // U: only the rows the interface-velocity interpolation reads
+    bool uDone = false;
+    if (h->sparseIO) {
+        const int g256 = sparseGrid(h, 256);
+        LAUNCH(h, k_clear_u_bits, g256, 256, h->uList, h->ctl, h->uBits, h->capU);
+        CK(cudaMemsetAsync(&h->ctl->nUCells, 0, sizeof(int), st));
+        LAUNCH(h, k_mark_u_cells, g256, 256, h->md, h->mixedCells, h->cellStatus, h->ctl, h->uBits, h->uList, h->capU);
+        int nU = 0;
+        CK(cudaMemcpyAsync(&nU, &h->ctl->nUCells, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (nU <= h->capU) {
+            if (nU) {
+                CK(cudaMemcpyAsync(h->hUList, h->uList, sizeof(int) * nU, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                for (int i = 0; i < nU; ++i) {
+                    const double* src = U + 3 * (size_t)h->hUList[i];
+                    double* dst = h->hUPacked + 3 * (size_t)i;
+                    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+                }
+                CK(cudaMemcpyAsync(h->uPacked, h->hUPacked, sizeof(double) * 3 * nU, cudaMemcpyHostToDevice, st));
+                LAUNCH(h, k_scatter_u, cdiv(nU, 256), 256, h->uList, nU, h->uPacked, h->U);
+                h->h2dBytes += 24LL * nU;
+                h->d2hBytes += 4LL * nU + 4;
+            }
+            uDone = true;
+        } else {
+            CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * h->nWords, st));  // list overflowed: bits were left set
+        }
+    }
+    if (!uDone) {
+        CK(cudaMemcpyAsync(h->U, U, sizeof(double) * 3 * h->nC, cudaMemcpyHostToDevice, st));
+        h->h2dBytes += 24LL * h->nC;
+    }
+    h->haveU = true;
+    h->inputsAfterNear = true;  // U landed after the near bitmaps were published
+    CK(cudaStreamWaitEvent(st, h->evCopy, 0));  // phi/Ub are on the device
     EventPair& e1 = beginTimed(h, 1);
     doAdvect(h, dt, nullptr, nullptr);
     endTimed(h, e1);
-    if (alpha_out) CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, h->stream));
-    if (alpha_phi_out) CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    // results: deltas against what the caller's buffers already hold, else full copies
+    if (alpha_out) {
+        bool done = false;
+        if (h->sparseIO && h->hostAlphaSynced == alpha_out)
+            done = deltaReadback(h, h->alphaBuf[h->cur], nullptr, h->alphaBuf[h->cur ^ 1], h->nC, &h->ctl->nDeltaA, alpha_out);
+        if (!done) {
+            CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, st));
+            h->d2hBytes += 8LL * h->nC;
+        }
+        h->hostAlphaSynced = alpha_out;
+    }
+    if (alpha_phi_out) {
+        bool done = false;
+        if (h->sparseIO && h->hostAlphaPhiSynced == alpha_phi_out)
+            done = deltaReadback(h, h->alphaPhi, h->alphaPhiPrev, nullptr, h->nF, &h->ctl->nDeltaF, alpha_phi_out);
+        if (!done) {
+            CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
+            if (h->sparseIO) CK(cudaMemcpyAsync(h->alphaPhiPrev, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, st));
+            h->d2hBytes += 8LL * h->nF;
+        }
+        h->hostAlphaPhiSynced = alpha_phi_out;
+    }
+    CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     return SVOF_OK;
     API_END(h)
@@ -1118,6 +1251,8 @@ int svof_get_info(svof_handle* h, int which, double* out)
         case SVOF_I_DENSE_KERNEL_MS: harvestEvents(h, true); *out = h->denseMs; return SVOF_OK;
         case SVOF_I_DENSE_KERNEL_LAUNCHES: harvestEvents(h, true); *out = (double)h->denseLaunches; return SVOF_OK;
         case SVOF_I_N_NEAR: fetchCtl(h); *out = h->hctl->nNear2; return SVOF_OK;
+        case SVOF_I_H2D_BYTES: *out = (double)h->h2dBytes; return SVOF_OK;
+        case SVOF_I_D2H_BYTES: *out = (double)h->d2hBytes; return SVOF_OK;
     }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_get_info: unknown item");
     API_END(h)
@@ -1164,6 +1299,7 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     CK(cudaStreamSynchronize(h->stream));
     if (!strcmp(name, "overlap")) { h->overlap = value != 0; return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");
     API_END(h)
 }

@@ -23,6 +23,9 @@ struct Ctl {
     int nMixed;   // mixedCells_.size()
     int nNear2;   // |near2|
     int nWork;    // (cut cell, downwind face) work items
+    int nUCells;  // cells whose U the interface-velocity interpolation reads (end-to-end path)
+    int nDeltaA, nDeltaF;  // changed alpha cells / alphaPhi faces of the last delta read-back
+    int pad2_;
     int err;      // SVERR_* flags
     int nOob[2];  // out-of-bounds lists (double buffered between sweeps)
     int nPend[SV_MAX_SWEEPS + 1];    // (unused)
@@ -673,6 +676,10 @@ __device__ __forceinline__ void blockMinMaxFast(double mn, double mx, unsigned l
 // Cells in near2 are left to the sparse kernels.  Also emits the next step's mixed-cell bitmap.
 // (A sliced-ELL row layout with batched loads was tried in round 1: it coalesces the row loads but
 // loses the L1 reuse of the 48-byte rows and needs 71 registers; measured 1.05 ms vs 0.58 ms.)
+#ifndef SV_DENSE_UNROLL
+#define SV_DENSE_UNROLL 1
+#endif
+constexpr int kDenseUnroll = SV_DENSE_UNROLL;
 __global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
                                                       const double* __restrict__ phi, const double* __restrict__ alphaB,
                                                       double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
@@ -687,6 +694,7 @@ __global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double
         const int k0 = __ldg(m.cellOff + c), k1 = __ldg(m.cellOff + c + 1);
         const double aC = __ldg(aOld + c);
         double sum = 0.0;
+#pragma unroll kDenseUnroll
         for (int k = k0; k < k1; ++k) {
             const int2 e = __ldg(m.cellAsc + k);
             const int f = e.x & 0x7fffffff;
@@ -1347,6 +1355,79 @@ __global__ void k_alpha_bc(MeshDev m, const PatchDev* patches, const int* bPatch
         } else v = internal;
     }
     alphaB[bf] = v;
+}
+
+// ---- end-to-end (host buffers) transfer reduction --------------------------------------------------
+// The PCIe link, not the GPU, bounds svof_step_host (816 MB in, 538 MB out per step at 256^3).  Two exact
+// reductions of what has to cross it:
+//  * U is only read by the interface-velocity interpolation (advection.C:91,126): the cells sharing a vertex
+//    with a cut cell.  k_mark_u_cells lists them; the host gathers just those rows of U.
+//  * alpha/alphaPhi come back as (index, value) deltas against what the host buffer already holds (the
+//    previous step's result == alpha.oldTime on the device); most of a VOF domain does not change bitwise.
+__global__ void k_mark_u_cells(MeshDev m, const int* mixedCells, const int* cellStatus, Ctl* ctl, unsigned int* uBits, int* uList,
+                               int cap)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (cellStatus[i] != 0) continue;
+        const int c = mixedCells[i];
+        for (int k = m.cellPtOff[c]; k < m.cellPtOff[c + 1]; ++k) {
+            const int p = m.cellPts[k];
+            for (int j = m.ptCellOff[p]; j < m.ptCellOff[p + 1]; ++j) {
+                const int y = m.ptCells[j];
+                const unsigned int bit = 1u << (y & 31);
+                if (uBits[y >> 5] & bit) continue;
+                const unsigned int old = atomicOr(&uBits[y >> 5], bit);
+                if (!(old & bit)) {
+                    const int pos = atomicAdd(&ctl->nUCells, 1);
+                    if (pos < cap) uList[pos] = y;
+                }
+            }
+        }
+    }
+}
+__global__ void k_clear_u_bits(const int* uList, const Ctl* ctl, unsigned int* uBits, int cap)
+{
+    const int n = min(ctl->nUCells, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) uBits[uList[i] >> 5] = 0u;
+}
+__global__ void k_scatter_u(const int* uList, int n, const double* packed, double* U)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = uList[i];
+    U[3 * (size_t)c] = packed[3 * (size_t)i];
+    U[3 * (size_t)c + 1] = packed[3 * (size_t)i + 1];
+    U[3 * (size_t)c + 2] = packed[3 * (size_t)i + 2];
+}
+// entries whose bit pattern changed: (index, value) appended with warp-aggregated atomics; if prev != nullptr
+// it is brought up to date at the same time
+__global__ void k_delta(const double* __restrict__ cur, double* prev, const double* __restrict__ ref, long long n, int* counter,
+                        int* idx, double* val, int cap)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool changed = false;
+    double v = 0.0;
+    if (i < n) {
+        v = cur[i];
+        const double o = ref ? ref[i] : prev[i];
+        changed = __double_as_longlong(v) != __double_as_longlong(o);
+        if (changed && prev) prev[i] = v;
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, changed);
+    if (mask) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(counter, __popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (changed) {
+            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            if (pos < cap) {
+                idx[pos] = (int)i;
+                val[pos] = v;
+            }
+        }
+    }
 }
 
 // ---- on-demand outputs ---------------------------------------------------------------------

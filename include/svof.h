@@ -183,7 +183,8 @@ int svof_reconstruct(svof_handle* h);
 int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su);
 
 /* Host-pointer convenience = set_phi + set_U + reconstruct + advect + read back
- * alpha (and alphaPhi if non-NULL): the end-to-end call bench.py times. */
+ * alpha (and alphaPhi if non-NULL): the end-to-end call bench.py times.  On return the caller's buffers
+ * hold the complete new fields (see the "sparse_io" option for how few bytes that takes). */
 int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U,
                    const double* Ub, double* alpha_out, double* alpha_phi_out);
 
@@ -231,6 +232,8 @@ typedef enum {
     SVOF_I_DENSE_KERNEL_MS = 16, /* cumulative device ms of the streaming kernel  */
     SVOF_I_DENSE_KERNEL_LAUNCHES = 17,
     SVOF_I_N_NEAR = 18,          /* |mixed U 2 face-neighbour layers| (sparse set) */
+    SVOF_I_H2D_BYTES = 19,       /* bytes the last svof_step_host copied host->device */
+    SVOF_I_D2H_BYTES = 20,       /* ... and device->host                          */
     SVOF_I_COUNT_
 } svof_info;
 
@@ -248,7 +251,11 @@ int svof_device_touch(svof_handle* h, int which);
 int svof_set_phi_device(svof_handle* h, const void* dphi);
 int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
 /* Runtime switches: "overlap" (0/1: run the streaming kernel on a second stream concurrently with
- * the sparse interface chain), "profile" (0/1: CUDA events around every launch, printed at destroy). */
+ * the sparse interface chain), "profile" (0/1: CUDA events around every launch, printed at destroy),
+ * "sparse_io" (0/1, default 1: svof_step_host uploads only the rows of U the interface-velocity interpolation
+ * reads and reads alpha/alphaPhi back as (index,value) deltas against what the SAME caller buffers received
+ * from the previous svof_step_host; a caller that modifies those buffers in between must call svof_set_alpha
+ * or pass 0). */
 int svof_set_option(svof_handle* h, const char* name, int value);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is ordered on, so a caller that
  * lives on the GPU (halo exchange in multigpu.py) can enqueue its own work in order without a host sync. */
