@@ -632,6 +632,7 @@ __global__ void k_ctl_reset_advect(Ctl* ctl)
 __global__ void k_ctl_reset_recon(Ctl* ctl)
 {
     ctl->nNear2 = 0;
+    ctl->plicNext = 0;
     ctl->minDense = ~0ull;
     ctl->maxDense = 0ull;
 }

@@ -142,7 +142,17 @@ void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedC
             cudaFuncSetAttribute(k_plic_group<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
             configured = true;
         }
-        k_plic_group<CP><<<grid, threads, smem, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
+        // persistent: exactly as many CTAs as fit on the device at once
+        static int resident = 0;
+        if (!resident) {
+            int perSm = 0, dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_plic_group<CP>, threads, smem);
+            resident = (perSm > 0 ? perSm : 1) * (sms > 0 ? sms : 148);
+        }
+        (void)grid;
+        k_plic_group<CP><<<resident, threads, smem, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
     } else {
         k_plic<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
     }

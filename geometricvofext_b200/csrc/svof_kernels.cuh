@@ -24,8 +24,9 @@ struct Ctl {
     int nNear2;   // |near2|
     int nWork;    // (cut cell, downwind face) work items
     int nUCells;  // cells whose U the interface-velocity interpolation reads (end-to-end path)
+    int plicNext; // batch counter of the persistent plane-positioning kernel
+    int pad3_;
     int nDeltaA, nDeltaF;  // changed alpha cells / alphaPhi faces of the last delta read-back
-    int pad2_;
     int err;      // SVERR_* flags
     int nOob[2];  // out-of-bounds lists (double buffered between sweeps)
     int nPend[SV_MAX_SWEEPS + 1];    // (unused)

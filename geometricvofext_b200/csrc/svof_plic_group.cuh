@@ -141,7 +141,15 @@ __global__ void __launch_bounds__(256) k_plic_group(MeshDev m, const int* mixedC
     const bool splitB = split != 0;
     int err = 0;
 
-    for (int base = blockIdx.x * cpb; base < nMixed; base += gridDim.x * cpb) {
+    // Persistent CTAs + an atomic batch counter: batches take 3..6 evaluations, and with a static grid of
+    // ceil(nMixed/cpb) CTAs the last, partially filled wave cost a whole wave (measured 906 CTAs on 296 slots).
+    __shared__ int sBase;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sBase = atomicAdd(&ctl->plicNext, 1) * cpb;
+        __syncthreads();
+        const int base = sBase;
+        if (base >= nMixed) break;
         // ---- leader role: stage the polyhedron (local face list, sorted vertex distances), init the search
         const int iL = base + threadIdx.x;
         const bool validL = leader && iL < nMixed;
