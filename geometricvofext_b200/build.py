@@ -19,13 +19,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 HEADERS = [os.path.join(CSRC, f) for f in ("svof_kernels.cuh", "svof_geom_kernels.cuh", "svof_geom.cuh", "svof_math.cuh", "svof_plic_group.cuh")] + \
           [os.path.join(HERE, "..", "include", "svof.h")]
-OUT = os.path.join(HERE, "lib", "libsvof_b200.so")
-OBJ = os.path.join(HERE, "lib", "obj")
+_TAG = os.environ.get("SVOF_BUILD_TAG", "")   # variants build beside the product: lib/libsvof_b200<tag>.so
+OUT = os.path.join(HERE, "lib", "libsvof_b200%s.so" % _TAG)
+OBJ = os.path.join(HERE, "lib", "obj" + _TAG)
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC"] + \
              (["-DSV_BOUND_STATS"] if os.environ.get("SVOF_BOUND_STATS") else []) + \
-             (["-DSV_DENSE_UNROLL=" + os.environ["SVOF_DENSE_UNROLL"]] if os.environ.get("SVOF_DENSE_UNROLL") else [])
+             (["-DSV_DENSE_UNROLL=" + os.environ["SVOF_DENSE_UNROLL"]] if os.environ.get("SVOF_DENSE_UNROLL") else []) + \
+             os.environ.get("SVOF_EXTRA_DEFS", "").split()   # kernel-variant experiments (with SVOF_BUILD_TAG)
 
 UNITS = [("svof_b200", "svof_b200.cu", [])] + \
         [("svof_inst%d" % v, "svof_inst.cu", ["-DSV_VARIANT=%d" % v]) for v in range(4)]

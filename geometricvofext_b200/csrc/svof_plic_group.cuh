@@ -64,23 +64,47 @@ __device__ __forceinline__ int loadLocalFace(const MeshDev& m, int cell, int f, 
     return 3;
 }
 
-// clip with cached n.p (bitwise the same sums as clipFace: dot(fp[i], n) + D)
+// Lane-private scratch in SHARED memory, strided so that element e of thread t sits at base[e * T + t]
+// (conflict-free when the lanes of a warp touch the same element).  The first version kept the cached face
+// (fp, n.p), the vertex signs and the clipped polygon in thread-local arrays; their dynamic indexing put them
+// in local memory, and with 512 threads per SM that working set no longer fits L1: ncu counted 61 M local
+// sectors per launch (2 GB through L2), 38% of the local loads and 70% of the stores missing L1, and
+// long-scoreboard as the second stall reason after the phase barriers.
 template <class CP>
-__device__ __forceinline__ int clipFaceCached(const d3* fp, const double* pn, int nv, double D, const d3& fullC, const d3& fullA,
-                                              d3& centre, d3& area, d3* ip, int& nip, int& err)
+struct LanePriv {
+    static constexpr int DOUBLES = 4 * CP::MAXFV;  // fp[MAXFV][3], pn[MAXFV]
+    double* base;
+    int T;
+    __device__ __forceinline__ d3 fp(int q) const { return mk3(base[(3 * q) * T], base[(3 * q + 1) * T], base[(3 * q + 2) * T]); }
+    __device__ __forceinline__ void setFp(int q, const d3& v) const
+    {
+        base[(3 * q) * T] = v.x;
+        base[(3 * q + 1) * T] = v.y;
+        base[(3 * q + 2) * T] = v.z;
+    }
+    __device__ __forceinline__ double& pn(int q) const { return base[(3 * CP::MAXFV + q) * T]; }
+};
+
+// cutFace::calcSubFace + calcSubFaceCentreAndArea (cutFace.C:37-96,136-259) on the cached face, without
+// materialising the clipped polygon: its points are generated twice in the reference's order (first pass: count,
+// point sum, first three points; second pass: the edge sums), which gives the same operands in the same order as
+// clipFace()/subFaceCentreAndArea() and therefore the same bits.  ip points to shared memory.
+template <class CP>
+__device__ __forceinline__ double liftedS(const LanePriv<CP>& lp, int q, double D)
 {
-    double s[CP::MAXFV];
+    double si = lp.pn(q) + D;
+    if (fabs(si) < SV_TSMALL) si += sgn(si) * SV_TSMALL;
+    return si;
+}
+template <class CP>
+__device__ __forceinline__ int clipFaceStream(const LanePriv<CP>& lp, int nv, double D, const d3& fullC, const d3& fullA, d3& centre,
+                                              d3& area, d3* ip, int& nip, int& err)
+{
     int nSub = 0, first = -1;
-#pragma unroll
-    for (int i = 0; i < CP::MAXFV; ++i) {
-        if (i < nv) {
-            double si = pn[i] + D;
-            if (fabs(si) < SV_TSMALL) si += sgn(si) * SV_TSMALL;
-            s[i] = si;
-            if (si < 0.0) {
-                nSub++;
-                if (first < 0) first = i;
-            }
+    for (int i = 0; i < nv; ++i) {
+        if (liftedS(lp, i, D) < 0.0) {
+            nSub++;
+            if (first < 0) first = i;
         }
     }
     nip = 0;
@@ -94,32 +118,109 @@ __device__ __forceinline__ int clipFaceCached(const d3* fp, const double* pn, in
         area = zero3();
         return 1;
     }
-    d3 sp[2 * CP::MAXFV];
+    // pass 1
+    d3 P0 = zero3(), P1 = zero3(), P2 = zero3(), sum = zero3();
     int np = 0;
-    int cur = first;
-    for (int i = 0; i < nv; ++i) {
-        const int nxt = (cur + 1 == nv) ? 0 : cur + 1;
-        if (s[cur] < 0) sp[np++] = fp[cur];
-        if ((s[cur] * s[nxt]) < 0) {
-            const double w = s[cur] / (s[cur] - s[nxt]);
-            const d3 cp = fp[cur] + w * (fp[nxt] - fp[cur]);
-            sp[np++] = cp;
-            if (nip < CP::MAXIP) ip[nip] = cp; else err |= SVERR_IFACE_POINTS;
-            nip++;
+    {
+        int cur = first;
+        double sc = liftedS(lp, cur, D);
+        for (int i = 0; i < nv; ++i) {
+            const int nxt = (cur + 1 == nv) ? 0 : cur + 1;
+            const double sn = liftedS(lp, nxt, D);
+            const d3 pc = lp.fp(cur);
+            if (sc < 0) {
+                if (np == 0) { P0 = pc; sum = pc; } else { sum += pc; if (np == 1) P1 = pc; else if (np == 2) P2 = pc; }
+                np++;
+            }
+            if ((sc * sn) < 0) {
+                const double w = sc / (sc - sn);
+                const d3 cp = pc + w * (lp.fp(nxt) - pc);
+                if (np == 0) { P0 = cp; sum = cp; } else { sum += cp; if (np == 1) P1 = cp; else if (np == 2) P2 = cp; }
+                np++;
+                if (nip < CP::MAXIP) ip[nip] = cp; else err |= SVERR_IFACE_POINTS;
+                nip++;
+            }
+            cur = nxt;
+            sc = sn;
         }
-        cur = nxt;
     }
     if (nip > CP::MAXIP) nip = CP::MAXIP;
-    if (np >= 3) {
-        subFaceCentreAndArea(sp, np, centre, area);
+    if (np < 3) {
+        centre = fullC;
+        area = fullA;
+        return -1;
+    }
+    if (np == 3) {
+        centre = (1.0 / 3.0) * (P0 + P1 + P2);
+        area = 0.5 * cross(P1 - P0, P2 - P0);
         return 0;
     }
-    centre = fullC;
-    area = fullA;
-    return -1;
+    // pass 2: edges (sp[i], sp[i+1]) in order, closing with (sp[np-1], sp[0])
+    d3 fC = sum;
+    fC /= double(np);
+    d3 sumN = zero3(), sumAc = zero3();
+    double sumA = 0.0;
+    d3 prev = P0;
+    {
+        int cur = first, k = 0, kc = 0;
+        double sc = liftedS(lp, cur, D);
+        for (int i = 0; i < nv; ++i) {
+            const int nxt = (cur + 1 == nv) ? 0 : cur + 1;
+            const double sn = liftedS(lp, nxt, D);
+            if (sc < 0) {
+                const d3 pc = lp.fp(cur);
+                if (k > 0) {
+                    const d3 c = prev + pc + fC;
+                    const d3 n = cross(pc - prev, fC - prev);
+                    const double a = mag(n);
+                    sumN += n;
+                    sumA += a;
+                    sumAc += a * c;
+                }
+                prev = pc;
+                k++;
+            }
+            if ((sc * sn) < 0) {
+                const d3 cp = ip[kc < CP::MAXIP ? kc : CP::MAXIP - 1];  // the point pass 1 stored (overflow is flagged in err)
+                kc++;
+                if (k > 0) {
+                    const d3 c = prev + cp + fC;
+                    const d3 n = cross(cp - prev, fC - prev);
+                    const double a = mag(n);
+                    sumN += n;
+                    sumA += a;
+                    sumAc += a * c;
+                }
+                prev = cp;
+                k++;
+            }
+            cur = nxt;
+            sc = sn;
+        }
+    }
+    {
+        const d3 c = prev + P0 + fC;
+        const d3 n = cross(P0 - prev, fC - prev);
+        const double a = mag(n);
+        sumN += n;
+        sumA += a;
+        sumAc += a * c;
+    }
+    if (sumA < SV_ROOTVSMALL) {
+        centre = fC;
+        area = zero3();
+    } else {
+        centre = (1.0 / 3.0) * sumAc / sumA;
+        area = 0.5 * sumN;
+    }
+    return 0;
 }
 
 #define SV_G 8  // lanes per cell
+#ifndef SV_PLIC_THREADS
+#define SV_PLIC_THREADS 128
+#define SV_PLIC_MINB 4
+#endif
 
 // CTA = cpb cells x 8 lanes.  Face phases (A, C, E): thread t works for cell t/8, lane t%8.
 // Leader phases (staging, B, D, F): the first cpb threads, one per cell (thread t <-> cell t), so the
@@ -127,12 +228,15 @@ __device__ __forceinline__ int clipFaceCached(const d3* fp, const double* pn, in
 // (measured on the first version: 9 of 32 lanes active on average, 10.8k warp-instructions per
 // evaluation; the leader phases dominated).
 template <class CP>
-__global__ void __launch_bounds__(256) k_plic_group(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
+__global__ void __launch_bounds__(SV_PLIC_THREADS, SV_PLIC_MINB) k_plic_group(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
                                                     const double* iN, int split, int* cellStatus, double* iD, double* iC, double* iS)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     GCellShared<CP>* shAll = reinterpret_cast<GCellShared<CP>*>(smemRaw);
     const int cpb = blockDim.x / SV_G;  // cells per block
+    LanePriv<CP> lp;
+    lp.base = reinterpret_cast<double*>(smemRaw + size_t(cpb) * sizeof(GCellShared<CP>)) + threadIdx.x;
+    lp.T = blockDim.x;
     const int gidF = threadIdx.x / SV_G, lane = threadIdx.x % SV_G;
     const bool leader = (threadIdx.x < cpb);
     GCellShared<CP>& shF = shAll[gidF];                      // the cell this thread clips faces for
@@ -238,15 +342,15 @@ __global__ void __launch_bounds__(256) k_plic_group(MeshDev m, const int* mixedC
         const d3 nF = validF ? ld3(iN, cellF) : mk3(1.0, 0.0, 0.0);
         const int nLocal = shF.nLocal;
         const bool cached = nLocal <= SV_G;
-        d3 fpC[CP::MAXFV];
-        double pnC[CP::MAXFV];
         d3 fullC = zero3(), fullA = zero3();
         int nvC = 0;
         if (validF && shF.active && cached && lane < nLocal) {
+            d3 fpC[CP::MAXFV];
             nvC = loadLocalFace<CP>(m, cellF, shF.lfFace[lane], shF.lfTri[lane], splitB, fpC, err);
-#pragma unroll
-            for (int q = 0; q < CP::MAXFV; ++q)
-                if (q < nvC) pnC[q] = dot(fpC[q], nF);
+            for (int q = 0; q < nvC; ++q) {
+                lp.setFp(q, fpC[q]);
+                lp.pn(q) = dot(fpC[q], nF);
+            }
             fullC = faceCentreOF(fpC, nvC);
             fullA = faceAreaNormalOF(fpC, nvC);
         }
@@ -258,20 +362,20 @@ __global__ void __launch_bounds__(256) k_plic_group(MeshDev m, const int* mixedC
                 const double D = shF.D;
                 for (int k = lane; k < nLocal; k += SV_G) {
                     GFaceRes<CP>& r = shF.res[k];
-                    d3 c, a, ipl[CP::MAXIP];
+                    d3 c, a;
                     int nip, st;
                     if (cached) {
-                        st = clipFaceCached<CP>(fpC, pnC, nvC, D, fullC, fullA, c, a, ipl, nip, err);
+                        st = clipFaceStream<CP>(lp, nvC, D, fullC, fullA, c, a, r.ip, nip, err);
                     } else {
-                        d3 fp[CP::MAXFV];
+                        d3 fp[CP::MAXFV], ipl[CP::MAXIP];
                         const int nv = loadLocalFace<CP>(m, cellF, shF.lfFace[k], shF.lfTri[k], splitB, fp, err);
                         st = clipFace<CP>(fp, nv, nF, D, c, a, ipl, nip, err);
+                        for (int q = 0; q < nip; ++q) r.ip[q] = ipl[q];
                     }
                     r.st = st;
                     r.nip = nip;
                     r.c = c;
                     r.a = a;
-                    for (int q = 0; q < nip; ++q) r.ip[q] = ipl[q];
                 }
             }
             __syncthreads();
