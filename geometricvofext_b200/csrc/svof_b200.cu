@@ -42,7 +42,8 @@ struct svof_handle {
     cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
     cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr, evCopy = nullptr;
     bool inputsAfterNear = false, freshRecon = false;
-    bool overlap = true;   // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=0 / svof_set_option to disable)
+    bool overlap = false;  // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=1 / svof_set_option);
+                           // off by default: measured slower at 256^3 (1.57 vs 1.31 ms/step), see DESIGN.md section 6
     int advectCount = 0;
     int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
     std::vector<svof_patch> patches;
@@ -878,7 +879,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
-        h->overlap = !(getenv("SVOF_OVERLAP") && atoi(getenv("SVOF_OVERLAP")) == 0);  // default on
+        h->overlap = getenv("SVOF_OVERLAP") && atoi(getenv("SVOF_OVERLAP")) != 0;  // default off
         h->prof = getenv("SVOF_PROFILE") && atoi(getenv("SVOF_PROFILE")) > 0;
         h->prm = *params;
         h->sp.mixedTol = params->mixed_cell_tol;
