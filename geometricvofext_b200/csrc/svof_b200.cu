@@ -42,7 +42,9 @@ struct svof_handle {
     cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
     cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr, evCopy = nullptr;
     bool inputsAfterNear = false, freshRecon = false;
-    bool overlap = false;  // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=1 / svof_set_option);
+    std::map<std::string, double> hostAcc;  // profile: host wall time per phase of svof_step_host (ms)
+    std::chrono::steady_clock::time_point hostT;
+    int overlap = 0;       // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=1 / svof_set_option);
                            // off by default: measured slower at 256^3 (1.57 vs 1.31 ms/step), see DESIGN.md section 6
     int advectCount = 0;
     int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
@@ -217,6 +219,10 @@ void profPrint(svof_handle* h)
         fprintf(stderr, "[svof profile] last step: nMixed %d nNear2 %d nWork %d | sweep: nAff %d %d %d nPend %d %d %d nearOob %d %d %d %d nOob(left) %d %d\n",
                 c.nMixed, c.nNear2, c.nWork, c.nAff[0], c.nAff[1], c.nAff[2], c.nPend[0], c.nPend[1], c.nPend[2], c.nearOob[0],
                 c.nearOob[1], c.nearOob[2], c.nearOob[3], c.nOob[0], c.nOob[1]);
+    }
+    if (!h->hostAcc.empty()) {
+        fprintf(stderr, "[svof profile] svof_step_host: host wall time per phase (ms total)\n");
+        for (auto& kv : h->hostAcc) fprintf(stderr, "  %-40s %10.3f ms\n", kv.first.c_str(), kv.second);
     }
     double tot = 0;
     for (auto& kv : h->profAcc) tot += kv.second.first;
@@ -712,6 +718,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
 
     // ---- sparse chain
     LAUNCH(h, k_ctl_reset_advect, 1, 1, h->ctl);
+    if (h->overlap == 2) CK(cudaStreamWaitEvent(sS, h->evDense, 0));  // overlap with the tail of reconstruct() only
     // A7-A9: geometric fluxes on the downwind faces of cut cells
     LAUNCH(h, k_un0_worklist, g128, 128, d, h->mixedCells, h->cellStatus, h->ctl, h->iN, h->iC, h->U, h->Ub, h->phi, h->Un0, h->work,
            h->capWork);
@@ -738,7 +745,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         LAUNCH(h, k_bound_flip, 1, 1, h->ctl, sidx);
     }
     // join: the finalize kernel ORs into the bitmap words the streaming kernel wrote
-    if (h->overlap) CK(cudaStreamWaitEvent(sS, h->evDense, 0));
+    if (h->overlap == 1) CK(cudaStreamWaitEvent(sS, h->evDense, 0));
     // A12: snap/clip + alphaPhi for near2; boundary values of the new field
     LAUNCH(h, k_near_finalize, g128, 128, d, h->near2List, h->ctl, aNew, h->dVf, h->alphaPhi, h->mixedBits, dt, h->sp, h->oobState);
     h->cur ^= 1;
@@ -879,7 +886,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
-        h->overlap = getenv("SVOF_OVERLAP") && atoi(getenv("SVOF_OVERLAP")) != 0;  // default off
+        h->overlap = getenv("SVOF_OVERLAP") ? atoi(getenv("SVOF_OVERLAP")) : 0;  // default off
         h->prof = getenv("SVOF_PROFILE") && atoi(getenv("SVOF_PROFILE")) > 0;
         h->prm = *params;
         h->sp.mixedTol = params->mixed_cell_tol;
@@ -1031,6 +1038,16 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
     API_END(h)
 }
 
+// profile only: host wall time since the previous tick goes to bucket `name` (ticks sit after existing syncs)
+inline void hostTick(svof_handle* h, const char* name)
+{
+    if (!h->prof) return;
+    const auto now = std::chrono::steady_clock::now();
+    if (name) h->hostAcc[name] += std::chrono::duration<double, std::milli>(now - h->hostT).count();
+    h->hostT = now;
+}
+
+
 namespace {
 // (index, value) read-back of the entries of `cur` that differ bitwise from what the host buffer holds
 bool deltaReadback(svof_handle* h, const double* cur, double* prevDev, const double* refDev, long long n, int* counter, double* hostOut)
@@ -1040,12 +1057,14 @@ bool deltaReadback(svof_handle* h, const double* cur, double* prevDev, const dou
     int cnt = 0;
     CK(cudaMemcpyAsync(&cnt, counter, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    hostTick(h, "4 wait: GPU step + k_delta + count");
     h->d2hBytes += sizeof(int);
     if (cnt > h->capDelta) return false;  // too many changes: the caller falls back to a full copy
     if (cnt) {
         CK(cudaMemcpyAsync(h->hIdx, h->dIdx, sizeof(int) * cnt, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(h->hVal, h->dVal, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        hostTick(h, "5 delta D2H");
         h->d2hBytes += 12LL * cnt;
         // scatter into the caller's buffer; a few host threads (random writes into a field-sized array)
         const int nT = cnt > (1 << 16) ? 8 : 1;
@@ -1059,6 +1078,7 @@ bool deltaReadback(svof_handle* h, const double* cur, double* prevDev, const dou
             for (int t = 0; t < nT; ++t) th.emplace_back(work, t);
             for (auto& x : th) x.join();
         }
+        hostTick(h, "6 host scatter");
     }
     return true;
 }
@@ -1073,6 +1093,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     h->h2dBytes = h->d2hBytes = 0;
+    hostTick(h, nullptr);
     // phi (the one field that has to cross PCIe in full) goes up on the second stream while reconstruct() and the
     // sparse-U round trip run on the main one
     CK(cudaEventRecord(h->evInputs, st));
@@ -1098,15 +1119,18 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
         int nU = 0;
         CK(cudaMemcpyAsync(&nU, &h->ctl->nUCells, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        hostTick(h, "1 wait: reconstruct + U-row marking");
         if (nU <= h->capU) {
             if (nU) {
                 CK(cudaMemcpyAsync(h->hUList, h->uList, sizeof(int) * nU, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
+                hostTick(h, "2 U-row list D2H");
                 for (int i = 0; i < nU; ++i) {
                     const double* src = U + 3 * (size_t)h->hUList[i];
                     double* dst = h->hUPacked + 3 * (size_t)i;
                     dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
                 }
+                hostTick(h, "3 host gather of U rows");
                 CK(cudaMemcpyAsync(h->uPacked, h->hUPacked, sizeof(double) * 3 * nU, cudaMemcpyHostToDevice, st));
                 LAUNCH(h, k_scatter_u, cdiv(nU, 256), 256, h->uList, nU, h->uPacked, h->U);
                 h->h2dBytes += 24LL * nU;
@@ -1150,6 +1174,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
         h->hostAlphaPhiSynced = alpha_phi_out;
     }
     CK(cudaStreamSynchronize(st));
+    hostTick(h, "7 final sync");
     CK(cudaGetLastError());
     return SVOF_OK;
     API_END(h)
@@ -1299,7 +1324,7 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->streamD));
     CK(cudaStreamSynchronize(h->stream));
-    if (!strcmp(name, "overlap")) { h->overlap = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "overlap")) { h->overlap = value; return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
     if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");

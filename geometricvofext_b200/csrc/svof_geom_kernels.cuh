@@ -151,6 +151,7 @@ void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedC
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_plic_group<CP>, threads, smem);
+            if (const char* e = getenv("SVOF_PLIC_CTAS")) perSm = atoi(e) < perSm ? atoi(e) : perSm;  // experiments
             resident = (perSm > 0 ? perSm : 1) * (sms > 0 ? sms : 148);
         }
         (void)grid;
