@@ -677,7 +677,10 @@ void doReconstruct(svof_handle* h)
     h->inputsAfterNear = false;
     h->freshRecon = true;
     // A2: LS normals; A3-A5: plane positions
-    LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
+    if (h->prm.orientation_method == SVOF_ORIENT_ALPHA_GRAD)
+        LAUNCH(h, k_alpha_grad_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->iN);
+    else
+        LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
     GEO(h, plic, s, g128, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
     h->bitsValid = false;  // consumed
 }
@@ -862,8 +865,8 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
 {
     if (!mesh || !params || !out) { g_createError = "svof_create: null argument"; return SVOF_ERR_INVALID_ARG; }
     if (comm && comm->world_size > 1) { g_createError = "decomposed runs: use svof_create on each rank with processor patches (not yet enabled)"; return SVOF_ERR_UNSUPPORTED; }
-    if (params->orientation_method != SVOF_ORIENT_ISO_ALPHA_GRAD) {
-        g_createError = "orientationMethod: only isoAlphaGrad/LS is implemented on the device (alphaGrad, isoRDF: SURVEY.md 8f)";
+    if (params->orientation_method == SVOF_ORIENT_ISO_RDF) {
+        g_createError = "orientationMethod isoRDF is not implemented (needs OpenFOAM's reconstructedDistanceFunction; SURVEY.md 8f)";
         return SVOF_ERR_UNSUPPORTED;
     }
     if (params->n_alpha_bounds > SV_MAX_SWEEPS) { g_createError = "nAlphaBounds exceeds 32"; return SVOF_ERR_INVALID_ARG; }

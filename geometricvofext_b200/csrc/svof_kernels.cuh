@@ -406,6 +406,49 @@ __global__ void __launch_bounds__(128) k_ls_normals(MeshDev m, const int* mixedC
     }
 }
 
+// A2, orientationMethod alphaGrad: reconstruction::calcInterfaceNFromRegAlphaGrad (reconstruction.C:74-82),
+// -fvc::grad(alpha1) with `Gauss linear` (OF, recalled: makeWeights, linear interpolate, GaussGrad::calcGrad).
+// Thread per mixed cell over its ascending-face row: the order GaussGrad accumulates in (internal faces ascending,
+// then the patches).  Only mixed cells are evaluated (nothing on the path reads the others).
+__global__ void __launch_bounds__(128) k_alpha_grad_normals(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
+                                                            const double* __restrict__ alphaB, double* iN)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int celli = mixedCells[i];
+        const d3 Ci = ld3(m.C, celli);
+        const double ai = alpha[celli];
+        d3 g = zero3();
+        for (int k = m.cellOff[celli]; k < m.cellOff[celli + 1]; ++k) {
+            const int2 e = m.cellAsc[k];
+            const int f = e.x & 0x7fffffff;
+            const bool isNei = e.x < 0;  // the cell is the neighbour of this face
+            const d3 Sf = ld3(m.Sf, f);
+            if (e.y >= 0) {
+                const d3 Cf = ld3(m.Cf, f), Co = ld3(m.C, e.y);
+                const double ao = alpha[e.y];
+                const d3 CP = isNei ? Co : Ci, CN = isNei ? Ci : Co;
+                const double aP = isNei ? ao : ai, aN = isNei ? ai : ao;
+                const double SfdOwn = fabs(dot(Sf, Cf - CP));
+                const double SfdNei = fabs(dot(Sf, CN - Cf));
+                const double w = (fabs(SfdOwn + SfdNei) > SV_ROOTVSMALL) ? SfdNei / (SfdOwn + SfdNei) : 0.5;
+                const double af = w * (aP - aN) + aN;
+                const d3 t = Sf * af;
+                if (isNei) g -= t;
+                else g += t;
+            } else {
+                const int bf = -1 - e.y;
+                if (m.bKind[bf] != 0) continue;  // empty (and processor) patches carry no value here
+                g += Sf * alphaB[bf];
+            }
+        }
+        g /= m.V[celli];
+        d3 nn = -g;
+        nn /= (mag(nn) + SV_SMALL);
+        st3(iN, celli, nn);
+    }
+}
+
 // ========================================================================= advect ====
 // volPointInterpolation evaluated lazily at one point (OF, recalled)
 __device__ d3 pointU(const MeshDev& m, int p, const double* __restrict__ U, const double* __restrict__ Ub)

@@ -122,8 +122,8 @@ struct Solver {
         for (const svof_patch& pt : mesh.patches)
             if (pt.kind == SVOF_PATCH_PROCESSOR && pt.size > 0)
                 throw std::invalid_argument("the CPU oracle is single-domain: processor patches are not supported");
-        if (prm.orientation_method != SVOF_ORIENT_ISO_ALPHA_GRAD)
-            throw std::invalid_argument("the CPU oracle restates orientationMethod LS/isoAlphaGrad only");
+        if (prm.orientation_method == SVOF_ORIENT_ISO_RDF)
+            throw std::invalid_argument("orientationMethod isoRDF needs OpenFOAM's reconstructedDistanceFunction (not in the tree): not restated");
         const label nC = mesh.nCells, nF = mesh.nFaces;
         alpha.assign(nC, 0);
         alphaOld.assign(nC, 0);
@@ -237,6 +237,42 @@ struct Solver {
     }
 
     // ---------------------------------------------------------------- A2 ----
+    // reconstruction.C:74-82: interfaceN = -fvc::grad(alpha1) with the case's gradScheme, which every shipped case sets
+    // to `Gauss linear` (e.g. tutorials/test/plicVofAdvectionFoam/system/fvSchemes).  OF, recalled:
+    //   surfaceInterpolation::makeWeights   w = |Sf.(C_N - Cf)| / (|Sf.(Cf - C_P)| + |Sf.(C_N - Cf)|)
+    //   linear interpolate                  a_f = w*(a_P - a_N) + a_N ; boundary faces take the patch value
+    //   GaussGrad::calcGrad                 faces ascending: grad[P] += Sf*a_f, grad[N] -= Sf*a_f; patches; then /V
+    // Only the mixed cells are evaluated: the reference fills every cell, but nothing on the path reads the others.
+    void calcInterfaceNFromRegAlphaGrad()
+    {
+        std::vector<label> fs;
+        for (size_t i = 0; i < mixedCells.size(); ++i) {
+            const label celli = mixedCells[i];
+            fs.assign(mesh.cells.row(celli), mesh.cells.row(celli) + mesh.cells.size(celli));
+            std::sort(fs.begin(), fs.end());
+            vec g;
+            for (label f : fs) {
+                if (f < mesh.nInternalFaces) {
+                    const label P = mesh.owner[f], N = mesh.neighbour[f];
+                    const scalar SfdOwn = std::fabs(mesh.Sf[f] & (mesh.Cf[f] - mesh.C[P]));
+                    const scalar SfdNei = std::fabs(mesh.Sf[f] & (mesh.C[N] - mesh.Cf[f]));
+                    const scalar w = (std::fabs(SfdOwn + SfdNei) > ROOTVSMALL) ? SfdNei / (SfdOwn + SfdNei) : 0.5;
+                    const scalar af = w * (alpha[P] - alpha[N]) + alpha[N];
+                    const vec Sfssf = mesh.Sf[f] * af;
+                    if (celli == P) g += Sfssf;
+                    else g -= Sfssf;
+                } else {
+                    const label bf = f - mesh.nInternalFaces;
+                    if (!mesh.isPatchFace[bf]) continue;  // empty patches have no faces in fvMesh
+                    g += mesh.Sf[f] * alphaB[bf];
+                }
+            }
+            g /= mesh.V[celli];
+            interfaceN[celli] = -g;
+            interfaceN[celli] /= (mag(interfaceN[celli]) + SMALL);
+        }
+    }
+
     void calcInterfaceNFromIsoAlphaGrad()  // reconstruction.C:85-141
     {
         int nDims = 0;
@@ -286,7 +322,8 @@ struct Solver {
         initialize();
         Un0.assign(mixedCells.size(), 0.0);
         if (mixedCells.empty()) return;
-        calcInterfaceNFromIsoAlphaGrad();
+        if (prm.orientation_method == SVOF_ORIENT_ALPHA_GRAD) calcInterfaceNFromRegAlphaGrad();  // reconstruction.C:694-713
+        else calcInterfaceNFromIsoAlphaGrad();
         for (size_t i = 0; i < mixedCells.size(); ++i) {
             const label c = mixedCells[i];
             cellStatus[i] = cutCell_->findSignedDistance(c, alpha[c], interfaceN[c], prm.split_warped_face != 0,
