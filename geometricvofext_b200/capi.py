@@ -90,6 +90,8 @@ SYMBOLS = [
                                             c_double_p, c_double_p, c_double_p]),
     ("svof_face_fluxes", C.c_int, [_H, C.c_int32, c_int32_p, c_double_p, c_double_p, c_double_p, C.c_double,
                                    c_double_p, c_double_p]),
+    ("svof_plic_surface", C.c_int, [_H, C.c_int64, C.c_int64, c_double_p, c_int32_p, c_int32_p, C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_int64)]),
 ]
 
 PRODUCT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsvof_b200.so")

@@ -1528,4 +1528,66 @@ int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const doub
     API_END(h)
 }
 
+int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, double* points, int32_t* face_offsets, int32_t* cells,
+                      int64_t* n_points, int64_t* n_faces)
+{
+    if (!h || !n_points || !n_faces) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    PRIM_PROLOGUE
+    (void)down;
+    fetchCtl(h);
+    const int nM = h->hctl->nMixed;
+    int maxEp = 0;
+    switch (h->variant) {
+        case 0: maxEp = GeoLaunch<CapsHex>::maxPolyPoints(); break;
+        case 1: maxEp = GeoLaunch<CapsSmall>::maxPolyPoints(); break;
+        case 2: maxEp = GeoLaunch<CapsPoly>::maxPolyPoints(); break;
+        default: maxEp = GeoLaunch<CapsSplit>::maxPolyPoints(); break;
+    }
+    double* dPts = (double*)up(nullptr, sizeof(double) * 3 * (size_t)std::max(nM, 1) * maxEp);
+    int* dCnt = (int*)up(nullptr, sizeof(int) * (size_t)std::max(nM, 1));
+    std::vector<int> cnt(nM), mixed(nM);
+    std::vector<double> pts;
+    if (nM) {
+        GEO(h, plicPolygons, h->stream, sparseGrid(h, 128), h->md, h->mixedCells, h->ctl, h->iN, h->iD, dPts, dCnt);
+        CK(cudaMemcpyAsync(cnt.data(), dCnt, sizeof(int) * nM, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(mixed.data(), h->mixedCells, sizeof(int) * nM, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    int64_t nP = 0, nFc = 0;
+    for (int i = 0; i < nM; ++i)
+        if (cnt[i] > 0) { nP += cnt[i]; nFc++; }
+    *n_points = nP;
+    *n_faces = nFc;
+    int rc = SVOF_OK;
+    if (points) {
+        if (cap_points < nP || cap_faces < nFc || !face_offsets || !cells) {
+            rc = SVOF_ERR_CAPACITY;
+        } else if (nM) {
+            pts.resize((size_t)3 * nM * maxEp);
+            CK(cudaMemcpyAsync(pts.data(), dPts, sizeof(double) * pts.size(), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            int64_t p = 0, f = 0;
+            face_offsets[0] = 0;
+            for (int i = 0; i < nM; ++i) {
+                if (cnt[i] <= 0) continue;
+                std::memcpy(points + 3 * p, pts.data() + (size_t)3 * i * maxEp, sizeof(double) * 3 * cnt[i]);
+                p += cnt[i];
+                cells[f] = mixed[i];
+                face_offsets[++f] = (int32_t)p;
+            }
+        } else {
+            face_offsets[0] = 0;
+        }
+    }
+    fetchCtl(h);
+    hErr = h->hctl->err;
+    for (void* q : tmp) cudaFree(q);
+    CK(cudaGetLastError());
+    if (rc != SVOF_OK) return fail(h, rc, "svof_plic_surface: output arrays too small");
+    if (hErr) return fail(h, SVOF_ERR_CAPACITY, "svof_plic_surface: a cell exceeded a compiled capacity");
+    return SVOF_OK;
+    API_END(h)
+}
+
 }  // extern "C"

@@ -336,6 +336,9 @@ struct SubCellOut {
     int status;
     double VOF, subVol;
     d3 iC, iS;  // interface centre / area vector
+    // optional: the interface edge points of a cut cell (cutCell::interfaceEdges_, flattened), for surface extraction
+    d3* epOut = nullptr;
+    int nEp = 0;
 };
 
 // face::reverseFace keeps vertex 0 and reverses the rest (cutCell.C:189,211,232)
@@ -465,6 +468,10 @@ __device__ __noinline__ void subCell(const MeshDev& m, int cell, const d3& n, do
                 out.VOF = 1.0;
             }
             return;
+        }
+        if (out.epOut) {
+            for (int q = 0; q < nEp; ++q) out.epOut[q] = ep[q];
+            out.nEp = nEp;
         }
         cfc[nCut] = iC;
         cfa[nCut] = iS;

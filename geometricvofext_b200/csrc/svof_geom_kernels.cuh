@@ -27,6 +27,10 @@ struct GeoLaunch {
                              int split, int* status, double* dists, double* ic, double* ia, int* errOut);
     static void faceFluxes(cudaStream_t st, MeshDev m, int n, const int* faces, const double* normals, const double* dists,
                            const double* Un0, double dt, const double* phi, double* out, int* errOut);
+    // reconstruction::interface(): up to maxPolyPoints() points per mixed cell into polyPts[i*maxPolyPoints()..], count in polyCount[i]
+    static int maxPolyPoints() { return CP::MAXEP; }
+    static void plicPolygons(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
+                             double* polyPts, int* polyCount);
 };
 
 #ifdef SV_VARIANT
@@ -98,6 +102,54 @@ __global__ void k_cut_cells(MeshDev m, int n, const int* cells, const double* no
     st3(ic, i, sc.iC);
     st3(ia, i, sc.iS);
     if (err) atomicOr(errOut, err);
+}
+// reconstruction::interface() (reconstruction.C:787-835) + cutCell::interfacePoints (cutCell.C:545-608): thread per mixed
+// cell; the cut is re-evaluated WITHOUT splitWarpedFace (as the reference does), the interface edge points are sorted
+// by angle about the interface centre in the plane of the interface (stable, ascending) and points within 1e-8 rad of
+// their predecessor are dropped.
+template <class CP>
+__global__ void __launch_bounds__(128) k_plic_polygons(MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
+                                                       double* polyPts, int* polyCount)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = mixedCells[i];
+        d3 ep[CP::MAXEP];
+        SubCellOut sc;
+        sc.epOut = ep;
+        int err = 0, cnt = 0;
+        subCell<CP>(m, c, ld3(iN, c), iD[c], false, sc, err);
+        if (sc.status == 0 && sc.nEp > 0) {
+            const d3 zhat = sc.iS / mag(sc.iS);
+            d3 xhat = ep[0] - sc.iC;
+            xhat = xhat - dot(xhat, zhat) * zhat;
+            xhat /= mag(xhat);
+            d3 yhat = cross(zhat, xhat);
+            yhat /= mag(yhat);
+            double ang[CP::MAXEP];
+            short ord[CP::MAXEP];
+            for (int q = 0; q < sc.nEp; ++q) {
+                const d3 d = ep[q] - sc.iC;
+                const double a = atan2(dot(d, yhat), dot(d, xhat));
+                int j = q - 1;  // stable insertion: equal angles keep their original order
+                while (j >= 0 && ang[j] > a) {
+                    ang[j + 1] = ang[j];
+                    ord[j + 1] = ord[j];
+                    --j;
+                }
+                ang[j + 1] = a;
+                ord[j + 1] = (short)q;
+            }
+            double* out = polyPts + 3 * (size_t)i * CP::MAXEP;
+            for (int pi = 0; pi < sc.nEp; ++pi) {
+                if (pi > 0 && !(fabs(ang[pi] - ang[pi - 1]) > 1e-8)) continue;
+                st3(out, cnt, ep[ord[pi]]);
+                cnt++;
+            }
+        }
+        polyCount[i] = cnt;
+        if (err) atomicOr(&ctl->err, err);
+    }
 }
 template <class CP>
 __global__ void k_find_distance(MeshDev m, int n, const int* cells, const double* alphas, const double* normals, int split,
@@ -177,6 +229,12 @@ void GeoLaunch<CP>::cutCells(cudaStream_t st, MeshDev m, int n, const int* cells
                              int* status, double* vof, double* subVol, double* ic, double* ia, int* errOut)
 {
     k_cut_cells<CP><<<(n + 127) / 128, 128, 0, st>>>(m, n, cells, normals, dists, status, vof, subVol, ic, ia, errOut);
+}
+template <class CP>
+void GeoLaunch<CP>::plicPolygons(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
+                                 double* polyPts, int* polyCount)
+{
+    k_plic_polygons<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, iN, iD, polyPts, polyCount);
 }
 template <class CP>
 void GeoLaunch<CP>::findDistance(cudaStream_t st, MeshDev m, int n, const int* cells, const double* alphas, const double* normals,

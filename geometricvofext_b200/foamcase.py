@@ -260,6 +260,30 @@ class FoamCase:
         return path
 
 
+def plic_surface_functions(control_dict):
+    """(function object name, surface name) of every `type surfaces` function object that samples a `plicSurface`
+    (tutorials/test/plicVofAdvectionFoam/system/controlDict:53-72)."""
+    out = []
+    fns = control_dict.get("functions") or {}
+    for fname, fd in fns.items():
+        if not isinstance(fd, dict) or str(fd.get("type")) != "surfaces":
+            continue
+        for item in fd.get("surfaces", []) or []:
+            if isinstance(item, tuple) and isinstance(item[1], dict) and str(item[1].get("type")) == "plicSurface":
+                out.append((fname, item[0]))
+    return out
+
+
+def _write_surfaces(case, s, time_name, surfaces):
+    if not surfaces:
+        return
+    pts, off, cells = s.interface()
+    a = s.alpha()
+    for fname, sname in surfaces:
+        foamfile.write_vtk_polydata(os.path.join(case.dir, "postProcessing", fname, time_name, sname + ".vtk"), pts, off,
+                                    {"cellIds": cells, case.alpha_name: a[cells]})
+
+
 def _time_name(t, precision=6):
     """Time::timeName with timeFormat general, timePrecision 6."""
     s = "%.*g" % (precision, t)
@@ -291,7 +315,9 @@ def run_plic_vof_advection(case, lib=None, end_time=None, renumber=False, alpha0
     t_end = float(end_time if end_time is not None else cd.get("endTime"))
     w_int = float(cd.get("writeInterval", t_end))
     by_time = str(cd.get("writeControl", "adjustableRunTime")) in ("adjustableRunTime", "runTime")
-    s.reconstruct()                       # plicVof.H:8: interface at the initial time
+    s.reconstruct()                       # plicVof.H:8-9: interface at the initial time, function objects executed
+    surfaces = plic_surface_functions(cd) if write else []
+    _write_surfaces(case, s, _time_name(drv.t), surfaces)
     written, vols = [], []
     next_write = drv.t + w_int if by_time else None
     while drv.t < t_end - 1e-12:
@@ -303,6 +329,7 @@ def run_plic_vof_advection(case, lib=None, end_time=None, renumber=False, alpha0
             name = _time_name(drv.t)
             if write:
                 case.write_alpha(mesh, name, s.alpha())
+                _write_surfaces(case, s, name, surfaces)   # the polygons of the step's reconstruct()
             written.append(name)
             log("Time = %s  steps %d  Phase-1 volume = %.15g" % (name, drv.steps, vols[-1]))
             if by_time:

@@ -704,3 +704,27 @@ def apply_alpha_boundary(mesh, field):
         else:
             raise FoamFormatError("patch %s: alpha boundary type '%s' is not supported (zeroGradient, fixedValue, inletOutlet)" % (p.name, t))
     return mesh
+
+
+def write_vtk_polydata(path, points, face_offsets, cell_data=None, title="PLIC interface"):
+    """Legacy-VTK polydata (ascii): the polygons of SolveVofEqu.interface() with per-polygon data
+    (the reference's sampler writes the same surface as .vtp, controlDict `surfaceFormat vtp`)."""
+    points = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    off = np.asarray(face_offsets, dtype=np.int64)
+    nF = off.shape[0] - 1
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "w") as f:
+        f.write("# vtk DataFile Version 3.0\n%s\nASCII\nDATASET POLYDATA\nPOINTS %d double\n" % (title, points.shape[0]))
+        for p in points:
+            f.write("%.17g %.17g %.17g\n" % (p[0], p[1], p[2]))
+        f.write("POLYGONS %d %d\n" % (nF, nF + int(off[-1]) if nF else 0))
+        for i in range(nF):
+            f.write("%d %s\n" % (off[i + 1] - off[i], " ".join(str(v) for v in range(off[i], off[i + 1]))))
+        if cell_data and nF:
+            f.write("CELL_DATA %d\n" % nF)
+            for name, arr in cell_data.items():
+                arr = np.asarray(arr)
+                kind = "int" if arr.dtype.kind in "iu" else "double"
+                f.write("SCALARS %s %s 1\nLOOKUP_TABLE default\n" % (name, kind))
+                f.write("\n".join(("%d" % v) if kind == "int" else ("%.17g" % v) for v in arr) + "\n")
+    return path

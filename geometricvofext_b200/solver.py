@@ -162,6 +162,17 @@ class SolveVofEqu:
     def faceFlatness(self):
         return self.field(capi.F_FACE_FLATNESS)
 
+    def interface(self):
+        """reconstruction::interface() (reconstruction.C:787-835): the PLIC polygons of the last reconstruct() as
+        (points [nP,3], face_offsets [nFaces+1], meshCells [nFaces]) -- what the plicSurface sampler reads."""
+        nP, nFc = C.c_int64(), C.c_int64()
+        self._chk(self.lib.svof_plic_surface(self._h, 0, 0, None, None, None, C.byref(nP), C.byref(nFc)))
+        pts = np.empty((nP.value, 3))
+        off, cells = np.zeros(nFc.value + 1, np.int32), np.empty(nFc.value, np.int32)
+        self._chk(self.lib.svof_plic_surface(self._h, nP.value, nFc.value, capi.dptr(pts), capi.iptr(off), capi.iptr(cells),
+                                             C.byref(nP), C.byref(nFc)))
+        return pts, off, cells
+
     # -- generic access ---------------------------------------------------------------
     _SHAPES = {
         capi.F_ALPHA: ("nC", 1, np.float64), capi.F_ALPHA_PHI: ("nF", 1, np.float64),

@@ -306,6 +306,16 @@ int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const doub
                      const double* dists, const double* Un0, double dt, const double* phi,
                      double* dVf);
 
+/* reconstruction::interface() (reconstruction.C:787-835): the PLIC polygons of the cut cells of the last
+ * svof_reconstruct -- per mixed cell with cut status 0, cutCell::interfacePoints (cutCell.C:545-608; evaluated
+ * WITHOUT splitWarpedFace, as the reference does).  Face i is points[face_offsets[i] .. face_offsets[i+1]) and belongs
+ * to mesh cell cells[i] (ascending).  *n_points / *n_faces always return the sizes; the arrays are filled when
+ * points != NULL and the capacities suffice (else SVOF_ERR_CAPACITY).  This is what the plicSurface sampler
+ * (src/SimPLIC/sampling) reads.  The angle sort uses atan2, so point coordinates agree between implementations to
+ * round-off (1e-13), not bitwise, where two coincident points compete. */
+int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, double* points, int32_t* face_offsets,
+                      int32_t* cells, int64_t* n_points, int64_t* n_faces);
+
 #ifdef __cplusplus
 }
 #endif

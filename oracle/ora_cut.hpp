@@ -647,6 +647,34 @@ class cutCell {
     scalar subCellVolume() const { return subCellVolume_; }
     const point& subCellCentre() const { return subCellCentre_; }
     const point& interfaceCentre() const { return interfaceCentre_; }
+
+    // cutCell::interfacePoints (cutCell.C:545-608): the interface polygon of the last calcSubCell, its points sorted by
+    // angle about the interface centre in the plane of the interface; points closer than 1e-8 rad are merged.
+    // sortedOrder is a stable ascending sort (OF, recalled).
+    void interfacePolygon(std::vector<point>& out) const
+    {
+        out.clear();
+        if (cellStatus_ != 0 || interfaceEdges_.empty()) return;
+        const vec zhat = interfaceArea_ / mag(interfaceArea_);
+        vec xhat = interfaceEdges_[0][0] - interfaceCentre_;
+        xhat = (xhat - (xhat & zhat) * zhat);
+        xhat /= mag(xhat);      // Vector::normalise(): divides when mag >= ROOTVSMALL (OF, recalled)
+        vec yhat = zhat ^ xhat;
+        yhat /= mag(yhat);
+        std::vector<point> pts;
+        std::vector<scalar> ang;
+        for (const std::vector<point>& edgePoints : interfaceEdges_)
+            for (const point& p : edgePoints) {
+                pts.push_back(p);
+                ang.push_back(std::atan2((p - interfaceCentre_) & yhat, (p - interfaceCentre_) & xhat));
+            }
+        std::vector<label> order(pts.size());
+        for (size_t i = 0; i < order.size(); ++i) order[i] = label(i);
+        std::stable_sort(order.begin(), order.end(), [&](label a, label b) { return ang[a] < ang[b]; });
+        out.push_back(pts[order[0]]);
+        for (size_t pi = 1; pi < order.size(); ++pi)
+            if (std::fabs(ang[order[pi]] - ang[order[pi - 1]]) > 1e-8) out.push_back(pts[order[pi]]);
+    }
     const vec& interfaceArea() const { return interfaceArea_; }
     label cellStatus() const { return cellStatus_; }
     cutFace& faceCutter() { return cutFace_; }

@@ -348,6 +348,33 @@ int svof_cut_cells(svof_handle* h, int32_t n, const int32_t* cells, const double
     return SVOF_OK;
 }
 
+int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, double* points, int32_t* face_offsets, int32_t* cells,
+                      int64_t* n_points, int64_t* n_faces)
+{
+    if (!h || !n_points || !n_faces) return SVOF_ERR_INVALID_ARG;
+    Solver& s = h->s;
+    cutCell cc(s.mesh);
+    std::vector<point> poly, pts;
+    std::vector<int32_t> off(1, 0), cl;
+    for (size_t i = 0; i < s.mixedCells.size(); ++i) {
+        const label c = s.mixedCells[i];
+        if (cc.calcSubCell(c, s.interfaceN[c], s.interfaceD[c], false) != 0) continue;  // reconstruction.C:800-806
+        cc.interfacePolygon(poly);
+        if (poly.empty()) continue;
+        pts.insert(pts.end(), poly.begin(), poly.end());
+        off.push_back(int32_t(pts.size()));
+        cl.push_back(c);
+    }
+    *n_points = int64_t(pts.size());
+    *n_faces = int64_t(cl.size());
+    if (!points) return SVOF_OK;
+    if (cap_points < *n_points || cap_faces < *n_faces || !face_offsets || !cells) return SVOF_ERR_CAPACITY;
+    for (size_t i = 0; i < pts.size(); ++i) { points[3 * i] = pts[i].x; points[3 * i + 1] = pts[i].y; points[3 * i + 2] = pts[i].z; }
+    std::copy(off.begin(), off.end(), face_offsets);
+    std::copy(cl.begin(), cl.end(), cells);
+    return SVOF_OK;
+}
+
 int svof_find_signed_distance(svof_handle* h, int32_t n, const int32_t* cells, const double* alphas, const double* normals,
                               int32_t* status, double* dists, double* ic, double* ia)
 {

@@ -42,7 +42,12 @@ application plicVofAdvectionFoam;
 startTime 0.0;  endTime %(end)g;  deltaT 0.001;
 writeControl adjustableRunTime;  writeInterval %(wi)g;  writeFormat binary;
 adjustTimeStep yes;  maxCo 0.5;  maxAlphaCo 0.5;  maxDeltaT 0.2;
-functions { probe { type coded; codeWrite #{ Info<< "x" << endl; #}; } }
+functions
+{
+    probe { type coded; codeWrite #{ Info<< "x" << endl; #}; }
+    plicInterface { type surfaces; libs (SimPLIC sampling); surfaceFormat vtp; fields ( alpha.water cellIds );
+                    surfaces ( plicSurf { type plicSurface; interpolate false; } ); }
+}
 """
 
 BLOCK_MESH_DICT = """
@@ -188,6 +193,11 @@ def test_case_run_matches_direct_driver_and_writes_openfoam_fields(tmp_path):
         while drv.t < te - 1e-12:
             drv.step(end_time=te)
     assert drv.steps == out["steps"]
+    # the plicSurface sampler of the controlDict: polygons written at t = 0 and at every write time
+    assert foamcase.plic_surface_functions(case.control_dict) == [("plicInterface", "plicSurf")]
+    for t in ("0", "0.002", "0.004"):
+        vtk = os.path.join(case.dir, "postProcessing", "plicInterface", t, "plicSurf.vtk")
+        assert os.path.isfile(vtk) and "POLYGONS" in open(vtk).read()
     f = foamfile.read_field(os.path.join(case.dir, "0.004", "alpha.water"))
     assert f.header["format"] == "binary" and np.array_equal(f.internal, s.alpha()) and np.array_equal(out["alpha"], s.alpha())
     assert abs(out["volume"] - (a0 / 16 ** 3).sum()) < 1e-15
