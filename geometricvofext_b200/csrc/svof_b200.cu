@@ -745,7 +745,6 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         if (h->maxCF <= 8) BOUND_SWEEP(8);
         else if (h->maxCF <= 16) BOUND_SWEEP(16);
         else BOUND_SWEEP(64);
-        LAUNCH(h, k_bound_flip, 1, 1, h->ctl, sidx);
     }
     // join: the finalize kernel ORs into the bitmap words the streaming kernel wrote
     if (h->overlap == 1) CK(cudaStreamWaitEvent(sS, h->evDense, 0));

@@ -1059,9 +1059,14 @@ __device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const
 template <int SV_MAXBF>
 __device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch& b, int tag, double dt, double rDeltaT)
 {
+    // Small records (hex, prism, tet: MAXBF <= 16) are walked with FULLY UNROLLED, predicated face loops so that the
+    // record and the scratch arrays live in registers: k_bound_run is a chain of single-thread evaluations, and with
+    // dynamically indexed (local-memory) arrays one cell cost 9.8k cycles (measured), most of it exposed load latency.
+    constexpr int UNR = SV_MAXBF <= 16 ? SV_MAXBF : 1;
     bool hadRoom = false;
     const double Vi = cb.V;
     const int nf = cb.nf;
+    const int qEnd = SV_MAXBF <= 16 ? SV_MAXBF : nf;
     double room[SV_MAXBF];
     int recPos[SV_MAXBF];
     unsigned long long modMask = 0, recMask = 0;
@@ -1081,7 +1086,9 @@ __device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
         // facesToPassFluidThrough / dVfmax / dVftot: fixed before any correction of this iteration
         double dVftot = 0;
         nFacesToPassFluidThrough = 0;
-        for (int q = 0; q < nf; ++q) {
+#pragma unroll UNR
+        for (int q = 0; q < qEnd; ++q) {
+            if (q >= nf) continue;
             double r = -1.0;
             if ((cb.downMask >> q) & 1ull) {
                 const double dVff = cb.fDvf[q] + cb.fCorr[q];
@@ -1093,8 +1100,9 @@ __device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
             }
             room[q] = r;
         }
-        for (int q = 0; q < nf; ++q) {
-            if (room[q] < 0.0) continue;
+#pragma unroll UNR
+        for (int q = 0; q < qEnd; ++q) {
+            if (q >= nf || room[q] < 0.0) continue;
             double through = fabs(fluidToPassOn) * fabs(cb.fPhi[q] * dt) / dVftot;
             nFacesToPassFluidThrough += int(pos0(room[q] - through));
             through = dmin(through, room[q]);
@@ -1110,7 +1118,9 @@ __device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
         }
         firstLoop = false;
         double nfl = 0.0, nc = 0.0;  // netFlux(dVf_), netFlux(dVfCorrectionValues)  (advection.C:259-288)
-        for (int q = 0; q < nf; ++q) {
+#pragma unroll UNR
+        for (int q = 0; q < qEnd; ++q) {
+            if (q >= nf) continue;
             if ((cb.ownMask >> q) & 1ull) {
                 nfl += cb.fDvf[q];
                 nc += cb.fCorr[q];
@@ -1123,8 +1133,9 @@ __device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
         alphaOvershoot = pos0(alpha1New - 1.0) * (alpha1New - 1.0) + neg0(alpha1New) * alpha1New;
         fluidToPassOn = alphaOvershoot * Vi;
     }
-    for (int q = 0; q < nf; ++q) {
-        if (!((modMask >> q) & 1ull)) continue;
+#pragma unroll UNR
+    for (int q = 0; q < qEnd; ++q) {
+        if (q >= nf || !((modMask >> q) & 1ull)) continue;
         const int f = cb.fId[q];
         b.corr[f] = cb.fCorr[q];
         b.tagV[f] = tag;
@@ -1220,10 +1231,19 @@ __global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, cons
 #endif
             CellBound<SV_MAXBF> cb = recs[i];
             // corrections its predecessors wrote (they are complete: this cell was released by the last of them)
-            for (unsigned long long pm = cb.predMask; pm; pm &= pm - 1) {
-                const int q = __ffsll((long long)pm) - 1;
-                const int f = cb.fId[q];
-                cb.fCorr[q] = (__ldcg(b.tagV + f) == tag) ? __ldcg(b.corr + f) : 0.0;
+            if (SV_MAXBF <= 16) {
+#pragma unroll
+                for (int q = 0; q < (SV_MAXBF <= 16 ? SV_MAXBF : 1); ++q) {
+                    if (!((cb.predMask >> q) & 1ull)) continue;
+                    const int f = cb.fId[q];
+                    cb.fCorr[q] = (__ldcg(b.tagV + f) == tag) ? __ldcg(b.corr + f) : 0.0;
+                }
+            } else {
+                for (unsigned long long pm = cb.predMask; pm; pm &= pm - 1) {
+                    const int q = __ffsll((long long)pm) - 1;
+                    const int f = cb.fId[q];
+                    cb.fCorr[q] = (__ldcg(b.tagV + f) == tag) ? __ldcg(b.corr + f) : 0.0;
+                }
             }
 #ifdef SV_BOUND_STATS
             const long long t1 = clock64();
@@ -1240,11 +1260,22 @@ __global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, cons
 #endif
             if (cb.succMask) {
                 __threadfence();  // corrections visible before any successor is released
-                for (unsigned long long sm = cb.succMask; sm; sm &= sm - 1) {
-                    const int q = __ffsll((long long)sm) - 1;
-                    const int y = cb.other[q];
-                    if (atomicSub(&depLeft[y], 1) == 1) {  // last predecessor: run y next on this thread
-                        if (sp < SV_BSTACK) stack[sp++] = y; else atomicOr(&ctl->err, SVERR_LIST);
+                if (SV_MAXBF <= 16) {
+#pragma unroll
+                    for (int q = 0; q < (SV_MAXBF <= 16 ? SV_MAXBF : 1); ++q) {
+                        if (!((cb.succMask >> q) & 1ull)) continue;
+                        const int y = cb.other[q];
+                        if (atomicSub(&depLeft[y], 1) == 1) {  // last predecessor: run y next on this thread
+                            if (sp < SV_BSTACK) stack[sp++] = y; else atomicOr(&ctl->err, SVERR_LIST);
+                        }
+                    }
+                } else {
+                    for (unsigned long long sm = cb.succMask; sm; sm &= sm - 1) {
+                        const int q = __ffsll((long long)sm) - 1;
+                        const int y = cb.other[q];
+                        if (atomicSub(&depLeft[y], 1) == 1) {
+                            if (sp < SV_BSTACK) stack[sp++] = y; else atomicOr(&ctl->err, SVERR_LIST);
+                        }
                     }
                 }
             }
@@ -1268,6 +1299,9 @@ __global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s,
                                                      unsigned char* oobState)
 {
     const int n = ctl->nAff[s];
+    // the list sweep s consumed (deps and run are complete) becomes the empty output list of sweep s+1;
+    // nobody in this kernel reads its counter
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->nOob[s & 1] = 0;
     int delta = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = affList[i];
@@ -1349,8 +1383,6 @@ __global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s,
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->nearOob[s + 1], ctl->nearOob[s]);
 }
 
-// between sweeps: the list sweep s consumed becomes the (empty) output list of sweep s+1
-__global__ void k_bound_flip(Ctl* ctl, int s) { ctl->nOob[s & 1] = 0; }
 
 // A12 for the near2 cells + alphaPhi on the faces they own + their bits of the next mixed bitmap
 __global__ void __launch_bounds__(128) k_near_finalize(MeshDev m, const int* near2List, Ctl* ctl, double* alpha, const double* dVf,
