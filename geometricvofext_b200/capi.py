@@ -67,6 +67,7 @@ SYMBOLS = [
     ("svof_set_U", C.c_int, [_H, c_double_p, c_double_p]),
     ("svof_reconstruct", C.c_int, [_H]),
     ("svof_advect", C.c_int, [_H, C.c_double, c_double_p, c_double_p]),
+    ("svof_step_device", C.c_int, [_H, C.c_double]),
     ("svof_step_host", C.c_int, [_H, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     ("svof_get_field", C.c_int64, [_H, C.c_int, C.c_void_p, C.c_int64]),
     ("svof_get_info", C.c_int, [_H, C.c_int, c_double_p]),

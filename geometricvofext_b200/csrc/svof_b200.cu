@@ -102,6 +102,10 @@ struct svof_handle {
     bool haveAlpha = false, havePhi = false, haveU = false, bitsValid = false, advected = false;
     double lastDt = 0.0;
     long long launches = 0;
+    // svof_step_device: one captured CUDA graph per (alpha buffer parity, patch-value buffer parity, mixed bitmap valid), valid for one dt
+    struct StepGraph { cudaGraphExec_t exec = nullptr; double dt = 0; long long nLaunches = 0; };
+    StepGraph graphs[8];
+    bool capturing = false;
     double reconTime = 0, advTime = 0, lastReconMs = 0, lastAdvMs = 0;
     double flatMin = 1, flatMax = 1, flatAvg = 1;
     std::vector<EventPair> events;
@@ -630,6 +634,7 @@ void endTimed(svof_handle* h, EventPair& e)
 __global__ void k_ctl_reset_advect(Ctl* ctl)
 {
     ctl->nWork = 0;
+    ctl->epoch++;
     ctl->nOob[0] = ctl->nOob[1] = 0;
     for (int s = 0; s <= SV_MAX_SWEEPS; ++s) ctl->nPend[s] = ctl->nAff[s] = ctl->nearOob[s] = 0;
     ctl->minNear0 = ctl->minNearF = ~0ull;
@@ -673,7 +678,7 @@ void doReconstruct(svof_handle* h)
     CK(cudaMemsetAsync(h->near2, 0, sizeof(unsigned int) * h->nWords, s));
     LAUNCH(h, k_ctl_reset_recon, 1, 1, h->ctl);
     LAUNCH(h, k_mark_near, g256, 256, d, h->mixedCells, h->ctl, h->near1, h->near2, h->near2List, h->capNear);
-    CK(cudaEventRecord(h->evNear, s));  // the streaming kernel of the coming advect() may start from here
+    if (!h->capturing) CK(cudaEventRecord(h->evNear, s));  // the streaming kernel of the coming advect() may start from here
     h->inputsAfterNear = false;
     h->freshRecon = true;
     // A2: LS normals; A3-A5: plane positions
@@ -706,7 +711,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         }
     }
     if (h->prof) profBegin(h, "k_dense_update", sD);
-    EventPair& ed = beginTimedOn(h, 2, sD);
+    EventPair* ed = h->capturing ? nullptr : &beginTimedOn(h, 2, sD);
     if (h->useStaged)
         k_dense_update_staged<<<cdiv(h->nC, 256), 256, h->dstageSmem, sD>>>(d, h->dstage, aOld, aNew, h->phi, h->alphaBBuf[h->cb],
                                                                              h->alphaPhi, h->near2, h->mixedBits, dt, rDt, dSp, dSu,
@@ -715,7 +720,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         k_dense_update<<<cdiv(h->nC, 256), 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
                                                           dt, rDt, dSp, dSu, h->sp, h->ctl);
     h->launches++;
-    endTimedOn(h, ed, sD);
+    if (ed) endTimedOn(h, *ed, sD);
     if (h->prof) profEnd(h, sD);
     if (h->overlap) CK(cudaEventRecord(h->evDense, sD));
 
@@ -732,14 +737,13 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     // A11: conservative bounding sweeps, each proportional to the number of out-of-bounds cells
     const int gB = std::max(1, h->sms / 2);
     for (int sidx = 0; sidx < h->sp.nAlphaBounds; ++sidx) {
-        const int tag = h->advectCount * (SV_MAX_SWEEPS + 1) + sidx + 1;
 #define BOUND_SWEEP(MB)                                                                                                       \
     do {                                                                                                                     \
-        LAUNCH(h, k_bound_deps<MB>, gB, 128, d, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, \
+        LAUNCH(h, k_bound_deps<MB>, gB, 128, d, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, \
                dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList);           \
-        LAUNCH(h, k_bound_run<MB>, 2 * gB, 64, h->ctl, sidx, tag, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx, \
+        LAUNCH(h, k_bound_run<MB>, 2 * gB, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx, \
                (const CellBound<MB>*)h->boundRecs, h->capRec, dt, rDt);                                                      \
-        LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, tag, h->affList, h->near1, aNew, h->dVf, h->bs,               \
+        LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs,               \
                h->oobList[(sidx + 1) & 1], h->oobState);                                                                     \
     } while (0)
         if (h->maxCF <= 8) BOUND_SWEEP(8);
@@ -761,6 +765,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         CK(cudaMemsetAsync(h->bs.tagV, 0, sizeof(int) * h->nF, sS));
         CK(cudaMemsetAsync(h->bs.tagR, 0, sizeof(int) * h->nF, sS));
         CK(cudaMemsetAsync(h->bs.affStamp, 0, sizeof(int) * h->nC, sS));
+        CK(cudaMemsetAsync(&h->ctl->epoch, 0, sizeof(int), sS));
         h->advectCount = 0;
     }
 }
@@ -929,6 +934,7 @@ int svof_destroy(svof_handle* h)
         if (e.b) cudaEventDestroy(e.b);
     }
     for (int i = 0; i < 8; ++i) if (h->marks[i]) cudaEventDestroy(h->marks[i]);
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->evNear) cudaEventDestroy(h->evNear);
     if (h->evDense) cudaEventDestroy(h->evDense);
     if (h->evInputs) cudaEventDestroy(h->evInputs);
@@ -1036,6 +1042,76 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
     h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;  // the caller's buffers no longer mirror the device
     CK(cudaGetLastError());
     if (Sp || Su) CK(cudaStreamSynchronize(h->stream));  // caller's buffers may be pageable
+    return SVOF_OK;
+    API_END(h)
+}
+
+// reconstruct() + advect(dt) with device-resident inputs as ONE CUDA-graph launch.  The step is ~27 dependent launches,
+// most of them a few microseconds long; replaying a captured graph removes the per-launch gaps.  Every launch size is
+// host-known and every count lives on the device, so the captured graph is valid for any state of the fields; it is
+// keyed by the two buffer parities and re-captured when dt changes.
+int svof_step_device(svof_handle* h, double dt)
+{
+    if (!h || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
+    if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_step_device: alpha/phi/U not set");
+    if (h->prof || h->overlap || h->advectCount >= (1 << 25) - 2) {   // instrumented / two-stream schedules: plain launches
+        const int rc = svof_reconstruct(h);
+        return rc ? rc : svof_advect(h, dt, nullptr, nullptr);
+    }
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    svof_handle::StepGraph& g = h->graphs[h->cur * 4 + h->cb * 2 + (h->bitsValid ? 1 : 0)];
+    if (!g.exec || g.dt != dt) {
+        if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        // run the first step of this kind with plain launches (warms every lazily initialised launcher), then capture
+        const int cur0 = h->cur, cb0 = h->cb;
+        const bool bits0 = h->bitsValid;
+        const int rc = svof_reconstruct(h);
+        if (rc) return rc;
+        const int rc2 = svof_advect(h, dt, nullptr, nullptr);
+        if (rc2) return rc2;
+        // capture the step that starts from (cur0, cb0) without executing it: restore the host-side state it starts from
+        const int curN = h->cur, cbN = h->cb;
+        const long long l0 = h->launches;
+        const int ac0 = h->advectCount;
+        h->cur = cur0; h->cb = cb0; h->bitsValid = bits0;
+        h->capturing = true;
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        if (ce == cudaSuccess) {
+            try {
+                doReconstruct(h);
+                doAdvect(h, dt, nullptr, nullptr);
+            } catch (...) {
+                cudaStreamEndCapture(h->stream, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                h->capturing = false;
+                h->cur = curN; h->cb = cbN; h->advectCount = ac0; h->launches = l0;
+                throw;
+            }
+            ce = cudaStreamEndCapture(h->stream, &graph);
+        }
+        h->capturing = false;
+        g.nLaunches = h->launches - l0;
+        h->cur = curN; h->cb = cbN; h->advectCount = ac0; h->launches = l0;   // the capture executed nothing
+        if (ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { g.exec = nullptr; (void)cudaGetLastError(); }   // graphs unavailable: keep using plain launches
+        g.dt = dt;
+        return SVOF_OK;
+    }
+    CK(cudaGraphLaunch(g.exec, h->stream));
+    // the host-side state transitions of doReconstruct() + doAdvect()
+    h->launches += g.nLaunches;
+    h->cur ^= 1;
+    h->cb ^= 1;
+    h->bitsValid = true;
+    h->advected = true;
+    h->freshRecon = false;
+    h->inputsAfterNear = false;
+    h->lastDt = dt;
+    h->advectCount++;
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;
     return SVOF_OK;
     API_END(h)
 }

@@ -25,7 +25,7 @@ struct Ctl {
     int nWork;    // (cut cell, downwind face) work items
     int nUCells;  // cells whose U the interface-velocity interpolation reads (end-to-end path)
     int plicNext; // batch counter of the persistent plane-positioning kernel
-    int pad3_;
+    int epoch;    // advect() counter kept on the DEVICE (a captured CUDA graph replays correctly): bounding tags derive from it
     int nDeltaA, nDeltaF;  // changed alpha cells / alphaPhi faces of the last delta read-back
     int err;      // SVERR_* flags
     int nOob[2];  // out-of-bounds lists (double buffered between sweeps)
@@ -969,6 +969,8 @@ __global__ void __launch_bounds__(128) k_near_update(MeshDev m, const int* near2
 #ifdef SV_BOUND_STATS
 __device__ unsigned long long g_dbg[8];
 #endif
+// per-(step, sweep) validity tag of the bounding scratch arrays
+__device__ __forceinline__ int boundTag(const Ctl* ctl, int s) { return ctl->epoch * (SV_MAX_SWEEPS + 1) + s + 1; }
 struct BoundScratch {
     double* corr;   // dVfCorrectionValues, valid where tagV == tag
     int* tagV;
@@ -1157,13 +1159,14 @@ __device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
 //   k_bound_run  : roots start at once; whoever finishes the last predecessor of a cell runs that
 //                  cell next (continuation passing) -- no polling, no single-CTA drain loop.
 template <int SV_MAXBF>
-__global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, int tag, const int* oobList,
+__global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, const int* oobList,
                                                     const unsigned char* oobState, const double* alpha, const double* aOld,
                                                     const double* __restrict__ phi, const double* dVf, const double* Sp,
                                                     const double* Su, BoundScratch b, int* depInit, int* depLeft, int* oobIdx,
                                                     CellBound<SV_MAXBF>* recs, int capRec, int* affList)
 {
     const int n = ctl->nOob[s & 1];
+    const int tag = boundTag(ctl, s);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = oobList[i];
         CellBound<SV_MAXBF> cb;
@@ -1213,12 +1216,13 @@ __global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, 
 
 #define SV_BSTACK 64
 template <int SV_MAXBF>
-__global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, const int* oobList, unsigned char* oobState, BoundScratch b,
+__global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, const int* oobList, unsigned char* oobState, BoundScratch b,
                                                   const int* depInit,
                                                   int* depLeft, const int* oobIdx, const CellBound<SV_MAXBF>* recs, int capRec,
                                                   double dt, double rDt)
 {
     const int n = min(ctl->nOob[s & 1], capRec);
+    const int tag = boundTag(ctl, s);
     for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += gridDim.x * blockDim.x) {
         int c = oobList[i0];
         if (depInit[c] != 0) continue;  // released later by whoever finishes its last predecessor
@@ -1294,11 +1298,12 @@ __global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, int tag, cons
 // alpha[own]/alpha[nei]/dVf, in the order of the reference's correctedFaces list (= ascending
 // corrector cell, then position in its first-iteration face list); then build the next sweep's list.
 template <int SV_MAXBF>
-__global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s, int tag, const int* affList, const unsigned int* near1,
+__global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s, const int* affList, const unsigned int* near1,
                                                      double* alpha, double* dVf, BoundScratch b, int* oobListNext,
                                                      unsigned char* oobState)
 {
     const int n = ctl->nAff[s];
+    const int tag = boundTag(ctl, s);
     // the list sweep s consumed (deps and run are complete) becomes the empty output list of sweep s+1;
     // nobody in this kernel reads its counter
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->nOob[s & 1] = 0;

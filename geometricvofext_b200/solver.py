@@ -103,6 +103,10 @@ class SolveVofEqu:
         su = capi.f64(Su, (self.nC,)) if Su is not None else None
         self._chk(self.lib.svof_advect(self._h, float(dt), capi.dptr(sp), capi.dptr(su)))
 
+    def step(self, dt):
+        """reconstruct() + advect(dt) on the device-resident fields, one CUDA-graph launch in the steady state."""
+        self._chk(self.lib.svof_step_device(self._h, float(dt)))
+
     def step_host(self, dt, phi, U, Ub=None, alpha_out=None, alpha_phi_out=None):
         """set phi/U from host buffers, reconstruct, advect, read alpha back."""
         ub = Ub if Ub is not None else np.zeros((self.nBF, 3))

@@ -182,6 +182,11 @@ int svof_reconstruct(svof_handle* h);
  * (interPlicFoam/alphaSuSp.H:1-2).  alpha.oldTime() is the alpha held at entry. */
 int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su);
 
+/* reconstruct() + advect(dt, zeroField, zeroField) on the fields already on the device, enqueued as ONE CUDA-graph
+ * launch in the steady state (same results as the two calls; the per-phase timers are not updated by graph
+ * launches).  Inputs are refreshed between calls with svof_set_phi/_U or their _device variants.  CUDA library only. */
+int svof_step_device(svof_handle* h, double dt);
+
 /* Host-pointer convenience = set_phi + set_U + reconstruct + advect + read back
  * alpha (and alphaPhi if non-NULL): the end-to-end call bench.py times.  On return the caller's buffers
  * hold the complete new fields (see the "sparse_io" option for how few bytes that takes). */

@@ -348,6 +348,12 @@ int svof_cut_cells(svof_handle* h, int32_t n, const int32_t* cells, const double
     return SVOF_OK;
 }
 
+int svof_step_device(svof_handle* h, double dt)
+{
+    const int rc = svof_reconstruct(h);
+    return rc ? rc : svof_advect(h, dt, nullptr, nullptr);
+}
+
 int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, double* points, int32_t* face_offsets, int32_t* cells,
                       int64_t* n_points, int64_t* n_faces)
 {

@@ -12,10 +12,14 @@ U, phi = bench.velocity_fields(s, dt, dt)
 s.setAlpha(a0); s.setPhi(phi); s.setU(U, np.zeros((s.nBF, 3)))
 for ov in [int(x) for x in os.environ.get("OV", "0").split(",")]:
     s.setOption("overlap", ov)
-    for _ in range(5): s.reconstruct(); s.advect(dt)
+    graph = int(os.environ.get("GRAPH", "0"))
+    def one():
+        if graph: s.step(dt)
+        else: s.reconstruct(); s.advect(dt)
+    for _ in range(5): one()
     s.synchronize()
     s.lib.svof_mark(s._h, 0)
-    for _ in range(steps): s.reconstruct(); s.advect(dt)
+    for _ in range(steps): one()
     s.lib.svof_mark(s._h, 1)
     ms = C.c_double(); s.lib.svof_elapsed_ms(s._h, 0, 1, C.byref(ms)); s.synchronize()
     print("overlap %d: %.4f ms/step  volume %.17g" % (ov, ms.value / steps, s.volume()))

@@ -254,3 +254,36 @@ def test_overlap_schedule_is_bitwise_identical(product):
         res.append((s.alpha(), s.alphaPhi(), s.mixedCells()))
     for a, b in zip(*res):
         assert np.array_equal(a, b)
+
+
+def test_graph_step_is_bitwise_the_two_calls(product):
+    """svof_step_device (one CUDA-graph launch per step in the steady state) against reconstruct() + advect()."""
+    m = meshmod.hex_block(32)
+    a, b = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=product), SolveVofEqu(m, LEVEQUE_CONTROLS, lib=product)
+    a0 = exact_sphere_alpha(m)
+    C, Cf, Sf = a.field(capi.F_C), a.field(capi.F_CF), a.field(capi.F_SF)
+    U0, phi0 = fields.leveque_velocity(C), fields.face_flux(Cf, Sf)
+    dt = 0.25 / 32
+    for s in (a, b):
+        s.setAlpha(a0)
+        s.setPhi(phi0)
+        s.setU(U0)
+    l0 = b.info(capi.I_GPU_LAUNCHES)
+    for k in range(9):
+        if k == 5:   # inputs refreshed between graph launches
+            for s in (a, b):
+                s.setPhi(0.5 * phi0)
+                s.setU(0.5 * U0)
+        a.reconstruct()
+        a.advect(dt)
+        b.step(dt)
+        assert np.array_equal(a.alpha(), b.alpha()), "step %d" % k
+        assert np.array_equal(a.alphaPhi(), b.alphaPhi())
+    assert np.array_equal(a.mixedCells(), b.mixedCells()) and np.array_equal(a.interfaceD(), b.interfaceD())
+    assert a.info(capi.I_N_BOUND_SWEEPS) == b.info(capi.I_N_BOUND_SWEEPS)
+    assert b.info(capi.I_GPU_LAUNCHES) - l0 > 9 * 20      # graph launches are counted by the kernels they contain
+    b.step(0.5 * dt)                                       # a new dt re-captures
+    a.reconstruct()
+    a.advect(0.5 * dt)
+    assert np.array_equal(a.alpha(), b.alpha())
+    assert b.info(capi.I_ERROR_FLAGS) == 0
