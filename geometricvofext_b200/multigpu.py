@@ -228,6 +228,8 @@ def bench(args, controls, metric, unit):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout: keep rank 0's stdout to the one JSON line
     if not dist.is_initialized():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     grid = np.array(block_grid(world))
