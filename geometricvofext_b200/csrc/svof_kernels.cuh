@@ -296,27 +296,41 @@ __global__ void k_write_mixed(const unsigned int* bits, int nWords, const unsign
 // advection.C:54-82); near2 = near1 U face-neighbours (cells a bounding correction can touch).
 // Bits are set with atomicOr; the thread that flips a near2 bit appends the cell to the list,
 // so the list is a duplicate-free SET (its order is irrelevant: every consumer is per-cell).
+// Most marks are duplicates (43 per mixed cell, ~3 of them new), and atomics on the same bitmap word serialise in L2:
+// a plain L2 read filters the duplicates first (a stale read only costs a redundant atomic).  8 lanes per mixed cell,
+// one face-neighbour (and its own neighbours) per lane.  Measured at 256^3: 38 us (thread per cell, every mark an
+// atomic) -> see DESIGN.md; firing a lane's atomics back to back instead made it slower (59 us): the limit is
+// same-address atomic throughput, not the length of the dependent chain.
 __device__ __forceinline__ void markNear2(int c, unsigned int* near2, int* near2List, Ctl* ctl, int cap)
 {
     const unsigned int bit = 1u << (c & 31);
+    if (__ldcg(&near2[c >> 5]) & bit) return;
     const unsigned int old = atomicOr(&near2[c >> 5], bit);
     if (!(old & bit)) {
         const int pos = atomicAdd(&ctl->nNear2, 1);
         if (pos < cap) near2List[pos] = c; else atomicOr(&ctl->err, SVERR_LIST);
     }
 }
+__device__ __forceinline__ void markNear1(int c, unsigned int* near1)
+{
+    const unsigned int bit = 1u << (c & 31);
+    if (!(__ldcg(&near1[c >> 5]) & bit)) atomicOr(&near1[c >> 5], bit);
+}
 __global__ void k_mark_near(MeshDev m, const int* mixedCells, Ctl* ctl, unsigned int* near1, unsigned int* near2,
                             int* near2List, int cap)
 {
     const int n = ctl->nMixed;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 7;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n; i += (gridDim.x * blockDim.x) >> 3) {
         const int c = mixedCells[i];
-        atomicOr(&near1[c >> 5], 1u << (c & 31));
-        markNear2(c, near2, near2List, ctl, cap);
-        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+        if (lane == 0) {
+            markNear1(c, near1);
+            markNear2(c, near2, near2List, ctl, cap);
+        }
+        for (int k = m.cellOff[c] + lane; k < m.cellOff[c + 1]; k += 8) {
             const int y = m.cellAsc[k].y;
             if (y < 0) continue;
-            atomicOr(&near1[y >> 5], 1u << (y & 31));
+            markNear1(y, near1);
             markNear2(y, near2, near2List, ctl, cap);
             for (int q = m.cellOff[y]; q < m.cellOff[y + 1]; ++q) {
                 const int z = m.cellAsc[q].y;
@@ -575,6 +589,9 @@ __device__ d3 interpolateU(const MeshDev& m, const d3& position, int celli, cons
     return t;
 }
 
+// (Round 1 also tried 8 lanes per cut cell -- tets of different faces tested at once, the inverse-distance sums taken
+// with shuffles: 87 us against 80 us for this thread-per-cell form.  The kernel is bound by its instruction count at
+// 4 warps per scheduler (122 registers), not by the length of one thread's chain, and the shuffles added a third more.)
 // A7 first half (advection.C:112-175): interface speed per cut cell + the compacted work list of
 // (cut cell, downwind face) pairs.  Each face has exactly one upwind cell, so the list is
 // duplicate free and the flux kernel's writes are conflict free.
