@@ -73,6 +73,7 @@ SYMBOLS = [
     ("svof_get_info", C.c_int, [_H, C.c_int, c_double_p]),
     ("svof_device_ptr", C.c_int, [_H, C.c_int, C.POINTER(C.c_void_p)]),
     ("svof_device_touch", C.c_int, [_H, C.c_int]),
+    ("svof_scatter_alpha_device", C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64]),
     ("svof_set_phi_device", C.c_int, [_H, C.c_void_p]),
     ("svof_set_U_device", C.c_int, [_H, C.c_void_p, C.c_void_p]),
     ("svof_set_option", C.c_int, [_H, C.c_char_p, C.c_int]),

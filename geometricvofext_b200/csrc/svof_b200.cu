@@ -989,6 +989,21 @@ int svof_set_U(svof_handle* h, const double* U, const double* Ub)
     API_END(h)
 }
 
+int svof_scatter_alpha_device(svof_handle* h, const int32_t* d_idx, const double* d_vals, int64_t n)
+{
+    if (!h || n < 0 || (n > 0 && (!d_idx || !d_vals))) return SVOF_ERR_INVALID_ARG;
+    if (!h->haveAlpha) return fail(h, SVOF_ERR_STATE, "svof_scatter_alpha_device: alpha not set");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    if (n) LAUNCH(h, k_scatter_alpha, (int)cdiv(n, 256), 256, d_idx, d_vals, (long long)n, h->prm.mixed_cell_tol, h->alphaBuf[h->cur],
+                  h->mixedBits, h->bitsValid ? 1 : 0);
+    alphaBC(h);
+    h->advected = false;
+    h->hostAlphaSynced = nullptr;
+    return SVOF_OK;
+    API_END(h)
+}
+
 int svof_set_phi_device(svof_handle* h, const void* dphi)
 {
     if (!h || !dphi) return SVOF_ERR_INVALID_ARG;

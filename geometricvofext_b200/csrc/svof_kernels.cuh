@@ -197,6 +197,23 @@ __global__ void k_mixed_bits(const double* __restrict__ alpha, int nCells, doubl
     if ((threadIdx.x & 31) == 0 && c < nCells) bits[c >> 5] = w;
 }
 
+// alpha[idx[i]] = vals[i] (halo cells refreshed from their owning rank) with the mixed-cell bitmap kept up to date,
+// so a decomposed run needs no dense bitmap pass after its halo swap
+__global__ void k_scatter_alpha(const int* __restrict__ idx, const double* __restrict__ vals, long long n, double tol, double* alpha,
+                                unsigned int* bits, int updateBits)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = idx[i];
+    const double a = vals[i];
+    alpha[c] = a;
+    if (updateBits) {
+        const unsigned int bit = 1u << (c & 31);
+        if ((tol < a) && (a < 1.0 - tol)) atomicOr(&bits[c >> 5], bit);
+        else atomicAnd(&bits[c >> 5], ~bit);
+    }
+}
+
 // ordered compaction of a bitmap into an ascending list (keeps mixedCells_ bit-exact in ORDER too)
 #define SV_SCAN_WORDS 1024  // words per block
 __global__ void k_count_bits(const unsigned int* bits, int nWords, unsigned int* blockSums)

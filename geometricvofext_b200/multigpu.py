@@ -127,9 +127,19 @@ class DecomposedSolveVofEqu:
             import torch
             self.torch = torch
             dev = torch.device("cuda", device)
-            self.send_idx = {r: torch.as_tensor(v, device=dev) for r, v in self.plan["send"].items()}
-            self.recv_idx = {r: torch.as_tensor(v, device=dev) for r, v in self.plan["recv"].items()}
-            self.recv_buf = {r: torch.empty(v.numel(), dtype=torch.float64, device=dev) for r, v in self.recv_idx.items()}
+            # one gather and one scatter per step whatever the number of neighbours: the send indices of all peers are
+            # concatenated (each peer's message is a slice of the packed buffer), and so are the receive indices
+            def cat(d):
+                ranks = sorted(d)
+                sizes = [len(d[r]) for r in ranks]
+                idx = np.concatenate([np.asarray(d[r], dtype=np.int64) for r in ranks]) if ranks else np.zeros(0, np.int64)
+                return ranks, sizes, idx
+            self.send_ranks, self.send_sizes, sidx = cat(self.plan["send"])
+            self.recv_ranks, self.recv_sizes, ridx = cat(self.plan["recv"])
+            self.send_idx_all = torch.as_tensor(sidx, device=dev)
+            self.recv_idx_all = torch.as_tensor(ridx.astype(np.int32), device=dev)
+            self.send_buf_all = torch.empty(len(sidx), dtype=torch.float64, device=dev)
+            self.recv_buf_all = torch.empty(len(ridx), dtype=torch.float64, device=dev)
             st = C.c_void_p()
             self.s._chk(self.s.lib.svof_get_stream(self.s._h, C.byref(st)))
             self.ext_stream = torch.cuda.ExternalStream(st.value, device=dev)
@@ -148,19 +158,20 @@ class DecomposedSolveVofEqu:
             self.s._chk(self.s.lib.svof_device_ptr(self.s._h, capi.F_ALPHA, C.byref(p)))
             with torch.cuda.stream(self.ext_stream):
                 a = torch.as_tensor(_DevArr(p.value, self.s.nC), device=torch.device("cuda", self.device))
-                ops, keep = [], []
-                for r, idx in self.send_idx.items():
-                    buf = a.index_select(0, idx)
-                    keep.append(buf)
-                    ops.append(dist.P2POp(dist.isend, buf, r))
-                for r, buf in self.recv_buf.items():
-                    ops.append(dist.P2POp(dist.irecv, buf, r))
+                torch.index_select(a, 0, self.send_idx_all, out=self.send_buf_all)
+                ops, o = [], 0
+                for r, n in zip(self.send_ranks, self.send_sizes):
+                    ops.append(dist.P2POp(dist.isend, self.send_buf_all[o:o + n], r))
+                    o += n
+                o = 0
+                for r, n in zip(self.recv_ranks, self.recv_sizes):
+                    ops.append(dist.P2POp(dist.irecv, self.recv_buf_all[o:o + n], r))
+                    o += n
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()          # stream-level wait (no host block) for NCCL work
-                for r, idx in self.recv_idx.items():
-                    a.index_copy_(0, idx, self.recv_buf[r])
-                self._keep = keep     # buffers stay alive until the next exchange
-            self.s._chk(self.s.lib.svof_device_touch(self.s._h, capi.F_ALPHA))
+            # halo cells <- received values, mixed-cell bitmap and patch values kept up to date (same stream)
+            self.s._chk(self.s.lib.svof_scatter_alpha_device(self.s._h, self.recv_idx_all.data_ptr(), self.recv_buf_all.data_ptr(),
+                                                             self.recv_idx_all.numel()))
         else:
             import torch
             a = self.s.alpha()

@@ -251,6 +251,10 @@ int svof_device_ptr(svof_handle* h, int which, void** dptr);
 /* Tell the handle that a device-resident input (ALPHA, via svof_device_ptr) was
  * overwritten in place by the caller. */
 int svof_device_touch(svof_handle* h, int which);
+/* alpha[idx[i]] = vals[i] for i < n, idx/vals DEVICE arrays, enqueued on the handle's stream: how a decomposed run
+ * refreshes its halo cells after the swap (the mixed-cell bitmap and the patch values follow; no dense pass).
+ * CUDA library only. */
+int svof_scatter_alpha_device(svof_handle* h, const int32_t* d_idx, const double* d_vals, int64_t n);
 /* phi/U staged on device already: same as svof_set_phi/svof_set_U but
  * device-to-device (CUDA library only). */
 int svof_set_phi_device(svof_handle* h, const void* dphi);

@@ -275,6 +275,7 @@ int svof_get_info(svof_handle* h, int which, double* out)
 
 int svof_device_ptr(svof_handle*, int, void**) { return SVOF_ERR_UNSUPPORTED; }
 int svof_device_touch(svof_handle*, int) { return SVOF_ERR_UNSUPPORTED; }
+int svof_scatter_alpha_device(svof_handle*, const int32_t*, const double*, int64_t) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_phi_device(svof_handle*, const void*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_U_device(svof_handle*, const void*, const void*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_set_option(svof_handle* h, const char* name, int) { return (h && name) ? SVOF_OK : SVOF_ERR_INVALID_ARG; }
