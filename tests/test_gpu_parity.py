@@ -287,3 +287,41 @@ def test_graph_step_is_bitwise_the_two_calls(product):
     a.advect(0.5 * dt)
     assert np.array_equal(a.alpha(), b.alpha())
     assert b.info(capi.I_ERROR_FLAGS) == 0
+
+
+def test_scatter_alpha_device_matches_set_alpha(product):
+    """svof_scatter_alpha_device (the halo refresh of decomposed runs): alpha, patch values and the mixed-cell bitmap
+    end up exactly as after svof_set_alpha with the same field, and the graph-replayed steps that follow agree."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    m = meshmod.hex_block(24)
+    a, b = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=product), SolveVofEqu(m, LEVEQUE_CONTROLS, lib=product)
+    a0 = exact_sphere_alpha(m)
+    Cc, Cf, Sf = a.field(capi.F_C), a.field(capi.F_CF), a.field(capi.F_SF)
+    U0, phi0 = fields.leveque_velocity(Cc), fields.face_flux(Cf, Sf)
+    dt = 0.25 / 24
+    for s in (a, b):
+        s.setAlpha(a0)
+        s.setPhi(phi0)
+        s.setU(U0)
+        for _ in range(3):
+            s.step(dt)
+    # overwrite a slab of cells (some become mixed, some stop being mixed) in both solvers, two ways
+    rng = np.random.default_rng(5)
+    idx = np.sort(rng.choice(m.n_cells, 3000, replace=False)).astype(np.int32)
+    vals = np.where(rng.random(idx.size) < 0.5, rng.random(idx.size), np.round(rng.random(idx.size)))
+    cur = a.alpha()
+    cur[idx] = vals
+    a.setAlpha(cur)
+    d_idx, d_vals = torch.as_tensor(idx, device="cuda"), torch.as_tensor(vals, device="cuda")
+    torch.cuda.synchronize()
+    b._chk(b.lib.svof_scatter_alpha_device(b._h, d_idx.data_ptr(), d_vals.data_ptr(), idx.size))
+    assert np.array_equal(a.alpha(), b.alpha())
+    assert np.array_equal(a.field(capi.F_ALPHA_BOUNDARY), b.field(capi.F_ALPHA_BOUNDARY))
+    for k in range(4):
+        a.reconstruct()
+        a.advect(dt)
+        b.step(dt)
+        assert np.array_equal(a.mixedCells(), b.mixedCells()), "step %d" % k
+        assert np.array_equal(a.alpha(), b.alpha())
+    assert b.info(capi.I_ERROR_FLAGS) == 0
