@@ -293,6 +293,45 @@ def prism_mesh(n):
     return build_polymesh(P, cells)
 
 
+def kelvin_mesh(n):
+    """2 n^3 truncated octahedra (Kelvin cells, the Voronoi cells of a BCC lattice): 14 faces (6 squares, 8 hexagons)
+    and 24 points per cell -- the cell population of a polyDualMesh (BASELINE.json configs[2]: ~14 faces per cell,
+    ~5 vertices per face).  Whole cells only, so the outer boundary is faceted; it fits inside the unit cube."""
+    import itertools
+    # one cell about the origin in integer coordinates: vertices = all permutations of (0, +-1, +-2)
+    verts = sorted({p for perm in itertools.permutations((0, 1, 2)) for p in
+                    itertools.product(*[(v, -v) if v else (0,) for v in perm])})
+    V = np.array(verts, dtype=np.int64)
+    normals = [np.array(e) * sgn for e in ((1, 0, 0), (0, 1, 0), (0, 0, 1)) for sgn in (1, -1)]
+    normals += [np.array(sg) for sg in itertools.product((1, -1), repeat=3)]
+    faces = []
+    for nrm in normals:
+        d = 2 if np.abs(nrm).sum() == 1 else 3
+        on = np.nonzero(V @ nrm == d)[0]
+        fc = V[on].mean(axis=0)
+        u = (V[on[0]] - fc).astype(np.float64)
+        u /= np.linalg.norm(u)
+        w = np.cross(nrm / np.linalg.norm(nrm), u)
+        ang = np.arctan2((V[on] - fc) @ w, (V[on] - fc) @ u)
+        faces.append([int(i) for i in on[np.argsort(ang)]])       # counter-clockwise about the outward normal
+    ids, pts, cells = {}, [], []
+    centres = [(4 * i + o, 4 * j + o, 4 * k + o) for o in (0, 2) for k in range(n) for j in range(n) for i in range(n)]
+    for c in centres:
+        loc = []
+        for v in verts:
+            key = (v[0] + c[0], v[1] + c[1], v[2] + c[2])
+            if key not in ids:
+                ids[key] = len(pts)
+                pts.append(key)
+            loc.append(ids[key])
+        cells.append([[loc[i] for i in f] for f in faces])
+    P = (np.array(pts, dtype=np.float64) + 2.0) / (4.0 * n + 2.0)
+    m = build_polymesh(P, cells)
+    m.meta["kind"] = "kelvin"
+    m.meta["cell_volume"] = 32.0 / (4.0 * n + 2.0) ** 3
+    return m
+
+
 def refined_interface_mesh(n):
     """2:1 refinement interface (what dynamicRefineFvMesh produces in the reference's AMR cases): the half
     x < 0.5 is meshed with n^3/2 coarse hexes, the half x > 0.5 with 8x finer ones; the coarse cells on the

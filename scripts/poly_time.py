@@ -7,6 +7,7 @@ from geometricvofext_b200 import capi, fields, mesh as meshmod
 from geometricvofext_b200.solver import SolveVofEqu
 
 CASES = {
+    "Kelvin cells 2x48^3 (14 faces/cell)": (lambda: meshmod.kelvin_mesh(48), {}),
     "prisms 2x64^3": (lambda: meshmod.prism_mesh(64), {}),
     "warped hexes 128^3": (lambda: meshmod.perturb_points(meshmod.hex_block(128), 0.2, 3), {}),
     "warped hexes 128^3, splitWarpedFace": (lambda: meshmod.perturb_points(meshmod.hex_block(128), 0.2, 3), {"splitWarpedFace": True}),

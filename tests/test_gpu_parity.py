@@ -187,6 +187,7 @@ _POLY_CASES = {
     "refinement-interface polyhedra": (lambda: meshmod.refined_interface_mesh(8), {}),
     "warped hexes": (lambda: meshmod.perturb_points(meshmod.hex_block(12), 0.2, 3), {}),
     "warped hexes, splitWarpedFace": (lambda: meshmod.perturb_points(meshmod.hex_block(12), 0.2, 3), {"splitWarpedFace": True}),
+    "Kelvin cells (14 faces, 24 points: polyDualMesh population)": (lambda: meshmod.kelvin_mesh(10), {}),
     # orientationMethod alphaGrad (reconstruction.C:74-82) on hexes and on polyhedra with non-orthogonal faces
     "hexes, alphaGrad": (lambda: meshmod.hex_block(14), {"orientationMethod": "alphaGrad"}),
     "refinement-interface polyhedra, alphaGrad": (lambda: meshmod.refined_interface_mesh(8), {"orientationMethod": "alphaGrad"}),
