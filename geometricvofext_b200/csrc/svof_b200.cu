@@ -412,6 +412,7 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
     // upload
     MeshDev& d = h->md;
     d.nPoints = nP; d.nFaces = nF; d.nIF = nIF; d.nCells = nC; d.nBF = nBF;
+    d.maxFV = maxFV; d.maxLocalFaces = maxLocalFaces;
     d.points = dupload(h, m.points, (size_t)3 * nP);
     d.faceOff = dupload(h, fo, (size_t)nF + 1);
     d.facePts = dupload(h, fp, (size_t)nFP);

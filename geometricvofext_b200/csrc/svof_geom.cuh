@@ -30,6 +30,7 @@ enum {
 // Device view of the mesh: CSR/SoA, int32 labels, f64 scalars (DESIGN.md "data layout").
 struct MeshDev {
     int nPoints, nFaces, nIF, nCells, nBF;
+    int maxFV, maxLocalFaces;   // mesh maxima: vertices per (local) face, local faces per cell (with splitWarpedFace: triangulated)
     const double* points;       // [3*nPoints]
     const int* faceOff;         // [nFaces+1]
     const int* facePts;

@@ -184,7 +184,9 @@ void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedC
                          int split, int* cellStatus, double* iD, double* iC, double* iS)
 {
     // lane-cooperative kernel (8 lanes per cell) whenever the per-cell staging area fits shared memory
-    const size_t perCell = sizeof(GCellShared<CP>) + SV_G * LanePriv<CP>::DOUBLES * sizeof(double);
+    size_t perCell = sizeof(GCellShared<CP>) + SV_G * LanePriv<CP>::DOUBLES * sizeof(double);
+    if (CP::MAXCF > SV_G)   // per-face records for cells with more than one face per lane, sized from the mesh's maxima
+        perCell += sizeof(double) * ((size_t)m.maxLocalFaces * FaceRec::doubles(m.maxFV) + (m.maxLocalFaces + 1) / 2);
     // 16 cells x 8 lanes, 4 CTAs per SM: measured 357 us at 256^3 against 391 us for 32 x 8 with 2 CTAs per SM
     // (the CTA barrier between the face and leader phases then holds up 3 warps instead of 7)
     int threads = SV_PLIC_THREADS;
