@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(128) k_plic(MeshDev m, const int* mixedCells, 
 }
 
 // A8+A9: thread per (cut cell, downwind face)
+// (Round 1 tried staging the face in shared memory and an area-only streaming clip for the up to 11 calcSubFace
+// evaluations of the Simpson rule, as in k_plic_group: 68 us against 66 us for this form -- not where the time goes.)
 template <class CP>
 __global__ void __launch_bounds__(128) k_face_flux(MeshDev m, const int2* work, Ctl* ctl, const int* mixedCells, const double* iN,
                                                    const double* iD, const double* Un0, const double* __restrict__ phi, double dt,

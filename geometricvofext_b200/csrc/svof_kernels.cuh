@@ -489,6 +489,31 @@ __device__ d3 pointU(const MeshDev& m, int p, const double* __restrict__ U, cons
     if (!m.isPatchPoint[p]) {
         const int j0 = m.ptCellOff[p], j1 = m.ptCellOff[p + 1];
         double sumW = 0.0;
+        if (j1 - j0 <= 8) {
+            // the inverse distances are needed twice (normalisation, then the weighted sum): keep them instead of
+            // recomputing a square root and a divide per cell (a third of this kernel's instructions)
+            double inv[8];
+            int cs[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                inv[q] = 0.0;
+                cs[q] = -1;
+                if (j0 + q < j1) {
+                    cs[q] = m.ptCells[j0 + q];
+                    inv[q] = 1.0 / mag(pt - ld3(m.C, cs[q]));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (cs[q] >= 0) sumW += inv[q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (cs[q] < 0) continue;
+                const double pw = inv[q] / sumW;
+                val += pw * ld3(U, cs[q]);
+            }
+            return val;
+        }
         for (int j = j0; j < j1; ++j) sumW += 1.0 / mag(pt - ld3(m.C, m.ptCells[j]));
         for (int j = j0; j < j1; ++j) {
             const int c = m.ptCells[j];
