@@ -200,15 +200,18 @@ void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedC
             cudaFuncSetAttribute(k_plic_group<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
             configured = true;
         }
-        // persistent: exactly as many CTAs as fit on the device at once
-        static int resident = 0;
-        if (!resident) {
+        // persistent: exactly as many CTAs as fit on the device at once (the staging size depends on the mesh)
+        static int resident = 0, residentThreads = 0;
+        static size_t residentSmem = 0;
+        if (!resident || residentThreads != threads || residentSmem != smem) {
             int perSm = 0, dev = 0, sms = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_plic_group<CP>, threads, smem);
             if (const char* e = getenv("SVOF_PLIC_CTAS")) perSm = atoi(e) < perSm ? atoi(e) : perSm;  // experiments
             resident = (perSm > 0 ? perSm : 1) * (sms > 0 ? sms : 148);
+            residentThreads = threads;
+            residentSmem = smem;
         }
         (void)grid;
         k_plic_group<CP><<<resident, threads, smem, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);

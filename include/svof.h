@@ -259,8 +259,9 @@ int svof_scatter_alpha_device(svof_handle* h, const int32_t* d_idx, const double
  * device-to-device (CUDA library only). */
 int svof_set_phi_device(svof_handle* h, const void* dphi);
 int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
-/* Runtime switches: "overlap" (0/1, default 0: run the streaming kernel on a second stream concurrently with
- * the sparse interface chain -- bitwise the same result; measured slower on B200), "profile" (0/1: CUDA events around every launch, printed at destroy),
+/* Runtime switches: "overlap" (default 0; 1: run the streaming kernel on a second stream concurrently with
+ * the whole sparse interface chain, 2: only with the tail of reconstruct() -- bitwise the same result either way;
+ * both measured slower on B200), "profile" (0/1: CUDA events around every launch, printed at destroy),
  * "sparse_io" (0/1, default 1: svof_step_host uploads only the rows of U the interface-velocity interpolation
  * reads and reads alpha/alphaPhi back as (index,value) deltas against what the SAME caller buffers received
  * from the previous svof_step_host; a caller that modifies those buffers in between must call svof_set_alpha
