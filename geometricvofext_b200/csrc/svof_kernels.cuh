@@ -3,10 +3,10 @@
 //
 //   once per mesh   k_face_geom, k_cell_geom, k_flatness_tetbase        (K0)
 //   reconstruct()   k_clear_prev, k_mixed_bits, k_count_bits, k_scan_blocks, k_write_mixed,
-//                   k_mark_near, k_ls_normals (K2), k_plic<Caps> (K3)
+//                   k_mark_near, k_ls_normals | k_alpha_grad_normals (K2), k_plic_group<Caps> (K3, svof_plic_group.cuh)
 //   advect()        k_un0_worklist (K5), k_face_flux<Caps> (K6), k_dense_update (K7, THE
 //                   streaming kernel: the only pass over all cells/faces), k_near_update,
-//                   k_bound_find / k_bound_wave / k_bound_drain / k_bound_apply (K8),
+//                   k_bound_deps / k_bound_run / k_bound_apply (K8: bounding as a dependency-counted DAG),
 //                   k_near_finalize, k_alpha_bc (K9)
 //
 // Every list is built on the device and every launch has a size known on the host
