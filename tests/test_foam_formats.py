@@ -276,3 +276,15 @@ def test_gpu_reference_case_64_first_golden_instant(tmp_path):
     (t, ev, amin, omax, es), = foamcase.calc_vof_advection_errors(case)
     assert t == 0.25 and abs(ev) < 1e-10 and amin > -1e-5 and omax > -1e-5
     assert abs(es - 2.309e-2) / 2.309e-2 < 0.05          # the oracle's pinned E_s(0.25) (tests/test_oracle_golden.py)
+
+
+def test_cli_block_mesh_writes_a_readable_polymesh(tmp_path):
+    case = make_case(str(tmp_path / "c"), n=5)
+    assert foamcase.main(["blockMesh", case.dir, "--renumber"]) == 0
+    assert case.has_poly_mesh()
+    m = case.mesh()                                  # now read back from constant/polyMesh
+    ref, _ = foamcase.renumber_mesh(meshmod.hex_block(5))
+    assert m.n_cells == 125 and np.array_equal(m.owner, ref.owner) and np.array_equal(m.neighbour, ref.neighbour)
+    assert np.array_equal(m.face_points, ref.face_points) and np.array_equal(m.points, ref.points)
+    assert [p.name for p in m.patches] == ["top", "left", "back", "right", "bottom", "front"]
+    assert set(m.meta["patch_types"].values()) == {"wall"}
