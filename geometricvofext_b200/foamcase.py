@@ -274,6 +274,25 @@ def plic_surface_functions(control_dict):
     return out
 
 
+def _write_plic_fields(case, mesh, s, time_name):
+    """writePlicFields true (reconstruction.C:520-570): interfaceN [1/m], interfaceD [m], interfaceC [m], interfaceS [m^2]
+    are AUTO_WRITE fields of the reconstruction; `calculated` patches with the zero-gradient value."""
+    fmt = str(case.control_dict.get("writeFormat", "binary"))
+    nIF = mesh.n_internal_faces
+    for name, which, cls, dims in (("interfaceN", capi.F_INTERFACE_N, "volVectorField", (0, -1, 0, 0, 0, 0, 0)),
+                                   ("interfaceD", capi.F_INTERFACE_D, "volScalarField", (0, 1, 0, 0, 0, 0, 0)),
+                                   ("interfaceC", capi.F_INTERFACE_C, "volVectorField", (0, 1, 0, 0, 0, 0, 0)),
+                                   ("interfaceS", capi.F_INTERFACE_S, "volVectorField", (0, 2, 0, 0, 0, 0, 0))):
+        f = s.field(which)
+        bnd = {}
+        for p in mesh.patches:
+            if p.kind == capi.PATCH_EMPTY:
+                bnd[p.name] = {"type": "empty"}
+            else:
+                bnd[p.name] = {"type": "calculated", "value": np.ascontiguousarray(f[mesh.owner[p.start:p.start + p.size]])}
+        foamfile.write_field(os.path.join(case.dir, time_name, name), cls, name, f, bnd, dimensions=dims, fmt=fmt, location=time_name)
+
+
 def _write_surfaces(case, s, time_name, surfaces):
     if not surfaces:
         return
@@ -317,6 +336,7 @@ def run_plic_vof_advection(case, lib=None, end_time=None, renumber=False, alpha0
     by_time = str(cd.get("writeControl", "adjustableRunTime")) in ("adjustableRunTime", "runTime")
     s.reconstruct()                       # plicVof.H:8-9: interface at the initial time, function objects executed
     surfaces = plic_surface_functions(cd) if write else []
+    write_plic = write and str(controls.get("writePlicFields", "false")).lower() in ("true", "yes", "on", "1")
     _write_surfaces(case, s, _time_name(drv.t), surfaces)
     written, vols = [], []
     next_write = drv.t + w_int if by_time else None
@@ -329,6 +349,8 @@ def run_plic_vof_advection(case, lib=None, end_time=None, renumber=False, alpha0
             name = _time_name(drv.t)
             if write:
                 case.write_alpha(mesh, name, s.alpha())
+                if write_plic:
+                    _write_plic_fields(case, mesh, s, name)
                 _write_surfaces(case, s, name, surfaces)   # the polygons of the step's reconstruct()
             written.append(name)
             log("Time = %s  steps %d  Phase-1 volume = %.15g" % (name, drv.steps, vols[-1]))

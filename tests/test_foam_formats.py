@@ -26,6 +26,7 @@ solvers
         mixedCellTol        $tolBase;
         orientationMethod   LS;
         splitWarpedFace     false;
+        writePlicFields     true;
         period              6.0;
         reverseTime         0.0;
     };
@@ -193,6 +194,12 @@ def test_case_run_matches_direct_driver_and_writes_openfoam_fields(tmp_path):
         while drv.t < te - 1e-12:
             drv.step(end_time=te)
     assert drv.steps == out["steps"]
+    # writePlicFields true: the four reconstruction fields next to alpha, as OpenFOAM fields
+    fN = foamfile.read_field(os.path.join(case.dir, "0.004", "interfaceN"))
+    fD = foamfile.read_field(os.path.join(case.dir, "0.004", "interfaceD"))
+    assert fN.cls == "volVectorField" and fN.dimensions == (0, -1, 0, 0, 0, 0, 0) and fD.dimensions == (0, 1, 0, 0, 0, 0, 0)
+    assert np.array_equal(fN.internal, s.interfaceN()) and np.array_equal(fD.internal, s.interfaceD())
+    assert fN.boundary.lookup("top")["type"] == "calculated"
     # the plicSurface sampler of the controlDict: polygons written at t = 0 and at every write time
     assert foamcase.plic_surface_functions(case.control_dict) == [("plicInterface", "plicSurf")]
     for t in ("0", "0.002", "0.004"):
