@@ -30,7 +30,7 @@ NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompile
              os.environ.get("SVOF_EXTRA_DEFS", "").split()   # kernel-variant experiments (with SVOF_BUILD_TAG)
 
 UNITS = [("svof_b200", "svof_b200.cu", [])] + \
-        [("svof_inst%d" % v, "svof_inst.cu", ["-DSV_VARIANT=%d" % v]) for v in range(4)]
+        [("svof_inst%d" % v, "svof_inst.cu", ["-DSV_VARIANT=%d" % v]) for v in range(5)]
 
 
 def _stale(target, deps):

@@ -173,6 +173,7 @@ void profEnd(svof_handle* h, cudaStream_t st);
             case 0: GeoLaunch<CapsHex>::fn(__VA_ARGS__); break;       \
             case 1: GeoLaunch<CapsSmall>::fn(__VA_ARGS__); break;     \
             case 2: GeoLaunch<CapsPoly>::fn(__VA_ARGS__); break;      \
+            case 4: GeoLaunch<CapsHexSplit>::fn(__VA_ARGS__); break;  \
             default: GeoLaunch<CapsSplit>::fn(__VA_ARGS__); break;    \
         }                                                             \
         if ((h)->prof) profEnd(h, (h)->stream);                       \
@@ -398,6 +399,7 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
     auto fits = [&](int fv, int cf, int cp) { return maxFV <= fv && maxLocalFaces <= cf && maxLocalPts <= cp; };
     if (fits(CapsHex::MAXFV, CapsHex::MAXCF, CapsHex::MAXCP)) h->variant = 0;
     else if (fits(CapsSmall::MAXFV, CapsSmall::MAXCF, CapsSmall::MAXCP)) h->variant = 1;
+    else if (fits(CapsHexSplit::MAXFV, CapsHexSplit::MAXCF, CapsHexSplit::MAXCP)) h->variant = 4;
     else if (fits(CapsPoly::MAXFV, CapsPoly::MAXCF, CapsPoly::MAXCP)) h->variant = 2;
     else if (fits(CapsSplit::MAXFV, CapsSplit::MAXCF, CapsSplit::MAXCP)) h->variant = 3;
     else {
@@ -1560,7 +1562,7 @@ int svof_cut_cells(svof_handle* h, int32_t n, const int32_t* cells, const double
     double* dia = (double*)up(nullptr, sizeof(double) * 3 * n);
     if (n) {
         // the non-split capacity variant of this mesh
-        const int v = (h->variant == 3) ? 2 : h->variant;
+        const int v = (h->variant >= 3) ? 2 : h->variant;
         switch (v) {
             case 0: GeoLaunch<CapsHex>::cutCells(h->stream, h->md, n, dcell, dn, dd, ds, dv, dsv, dic, dia, dErr); break;
             case 1: GeoLaunch<CapsSmall>::cutCells(h->stream, h->md, n, dcell, dn, dd, ds, dv, dsv, dic, dia, dErr); break;
@@ -1633,6 +1635,7 @@ int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, dou
         case 0: maxEp = GeoLaunch<CapsHex>::maxPolyPoints(); break;
         case 1: maxEp = GeoLaunch<CapsSmall>::maxPolyPoints(); break;
         case 2: maxEp = GeoLaunch<CapsPoly>::maxPolyPoints(); break;
+        case 4: maxEp = GeoLaunch<CapsHexSplit>::maxPolyPoints(); break;
         default: maxEp = GeoLaunch<CapsSplit>::maxPolyPoints(); break;
     }
     double* dPts = (double*)up(nullptr, sizeof(double) * 3 * (size_t)std::max(nM, 1) * maxEp);

@@ -11,6 +11,7 @@ typedef Caps<4, 6, 8> CapsHex;         // hexahedra (blockMesh), flat faces
 typedef Caps<8, 16, 32> CapsSmall;     // tets/prisms/small polyhedra
 typedef Caps<16, 40, 72> CapsPoly;     // polyDualMesh cells (~14 faces, 24+ vertices)
 typedef Caps<16, 200, 128> CapsSplit;  // splitWarpedFace local triangulations
+typedef Caps<4, 24, 16> CapsHexSplit;  // hexahedra with splitWarpedFace: 6 x 4 triangles, 8 + 6 points (variant index 4)
 
 // host-callable launchers, one explicit instantiation per variant
 template <class CP>

@@ -1,5 +1,5 @@
 // svof_inst.cu -- explicit instantiation of the capacity-variant kernels.
-// Compiled once per variant: nvcc -DSV_VARIANT=0|1|2|3 (see geometricvofext_b200/build.py).
+// Compiled once per variant: nvcc -DSV_VARIANT=0|1|2|3|4 (see geometricvofext_b200/build.py).
 #include "svof_geom_kernels.cuh"
 
 namespace svof {
@@ -9,7 +9,9 @@ template struct GeoLaunch<CapsHex>;
 template struct GeoLaunch<CapsSmall>;
 #elif SV_VARIANT == 2
 template struct GeoLaunch<CapsPoly>;
-#else
+#elif SV_VARIANT == 3
 template struct GeoLaunch<CapsSplit>;
+#else
+template struct GeoLaunch<CapsHexSplit>;
 #endif
 }  // namespace svof
