@@ -256,3 +256,32 @@ def test_alpha_grad_orientation_known_answers():
     assert out["LS"].mean() < 4 and out["LS"].mean() < out["alphaGrad"].mean() < 12
     with pytest.raises(Exception):
         SolveVofEqu(meshmod.hex_block(4), {"orientationMethod": "isoRDF"}, lib=oracle_lib())
+
+
+def test_cut_cell_symmetries_on_polyhedra():
+    """Properties every exact cell cutter has, on hexes, prisms, 9-face and 14-face polyhedra: the two sides of a plane
+    fill the cell (VOF(n, D) + VOF(-n, -D) = 1), the sub-volume is monotone in D, the interface area vector is parallel
+    to the normal and the two sides share the interface polygon."""
+    rng = np.random.default_rng(11)
+    for m in (meshmod.hex_block(4), meshmod.prism_mesh(3), meshmod.refined_interface_mesh(4), meshmod.kelvin_mesh(2)):
+        s = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=oracle_lib())
+        C, V = s.field(capi.F_C), s.field(capi.F_V)
+        n = 200
+        cells = rng.integers(0, m.n_cells, n).astype(np.int32)
+        nrm = rng.normal(size=(n, 3))
+        nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        h = np.cbrt(V[cells])
+        D = -np.sum(nrm * C[cells], axis=1) + rng.uniform(-0.3, 0.3, n) * h      # planes through the cells
+        st, vof, sv, ic, ia = s.cutCells(cells, nrm, D)
+        st2, vof2, sv2, ic2, ia2 = s.cutCells(cells, -nrm, -D)
+        cut = st == 0
+        assert cut.sum() > 100 and np.array_equal(cut, st2 == 0)
+        assert np.abs(vof[cut] + vof2[cut] - 1.0).max() < 1e-12
+        assert np.abs(sv[cut] - vof[cut] * V[cells][cut]).max() < 1e-16
+        an = np.linalg.norm(ia[cut], axis=1)
+        assert np.abs(np.abs(np.sum(ia[cut] * nrm[cut], axis=1)) - an).max() < 1e-13       # parallel to the plane normal
+        assert np.abs(an - np.linalg.norm(ia2[cut], axis=1)).max() < 1e-13 and np.abs(ic[cut] - ic2[cut]).max() < 1e-12
+        # monotone: the submerged side is n.x + D < 0, so raising D can only uncover more of the cell
+        vof_hi = s.cutCells(cells, nrm, D + 0.05 * h)[1]
+        assert np.all(vof_hi <= vof + 1e-14) and np.any(vof_hi < vof - 1e-3)
+        s.close()
