@@ -17,7 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-HEADERS = [os.path.join(CSRC, f) for f in ("svof_kernels.cuh", "svof_geom_kernels.cuh", "svof_geom.cuh", "svof_math.cuh", "svof_plic_group.cuh")] + \
+HEADERS = [os.path.join(CSRC, f) for f in ("svof_kernels.cuh", "svof_geom_kernels.cuh", "svof_geom.cuh", "svof_math.cuh", "svof_plic_group.cuh", "svof_plic_warp.cuh")] + \
           [os.path.join(HERE, "..", "include", "svof.h")]
 _TAG = os.environ.get("SVOF_BUILD_TAG", "")   # variants build beside the product: lib/libsvof_b200<tag>.so
 OUT = os.path.join(HERE, "lib", "libsvof_b200%s.so" % _TAG)

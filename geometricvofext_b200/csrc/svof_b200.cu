@@ -28,6 +28,10 @@ namespace {
 
 thread_local std::string g_createError;
 
+struct Unsupported : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 struct EventPair {
     cudaEvent_t a = nullptr, b = nullptr;
     int kind = -1;  // 0 reconstruct, 1 advect
@@ -95,6 +99,10 @@ struct svof_handle {
     DenseStage dstage;
     size_t dstageSmem = 0;
     bool useStaged = false;
+    DenseFast dfast;                 // owner-sorted connectivity of the streaming kernel (k_dense_update2)
+    int plicCtas = 0;                // "plic_ctas" option: cap on resident CTAs/SM of the plane-positioning kernel (0 = all that fit)
+    int denseCtas = 0;               // "dense_ctas" option: cap on resident CTAs/SM of the streaming kernel (0 = no cap)
+    int forkAt = 1;                  // "fork" option (overlap != 0): 1 = streaming kernel may start after the near sets, 2 = after plane positioning
     int* bPatch = nullptr;
     double* partial = nullptr;
     double* hpartial = nullptr;
@@ -103,7 +111,7 @@ struct svof_handle {
     double lastDt = 0.0;
     long long launches = 0;
     // svof_step_device: one captured CUDA graph per (alpha buffer parity, patch-value buffer parity, mixed bitmap valid), valid for one dt
-    struct StepGraph { cudaGraphExec_t exec = nullptr; double dt = 0; long long nLaunches = 0; };
+    struct StepGraph { cudaGraphExec_t exec = nullptr; double dt = 0; long long nLaunches = 0; int sched = -1; };
     StepGraph graphs[8];
     bool capturing = false;
     double reconTime = 0, advTime = 0, lastReconMs = 0, lastAdvMs = 0;
@@ -273,6 +281,12 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
         if (p.start != expect || p.size < 0 || p.start + p.size > nF)
             throw std::invalid_argument("svof_mesh: patches must tile the boundary faces in order");
         if (p.kind < 0 || p.kind > 2) throw std::invalid_argument("svof_mesh: unknown patch kind");
+        // advection.C:311-393 (syncProcPatches) is replaced by ghost layers: a decomposed run hands every rank its cells plus
+        // halo layers (svof_decompose) and the library refreshes them (svof_halo_*); raw processor patches would advect
+        // alpha = 0 through the cut, so they are refused instead of silently accepted
+        if (p.kind == SVOF_PATCH_PROCESSOR && p.size > 0)
+            throw Unsupported("svof_mesh: non-empty processor patch: decomposed runs go through svof_decompose + svof_halo_setup "
+                              "(ghost layers), not through processor patches");
         for (int k = 0; k < p.size; ++k) {
             bKind[p.start - nIF + k] = (unsigned char)p.kind;
             bPatch[p.start - nIF + k] = (int)pi;
@@ -334,6 +348,38 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
             const int cA = b * 256, cB = std::min(nC, cA + 256);
             maxRowSlab = std::max(maxRowSlab, cellOff[cB] - (cellOff[cA] & ~1));
             if (ownerSorted) maxPhiSlab = std::max(maxPhiSlab, ctaFace[b + 1] - (ctaFace[b] & ~1));
+        }
+    }
+    // owner-sorted connectivity of the streaming kernel (k_dense_update2): count byte per cell, {first owned internal
+    // face, first neighbour-side row} per 32 cells, {face, owner} rows of the neighbour-side faces
+    std::vector<unsigned char> dfCnt;
+    std::vector<int2> dfWarpBase, dfLowRows;
+    std::vector<unsigned int> dfSlow;
+    // measured at 256^3 (profiles/r2c_*): 568 us against 432 us for the int2-row kernel (the batched, unconditional neighbour
+    // loads spill at 32 registers and double the alpha gathers) -> opt-in (SVOF_DENSE_V2=1) until that is fixed
+    bool dfOk = getenv("SVOF_DENSE_V2") != nullptr && atoi(getenv("SVOF_DENSE_V2")) > 0;
+    {
+        for (int f = 1; f < nIF && dfOk; ++f) dfOk = (own[f - 1] <= own[f]);
+        std::vector<int> nOwnI(nC, 0), nLow(nC, 0);
+        for (int f = 0; f < nIF; ++f) { nOwnI[own[f]]++; nLow[nei[f]]++; }
+        for (int c = 0; c < nC && dfOk; ++c) dfOk = (nOwnI[c] <= 15 && nLow[c] <= 15);
+        if (dfOk) {
+            const int nW = (nC + 31) / 32;
+            dfCnt.resize(nC);
+            dfWarpBase.resize(nW);
+            dfSlow.assign(nW, 0u);
+            dfLowRows.resize(std::max(nIF, 1));
+            std::vector<int> lowOff(nC + 1, 0);
+            int fo0 = 0;
+            for (int c = 0; c < nC; ++c) {
+                if ((c & 31) == 0) dfWarpBase[c >> 5] = make_int2(fo0, lowOff[c]);
+                dfCnt[c] = (unsigned char)(nOwnI[c] | (nLow[c] << 4));
+                fo0 += nOwnI[c];
+                lowOff[c + 1] = lowOff[c] + nLow[c];
+            }
+            std::vector<int> fill(lowOff.begin(), lowOff.end() - 1);
+            for (int f = 0; f < nIF; ++f) dfLowRows[fill[nei[f]]++] = make_int2(f, own[f]);  // ascending face within each cell
+            for (int f = nIF; f < nF; ++f) dfSlow[own[f] >> 5] |= 1u << (own[f] & 31);        // cells with boundary faces: generic rows
         }
     }
     // cellPoints ascending; pointCells ascending
@@ -414,7 +460,7 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
     // upload
     MeshDev& d = h->md;
     d.nPoints = nP; d.nFaces = nF; d.nIF = nIF; d.nCells = nC; d.nBF = nBF;
-    d.maxFV = maxFV; d.maxLocalFaces = maxLocalFaces;
+    d.maxFV = maxFV; d.maxLocalFaces = maxLocalFaces; d.maxLocalPts = maxLocalPts;
     d.points = dupload(h, m.points, (size_t)3 * nP);
     d.faceOff = dupload(h, fo, (size_t)nF + 1);
     d.facePts = dupload(h, fp, (size_t)nFP);
@@ -442,6 +488,13 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
     h->useStaged = getenv("SVOF_DENSE_STAGED") && atoi(getenv("SVOF_DENSE_STAGED")) > 0;
     CK(cudaFuncSetAttribute(k_dense_update_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dstageSmem));
     h->bPatch = dupload(h, bPatch.data(), bPatch.size());
+    h->dfast.enabled = dfOk ? 1 : 0;
+    if (dfOk) {
+        h->dfast.cnt = dupload(h, dfCnt.data(), dfCnt.size());
+        h->dfast.warpBase = dupload(h, dfWarpBase.data(), dfWarpBase.size());
+        h->dfast.lowRows = dupload(h, dfLowRows.data(), dfLowRows.size());
+        h->dfast.slowBits = dupload(h, dfSlow.data(), dfSlow.size());
+    }
 
     double* Cf = dalloc<double>(h, (size_t)3 * nF);
     double* Sf = dalloc<double>(h, (size_t)3 * nF);
@@ -681,7 +734,9 @@ void doReconstruct(svof_handle* h)
     CK(cudaMemsetAsync(h->near2, 0, sizeof(unsigned int) * h->nWords, s));
     LAUNCH(h, k_ctl_reset_recon, 1, 1, h->ctl);
     LAUNCH(h, k_mark_near, g256, 256, d, h->mixedCells, h->ctl, h->near1, h->near2, h->near2List, h->capNear);
-    if (!h->capturing) CK(cudaEventRecord(h->evNear, s));  // the streaming kernel of the coming advect() may start from here
+    // the streaming kernel of the coming advect() only needs alpha.oldTime, phi and the near2 bitmap: with the two-stream
+    // schedule it may start from here (fork 1) or once the plane-positioning kernel has been issued (fork 2)
+    if (h->overlap && h->forkAt == 1) CK(cudaEventRecord(h->evNear, s));
     h->inputsAfterNear = false;
     h->freshRecon = true;
     // A2: LS normals; A3-A5: plane positions
@@ -689,7 +744,8 @@ void doReconstruct(svof_handle* h)
         LAUNCH(h, k_alpha_grad_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->iN);
     else
         LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
-    GEO(h, plic, s, g128, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
+    GEO(h, plic, s, h->plicCtas, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
+    if (h->overlap && h->forkAt != 1) CK(cudaEventRecord(h->evNear, s));
     h->bitsValid = false;  // consumed
 }
 
@@ -702,8 +758,8 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     const double rDt = 1.0 / dt;
     cudaStream_t sS = h->stream, sD = h->overlap ? h->streamD : h->stream;
 
-    // ---- streaming kernel on its own stream: depends only on alpha.oldTime, phi and the near2 bitmap,
-    //      so it overlaps the tail of reconstruct() and the whole sparse chain below
+    // ---- streaming kernel: depends only on alpha.oldTime, phi and the near2 bitmap.  With the two-stream schedule it runs
+    //      on its own low-priority stream beside the interface kernels and is joined before k_near_finalize.
     if (!h->freshRecon) LAUNCH(h, k_ctl_reset_dense, 1, 1, h->ctl);  // advect() without a new reconstruct()
     if (h->overlap) {
         if (h->inputsAfterNear || dSp || dSu || !h->freshRecon) {
@@ -715,13 +771,19 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     }
     if (h->prof) profBegin(h, "k_dense_update", sD);
     EventPair* ed = h->capturing ? nullptr : &beginTimedOn(h, 2, sD);
-    if (h->useStaged)
-        k_dense_update_staged<<<cdiv(h->nC, 256), 256, h->dstageSmem, sD>>>(d, h->dstage, aOld, aNew, h->phi, h->alphaBBuf[h->cb],
-                                                                             h->alphaPhi, h->near2, h->mixedBits, dt, rDt, dSp, dSu,
-                                                                             h->sp, h->ctl);
-    else
-        k_dense_update<<<cdiv(h->nC, 256), 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
-                                                          dt, rDt, dSp, dSu, h->sp, h->ctl);
+    {
+        const int nTiles = cdiv(h->nC, 256);
+        const int grid = (h->denseCtas > 0) ? std::min(nTiles, h->denseCtas * h->sms) : nTiles;
+        if (h->useStaged)
+            k_dense_update_staged<<<nTiles, 256, h->dstageSmem, sD>>>(d, h->dstage, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi,
+                                                                    h->near2, h->mixedBits, dt, rDt, dSp, dSu, h->sp, h->ctl);
+        else if (h->dfast.enabled)
+            k_dense_update2<<<grid, 256, 0, sD>>>(d, h->dfast, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
+                                                  dt, rDt, dSp, dSu, h->sp, h->ctl, nTiles);
+        else
+            k_dense_update<<<nTiles, 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits, dt, rDt,
+                                                   dSp, dSu, h->sp, h->ctl);
+    }
     h->launches++;
     if (ed) endTimedOn(h, *ed, sD);
     if (h->prof) profEnd(h, sD);
@@ -729,7 +791,6 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
 
     // ---- sparse chain
     LAUNCH(h, k_ctl_reset_advect, 1, 1, h->ctl);
-    if (h->overlap == 2) CK(cudaStreamWaitEvent(sS, h->evDense, 0));  // overlap with the tail of reconstruct() only
     // A7-A9: geometric fluxes on the downwind faces of cut cells
     LAUNCH(h, k_un0_worklist, g128, 128, d, h->mixedCells, h->cellStatus, h->ctl, h->iN, h->iC, h->U, h->Ub, h->phi, h->Un0, h->work,
            h->capWork);
@@ -754,7 +815,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         else BOUND_SWEEP(64);
     }
     // join: the finalize kernel ORs into the bitmap words the streaming kernel wrote
-    if (h->overlap == 1) CK(cudaStreamWaitEvent(sS, h->evDense, 0));
+    if (h->overlap) CK(cudaStreamWaitEvent(sS, h->evDense, 0));
     // A12: snap/clip + alphaPhi for near2; boundary values of the new field
     LAUNCH(h, k_near_finalize, g128, 128, d, h->near2List, h->ctl, aNew, h->dVf, h->alphaPhi, h->mixedBits, dt, h->sp, h->oobState);
     h->cur ^= 1;
@@ -897,6 +958,8 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
         h->overlap = getenv("SVOF_OVERLAP") ? atoi(getenv("SVOF_OVERLAP")) : 0;  // default off
+        if (getenv("SVOF_FORK")) h->forkAt = atoi(getenv("SVOF_FORK"));
+        if (getenv("SVOF_DENSE_CTAS")) h->denseCtas = atoi(getenv("SVOF_DENSE_CTAS"));
         h->prof = getenv("SVOF_PROFILE") && atoi(getenv("SVOF_PROFILE")) > 0;
         h->prm = *params;
         h->sp.mixedTol = params->mixed_cell_tol;
@@ -907,7 +970,8 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         buildMesh(h, *mesh);
         allocFields(h);
         CK(cudaStreamSynchronize(h->stream));
-    } catch (const std::invalid_argument& e) { g_createError = e.what(); rc = SVOF_ERR_BAD_MESH; }
+    } catch (const Unsupported& e) { g_createError = e.what(); rc = SVOF_ERR_UNSUPPORTED; }
+    catch (const std::invalid_argument& e) { g_createError = e.what(); rc = SVOF_ERR_BAD_MESH; }
     catch (const std::length_error& e) { g_createError = e.what(); rc = SVOF_ERR_CAPACITY; }
     catch (const std::exception& e) { g_createError = e.what(); rc = SVOF_ERR_CUDA; }
     if (rc) {
@@ -1072,14 +1136,14 @@ int svof_step_device(svof_handle* h, double dt)
 {
     if (!h || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
     if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_step_device: alpha/phi/U not set");
-    if (h->prof || h->overlap || h->advectCount >= (1 << 25) - 2) {   // instrumented / two-stream schedules: plain launches
+    if (h->prof || h->advectCount >= (1 << 25) - 2) {   // instrumented runs: plain launches
         const int rc = svof_reconstruct(h);
         return rc ? rc : svof_advect(h, dt, nullptr, nullptr);
     }
     API_BEGIN
     CK(cudaSetDevice(h->device));
     svof_handle::StepGraph& g = h->graphs[h->cur * 4 + h->cb * 2 + (h->bitsValid ? 1 : 0)];
-    if (!g.exec || g.dt != dt) {
+    if (!g.exec || g.dt != dt || g.sched != h->overlap * 100000 + h->forkAt * 10000 + h->plicCtas * 100 + h->denseCtas) {
         if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
         // run the first step of this kind with plain launches (warms every lazily initialised launcher), then capture
         const int cur0 = h->cur, cb0 = h->cb;
@@ -1116,6 +1180,7 @@ int svof_step_device(svof_handle* h, double dt)
         if (graph) cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { g.exec = nullptr; (void)cudaGetLastError(); }   // graphs unavailable: keep using plain launches
         g.dt = dt;
+        g.sched = h->overlap * 100000 + h->forkAt * 10000 + h->plicCtas * 100 + h->denseCtas;
         return SVOF_OK;
     }
     CK(cudaGraphLaunch(g.exec, h->stream));
@@ -1421,6 +1486,9 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     CK(cudaStreamSynchronize(h->streamD));
     CK(cudaStreamSynchronize(h->stream));
     if (!strcmp(name, "overlap")) { h->overlap = value; return SVOF_OK; }
+    if (!strcmp(name, "fork")) { h->forkAt = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; return SVOF_OK; }
+    if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
     if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");

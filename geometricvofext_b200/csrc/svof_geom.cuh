@@ -30,7 +30,7 @@ enum {
 // Device view of the mesh: CSR/SoA, int32 labels, f64 scalars (DESIGN.md "data layout").
 struct MeshDev {
     int nPoints, nFaces, nIF, nCells, nBF;
-    int maxFV, maxLocalFaces;   // mesh maxima: vertices per (local) face, local faces per cell (with splitWarpedFace: triangulated)
+    int maxFV, maxLocalFaces, maxLocalPts;   // mesh maxima: vertices per (local) face, local faces / points per cell (with splitWarpedFace: triangulated)
     const double* points;       // [3*nPoints]
     const int* faceOff;         // [nFaces+1]
     const int* facePts;

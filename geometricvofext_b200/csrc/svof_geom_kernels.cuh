@@ -4,6 +4,7 @@
 #pragma once
 #include "svof_kernels.cuh"
 #include "svof_plic_group.cuh"
+#include "svof_plic_warp.cuh"
 
 namespace svof {
 
@@ -186,12 +187,41 @@ template <class CP>
 void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* alpha, const double* iN,
                          int split, int* cellStatus, double* iD, double* iC, double* iS)
 {
-    // lane-cooperative kernel (8 lanes per cell) whenever the per-cell staging area fits shared memory
+    // warp-cooperative kernel: self-contained groups of 8 lanes per cell, 4 cells per warp, staging sized from the mesh's maxima
+    static const bool useGroup = getenv("SVOF_PLIC") && !strcmp(getenv("SVOF_PLIC"), "group");  // round-1 CTA-phase kernel (A/B runs)
+    const PlicWarpLayout L = PlicWarpLayout::make(m.maxLocalFaces, m.maxFV, m.maxLocalPts);
+    const size_t cellBytes = (size_t)L.strideD * sizeof(double);
+    if (!useGroup && 4 * cellBytes <= 200 * 1024) {
+        int threads = SV_PW_THREADS;
+        while (threads > 32 && cellBytes * (threads / SV_G) > 56 * 1024) threads >>= 1;
+        const size_t smem = cellBytes * (threads / SV_G);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_plic_warp<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+            configured = true;
+        }
+        // persistent: as many CTAs as fit on the device at once, or `grid` per SM when the caller caps it (> 0: the
+        // "plic_ctas" option leaves room for the streaming kernel on every SM)
+        static int resident = 0, residentThreads = 0, residentCap = -1;
+        static size_t residentSmem = 0;
+        if (!resident || residentThreads != threads || residentSmem != smem || residentCap != grid) {
+            int perSm = 0, dev = 0, sms = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_plic_warp<CP>, threads, smem);
+            if (grid > 0 && grid < perSm) perSm = grid;
+            resident = (perSm > 0 ? perSm : 1) * (sms > 0 ? sms : 148);
+            residentThreads = threads;
+            residentSmem = smem;
+            residentCap = grid;
+        }
+        k_plic_warp<CP><<<resident, threads, smem, st>>>(m, L, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
+        return;
+    }
+    // round-1 kernel: CTA of cpb cells x 8 lanes with leader phases (kept for A/B timing)
     size_t perCell = sizeof(GCellShared<CP>) + SV_G * LanePriv<CP>::DOUBLES * sizeof(double);
     if (CP::MAXCF > SV_G)   // per-face records for cells with more than one face per lane, sized from the mesh's maxima
         perCell += sizeof(double) * ((size_t)m.maxLocalFaces * FaceRec::doubles(m.maxFV) + (m.maxLocalFaces + 1) / 2);
-    // 16 cells x 8 lanes, 4 CTAs per SM: measured 357 us at 256^3 against 391 us for 32 x 8 with 2 CTAs per SM
-    // (the CTA barrier between the face and leader phases then holds up 3 warps instead of 7)
     int threads = SV_PLIC_THREADS;
     while (threads > 32 && perCell * (threads / SV_G) > 100 * 1024) threads >>= 1;
     const size_t smem = perCell * (threads / SV_G);
@@ -201,7 +231,6 @@ void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedC
             cudaFuncSetAttribute(k_plic_group<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
             configured = true;
         }
-        // persistent: exactly as many CTAs as fit on the device at once (the staging size depends on the mesh)
         static int resident = 0, residentThreads = 0;
         static size_t residentSmem = 0;
         if (!resident || residentThreads != threads || residentSmem != smem) {
@@ -209,15 +238,13 @@ void GeoLaunch<CP>::plic(cudaStream_t st, int grid, MeshDev m, const int* mixedC
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_plic_group<CP>, threads, smem);
-            if (const char* e = getenv("SVOF_PLIC_CTAS")) perSm = atoi(e) < perSm ? atoi(e) : perSm;  // experiments
             resident = (perSm > 0 ? perSm : 1) * (sms > 0 ? sms : 148);
             residentThreads = threads;
             residentSmem = smem;
         }
-        (void)grid;
         k_plic_group<CP><<<resident, threads, smem, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
     } else {
-        k_plic<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);
+        k_plic<CP><<<148 * 8, 128, 0, st>>>(m, mixedCells, ctl, alpha, iN, split, cellStatus, iD, iC, iS);  // grid-stride, thread per cell
     }
 }
 template <class CP>
