@@ -105,8 +105,10 @@ def velocity_fields(s, t, dt):
     return U, phi
 
 
-def cpu_oracle_rate(m, a0, U, phi, dt, steps):
-    """The CPU restatement of the reference algorithm, timed on this box's host (1 core)."""
+def cpu_oracle_rate(m, a0, U, phi, dt, steps, keep=False):
+    """The CPU restatement of the reference algorithm, timed on this box's host (1 core).  keep=True also returns
+    its state after the 1 + steps steps it ran (alpha, alphaPhi, the interface-cell list of that alpha) so that the
+    GPU run of the same steps can be compared AT THE SIZE THE NUMBER IS QUOTED ON (checker use of oracle/, as in tests/)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build as oracle_build
     lib = capi.load(oracle_build.build_oracle())
@@ -122,8 +124,50 @@ def cpu_oracle_rate(m, a0, U, phi, dt, steps):
         so.advect(dt)
     el = time.perf_counter() - t0
     rate = m.n_cells * steps / el
+    state = None
+    if keep:
+        so.reconstruct()
+        state = {"alpha": so.alpha(), "alphaPhi": so.alphaPhi(), "mixed": so.mixedCells(), "status": so.cellStatus(),
+                 "volume": so.volume(), "steps": steps + 1}
     so.close()
-    return rate, el
+    return rate, el, state
+
+
+def parity_block(s, m, a0, dt, ref, label):
+    """GPU run of the same steps as the oracle's (same inputs), compared field by field."""
+    s.setAlpha(a0)
+    for _ in range(ref["steps"]):
+        s.step(dt)
+    s.reconstruct()
+    a, ap = s.alpha(), s.alphaPhi()
+    mixed_equal = bool(np.array_equal(s.mixedCells(), ref["mixed"]) and np.array_equal(s.cellStatus(), ref["status"]))
+    vol = s.volume()
+    out = {"case": label, "steps": ref["steps"], "cells": m.n_cells, "mixed_cells": int(ref["mixed"].size),
+           "mixed_set_equal": mixed_equal, "max_abs_alpha": float(np.abs(a - ref["alpha"]).max()),
+           "max_abs_alphaPhi": float(np.abs(ap - ref["alphaPhi"]).max()),
+           "bitwise_alpha": bool(np.array_equal(a, ref["alpha"])), "bitwise_alphaPhi": bool(np.array_equal(ap, ref["alphaPhi"])),
+           "volume_rel": float(abs(vol - ref["volume"]) / abs(ref["volume"])), "checker": "oracle/ (CPU restatement), same inputs"}
+    return out
+
+
+def advance_on_device(s, U0, phi0, t_end, dt, torch):
+    """plicVof.H loop with phi(t), U(t) refreshed on the device every step (updateU.H:59-69 scales the steady field)."""
+    dev = torch.device("cuda", 0)
+    tU0, tphi0 = torch.as_tensor(U0, device=dev), torch.as_tensor(phi0, device=dev)
+    tU, tphi = torch.empty_like(tU0), torch.empty_like(tphi0)
+    t, k = 0.0, 0
+    while t < t_end - 1e-12:
+        t += dt
+        f = fields.u_factor(t, dt, PERIOD)
+        torch.mul(tU0, f, out=tU)
+        torch.mul(tphi0, f, out=tphi)
+        torch.cuda.current_stream().synchronize()
+        s._chk(s.lib.svof_set_phi_device(s._h, tphi.data_ptr()))
+        s._chk(s.lib.svof_set_U_device(s._h, tU.data_ptr(), None))
+        s.step(dt)
+        s.synchronize()
+        k += 1
+    return t, k
 
 
 def run_ours(args):
@@ -217,14 +261,52 @@ def run_ours(args):
         except Exception:
             traffic = None
 
-    # ---- CPU baseline: the oracle on the same workload, bounded sample ---------------------------
-    cpu = None
+    # ---- CPU baseline: the oracle on the same workload, bounded sample; its fields are kept to check the GPU run ----
+    cpu, parity = None, []
     if not args.no_cpu:
         cs = max(1, args.cpu_steps)
-        rate, el = cpu_oracle_rate(m, a0, U, phi, dt, cs)
+        rate, el, ref = cpu_oracle_rate(m, a0, U, phi, dt, cs, keep=True)
         cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "same %d^3 workload and fields, %d steps (%.1f s) of the single-threaded CPU restatement "
                          "of the reference algorithm (oracle/), OpenFOAM itself is not installable here" % (n, cs, el)}
+        s.setPhi(phi)
+        s.setU(U, Ub)
+        parity.append(parity_block(s, m, a0, dt, ref, "t = 0 window"))
+
+    # ---- second window: the stretched interface near t = 1.5 (maximum deformation: ~3.5x the interface cells) ----
+    late = None
+    if args.late_steps > 0:
+        import torch
+        U1, phi1 = fields.leveque_velocity(s.field(capi.F_C)), None
+        phi1 = fields.face_flux(s.field(capi.F_CF), s.field(capi.F_SF))
+        s.setAlpha(a0)
+        t_adv0 = time.perf_counter()
+        t_late, k_adv = advance_on_device(s, U1, phi1, args.late_time, dt, torch)
+        adv_s_wall = time.perf_counter() - t_adv0
+        del U1, phi1
+        s.setPhi(phi)        # the timed window uses the same frozen flux field as the first one
+        s.setU(U, Ub)
+        a_late = s.alpha()
+        for _ in range(2 + args.warmup):
+            s.step(dt)
+        s.synchronize()
+        lib.svof_mark(h, 4)
+        for _ in range(args.late_steps):
+            s.step(dt)
+        lib.svof_mark(h, 5)
+        ms_late = C.c_double()
+        lib.svof_elapsed_ms(h, 4, 5, C.byref(ms_late))
+        s.synchronize()
+        late = {"window": "interface advanced to t = %.3f (%d steps with phi(t), U(t) refreshed on the device, %.1f s), then %d timed "
+                          "steps with the frozen flux field of the first window" % (t_late, k_adv, adv_s_wall, args.late_steps),
+                "steps": args.late_steps, "ms_per_step": ms_late.value / args.late_steps,
+                "value": m.n_cells * args.late_steps / (ms_late.value * 1e-3), "mixed_cells": int(s.info(capi.I_N_MIXED)),
+                "near_cells": int(s.info(capi.I_N_NEAR)),
+                "step_frac": (B / (ms_late.value / args.late_steps * 1e-3) / 1e9) / peak,
+                "error_flags": int(s.info(capi.I_ERROR_FLAGS))}
+        if not args.no_cpu and args.late_cpu_steps > 0:
+            _, _, ref_late = cpu_oracle_rate(m, a_late, U, phi, dt, max(0, args.late_cpu_steps - 1), keep=True)
+            parity.append(parity_block(s, m, a_late, dt, ref_late, "t = %.2f window" % t_late))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -253,6 +335,8 @@ def run_ours(args):
                              "just before the graph leg (same kernel, nothing runs beside it); step_frac: algorithmic bytes of the "
                              "whole step / graph-leg step time / peak" % args.steps},
         "cpu_baseline": cpu,
+        "parity": parity,
+        "late_window": late,
     }
     print(json.dumps(line))
 
@@ -328,8 +412,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--late-steps", type=int, default=200, help="timed steps of the second window (0: skip it)")
+    ap.add_argument("--late-time", type=float, default=1.5, help="flow time the interface is advanced to before the second window")
+    ap.add_argument("--late-cpu-steps", type=int, default=2, help="oracle steps for the parity block of the second window")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-size", dest="ref_n", type=int, default=0)
+    # N > 1: strong scaling of ONE problem (BASELINE.json configs[4]) unless --scaling weak (one 256^3 unit cube per GPU)
+    ap.add_argument("--scaling", default=os.environ.get("SVOF_BENCH_SCALING", "strong"), choices=["strong", "weak"])
+    ap.add_argument("--strong-size", dest="strong_n", type=int, default=int(os.environ.get("SVOF_BENCH_STRONG_N", "512")))
+    ap.add_argument("--layers", type=int, default=0, help="ghost layers (0: nAlphaBounds + 2)")
+    ap.add_argument("--mixed-weight", type=float, default=float(os.environ.get("SVOF_BENCH_MIXED_WEIGHT", "600")),
+                    help="partition weight of an interface cell relative to a bulk cell (strong scaling)")
+    ap.add_argument("--overlap", type=int, default=-1, help="two-stream schedule (library option 'overlap'); -1: library default")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

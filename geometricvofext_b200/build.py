@@ -2,7 +2,7 @@
 
     python -m geometricvofext_b200.build [--force] [--verbose]
 
-Five translation units are compiled in parallel (the host/streaming TU + one per
+Seven translation units are compiled in parallel (the host/streaming TU + one per
 polyhedron-capacity variant of the geometry kernels) and linked into
 geometricvofext_b200/lib/libsvof_b200.so.
 
@@ -29,7 +29,7 @@ NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompile
              (["-DSV_DENSE_UNROLL=" + os.environ["SVOF_DENSE_UNROLL"]] if os.environ.get("SVOF_DENSE_UNROLL") else []) + \
              os.environ.get("SVOF_EXTRA_DEFS", "").split()   # kernel-variant experiments (with SVOF_BUILD_TAG)
 
-UNITS = [("svof_b200", "svof_b200.cu", [])] + \
+UNITS = [("svof_b200", "svof_b200.cu", []), ("svof_decomp", "svof_decomp.cpp", [])] + \
         [("svof_inst%d" % v, "svof_inst.cu", ["-DSV_VARIANT=%d" % v]) for v in range(5)]
 
 
@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
                 raise RuntimeError("nvcc failed for %s" % name)
     objs = [os.path.join(OBJ, name + ".o") for name, _, _ in UNITS]
     if force or jobs or _stale(OUT, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-Xlinker", "-Bsymbolic", "-Xcompiler", "-pthread", "-o", OUT] + objs
+        cmd = [nvcc] + ARCH + ["-shared", "-cudart", "static", "-Xlinker", "-Bsymbolic", "-Xcompiler", "-pthread", "-o", OUT] + objs + ["-ldl"]
         subprocess.check_call(cmd)
     return OUT
 

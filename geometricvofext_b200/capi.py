@@ -26,7 +26,7 @@ BC_ZERO_GRADIENT, BC_FIXED_VALUE, BC_INLET_OUTLET = 0, 1, 2
 (I_N_MIXED, I_MIN_ALPHA_BEFORE, I_MAX_ALPHA_M1_BEFORE, I_MIN_ALPHA_AFTER, I_MAX_ALPHA_M1_AFTER, I_N_BOUND_SWEEPS,
  I_RECONSTRUCTION_TIME, I_ADVECTION_TIME, I_ALPHA_MAPPING_TIME, I_VOLUME, I_GPU_LAUNCHES, I_FLATNESS_MIN,
  I_FLATNESS_MAX, I_FLATNESS_AVG, I_DEVICE_BYTES, I_ERROR_FLAGS, I_DENSE_KERNEL_MS, I_DENSE_KERNEL_LAUNCHES,
- I_N_NEAR, I_H2D_BYTES, I_D2H_BYTES) = range(21)
+ I_N_NEAR, I_H2D_BYTES, I_D2H_BYTES, I_VOLUME_OWNED, I_HALO_BYTES) = range(23)
 
 
 class SvofPatch(C.Structure):
@@ -51,7 +51,8 @@ class SvofParams(C.Structure):
 
 
 class SvofComm(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("world_size", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("rank", C.c_int32), ("world_size", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32),
+                ("nccl_unique_id", C.c_void_p)]
 
 
 # every symbol include/svof.h declares: (name, restype, argtypes)
@@ -94,6 +95,16 @@ SYMBOLS = [
                                    c_double_p, c_double_p]),
     ("svof_plic_surface", C.c_int, [_H, C.c_int64, C.c_int64, c_double_p, c_int32_p, c_int32_p, C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int64)]),
+    # decomposed runs
+    ("svof_partition_rcb", C.c_int, [C.POINTER(SvofMesh), c_double_p, C.c_int32, c_int32_p]),
+    ("svof_decompose", C.c_int, [C.POINTER(SvofMesh), c_int32_p, C.c_int32, C.c_int32, C.POINTER(_H)]),
+    ("svof_submesh_mesh", C.c_int, [_H, C.POINTER(SvofMesh)]),
+    ("svof_submesh_maps", C.c_int, [_H, C.POINTER(C.c_int32)] + [C.POINTER(c_int32_p)] * 6),
+    ("svof_submesh_free", C.c_int, [_H]),
+    ("svof_decomp_last_error", C.c_char_p, []),
+    ("svof_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("svof_halo_setup", C.c_int, [_H, c_int32_p, c_int32_p]),
+    ("svof_halo_exchange", C.c_int, [_H]),
 ]
 
 PRODUCT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsvof_b200.so")

@@ -19,6 +19,9 @@
 #include <thread>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is dlopen()ed at run time (no link-time dependency, loads on CPU-only boxes)
+
 #include "../../include/svof.h"
 #include "svof_geom_kernels.cuh"
 
@@ -107,6 +110,16 @@ struct svof_handle {
     double* partial = nullptr;
     double* hpartial = nullptr;
 
+    // decomposed runs: NCCL communicator of this handle and the ghost-refresh plan (svof_halo_setup)
+    int rank = 0, world = 1;
+    ncclComm_t nccl = nullptr;
+    struct Halo {
+        bool active = false;
+        std::vector<int> peers, sendOff, recvOff;   // per peer: offsets into the packed send / receive buffers
+        int nSend = 0, nRecv = 0, nOwned = 0;
+        int *sendIdx = nullptr, *recvIdx = nullptr, *ownedIdx = nullptr;
+        double *sendBuf = nullptr, *recvBuf = nullptr;
+    } halo;
     bool haveAlpha = false, havePhi = false, haveU = false, bitsValid = false, advected = false;
     double lastDt = 0.0;
     long long launches = 0;
@@ -711,6 +724,110 @@ __global__ void k_ctl_reset_dense(Ctl* ctl)
     ctl->maxDense = 0ull;
 }
 
+
+// ---- NCCL, bound at run time ------------------------------------------------------------------------
+// dlopen instead of a link-time dependency: the library must load on CPU-only boxes (symbol checks, svof_decompose),
+// and a host process that already carries an NCCL (torch.distributed, an MPI build) must not end up with two copies.
+struct NcclApi {
+    bool tried = false, ok = false;
+    std::string why;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& ncclApi()
+{
+    static NcclApi a;
+    if (a.tried) return a;
+    a.tried = true;
+    void* lib = nullptr;
+    const char* names[] = {getenv("SVOF_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {   // an NCCL already in the process (torch's) wins over loading another one
+        if (n && !lib) lib = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    }
+    for (const char* n : names) {
+        if (n && !lib) lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!lib) {
+        a.why = std::string("libnccl.so.2 not loadable: ") + (dlerror() ? dlerror() : "?");
+        return a;
+    }
+#define SV_NCCL_SYM(field, name)                                   \
+    a.field = (decltype(a.field))dlsym(lib, name);                 \
+    if (!a.field) { a.why = std::string("missing symbol ") + name; return a; }
+    SV_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    SV_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    SV_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    SV_NCCL_SYM(GroupStart, "ncclGroupStart")
+    SV_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    SV_NCCL_SYM(Send, "ncclSend")
+    SV_NCCL_SYM(Recv, "ncclRecv")
+    SV_NCCL_SYM(AllGather, "ncclAllGather")
+    SV_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef SV_NCCL_SYM
+    a.ok = true;
+    return a;
+}
+struct CommError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+#define NK(call)                                                                                  \
+    do {                                                                                          \
+        ncclResult_t r_ = (call);                                                                 \
+        if (r_ != ncclSuccess) {                                                                  \
+            char buf_[512];                                                                       \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, ncclApi().GetErrorString(r_), __FILE__, __LINE__); \
+            throw CommError(buf_);                                                                \
+        }                                                                                         \
+    } while (0)
+
+__global__ void k_gather_alpha(const int* __restrict__ idx, int n, const double* __restrict__ alpha, double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = alpha[idx[i]];
+}
+__global__ void k_volume_partial_list(const int* __restrict__ idx, int n, const double* alpha, const double* V, double* partial)
+{
+    __shared__ double sh[256];
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += alpha[idx[i]] * V[idx[i]];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// ghost alpha <- owning rank: pack, one grouped NCCL send/recv, scatter (keeps the mixed-cell bitmap valid).  Everything
+// is enqueued on the handle's stream: no host synchronisation.  This one exchange stands where the reference has the
+// zoneDistribute stencil exchange (reconstruction.C:97-107) and 1 + 2 x sweeps calls of syncProcPatches (advection.C:311-393).
+void haloExchange(svof_handle* h)
+{
+    svof_handle::Halo& H = h->halo;
+    if (!H.active) return;
+    NcclApi& N = ncclApi();
+    double* alpha = h->alphaBuf[h->cur];
+    if (H.nSend) LAUNCH(h, k_gather_alpha, cdiv(H.nSend, 256), 256, H.sendIdx, H.nSend, alpha, H.sendBuf);
+    NK(N.GroupStart());
+    for (size_t p = 0; p < H.peers.size(); ++p) {
+        const int ns = H.sendOff[p + 1] - H.sendOff[p], nr = H.recvOff[p + 1] - H.recvOff[p];
+        if (ns) NK(N.Send(H.sendBuf + H.sendOff[p], (size_t)ns, ncclDouble, H.peers[p], h->nccl, h->stream));
+        if (nr) NK(N.Recv(H.recvBuf + H.recvOff[p], (size_t)nr, ncclDouble, H.peers[p], h->nccl, h->stream));
+    }
+    NK(N.GroupEnd());
+    if (H.nRecv)
+        LAUNCH(h, k_scatter_alpha, cdiv(H.nRecv, 256), 256, H.recvIdx, H.recvBuf, (long long)H.nRecv, h->prm.mixed_cell_tol, alpha,
+               h->mixedBits, h->bitsValid ? 1 : 0);
+}
+
 void alphaBC(svof_handle* h)
 {
     if (h->nBF > 0)
@@ -820,8 +937,11 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     LAUNCH(h, k_near_finalize, g128, 128, d, h->near2List, h->ctl, aNew, h->dVf, h->alphaPhi, h->mixedBits, dt, h->sp, h->oobState);
     h->cur ^= 1;
     h->cb ^= 1;  // keep the patch values alpha.oldTime() was advected with (for dVf materialisation)
-    alphaBC(h);
     h->bitsValid = true;
+    if (!(h->capturing && h->halo.active)) {  // decomposed runs: the ghost refresh (NCCL) stays outside the captured graph
+        haloExchange(h);
+        alphaBC(h);
+    }
     h->advected = true;
     h->freshRecon = false;
     h->lastDt = dt;
@@ -851,6 +971,7 @@ int fail(svof_handle* h, int code, const char* what)
     }                                                        \
     catch (const std::invalid_argument& e) { return fail(h, SVOF_ERR_INVALID_ARG, e.what()); } \
     catch (const std::length_error& e) { return fail(h, SVOF_ERR_CAPACITY, e.what()); }        \
+    catch (const CommError& e) { return fail(h, SVOF_ERR_COMM, e.what()); }                    \
     catch (const std::exception& e) { return fail(h, SVOF_ERR_CUDA, e.what()); }
 
 bool parseBool(const char* v, int32_t* out)
@@ -932,7 +1053,11 @@ int svof_params_set(svof_params* p, const char* key, const char* value)
 int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_comm* comm, svof_handle** out)
 {
     if (!mesh || !params || !out) { g_createError = "svof_create: null argument"; return SVOF_ERR_INVALID_ARG; }
-    if (comm && comm->world_size > 1) { g_createError = "decomposed runs: use svof_create on each rank with processor patches (not yet enabled)"; return SVOF_ERR_UNSUPPORTED; }
+    if (comm && comm->world_size > 1) {
+        if (comm->rank < 0 || comm->rank >= comm->world_size) { g_createError = "svof_comm: rank out of range"; return SVOF_ERR_INVALID_ARG; }
+        if (!comm->nccl_unique_id) { g_createError = "svof_comm: world_size > 1 needs nccl_unique_id (svof_comm_unique_id on one rank, broadcast)"; return SVOF_ERR_INVALID_ARG; }
+        if (!ncclApi().ok) { g_createError = "NCCL unavailable: " + ncclApi().why; return SVOF_ERR_COMM; }
+    }
     if (params->orientation_method == SVOF_ORIENT_ISO_RDF) {
         g_createError = "orientationMethod isoRDF is not implemented (needs OpenFOAM's reconstructedDistanceFunction; SURVEY.md 8f)";
         return SVOF_ERR_UNSUPPORTED;
@@ -970,9 +1095,17 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         buildMesh(h, *mesh);
         allocFields(h);
         CK(cudaStreamSynchronize(h->stream));
+        if (comm && comm->world_size > 1) {
+            h->rank = comm->rank;
+            h->world = comm->world_size;
+            ncclUniqueId id;
+            memcpy(&id, comm->nccl_unique_id, sizeof(id));
+            NK(ncclApi().CommInitRank(&h->nccl, h->world, id, h->rank));
+        }
     } catch (const Unsupported& e) { g_createError = e.what(); rc = SVOF_ERR_UNSUPPORTED; }
     catch (const std::invalid_argument& e) { g_createError = e.what(); rc = SVOF_ERR_BAD_MESH; }
     catch (const std::length_error& e) { g_createError = e.what(); rc = SVOF_ERR_CAPACITY; }
+    catch (const CommError& e) { g_createError = e.what(); rc = SVOF_ERR_COMM; }
     catch (const std::exception& e) { g_createError = e.what(); rc = SVOF_ERR_CUDA; }
     if (rc) {
         svof_destroy(h);
@@ -989,6 +1122,7 @@ int svof_destroy(svof_handle* h)
     if (h->prof) profPrint(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->streamD) cudaStreamSynchronize(h->streamD);
+    if (h->nccl && ncclApi().ok) ncclApi().CommDestroy(h->nccl);
     for (void* p : h->allocs) cudaFree(p);
     if (h->hctl) cudaFreeHost(h->hctl);
     if (h->hpartial) cudaFreeHost(h->hpartial);
@@ -1066,6 +1200,111 @@ int svof_scatter_alpha_device(svof_handle* h, const int32_t* d_idx, const double
                   h->mixedBits, h->bitsValid ? 1 : 0);
     alphaBC(h);
     h->advected = false;
+    h->hostAlphaSynced = nullptr;
+    return SVOF_OK;
+    API_END(h)
+}
+
+
+// ---- decomposed runs: NCCL bootstrap and the ghost-refresh plan --------------------------------------
+int svof_comm_unique_id(void* id128)
+{
+    if (!id128) return SVOF_ERR_INVALID_ARG;
+    NcclApi& N = ncclApi();
+    if (!N.ok) { g_createError = "NCCL unavailable: " + N.why; return SVOF_ERR_COMM; }
+    ncclUniqueId id;
+    if (N.GetUniqueId(&id) != ncclSuccess) { g_createError = "ncclGetUniqueId failed"; return SVOF_ERR_COMM; }
+    memcpy(id128, &id, sizeof(id));
+    return SVOF_OK;
+}
+
+int svof_halo_setup(svof_handle* h, const int32_t* cell_global, const int32_t* cell_owner_rank)
+{
+    if (!h || !cell_global || !cell_owner_rank) return SVOF_ERR_INVALID_ARG;
+    if (h->world > 1 && !h->nccl) return fail(h, SVOF_ERR_STATE, "svof_halo_setup: the handle was created without an NCCL id");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    NcclApi& N = ncclApi();
+    const int nC = h->nC, W = h->world, me = h->rank;
+    svof_handle::Halo& H = h->halo;
+    for (int c = 1; c < nC; ++c)
+        if (cell_global[c - 1] >= cell_global[c]) throw std::invalid_argument("svof_halo_setup: cell_global must ascend");
+    // ghosts by owner (local order == ascending global label)
+    std::vector<std::vector<int>> needLocal(W), needGlobal(W);
+    std::vector<int> owned;
+    for (int c = 0; c < nC; ++c) {
+        const int r = cell_owner_rank[c];
+        if (r < 0 || r >= W) throw std::invalid_argument("svof_halo_setup: owner rank out of range");
+        if (r == me) owned.push_back(c);
+        else { needLocal[r].push_back(c); needGlobal[r].push_back(cell_global[c]); }
+    }
+    H.nOwned = (int)owned.size();
+    H.ownedIdx = dupload(h, owned.data(), owned.size());
+    H.peers.clear(); H.sendOff.assign(1, 0); H.recvOff.assign(1, 0);
+    std::vector<int> sendIdx, recvIdx;
+    if (W > 1) {
+        // 1. who needs how many cells from whom: all-gather of the per-owner ghost counts
+        std::vector<int> myCounts(W), all((size_t)W * W);
+        for (int r = 0; r < W; ++r) myCounts[r] = (int)needLocal[r].size();
+        int* dMine = dupload(h, myCounts.data(), myCounts.size());
+        int* dAll = dalloc<int>(h, (size_t)W * W);
+        NK(N.AllGather(dMine, dAll, (size_t)W, ncclInt32, h->nccl, h->stream));
+        CK(cudaMemcpyAsync(all.data(), dAll, sizeof(int) * W * W, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        // 2. the global labels each peer wants from me
+        std::vector<int*> dWant(W, nullptr), dNeed(W, nullptr);
+        std::vector<int> wantCount(W, 0);
+        for (int r = 0; r < W; ++r) {
+            wantCount[r] = (r == me) ? 0 : all[(size_t)r * W + me];
+            if (wantCount[r]) dWant[r] = dalloc<int>(h, wantCount[r]);
+            if (!needGlobal[r].empty()) dNeed[r] = dupload(h, needGlobal[r].data(), needGlobal[r].size());
+        }
+        NK(N.GroupStart());
+        for (int r = 0; r < W; ++r) {
+            if (r == me) continue;
+            if (!needGlobal[r].empty()) NK(N.Send(dNeed[r], needGlobal[r].size(), ncclInt32, r, h->nccl, h->stream));
+            if (wantCount[r]) NK(N.Recv(dWant[r], (size_t)wantCount[r], ncclInt32, r, h->nccl, h->stream));
+        }
+        NK(N.GroupEnd());
+        CK(cudaStreamSynchronize(h->stream));
+        // 3. the plan: per peer, what I send (their wanted labels -> my local cells) and where what I receive goes
+        for (int r = 0; r < W; ++r) {
+            if (r == me || (wantCount[r] == 0 && needLocal[r].empty())) continue;
+            H.peers.push_back(r);
+            std::vector<int> want(wantCount[r]);
+            if (wantCount[r]) CK(cudaMemcpy(want.data(), dWant[r], sizeof(int) * wantCount[r], cudaMemcpyDeviceToHost));
+            for (int g : want) {
+                const int32_t* it = std::lower_bound(cell_global, cell_global + nC, g);
+                if (it == cell_global + nC || *it != g || cell_owner_rank[it - cell_global] != me)
+                    throw std::invalid_argument("svof_halo_setup: a peer asks for a cell this rank does not own");
+                sendIdx.push_back((int)(it - cell_global));
+            }
+            recvIdx.insert(recvIdx.end(), needLocal[r].begin(), needLocal[r].end());
+            H.sendOff.push_back((int)sendIdx.size());
+            H.recvOff.push_back((int)recvIdx.size());
+        }
+    }
+    H.nSend = (int)sendIdx.size();
+    H.nRecv = (int)recvIdx.size();
+    H.sendIdx = dupload(h, sendIdx.data(), sendIdx.size());
+    H.recvIdx = dupload(h, recvIdx.data(), recvIdx.size());
+    H.sendBuf = dalloc<double>(h, sendIdx.size());
+    H.recvBuf = dalloc<double>(h, recvIdx.size());
+    CK(cudaStreamSynchronize(h->stream));
+    H.active = (W > 1);
+    for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }   // the captured tail changes
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_halo_exchange(svof_handle* h)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    if (!h->haveAlpha) return fail(h, SVOF_ERR_STATE, "svof_halo_exchange: alpha not set");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    haloExchange(h);
+    alphaBC(h);
     h->hostAlphaSynced = nullptr;
     return SVOF_OK;
     API_END(h)
@@ -1189,6 +1428,10 @@ int svof_step_device(svof_handle* h, double dt)
     h->cur ^= 1;
     h->cb ^= 1;
     h->bitsValid = true;
+    if (h->halo.active) {
+        haloExchange(h);
+        alphaBC(h);
+    }
     h->advected = true;
     h->freshRecon = false;
     h->inputsAfterNear = false;
@@ -1430,6 +1673,19 @@ int svof_get_info(svof_handle* h, int which, double* out)
             *out = buf[0];
             return SVOF_OK;
         }
+        case SVOF_I_VOLUME_OWNED: {
+            if (!h->halo.ownedIdx) return fail(h, SVOF_ERR_STATE, "SVOF_I_VOLUME_OWNED: svof_halo_setup has not been called");
+            LAUNCH(h, k_volume_partial_list, 1024, 256, h->halo.ownedIdx, h->halo.nOwned, h->alphaBuf[h->cur], h->md.V, h->partial);
+            CK(cudaMemcpyAsync(h->hpartial, h->partial, 1024 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            double buf[1024];
+            memcpy(buf, h->hpartial, sizeof(buf));
+            for (int o = 512; o > 0; o >>= 1)
+                for (int i = 0; i < o; ++i) buf[i] += buf[i + o];
+            *out = buf[0];
+            return SVOF_OK;
+        }
+        case SVOF_I_HALO_BYTES: *out = 8.0 * h->halo.nRecv; return SVOF_OK;
         case SVOF_I_GPU_LAUNCHES: *out = (double)h->launches; return SVOF_OK;
         case SVOF_I_FLATNESS_MIN: *out = h->flatMin; return SVOF_OK;
         case SVOF_I_FLATNESS_MAX: *out = h->flatMax; return SVOF_OK;

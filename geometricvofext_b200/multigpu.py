@@ -1,33 +1,95 @@
-"""Decomposed (one process per GPU) SimPLIC step.
+"""Decomposed (one process per GPU) SimPLIC step: host-side driver.
 
 The reference runs in parallel the OpenFOAM way: one MPI rank per scotch sub-domain, processor
-patches, ~10 halo swaps / reductions per step.  Here every rank owns a box of
-cells of the global mesh and carries a halo of `G` cell layers around it (overlapping
-decomposition): the whole reconstruct()+advect() sequence runs on the extended block with the
-unchanged single-GPU kernels, and ONE exchange per step refreshes the halo alpha from the
-owning ranks.  Dependency radius of one step: LS normal (1 point layer) -> plane/flux of the
-upwind cell (1 face layer) -> bounding corrections (1 layer per sweep that actually moves
-fluid), so with G = 4 the owned cells reproduce the single-domain result (to round-off of the
-bounding order across the cut, which the reference itself does not preserve in parallel).
+patches, ~10 halo swaps / reductions per step.  Here every rank holds its cells
+plus `layers` point-neighbour layers of ghost cells (svof_decompose in the library, or -- for
+uniform boxes that are too big to materialise globally -- the same sub-mesh generated directly by
+`hex_block`), runs the unchanged single-domain step on that sub-mesh, and ONE exchange per step
+refreshes ghost alpha from the owning ranks.
 
-Transport is torch.distributed: NCCL over NVLink/NVSwitch between GPUs (device tensors wrapped
-around the solver's own alpha buffer -- no host staging), gloo on CPU for the tests.
+On GPUs the exchange lives in the library (include/svof.h "decomposed runs": pack kernel, grouped
+ncclSend/ncclRecv on the handle's stream, scatter kernel); Python only broadcasts the 128-byte NCCL
+id (torch.distributed is the bootstrap transport, as MPI_Bcast would be inside OpenFOAM).  On CPUs
+(tests: gloo, world_size 2..4, the oracle as per-rank engine) the same plan is executed with
+torch.distributed send/recv of host arrays.
+
+Dependency radius of one step: LS normal (1 point layer) -> plane/flux of the upwind cell (1 face
+layer) -> one layer per bounding sweep, hence the default layers = nAlphaBounds + 2.
 """
 import ctypes as C
 import json
 import os
-import sys
 import time
 
 import numpy as np
 
 from . import capi, fields
-from .mesh import hex_block
+from .mesh import Patch, PolyMesh, hex_block
 from .solver import SolveVofEqu
 
-HALO = 4
+
+def default_layers(controls):
+    return int((controls or {}).get("nAlphaBounds", 10)) + 2
 
 
+# ------------------------------------------------------------------------ general meshes ----
+def partition_rcb(mesh, n_parts, weights=None, lib=None):
+    """cell -> rank by the library's weighted recursive coordinate bisection (scotch stand-in)."""
+    lib = lib or capi.load_product()
+    cm, keep = mesh.to_c()
+    out = np.empty(mesh.n_cells, np.int32)
+    w = capi.f64(weights, (mesh.n_cells,)) if weights is not None else None
+    rc = lib.svof_partition_rcb(C.byref(cm), capi.dptr(w), int(n_parts), capi.iptr(out))
+    del keep
+    if rc:
+        raise capi.SvofError(rc, lib.svof_decomp_last_error().decode())
+    return out
+
+
+def _np_from(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
+def decompose(mesh, cell_rank, rank, layers, lib=None):
+    """(sub-mesh PolyMesh, maps) of `rank`: owned cells + `layers` ghost layers (svof_decompose)."""
+    lib = lib or capi.load_product()
+    cm, keep = mesh.to_c()
+    cr = capi.i32(cell_rank)
+    h = C.c_void_p()
+    rc = lib.svof_decompose(C.byref(cm), capi.iptr(cr), int(rank), int(layers), C.byref(h))
+    del keep
+    if rc:
+        raise capi.SvofError(rc, lib.svof_decomp_last_error().decode())
+    try:
+        sm = capi.SvofMesh()
+        lib.svof_submesh_mesh(h, C.byref(sm))
+        n_owned = C.c_int32()
+        ptrs = [capi.c_int32_p() for _ in range(6)]
+        lib.svof_submesh_maps(h, C.byref(n_owned), *[C.byref(p) for p in ptrs])
+        nC, nF, nP, nIF = sm.n_cells, sm.n_faces, sm.n_points, sm.n_internal_faces
+        fo = _np_from(sm.face_offsets, nF + 1, np.int32)
+        patches = []
+        for i in range(sm.n_patches):
+            p = sm.patches[i]
+            src = mesh.patches[i] if i < len(mesh.patches) else None
+            patches.append(Patch(src.name if src else "cut", p.start, p.size, p.kind, p.nbr_rank, p.alpha_bc, p.alpha_value))
+        sub = PolyMesh(points=_np_from(sm.points, 3 * nP, np.float64).reshape(-1, 3), face_offsets=fo,
+                       face_points=_np_from(sm.face_points, int(fo[-1]), np.int32),
+                       owner=_np_from(sm.owner, nF, np.int32), neighbour=_np_from(sm.neighbour, nIF, np.int32),
+                       patches=patches, n_cells=nC, meta=dict(mesh.meta, kind="submesh", rank=int(rank), layers=int(layers)))
+        maps = {"n_owned": int(n_owned.value),
+                "cell_global": _np_from(ptrs[0], nC, np.int32), "cell_owner_rank": _np_from(ptrs[1], nC, np.int32),
+                "cell_layer": _np_from(ptrs[2], nC, np.int32), "owned_local": _np_from(ptrs[3], n_owned.value, np.int32),
+                "face_global": _np_from(ptrs[4], nF, np.int32), "point_global": _np_from(ptrs[5], nP, np.int32)}
+        sub.cell_global = maps["cell_global"].astype(np.int64)
+    finally:
+        lib.svof_submesh_free(h)
+    return sub, maps
+
+
+# --------------------------------------------------------------------------- uniform boxes ----
 def block_grid(p):
     """(px, py, pz) with px*py*pz == p, as cubic as possible, z split first (slabs for small p)."""
     best = None
@@ -45,147 +107,158 @@ def block_grid(p):
     return best[1]
 
 
-class Decomposition:
-    """Box decomposition of an N=(Nx,Ny,Nz) hex mesh over `world` ranks with a G-layer halo."""
+def box_rcb(n, world, weight_fn=None):
+    """Recursive bisection of the index box [0,n) into `world` boxes of (nearly) equal weight.
+    weight_fn(axis, lo, hi) -> 1-D array of the summed cell weights of each index plane of box [lo,hi) along
+    `axis` (None: uniform).  Returns a list of (lo, hi) integer triples; box r belongs to rank r."""
+    N = np.array(n if np.ndim(n) else (n, n, n), dtype=np.int64)
 
-    def __init__(self, n, world, halo=HALO, length=(1.0, 1.0, 1.0)):
+    def split(lo, hi, parts):
+        if parts == 1:
+            return [(lo.copy(), hi.copy())]
+        ext = hi - lo
+        ax = int(np.argmax(ext))   # first longest axis
+        w = weight_fn(ax, lo, hi) if weight_fn is not None else np.full(int(ext[ax]), float(np.prod(ext) // ext[ax]))
+        pl = parts // 2
+        cum = np.cumsum(w)
+        target = cum[-1] * pl / parts
+        cut = int(np.searchsorted(cum, target, side="left")) + 1
+        cut = max(1, min(int(ext[ax]) - 1, cut))
+        hi_l, lo_r = hi.copy(), lo.copy()
+        hi_l[ax] = lo[ax] + cut
+        lo_r[ax] = lo[ax] + cut
+        return split(lo, hi_l, pl) + split(lo_r, hi, parts - pl)
+
+    return split(np.zeros(3, np.int64), N, int(world))
+
+
+class BoxDecomposition:
+    """Decomposition of an N=(Nx,Ny,Nz) uniform hex box into `world` boxes with `layers` ghost layers, generated
+    per rank without ever materialising the global mesh (512^3 = 134 M cells).  Produces exactly what svof_decompose
+    would: cells in ascending global label, ghost addressing, cut faces closed by the physical patches."""
+
+    def __init__(self, n, world, layers, length=(1.0, 1.0, 1.0), boxes=None):
         self.N = np.array(n if np.ndim(n) else (n, n, n), dtype=np.int64)
-        self.world, self.G = world, halo
+        self.world, self.G = int(world), int(layers)
         self.length = tuple(float(x) for x in length)
-        self.grid = np.array(block_grid(world), dtype=np.int64)
-
-    def coords(self, rank):
-        px, py, pz = self.grid
-        return np.array([rank % px, (rank // px) % py, rank // (px * py)], dtype=np.int64)
+        if boxes is None:
+            grid = np.array(block_grid(world), dtype=np.int64)
+            boxes = []
+            for r in range(world):
+                c = np.array([r % grid[0], (r // grid[0]) % grid[1], r // (grid[0] * grid[1])], dtype=np.int64)
+                boxes.append(((self.N * c) // grid, (self.N * (c + 1)) // grid))
+        self.boxes = [(np.array(lo, dtype=np.int64), np.array(hi, dtype=np.int64)) for lo, hi in boxes]
 
     def owned_box(self, rank):
-        c = self.coords(rank)
-        lo = (self.N * c) // self.grid
-        hi = (self.N * (c + 1)) // self.grid
-        return lo, hi
+        return self.boxes[rank]
 
     def ext_box(self, rank):
-        lo, hi = self.owned_box(rank)
+        lo, hi = self.boxes[rank]
         return np.maximum(lo - self.G, 0), np.minimum(hi + self.G, self.N)
 
-    @staticmethod
-    def _overlap(a, b):
-        lo, hi = np.maximum(a[0], b[0]), np.minimum(a[1], b[1])
-        return (lo, hi) if np.all(hi > lo) else None
-
-    @staticmethod
-    def _local_ids(box, ext):
-        """local cell ids (natural order of the extended block) of the cells of `box`, in natural order"""
-        lo, hi = box
-        elo, ehi = ext
-        nx, ny = (ehi - elo)[0], (ehi - elo)[1]
-        k, j, i = np.meshgrid(np.arange(lo[2], hi[2]), np.arange(lo[1], hi[1]), np.arange(lo[0], hi[0]), indexing="ij")
-        return ((i - elo[0]) + nx * ((j - elo[1]) + ny * (k - elo[2]))).reshape(-1).astype(np.int64)
-
-    def plan(self, rank):
-        """owned ids + per-neighbour send/recv id lists (both sides enumerate the same global order)."""
-        ext = self.ext_box(rank)
-        own = self.owned_box(rank)
-        plan = {"owned": self._local_ids(own, ext), "send": {}, "recv": {}}
-        for r in range(self.world):
-            if r == rank:
-                continue
-            ov = self._overlap(ext, self.owned_box(r))          # my halo cells owned by r
-            if ov is not None:
-                plan["recv"][r] = self._local_ids(ov, ext)
-            ov = self._overlap(own, self.ext_box(r))              # my owned cells inside r's halo
-            if ov is not None:
-                plan["send"][r] = self._local_ids(ov, ext)
-        return plan
-
     def rank_mesh(self, rank):
-        lo, hi = self.ext_box(rank)
-        return hex_block(self.N, lo=lo, hi=hi, length=self.length, cut_as_wall=True)
+        """(sub-mesh, maps) of `rank`."""
+        elo, ehi = self.ext_box(rank)
+        m = hex_block(self.N, lo=elo, hi=ehi, length=self.length, cut_as_wall=True)
+        nx, ny, nz = (ehi - elo).tolist()
+        owner = np.full((nz, ny, nx), -1, dtype=np.int32)
+        for r, (lo, hi) in enumerate(self.boxes):
+            a, b = np.maximum(lo, elo) - elo, np.minimum(hi, ehi) - elo
+            if np.all(b > a):
+                owner[a[2]:b[2], a[1]:b[1], a[0]:b[0]] = r
+        owner = owner.reshape(-1)
+        assert owner.min() >= 0
+        maps = {"cell_global": m.cell_global.astype(np.int32) if int(np.prod(self.N)) < 2 ** 31 else m.cell_global,
+                "cell_owner_rank": owner, "owned_local": np.nonzero(owner == rank)[0].astype(np.int32)}
+        maps["n_owned"] = int(maps["owned_local"].size)
+        return m, maps
 
 
-class _DevArr:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
-
-
+# ------------------------------------------------------------------------------ the driver ----
 class DecomposedSolveVofEqu:
-    """solveVofEqu on one rank of a decomposed hex mesh; same member names as SolveVofEqu."""
+    """solveVofEqu on one rank of a decomposed mesh; same member names as SolveVofEqu.
 
-    def __init__(self, n, controls, rank, world, lib=None, device=None, halo=HALO, length=(1.0, 1.0, 1.0)):
+    sub, maps   the rank's sub-mesh and addressing (from decompose() or BoxDecomposition.rank_mesh())
+    device      CUDA ordinal -> the library's own NCCL exchange; None -> CPU engine (`lib`), gloo exchange
+    """
+
+    def __init__(self, sub, maps, controls, rank, world, lib=None, device=None):
         import torch.distributed as dist
         self.dist = dist
         self.rank, self.world = rank, world
-        self.dec = Decomposition(n, world, halo, length)
-        self.mesh = self.dec.rank_mesh(rank)
-        self.plan = self.dec.plan(rank)
+        self.mesh, self.maps = sub, maps
+        self.owned = np.asarray(maps["owned_local"], dtype=np.int64)
+        self.cell_global = np.asarray(maps["cell_global"])
+        self.owner_rank = np.asarray(maps["cell_owner_rank"], dtype=np.int32)
         self.on_gpu = device is not None
-        comm = (rank, 1, device if device is not None else -1)   # each handle is a single-domain solver of its block
-        self.s = SolveVofEqu(self.mesh, controls, lib=lib, comm=comm)
         self.device = device
-        self.owned = self.plan["owned"]
         if self.on_gpu:
             import torch
             self.torch = torch
-            dev = torch.device("cuda", device)
-            # one gather and one scatter per step whatever the number of neighbours: the send indices of all peers are
-            # concatenated (each peer's message is a slice of the packed buffer), and so are the receive indices
-            def cat(d):
-                ranks = sorted(d)
-                sizes = [len(d[r]) for r in ranks]
-                idx = np.concatenate([np.asarray(d[r], dtype=np.int64) for r in ranks]) if ranks else np.zeros(0, np.int64)
-                return ranks, sizes, idx
-            self.send_ranks, self.send_sizes, sidx = cat(self.plan["send"])
-            self.recv_ranks, self.recv_sizes, ridx = cat(self.plan["recv"])
-            self.send_idx_all = torch.as_tensor(sidx, device=dev)
-            self.recv_idx_all = torch.as_tensor(ridx.astype(np.int32), device=dev)
-            self.send_buf_all = torch.empty(len(sidx), dtype=torch.float64, device=dev)
-            self.recv_buf_all = torch.empty(len(ridx), dtype=torch.float64, device=dev)
-            st = C.c_void_p()
-            self.s._chk(self.s.lib.svof_get_stream(self.s._h, C.byref(st)))
-            self.ext_stream = torch.cuda.ExternalStream(st.value, device=dev)
-        self.halo_bytes = 8 * sum(len(v) for v in self.plan["recv"].values())
+            lib = lib or capi.load_product()
+            idbuf = (C.c_char * 128)()
+            if world > 1:
+                if rank == 0:
+                    rc = lib.svof_comm_unique_id(idbuf)
+                    if rc:
+                        raise capi.SvofError(rc, lib.svof_last_error(None).decode())
+                t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).clone()
+                if dist.get_backend() == "nccl":
+                    t = t.cuda(device)
+                dist.broadcast(t, 0)
+                idbuf = (C.c_char * 128).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+            self._idbuf = idbuf
+            self.s = SolveVofEqu(sub, controls, lib=lib, comm=(rank, world, device, C.addressof(idbuf) if world > 1 else None))
+            cg, co = capi.i32(self.cell_global), capi.i32(self.owner_rank)
+            self.s._chk(lib.svof_halo_setup(self.s._h, capi.iptr(cg), capi.iptr(co)))
+            self.halo_bytes = int(self.s.info(capi.I_HALO_BYTES))
+        else:
+            self.s = SolveVofEqu(sub, controls, lib=lib, comm=(rank, 1, -1, None))   # per-rank single-domain engine
+            self._plan_host()
 
-    # -- halo exchange: alpha of halo cells <- owning rank ---------------------------------------
-    def exchange_alpha(self):
+    # -- CPU path: the plan the library builds with NCCL, built with torch.distributed objects ------------
+    def _plan_host(self):
         dist = self.dist
+        ghosts = np.nonzero(self.owner_rank != self.rank)[0]
+        need = {}
+        for r in np.unique(self.owner_rank[ghosts]):
+            idx = ghosts[self.owner_rank[ghosts] == r]
+            need[int(r)] = (idx, self.cell_global[idx])
+        self.recv = {r: idx for r, (idx, _) in need.items()}
+        wants = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(wants, {r: g for r, (_, g) in need.items()})
+        self.send = {}
+        for q in range(self.world):
+            if q == self.rank or not wants[q] or self.rank not in wants[q]:
+                continue
+            g = np.asarray(wants[q][self.rank])
+            pos = np.searchsorted(self.cell_global, g)
+            assert np.array_equal(self.cell_global[pos], g) and np.all(self.owner_rank[pos] == self.rank)
+            self.send[q] = pos
+        self.halo_bytes = 8 * sum(len(v) for v in self.recv.values())
+
+    def exchange_alpha(self):
+        """ghost alpha <- owning rank"""
         if self.world == 1:
             return
         if self.on_gpu:
-            # Fully stream-ordered: gather -> NCCL send/recv -> scatter are enqueued on the solver's own CUDA
-            # stream (wrapped as a torch ExternalStream), so the step needs no host synchronisation.
-            torch = self.torch
-            p = C.c_void_p()
-            self.s._chk(self.s.lib.svof_device_ptr(self.s._h, capi.F_ALPHA, C.byref(p)))
-            with torch.cuda.stream(self.ext_stream):
-                a = torch.as_tensor(_DevArr(p.value, self.s.nC), device=torch.device("cuda", self.device))
-                torch.index_select(a, 0, self.send_idx_all, out=self.send_buf_all)
-                ops, o = [], 0
-                for r, n in zip(self.send_ranks, self.send_sizes):
-                    ops.append(dist.P2POp(dist.isend, self.send_buf_all[o:o + n], r))
-                    o += n
-                o = 0
-                for r, n in zip(self.recv_ranks, self.recv_sizes):
-                    ops.append(dist.P2POp(dist.irecv, self.recv_buf_all[o:o + n], r))
-                    o += n
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()          # stream-level wait (no host block) for NCCL work
-            # halo cells <- received values, mixed-cell bitmap and patch values kept up to date (same stream)
-            self.s._chk(self.s.lib.svof_scatter_alpha_device(self.s._h, self.recv_idx_all.data_ptr(), self.recv_buf_all.data_ptr(),
-                                                             self.recv_idx_all.numel()))
-        else:
-            import torch
-            a = self.s.alpha()
-            reqs, bufs = [], {}
-            for r, idx in self.plan["send"].items():
-                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(a[idx])), r))
-            for r, idx in self.plan["recv"].items():
-                bufs[r] = torch.empty(len(idx), dtype=torch.float64)
-                reqs.append(dist.irecv(bufs[r], r))
-            for q in reqs:
-                q.wait()
-            for r, idx in self.plan["recv"].items():
-                a[idx] = bufs[r].numpy()
-            self.s.setAlpha(a)
+            self.s._chk(self.s.lib.svof_halo_exchange(self.s._h))
+            return
+        import torch
+        dist = self.dist
+        a = self.s.alpha()
+        reqs, bufs = [], {}
+        for r, idx in self.send.items():
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(a[idx])), r))
+        for r, idx in self.recv.items():
+            bufs[r] = torch.empty(len(idx), dtype=torch.float64)
+            reqs.append(dist.irecv(bufs[r], r))
+        for q in reqs:
+            q.wait()
+        for r, idx in self.recv.items():
+            a[idx] = bufs[r].numpy()
+        self.s.setAlpha(a)
 
     # -- the reference's member functions -----------------------------------------------------------
     def setAlpha(self, alpha_local):
@@ -201,26 +274,31 @@ class DecomposedSolveVofEqu:
         self.s.reconstruct()
 
     def advect(self, dt, Sp=None, Su=None):
-        self.s.advect(dt, Sp, Su)
-        self.exchange_alpha()
+        self.s.advect(dt, Sp, Su)          # on the device the library appends the ghost refresh itself
+        if not self.on_gpu:
+            self.exchange_alpha()
 
     def step(self, dt):
-        """reconstruct() + advect(dt) as one CUDA-graph launch on the extended block, then the halo swap."""
+        """reconstruct() + advect(dt) (one CUDA-graph launch on the device) + the ghost refresh."""
         self.s.step(dt)
-        self.exchange_alpha()
+        if not self.on_gpu:
+            self.exchange_alpha()
 
     def alpha_owned(self):
         return self.s.alpha()[self.owned]
 
     def owned_global_ids(self):
-        return self.mesh.cell_global[self.owned]
+        return self.cell_global[self.owned]
 
     def volume(self):
         """gSum(alpha*V) over the owned cells of all ranks."""
         import torch
-        v = float(np.sum(self.s.alpha()[self.owned] * self.s.field(capi.F_V)[self.owned]))
-        t = torch.tensor([v], dtype=torch.float64)
         if self.on_gpu:
+            v = self.s.info(capi.I_VOLUME_OWNED)
+        else:
+            v = float(np.sum(self.s.alpha()[self.owned] * self.s.field(capi.F_V)[self.owned]))
+        t = torch.tensor([v], dtype=torch.float64)
+        if self.on_gpu and self.dist.get_backend() == "nccl":
             t = t.cuda(self.device)
         if self.world > 1:
             self.dist.all_reduce(t)
@@ -231,8 +309,41 @@ class DecomposedSolveVofEqu:
 
 
 # ------------------------------------------------------------------------------------ bench ----
+def sphere_plane_weights(n, mixed_weight, centre=(0.35, 0.35, 0.35), radius=0.15):
+    """weight_fn for box_rcb on the LeVeque initial field: 1 per cell + `mixed_weight` per interface cell, where the
+    interface cells of a sphere are counted per index plane from the spherical-shell area (no global field needed)."""
+    n = int(n)
+    h = 1.0 / n
+
+    def fn(axis, lo, hi):
+        ext = (hi - lo).astype(np.float64)
+        base = float(np.prod(ext) / ext[axis])
+        x = (np.arange(lo[axis], hi[axis]) + 0.5) * h
+        # area of the sphere surface inside the slab of plane i and inside the box's other two extents ~ a band of a sphere:
+        # 2*pi*r*h per plane for |x - c| < r (Archimedes), restricted by the fraction of the band inside the box
+        w = np.full(x.shape, base)
+        inside = np.abs(x - centre[axis]) < radius
+        if inside.any():
+            oth = [d for d in range(3) if d != axis]
+            frac = np.ones(x.shape)
+            # fraction of the circle of latitude inside the box (sampled)
+            th = np.linspace(0.0, 2 * np.pi, 256, endpoint=False)
+            for k in np.nonzero(inside)[0]:
+                rr = np.sqrt(max(radius ** 2 - (x[k] - centre[axis]) ** 2, 0.0))
+                p0 = centre[oth[0]] + rr * np.cos(th)
+                p1 = centre[oth[1]] + rr * np.sin(th)
+                ok = (p0 >= lo[oth[0]] * h) & (p0 < hi[oth[0]] * h) & (p1 >= lo[oth[1]] * h) & (p1 < hi[oth[1]] * h)
+                frac[k] = ok.mean()
+            band_cells = 2 * np.pi * radius * h / (h * h) * 1.5   # interface cells per plane (shell ~1.5 cells thick)
+            w = w + mixed_weight * band_cells * frac * inside
+        return w
+
+    return fn
+
+
 def bench(args, controls, metric, unit):
-    """N-GPU leg of bench.py: one rank per GPU, each owning a 256^3 block of the global mesh."""
+    """N-GPU leg of bench.py: STRONG scaling of one LeVeque problem (default 512^3, BASELINE.json configs[4]) over
+    `world` ranks, or (--scaling weak) one 256^3 unit cube per GPU."""
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -243,79 +354,102 @@ def bench(args, controls, metric, unit):
         os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout: keep rank 0's stdout to the one JSON line
     if not dist.is_initialized():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-    grid = np.array(block_grid(world))
-    # weak scaling: the LeVeque problem tiled grid[0] x grid[1] x grid[2] times -- every GPU owns one unit cube
-    # (args.n^3 cubic cells, its own sphere; the velocity field is 1-periodic and tangential on the tile faces),
-    # so the per-GPU work is identical to the N=1 run and the cells stay cubic (the analytic face fluxes are
-    # discretely divergence free only on cubic cells).  8 GPUs = 512^3 cells in total.
-    n_global = (args.n * grid).tolist()
+    strong = args.scaling == "strong"
+    layers = args.layers if args.layers > 0 else default_layers(controls)
     t0 = time.perf_counter()
-    ds = DecomposedSolveVofEqu(n_global, controls, rank, world, device=local, length=grid.astype(float).tolist())
+    if strong:
+        n = args.strong_n
+        wfn = sphere_plane_weights(n, args.mixed_weight) if args.mixed_weight > 0 else None
+        boxes = box_rcb(n, world, wfn)
+        dec = BoxDecomposition(n, world, layers, boxes=boxes)
+        centre = (0.35, 0.35, 0.35)
+        dt = 0.2 / n
+        workload = ("LeVeque 3-D deformation, sphere r=0.15, %d^3 hex blockMesh (BASELINE.json configs[4]), ONE problem split over "
+                    "%d ranks by weighted recursive bisection into boxes (interface cells weigh %g)" % (n, world, args.mixed_weight))
+    else:
+        grid = np.array(block_grid(world))
+        n_global = (args.n * grid).tolist()
+        dec = BoxDecomposition(n_global, world, layers, length=grid.astype(float).tolist())
+        c = np.array([rank % grid[0], (rank // grid[0]) % grid[1], rank // (grid[0] * grid[1])], dtype=float)
+        centre = tuple(c + 0.35)
+        dt = 0.2 / args.n
+        workload = ("LeVeque 3-D deformation tiled %dx%dx%d: one unit cube (%d^3 cubic hex cells, sphere r=0.15) per GPU" %
+                    (grid[0], grid[1], grid[2], args.n))
+    sub, maps = dec.rank_mesh(rank)
+    ds = DecomposedSolveVofEqu(sub, maps, controls, rank, world, device=local)
     s = ds.s
-    tile = ds.dec.coords(rank).astype(float)
-    a0 = fields.sphere_alpha_quadrature(ds.mesh, centre=tuple(tile + 0.35))
-    dt = 0.2 / args.n
+    a0 = fields.sphere_alpha_quadrature(sub, centre=centre)
     C_, Cf, Sf = s.field(capi.F_C), s.field(capi.F_CF), s.field(capi.F_SF)
     f = fields.u_factor(dt, dt, 6.0)
     U = fields.leveque_velocity(C_) * f
     phi = fields.face_flux(Cf, Sf) * f
+    del C_, Cf, Sf
     s.setAlpha(a0)
     s.setPhi(phi)
     s.setU(U, np.zeros((s.nBF, 3)))
+    del U, phi
+    if args.overlap >= 0:
+        s.setOption("overlap", args.overlap)
     ds.exchange_alpha()
     setup_s = time.perf_counter() - t0
 
-    def step():
+    for _ in range(2 + max(3, args.warmup)):
         ds.step(dt)
-
-    for _ in range(max(3, args.warmup)):
-        step()
     s.synchronize()
     l0 = s.info(capi.I_GPU_LAUNCHES)
     dist.barrier()
     torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.lib.svof_mark(s._h, 0)
-    ev0.record()
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        ds.step(dt)
     s.lib.svof_mark(s._h, 1)
-    ev1.record()
     s.synchronize()
     torch.cuda.synchronize()
     dist.barrier()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
     ms = C.c_double()
     s.lib.svof_elapsed_ms(s._h, 0, 1, C.byref(ms))
-    # device time of the region on this rank = max(own-stream events, torch-stream events); job time = max over ranks
-    t = torch.tensor([max(ms.value, ev0.elapsed_time(ev1))], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    tmin = t.clone()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)       # job time = slowest rank (CUDA events on each handle's stream)
+    dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     total_ms = float(t.item())
-    cells = torch.tensor([float(len(ds.owned))], dtype=torch.float64, device="cuda")
-    dist.all_reduce(cells)
+    stats = torch.tensor([float(len(ds.owned)), float(s.nC), float(s.info(capi.I_N_MIXED)), float(ds.halo_bytes)],
+                         dtype=torch.float64, device="cuda")
+    gathered = [torch.zeros_like(stats) for _ in range(world)]
+    dist.all_gather(gathered, stats)
+    per_rank = [[float(x) for x in g.tolist()] for g in gathered]
+    cells = sum(p[0] for p in per_rank)
     launches = int(s.info(capi.I_GPU_LAUNCHES) - l0)
-    value = float(cells.item()) * args.steps / (total_ms * 1e-3)
+    value = cells * args.steps / (total_ms * 1e-3)
     vol = ds.volume()
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "LeVeque 3-D deformation tiled %dx%dx%d: one unit cube (%d^3 cubic hex cells, sphere r=0.15) per GPU, "
-                                   "%dx%dx%d cells in total (8 GPUs: 512^3 cells, the size of BASELINE.json configs[4])" %
-                                   (grid[0], grid[1], grid[2], args.n, n_global[0], n_global[1], n_global[2]),
-                       "cells": int(cells.item()), "dt": dt, "controls": controls, "halo_layers": ds.dec.G,
-                       "halo_bytes_per_step_rank0": ds.halo_bytes, "exchange": "1 alpha halo swap per step, NCCL send/recv",
-                       "l2": "inputs larger than L2", "timing": "CUDA events, max over ranks; host wall %.3f ms/step" % (wall_ms / args.steps),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload, "cells": int(cells), "dt": dt, "controls": controls, "ghost_layers": layers,
+                       "per_rank": [{"owned_cells": int(p[0]), "local_cells": int(p[1]), "mixed_cells_local": int(p[2]),
+                                     "halo_bytes_per_step": int(p[3])} for p in per_rank],
+                       "exchange": "1 ghost-alpha refresh per step: library-side pack kernel + grouped ncclSend/ncclRecv + scatter kernel "
+                                   "on the solver's stream (no torch in the data path)",
+                       "l2": "inputs larger than L2", "timing": "CUDA events on each rank's stream, max over ranks (min %.4f ms/step); "
+                       "host wall %.3f ms/step" % (float(tmin.item()) / args.steps, wall_ms / args.steps),
                        "setup_s": setup_s, "volume": vol},
             "gpu_launches": launches,
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "note": "multi-GPU leg is device resident; the host-buffer end-to-end number is measured at N=1"},
+                    "note": "multi-GPU leg is device resident (no host copies declared); the host-buffer end-to-end number is measured at N=1"},
         }
+        if strong:
+            base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "strong_base_%d.json" % args.strong_n)
+            if os.path.exists(base):
+                try:
+                    line["config"]["single_gpu_same_problem"] = json.load(open(base))
+                except Exception:
+                    pass
         print(json.dumps(line))
     dist.barrier()
-    if rank == 0 or os.environ.get("SVOF_PROFILE_ALL"):
-        ds.close()
+    ds.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -40,7 +40,7 @@ class SolveVofEqu:
 
     lib      -- a library loaded with capi.load(); default: the CUDA product
     controls -- the fvSolution solvers."alpha.*" dictionary
-    comm     -- (rank, world_size, device) for decomposed runs
+    comm     -- (rank, world_size, device[, address of the NCCL unique id]) for decomposed runs (multigpu.py)
     """
 
     typeName = "solveVofEqu"
@@ -51,7 +51,10 @@ class SolveVofEqu:
         self.controls = dict(controls or {})
         self._params = make_params(self.lib, self.controls)
         cm, keep = mesh.to_c()
-        cc = capi.SvofComm(*(comm if comm is not None else (0, 1, -1)), 0)
+        c = tuple(comm) if comm is not None else (0, 1, -1, None)
+        if len(c) == 3:
+            c = c + (None,)
+        cc = capi.SvofComm(int(c[0]), int(c[1]), int(c[2]), 0, c[3])   # c[3]: address of the 128-byte NCCL id (world_size > 1)
         h = C.c_void_p()
         rc = self.lib.svof_create(C.byref(cm), C.byref(self._params), C.byref(cc), C.byref(h))
         del keep

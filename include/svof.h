@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SVOF_ABI_VERSION 1
+#define SVOF_ABI_VERSION 2
 
 typedef struct svof_handle svof_handle;
 
@@ -125,13 +125,16 @@ typedef struct {
 } svof_params;
 
 /* One handle <-> one rank <-> one GPU (one MPI rank of the reference).
- * Peer-memory halo exchange is bootstrapped by the host however it likes
- * (torch.distributed in bench.py, MPI inside OpenFOAM): see svof_comm_*. */
+ * world_size > 1: the library opens its own NCCL communicator from nccl_unique_id
+ * (128 bytes from svof_comm_unique_id on rank 0, broadcast by whatever transport the
+ * host has: MPI_Bcast inside OpenFOAM, torch.distributed in bench.py); svof_create is
+ * then a collective call.  See "decomposed runs" below. */
 typedef struct {
     int32_t rank;
     int32_t world_size;
     int32_t device;   /* CUDA device ordinal, -1 => rank % deviceCount */
     int32_t reserved;
+    const void* nccl_unique_id; /* [128 bytes] or NULL (world_size == 1) */
 } svof_comm;
 
 /* ---- configuration -------------------------------------------------------- */
@@ -239,6 +242,8 @@ typedef enum {
     SVOF_I_N_NEAR = 18,          /* |mixed U 2 face-neighbour layers| (sparse set) */
     SVOF_I_H2D_BYTES = 19,       /* bytes the last svof_step_host copied host->device */
     SVOF_I_D2H_BYTES = 20,       /* ... and device->host                          */
+    SVOF_I_VOLUME_OWNED = 21,    /* sum(alpha*V) over the cells this rank owns (== VOLUME without ghosts) */
+    SVOF_I_HALO_BYTES = 22,      /* bytes this rank receives per ghost refresh    */
     SVOF_I_COUNT_
 } svof_info;
 
@@ -325,6 +330,52 @@ int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const doub
  * round-off (1e-13), not bitwise, where two coincident points compete. */
 int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, double* points, int32_t* face_offsets,
                       int32_t* cells, int64_t* n_points, int64_t* n_faces);
+
+/* ---- decomposed runs ----------------------------------------------------------
+ * Replaces what the reference does across processor patches: the zoneDistribute stencil
+ * exchange (reconstruction.C:97-107), syncProcPatches (advection.C:311-393, called once
+ * after the geometric fluxes and twice per bounding sweep), setProcessorPatches
+ * (advection.C:412-432) and the gMin/gMax loop test (advectionTemplates.C:146-198).
+ * Instead of processor patches every rank holds its cells plus `layers` point-neighbour
+ * layers of GHOST cells, cut out of the global mesh with an order-preserving renumbering,
+ * runs the unchanged single-domain step on that sub-mesh, and ONE exchange per step
+ * (ghost alpha <- owning rank, NCCL send/recv on the handle's stream) replaces all of the
+ * above.  Owned cells reproduce the single-domain result when the ghost layers cover the
+ * dependency radius of a step: 2 + the number of bounding sweeps (default layers =
+ * nAlphaBounds + 2).  A mesh with raw processor patches is refused (SVOF_ERR_UNSUPPORTED). */
+
+typedef struct svof_submesh svof_submesh;
+
+/* Cell -> rank map by weighted recursive coordinate bisection (stand-in for decomposePar's
+ * scotch, damBreakWithObstacle/system/decomposeParDict:18-20; a cellProcAddressing-derived
+ * map from a real scotch run can be used instead).  cell_weight: [n_cells] or NULL. */
+int svof_partition_rcb(const svof_mesh* mesh, const double* cell_weight, int32_t n_parts, int32_t* cell_rank_out);
+
+/* Sub-domain of `rank`: owned cells (cell_rank == rank) + `layers` ghost layers.  Local
+ * cells/points ascend with their global labels; faces: internal (ascending), the global
+ * patches in order (possibly empty), then one extra zeroGradient patch holding the cut
+ * faces.  Host only (no CUDA needed). */
+int svof_decompose(const svof_mesh* global_mesh, const int32_t* cell_rank, int32_t rank, int32_t layers, svof_submesh** out);
+/* View of the sub-mesh (pointers stay owned by the svof_submesh). */
+int svof_submesh_mesh(const svof_submesh* s, svof_mesh* out);
+/* Addressing: per local cell its global label, owning rank and ghost layer (0 = owned), the
+ * local labels of the owned cells, and the global labels of local faces / points
+ * (cellProcAddressing / faceProcAddressing / pointProcAddressing).  Any pointer may be NULL. */
+int svof_submesh_maps(const svof_submesh* s, int32_t* n_owned, const int32_t** cell_global, const int32_t** cell_owner_rank,
+                      const int32_t** cell_layer, const int32_t** owned_local, const int32_t** face_global,
+                      const int32_t** point_global);
+int svof_submesh_free(svof_submesh* s);
+const char* svof_decomp_last_error(void);
+
+/* 128-byte NCCL unique id for svof_comm.nccl_unique_id (call on one rank, broadcast). */
+int svof_comm_unique_id(void* id128);
+/* Collective over the communicator of svof_create: tells the handle which local cells are
+ * ghosts (cell_owner_rank[i] != rank) and their global labels (ascending); the ranks
+ * exchange the lists once.  From then on svof_advect / svof_step_device end with the ghost
+ * refresh, enqueued on the handle's stream (no host synchronisation). */
+int svof_halo_setup(svof_handle* h, const int32_t* cell_global, const int32_t* cell_owner_rank);
+/* The ghost refresh on its own (after svof_set_alpha with stale ghost values). */
+int svof_halo_exchange(svof_handle* h);
 
 #ifdef __cplusplus
 }

@@ -414,4 +414,18 @@ int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const doub
     return SVOF_OK;
 }
 
+// decomposed runs: the CPU oracle is single-domain.  Sub-domain extraction and partitioning are host utilities of the
+// product library (no CUDA involved); the tests drive per-rank oracles on the sub-meshes it produces and exchange the
+// ghost values themselves (gloo).
+int svof_partition_rcb(const svof_mesh*, const double*, int32_t, int32_t*) { return SVOF_ERR_UNSUPPORTED; }
+int svof_decompose(const svof_mesh*, const int32_t*, int32_t, int32_t, svof_submesh**) { return SVOF_ERR_UNSUPPORTED; }
+int svof_submesh_mesh(const svof_submesh*, svof_mesh*) { return SVOF_ERR_UNSUPPORTED; }
+int svof_submesh_maps(const svof_submesh*, int32_t*, const int32_t**, const int32_t**, const int32_t**, const int32_t**,
+                      const int32_t**, const int32_t**) { return SVOF_ERR_UNSUPPORTED; }
+int svof_submesh_free(svof_submesh*) { return SVOF_ERR_UNSUPPORTED; }
+const char* svof_decomp_last_error(void) { return "the CPU oracle has no decomposition"; }
+int svof_comm_unique_id(void*) { return SVOF_ERR_UNSUPPORTED; }
+int svof_halo_setup(svof_handle*, const int32_t*, const int32_t*) { return SVOF_ERR_UNSUPPORTED; }
+int svof_halo_exchange(svof_handle*) { return SVOF_ERR_UNSUPPORTED; }
+
 }  // extern "C"
