@@ -105,6 +105,9 @@ SYMBOLS = [
     ("svof_comm_unique_id", C.c_int, [C.c_void_p]),
     ("svof_halo_setup", C.c_int, [_H, c_int32_p, c_int32_p]),
     ("svof_halo_exchange", C.c_int, [_H]),
+    ("svof_halo_setup_faces", C.c_int, [_H, c_int32_p, c_int32_p, c_int32_p]),
+    ("svof_halo_exchange_inputs", C.c_int, [_H]),
+    ("svof_submesh_face_maps", C.c_int, [_H, C.POINTER(c_int32_p), C.POINTER(c_int32_p)]),
 ]
 
 PRODUCT_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsvof_b200.so")

@@ -113,12 +113,17 @@ struct svof_handle {
     // decomposed runs: NCCL communicator of this handle and the ghost-refresh plan (svof_halo_setup)
     int rank = 0, world = 1;
     ncclComm_t nccl = nullptr;
+    struct Plan {   // who sends which local entries to whom, packed per peer
+        std::vector<int> peers, sendOff, recvOff;
+        int nSend = 0, nRecv = 0;
+        int *sendIdx = nullptr, *recvIdx = nullptr;
+        double *sendBuf = nullptr, *recvBuf = nullptr, *recvSign = nullptr;   // recvSign: -1 where the local face is flipped
+    };
     struct Halo {
-        bool active = false;
-        std::vector<int> peers, sendOff, recvOff;   // per peer: offsets into the packed send / receive buffers
-        int nSend = 0, nRecv = 0, nOwned = 0;
-        int *sendIdx = nullptr, *recvIdx = nullptr, *ownedIdx = nullptr;
-        double *sendBuf = nullptr, *recvBuf = nullptr;
+        bool active = false, facesReady = false;
+        Plan cells, faces;
+        int nOwned = 0;
+        int* ownedIdx = nullptr;
     } halo;
     bool haveAlpha = false, havePhi = false, haveU = false, bitsValid = false, advected = false;
     double lastDt = 0.0;
@@ -809,23 +814,133 @@ __global__ void k_volume_partial_list(const int* __restrict__ idx, int n, const 
 // ghost alpha <- owning rank: pack, one grouped NCCL send/recv, scatter (keeps the mixed-cell bitmap valid).  Everything
 // is enqueued on the handle's stream: no host synchronisation.  This one exchange stands where the reference has the
 // zoneDistribute stencil exchange (reconstruction.C:97-107) and 1 + 2 x sweeps calls of syncProcPatches (advection.C:311-393).
-void haloExchange(svof_handle* h)
+__global__ void k_gather_comps(const int* __restrict__ idx, int n, int comps, const double* __restrict__ src, double* __restrict__ out)
 {
-    svof_handle::Halo& H = h->halo;
-    if (!H.active) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * comps) return;
+    out[i] = src[(size_t)idx[i / comps] * comps + (i % comps)];
+}
+__global__ void k_scatter_comps(const int* __restrict__ idx, int n, int comps, const double* __restrict__ vals, const double* __restrict__ sign,
+                                double* __restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * comps) return;
+    const double v = vals[i];
+    dst[(size_t)idx[i / comps] * comps + (i % comps)] = sign ? sign[i / comps] * v : v;
+}
+
+void planSendRecv(svof_handle* h, const svof_handle::Plan& P, int comps)
+{
     NcclApi& N = ncclApi();
-    double* alpha = h->alphaBuf[h->cur];
-    if (H.nSend) LAUNCH(h, k_gather_alpha, cdiv(H.nSend, 256), 256, H.sendIdx, H.nSend, alpha, H.sendBuf);
     NK(N.GroupStart());
-    for (size_t p = 0; p < H.peers.size(); ++p) {
-        const int ns = H.sendOff[p + 1] - H.sendOff[p], nr = H.recvOff[p + 1] - H.recvOff[p];
-        if (ns) NK(N.Send(H.sendBuf + H.sendOff[p], (size_t)ns, ncclDouble, H.peers[p], h->nccl, h->stream));
-        if (nr) NK(N.Recv(H.recvBuf + H.recvOff[p], (size_t)nr, ncclDouble, H.peers[p], h->nccl, h->stream));
+    for (size_t p = 0; p < P.peers.size(); ++p) {
+        const int ns = P.sendOff[p + 1] - P.sendOff[p], nr = P.recvOff[p + 1] - P.recvOff[p];
+        if (ns) NK(N.Send(P.sendBuf + (size_t)P.sendOff[p] * comps, (size_t)ns * comps, ncclDouble, P.peers[p], h->nccl, h->stream));
+        if (nr) NK(N.Recv(P.recvBuf + (size_t)P.recvOff[p] * comps, (size_t)nr * comps, ncclDouble, P.peers[p], h->nccl, h->stream));
     }
     NK(N.GroupEnd());
-    if (H.nRecv)
-        LAUNCH(h, k_scatter_alpha, cdiv(H.nRecv, 256), 256, H.recvIdx, H.recvBuf, (long long)H.nRecv, h->prm.mixed_cell_tol, alpha,
+}
+
+// ghost alpha <- owning rank: pack, one grouped NCCL send/recv, scatter (keeps the mixed-cell bitmap valid).  Everything
+// is enqueued on the handle's stream: no host synchronisation.  This one exchange stands where the reference has the
+// zoneDistribute stencil exchange (reconstruction.C:97-107) and 1 + 2 x sweeps calls of syncProcPatches (advection.C:311-393).
+void haloExchange(svof_handle* h)
+{
+    if (!h->halo.active) return;
+    const svof_handle::Plan& P = h->halo.cells;
+    double* alpha = h->alphaBuf[h->cur];
+    if (P.nSend) LAUNCH(h, k_gather_alpha, cdiv(P.nSend, 256), 256, P.sendIdx, P.nSend, alpha, P.sendBuf);
+    planSendRecv(h, P, 1);
+    if (P.nRecv)
+        LAUNCH(h, k_scatter_alpha, cdiv(P.nRecv, 256), 256, P.recvIdx, P.recvBuf, (long long)P.nRecv, h->prm.mixed_cell_tol, alpha,
                h->mixedBits, h->bitsValid ? 1 : 0);
+}
+
+// ghost U (cells, 3 components) and phi (faces) <- owning ranks: what a flow solver that only holds its own cells needs
+// before the step (the harness with analytic fields evaluates them on the ghosts directly)
+void haloExchangeInputs(svof_handle* h)
+{
+    if (!h->halo.active) return;
+    const svof_handle::Plan& C = h->halo.cells;
+    if (C.nSend) LAUNCH(h, k_gather_comps, cdiv(3LL * C.nSend, 256), 256, C.sendIdx, C.nSend, 3, h->U, C.sendBuf);
+    planSendRecv(h, C, 3);
+    if (C.nRecv) LAUNCH(h, k_scatter_comps, cdiv(3LL * C.nRecv, 256), 256, C.recvIdx, C.nRecv, 3, C.recvBuf, (const double*)nullptr, h->U);
+    if (h->halo.facesReady) {
+        const svof_handle::Plan& F = h->halo.faces;
+        if (F.nSend) LAUNCH(h, k_gather_comps, cdiv(F.nSend, 256), 256, F.sendIdx, F.nSend, 1, h->phi, F.sendBuf);
+        planSendRecv(h, F, 1);
+        if (F.nRecv) LAUNCH(h, k_scatter_comps, cdiv(F.nRecv, 256), 256, F.recvIdx, F.nRecv, 1, F.recvBuf, F.recvSign, h->phi);
+    }
+}
+
+// Build the exchange plan of a set of labelled entities (cells or faces): every rank lists the global labels of the
+// entries it does not own, per owner; the owners map the labels they are asked for to their local entries.
+void buildPlan(svof_handle* h, int n, const int32_t* global, const int32_t* ownerRank, const int32_t* flip, int maxComps,
+               svof_handle::Plan& P, std::vector<int>* ownedOut)
+{
+    NcclApi& N = ncclApi();
+    const int W = h->world, me = h->rank;
+    std::vector<std::vector<int>> needLocal(W), needGlobal(W);
+    std::vector<std::pair<int, int>> mine;   // (global, local) of the entries this rank owns
+    for (int c = 0; c < n; ++c) {
+        const int r = ownerRank[c];
+        if (r < 0 || r >= W) throw std::invalid_argument("svof_halo_setup: owner rank out of range");
+        if (r == me) { mine.emplace_back(global[c], c); if (ownedOut) ownedOut->push_back(c); }
+        else { needLocal[r].push_back(c); needGlobal[r].push_back(global[c]); }
+    }
+    std::sort(mine.begin(), mine.end());
+    P.peers.clear(); P.sendOff.assign(1, 0); P.recvOff.assign(1, 0);
+    std::vector<int> sendIdx, recvIdx;
+    std::vector<double> recvSign;
+    if (W > 1) {
+        std::vector<int> myCounts(W), all((size_t)W * W);
+        for (int r = 0; r < W; ++r) myCounts[r] = (int)needLocal[r].size();
+        int* dMine = dupload(h, myCounts.data(), myCounts.size());
+        int* dAll = dalloc<int>(h, (size_t)W * W);
+        NK(N.AllGather(dMine, dAll, (size_t)W, ncclInt32, h->nccl, h->stream));
+        CK(cudaMemcpyAsync(all.data(), dAll, sizeof(int) * W * W, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        std::vector<int*> dWant(W, nullptr), dNeed(W, nullptr);
+        std::vector<int> wantCount(W, 0);
+        for (int r = 0; r < W; ++r) {
+            wantCount[r] = (r == me) ? 0 : all[(size_t)r * W + me];
+            if (wantCount[r]) dWant[r] = dalloc<int>(h, wantCount[r]);
+            if (!needGlobal[r].empty()) dNeed[r] = dupload(h, needGlobal[r].data(), needGlobal[r].size());
+        }
+        NK(N.GroupStart());
+        for (int r = 0; r < W; ++r) {
+            if (r == me) continue;
+            if (!needGlobal[r].empty()) NK(N.Send(dNeed[r], needGlobal[r].size(), ncclInt32, r, h->nccl, h->stream));
+            if (wantCount[r]) NK(N.Recv(dWant[r], (size_t)wantCount[r], ncclInt32, r, h->nccl, h->stream));
+        }
+        NK(N.GroupEnd());
+        CK(cudaStreamSynchronize(h->stream));
+        for (int r = 0; r < W; ++r) {
+            if (r == me || (wantCount[r] == 0 && needLocal[r].empty())) continue;
+            P.peers.push_back(r);
+            std::vector<int> want(wantCount[r]);
+            if (wantCount[r]) CK(cudaMemcpy(want.data(), dWant[r], sizeof(int) * wantCount[r], cudaMemcpyDeviceToHost));
+            for (int g : want) {
+                auto it = std::lower_bound(mine.begin(), mine.end(), std::make_pair(g, -1));
+                if (it == mine.end() || it->first != g) throw std::invalid_argument("svof_halo_setup: a peer asks for an entry this rank does not own");
+                sendIdx.push_back(it->second);
+            }
+            for (int c : needLocal[r]) {
+                recvIdx.push_back(c);
+                recvSign.push_back((flip && flip[c]) ? -1.0 : 1.0);
+            }
+            P.sendOff.push_back((int)sendIdx.size());
+            P.recvOff.push_back((int)recvIdx.size());
+        }
+    }
+    P.nSend = (int)sendIdx.size();
+    P.nRecv = (int)recvIdx.size();
+    P.sendIdx = dupload(h, sendIdx.data(), sendIdx.size());
+    P.recvIdx = dupload(h, recvIdx.data(), recvIdx.size());
+    P.sendBuf = dalloc<double>(h, sendIdx.size() * (size_t)maxComps);
+    P.recvBuf = dalloc<double>(h, recvIdx.size() * (size_t)maxComps);
+    P.recvSign = flip ? dupload(h, recvSign.data(), recvSign.size()) : nullptr;
+    CK(cudaStreamSynchronize(h->stream));
 }
 
 void alphaBC(svof_handle* h)
@@ -1224,75 +1339,39 @@ int svof_halo_setup(svof_handle* h, const int32_t* cell_global, const int32_t* c
     if (h->world > 1 && !h->nccl) return fail(h, SVOF_ERR_STATE, "svof_halo_setup: the handle was created without an NCCL id");
     API_BEGIN
     CK(cudaSetDevice(h->device));
-    NcclApi& N = ncclApi();
-    const int nC = h->nC, W = h->world, me = h->rank;
-    svof_handle::Halo& H = h->halo;
-    for (int c = 1; c < nC; ++c)
+    for (int c = 1; c < h->nC; ++c)
         if (cell_global[c - 1] >= cell_global[c]) throw std::invalid_argument("svof_halo_setup: cell_global must ascend");
-    // ghosts by owner (local order == ascending global label)
-    std::vector<std::vector<int>> needLocal(W), needGlobal(W);
     std::vector<int> owned;
-    for (int c = 0; c < nC; ++c) {
-        const int r = cell_owner_rank[c];
-        if (r < 0 || r >= W) throw std::invalid_argument("svof_halo_setup: owner rank out of range");
-        if (r == me) owned.push_back(c);
-        else { needLocal[r].push_back(c); needGlobal[r].push_back(cell_global[c]); }
-    }
-    H.nOwned = (int)owned.size();
-    H.ownedIdx = dupload(h, owned.data(), owned.size());
-    H.peers.clear(); H.sendOff.assign(1, 0); H.recvOff.assign(1, 0);
-    std::vector<int> sendIdx, recvIdx;
-    if (W > 1) {
-        // 1. who needs how many cells from whom: all-gather of the per-owner ghost counts
-        std::vector<int> myCounts(W), all((size_t)W * W);
-        for (int r = 0; r < W; ++r) myCounts[r] = (int)needLocal[r].size();
-        int* dMine = dupload(h, myCounts.data(), myCounts.size());
-        int* dAll = dalloc<int>(h, (size_t)W * W);
-        NK(N.AllGather(dMine, dAll, (size_t)W, ncclInt32, h->nccl, h->stream));
-        CK(cudaMemcpyAsync(all.data(), dAll, sizeof(int) * W * W, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        // 2. the global labels each peer wants from me
-        std::vector<int*> dWant(W, nullptr), dNeed(W, nullptr);
-        std::vector<int> wantCount(W, 0);
-        for (int r = 0; r < W; ++r) {
-            wantCount[r] = (r == me) ? 0 : all[(size_t)r * W + me];
-            if (wantCount[r]) dWant[r] = dalloc<int>(h, wantCount[r]);
-            if (!needGlobal[r].empty()) dNeed[r] = dupload(h, needGlobal[r].data(), needGlobal[r].size());
-        }
-        NK(N.GroupStart());
-        for (int r = 0; r < W; ++r) {
-            if (r == me) continue;
-            if (!needGlobal[r].empty()) NK(N.Send(dNeed[r], needGlobal[r].size(), ncclInt32, r, h->nccl, h->stream));
-            if (wantCount[r]) NK(N.Recv(dWant[r], (size_t)wantCount[r], ncclInt32, r, h->nccl, h->stream));
-        }
-        NK(N.GroupEnd());
-        CK(cudaStreamSynchronize(h->stream));
-        // 3. the plan: per peer, what I send (their wanted labels -> my local cells) and where what I receive goes
-        for (int r = 0; r < W; ++r) {
-            if (r == me || (wantCount[r] == 0 && needLocal[r].empty())) continue;
-            H.peers.push_back(r);
-            std::vector<int> want(wantCount[r]);
-            if (wantCount[r]) CK(cudaMemcpy(want.data(), dWant[r], sizeof(int) * wantCount[r], cudaMemcpyDeviceToHost));
-            for (int g : want) {
-                const int32_t* it = std::lower_bound(cell_global, cell_global + nC, g);
-                if (it == cell_global + nC || *it != g || cell_owner_rank[it - cell_global] != me)
-                    throw std::invalid_argument("svof_halo_setup: a peer asks for a cell this rank does not own");
-                sendIdx.push_back((int)(it - cell_global));
-            }
-            recvIdx.insert(recvIdx.end(), needLocal[r].begin(), needLocal[r].end());
-            H.sendOff.push_back((int)sendIdx.size());
-            H.recvOff.push_back((int)recvIdx.size());
-        }
-    }
-    H.nSend = (int)sendIdx.size();
-    H.nRecv = (int)recvIdx.size();
-    H.sendIdx = dupload(h, sendIdx.data(), sendIdx.size());
-    H.recvIdx = dupload(h, recvIdx.data(), recvIdx.size());
-    H.sendBuf = dalloc<double>(h, sendIdx.size());
-    H.recvBuf = dalloc<double>(h, recvIdx.size());
+    buildPlan(h, h->nC, cell_global, cell_owner_rank, nullptr, 3, h->halo.cells, &owned);
+    h->halo.nOwned = (int)owned.size();
+    h->halo.ownedIdx = dupload(h, owned.data(), owned.size());
     CK(cudaStreamSynchronize(h->stream));
-    H.active = (W > 1);
+    h->halo.active = (h->world > 1);
     for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }   // the captured tail changes
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_halo_setup_faces(svof_handle* h, const int32_t* face_global, const int32_t* face_owner_rank, const int32_t* face_flip)
+{
+    if (!h || !face_global || !face_owner_rank) return SVOF_ERR_INVALID_ARG;
+    if (h->world > 1 && !h->nccl) return fail(h, SVOF_ERR_STATE, "svof_halo_setup_faces: the handle was created without an NCCL id");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    buildPlan(h, h->nF, face_global, face_owner_rank, face_flip, 1, h->halo.faces, nullptr);
+    h->halo.facesReady = true;
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_halo_exchange_inputs(svof_handle* h)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    if (!h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_halo_exchange_inputs: phi/U not set");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    haloExchangeInputs(h);
+    h->inputsAfterNear = true;
     return SVOF_OK;
     API_END(h)
 }
@@ -1685,7 +1764,7 @@ int svof_get_info(svof_handle* h, int which, double* out)
             *out = buf[0];
             return SVOF_OK;
         }
-        case SVOF_I_HALO_BYTES: *out = 8.0 * h->halo.nRecv; return SVOF_OK;
+        case SVOF_I_HALO_BYTES: *out = 8.0 * h->halo.cells.nRecv; return SVOF_OK;
         case SVOF_I_GPU_LAUNCHES: *out = (double)h->launches; return SVOF_OK;
         case SVOF_I_FLATNESS_MIN: *out = h->flatMin; return SVOF_OK;
         case SVOF_I_FLATNESS_MAX: *out = h->flatMax; return SVOF_OK;

@@ -27,7 +27,7 @@ struct svof_submesh {
     std::vector<double> points;
     std::vector<int32_t> faceOff, facePts, owner, neighbour;
     std::vector<svof_patch> patches;
-    std::vector<int32_t> cellGlobal, cellOwnerRank, cellLayer, faceGlobal, pointGlobal, ownedLocal;
+    std::vector<int32_t> cellGlobal, cellOwnerRank, cellLayer, faceGlobal, pointGlobal, ownedLocal, faceOwnerRank, faceFlip;
     int32_t nCells = 0, nOwned = 0, nInternal = 0;
     std::string err;
 };
@@ -220,6 +220,12 @@ int svof_decompose(const svof_mesh* g, const int32_t* cell_rank, int32_t rank, i
         s->owner.resize(nLF);
         s->neighbour.resize((size_t)s->nInternal);
         s->faceGlobal.assign(faceList.begin(), faceList.end());
+        s->faceOwnerRank.resize(nLF);
+        s->faceFlip.resize(nLF);
+        for (size_t i = 0; i < nLF; ++i) {
+            s->faceOwnerRank[i] = cell_rank[own[faceList[i]]];
+            s->faceFlip[i] = flip[i];
+        }
         s->faceOff[0] = 0;
         for (size_t i = 0; i < nLF; ++i) {
             const int f = faceList[i];
@@ -275,6 +281,14 @@ int svof_submesh_maps(const svof_submesh* s, int32_t* n_owned, const int32_t** c
     if (owned_local) *owned_local = s->ownedLocal.data();
     if (face_global) *face_global = s->faceGlobal.data();
     if (point_global) *point_global = s->pointGlobal.data();
+    return SVOF_OK;
+}
+
+int svof_submesh_face_maps(const svof_submesh* s, const int32_t** face_owner_rank, const int32_t** face_flip)
+{
+    if (!s) return SVOF_ERR_INVALID_ARG;
+    if (face_owner_rank) *face_owner_rank = s->faceOwnerRank.data();
+    if (face_flip) *face_flip = s->faceFlip.data();
     return SVOF_OK;
 }
 

@@ -364,6 +364,8 @@ int svof_submesh_mesh(const svof_submesh* s, svof_mesh* out);
 int svof_submesh_maps(const svof_submesh* s, int32_t* n_owned, const int32_t** cell_global, const int32_t** cell_owner_rank,
                       const int32_t** cell_layer, const int32_t** owned_local, const int32_t** face_global,
                       const int32_t** point_global);
+/* Per local face: the rank owning its global owner cell, and whether it is flipped against the global face. */
+int svof_submesh_face_maps(const svof_submesh* s, const int32_t** face_owner_rank, const int32_t** face_flip);
 int svof_submesh_free(svof_submesh* s);
 const char* svof_decomp_last_error(void);
 
@@ -376,6 +378,12 @@ int svof_comm_unique_id(void* id128);
 int svof_halo_setup(svof_handle* h, const int32_t* cell_global, const int32_t* cell_owner_rank);
 /* The ghost refresh on its own (after svof_set_alpha with stale ghost values). */
 int svof_halo_exchange(svof_handle* h);
+/* For callers that only hold the fields of their own cells (an OpenFOAM rank under mpirun: adapter/solveVofEquB200.C):
+ * the same plan for faces -- face_owner_rank = rank owning the face's global owner cell, face_flip != 0 where the local
+ * face is oriented against the global one (cut faces kept from their neighbour side) -- and one call that refreshes
+ * ghost U (cells) and ghost phi (faces) from the owners after svof_set_phi / svof_set_U. */
+int svof_halo_setup_faces(svof_handle* h, const int32_t* face_global, const int32_t* face_owner_rank, const int32_t* face_flip);
+int svof_halo_exchange_inputs(svof_handle* h);
 
 #ifdef __cplusplus
 }

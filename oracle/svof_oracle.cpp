@@ -427,5 +427,8 @@ const char* svof_decomp_last_error(void) { return "the CPU oracle has no decompo
 int svof_comm_unique_id(void*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_halo_setup(svof_handle*, const int32_t*, const int32_t*) { return SVOF_ERR_UNSUPPORTED; }
 int svof_halo_exchange(svof_handle*) { return SVOF_ERR_UNSUPPORTED; }
+int svof_halo_setup_faces(svof_handle*, const int32_t*, const int32_t*, const int32_t*) { return SVOF_ERR_UNSUPPORTED; }
+int svof_halo_exchange_inputs(svof_handle*) { return SVOF_ERR_UNSUPPORTED; }
+int svof_submesh_face_maps(const svof_submesh*, const int32_t**, const int32_t**) { return SVOF_ERR_UNSUPPORTED; }
 
 }  // extern "C"
