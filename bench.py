@@ -105,17 +105,17 @@ def velocity_fields(s, t, dt):
     return U, phi
 
 
-def cpu_oracle_rate(m, a0, U, phi, dt, steps, keep=False):
+def cpu_oracle_rate(m, a0, U, phi, dt, steps, keep=False, controls=None, Ub=None):
     """The CPU restatement of the reference algorithm, timed on this box's host (1 core).  keep=True also returns
     its state after the 1 + steps steps it ran (alpha, alphaPhi, the interface-cell list of that alpha) so that the
     GPU run of the same steps can be compared AT THE SIZE THE NUMBER IS QUOTED ON (checker use of oracle/, as in tests/)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build as oracle_build
     lib = capi.load(oracle_build.build_oracle())
-    so = SolveVofEqu(m, CONTROLS, lib=lib)
+    so = SolveVofEqu(m, controls or CONTROLS, lib=lib)
     so.setAlpha(a0)
     so.setPhi(phi)
-    so.setU(U)
+    so.setU(U, Ub)
     so.reconstruct()   # warm-up (page faults, first-touch)
     so.advect(dt)
     t0 = time.perf_counter()
@@ -341,6 +341,148 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+# ---- the other BASELINE.json workloads (single GPU): --workload kelvin | dambreak --------------------------------
+DAMBREAK_CONTROLS = {"nAlphaBounds": 3, "mixedCellTol": 1e-10, "snapTol": 1e-12, "clip": True, "orientationMethod": "LS",
+                     "splitWarpedFace": False}   # damBreakWithObstacle/system/fvSolution:20-35
+
+
+def make_workload(name, size):
+    """mesh, controls, alpha0(solver), velocity, dt(solver), description"""
+    if name == "kelvin":
+        # BASELINE.json configs[2] (SURVEY.md 8d config 3): polyDualMesh-like cells (14 faces, 24 points), sphere r = 0.15
+        # at (0.5, 0.75, 0.5) in solid-body rotation about the z axis; size = cells per axis of each of the two lattices
+        m = meshmod.kelvin_mesh_fast(size)
+        ctl = dict(CONTROLS)
+
+        def alpha0(s):
+            C_, V = s.field(capi.F_C), s.field(capi.F_V)
+            return np.clip(0.5 - (np.linalg.norm(C_ - np.array([0.5, 0.75, 0.5]), axis=1) - 0.15) / np.cbrt(V), 0.0, 1.0)
+
+        def dt_of(s, U):
+            return 0.25 * float(np.cbrt(s.field(capi.F_V).min())) / float(np.abs(U).max())
+
+        desc = ("polyhedral mesh: %d truncated-octahedron (polyDualMesh-like, 14 faces / 24 points) cells, sphere r=0.15 in solid-body "
+                "rotation (BASELINE.json configs[2])" % m.n_cells)
+        return m, ctl, alpha0, fields.rotation_velocity, dt_of, desc
+    if name == "dambreak":
+        # BASELINE.json configs[3] substitute (SURVEY.md 8d config 4, advection only): the damBreakWithObstacle box
+        # (geometryAndMeshDimensions:1-3), water box of setVofFieldDict:33-39, the case's alpha controls, inletOutlet top
+        m = meshmod.hex_block(size)
+        for p_ in m.patches:
+            if p_.name == "top":
+                p_.alpha_bc, p_.alpha_value = capi.BC_INLET_OUTLET, 0.0
+        ctl = dict(DAMBREAK_CONTROLS)
+
+        def alpha0(s):
+            C_ = meshmod.cell_centres_hex(m)
+            return ((C_[:, 0] < 0.6) & (C_[:, 1] < 0.1875) & (C_[:, 2] < 0.75)).astype(np.float64)
+
+        def dt_of(s, U):
+            return 0.2 / size
+
+        desc = ("damBreakWithObstacle substitute, advection only: %d^3 hex box, water box (0.6 x 0.1875 x 0.75), clip true / snapTol 1e-12 / "
+                "mixedCellTol 1e-10, inletOutlet top patch, prescribed 3-D deformation velocity (BASELINE.json configs[3] scaled)" % size)
+        return m, ctl, alpha0, fields.leveque_velocity, dt_of, desc
+    raise ValueError(name)
+
+
+def run_workload(args):
+    t_setup = time.perf_counter()
+    m, ctl, alpha0, velocity, dt_of, desc = make_workload(args.workload, args.n)
+    s = SolveVofEqu(m, ctl)
+    lib, h = s.lib, s._h
+    a0 = alpha0(s)
+    C_, Cf, Sf = s.field(capi.F_C), s.field(capi.F_CF), s.field(capi.F_SF)
+    U, phi = velocity(C_), fields.face_flux(Cf, Sf, velocity)
+    Ub = velocity(Cf[m.n_internal_faces:]) if args.workload == "kelvin" else np.zeros((s.nBF, 3))
+    del C_, Cf, Sf
+    dt = dt_of(s, U)
+    s.setAlpha(a0)
+    s.setPhi(phi)
+    s.setU(U, Ub)
+    s.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    # let the interface develop (a sharp box has no mixed cells at t = 0), then keep that field as the start of every leg
+    for _ in range(args.develop_steps):
+        s.step(dt)
+    a1 = s.alpha()
+    clocks = ClockSampler()
+    clocks.start()
+    s.setAlpha(a1)
+    for _ in range(args.warmup):
+        s.reconstruct()
+        s.advect(dt)
+    s.synchronize()
+    d0, dn0 = s.info(capi.I_DENSE_KERNEL_MS), s.info(capi.I_DENSE_KERNEL_LAUNCHES)
+    for _ in range(args.steps):
+        s.reconstruct()
+        s.advect(dt)
+    s.synchronize()
+    dense_ms = (s.info(capi.I_DENSE_KERNEL_MS) - d0) / max(1.0, s.info(capi.I_DENSE_KERNEL_LAUNCHES) - dn0)
+    s.setAlpha(a1)
+    for _ in range(2 + args.warmup):
+        s.step(dt)
+    s.synchronize()
+    l0 = s.info(capi.I_GPU_LAUNCHES)
+    lib.svof_mark(h, 0)
+    for _ in range(args.steps):
+        s.step(dt)
+    lib.svof_mark(h, 1)
+    ms = C.c_double()
+    lib.svof_elapsed_ms(h, 0, 1, C.byref(ms))
+    s.synchronize()
+    launches = int(s.info(capi.I_GPU_LAUNCHES) - l0)
+    n_mixed, n_near, err = int(s.info(capi.I_N_MIXED)), int(s.info(capi.I_N_NEAR)), int(s.info(capi.I_ERROR_FLAGS))
+    value = m.n_cells * args.steps / (ms.value * 1e-3)
+    # end to end through svof_step_host with pinned host buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    phi_h, U_h, Ub_h = capi.pinned_array(lib, (s.nF,)), capi.pinned_array(lib, (s.nC, 3)), capi.pinned_array(lib, (max(s.nBF, 1), 3))
+    a_out, ap_out = capi.pinned_array(lib, (s.nC,)), capi.pinned_array(lib, (s.nF,))
+    phi_h[:] = phi
+    U_h[:] = U
+    Ub_h[:s.nBF] = Ub
+    s.setAlpha(a1)
+    for _ in range(1 + args.warmup):
+        s.step_host(dt, phi_h, U_h, Ub_h, a_out, ap_out)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.step_host(dt, phi_h, U_h, Ub_h, a_out, ap_out)
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    h2d, d2h = int(s.info(capi.I_H2D_BYTES)), int(s.info(capi.I_D2H_BYTES))
+    peak, peak_src = measured_peak()
+    B = b_alg(m)
+    cpu, parity = None, []
+    if not args.no_cpu:
+        cs = max(1, args.cpu_steps)
+        rate, el, ref = cpu_oracle_rate(m, a1, U, phi, dt, cs, keep=True, controls=ctl, Ub=Ub)
+        cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "same mesh and fields, %d steps (%.1f s) of the single-threaded CPU restatement of the reference algorithm" % (cs, el)}
+        s.setPhi(phi)
+        s.setU(U, Ub)
+        parity.append(parity_block(s, m, a1, dt, ref, args.workload))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms.value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "cells": m.n_cells, "faces": m.n_faces, "dt": dt, "controls": ctl, "mixed_cells": n_mixed,
+                   "near_cells": n_near, "develop_steps": args.develop_steps, "error_flags": err, "setup_s": setup_s,
+                   "l2": "inputs larger than L2 (%.2f GB per step)" % (B / 1e9),
+                   "schedule": "svof_step_device: one CUDA-graph launch per step (%d kernels inside)" % (launches // max(1, args.steps))},
+        "clocks": clk,
+        "e2e": {"value": m.n_cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": B / (dense_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": B / (dense_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_dense_update", "kernel_ms": dense_ms,
+                     "algorithmic_bytes_per_launch": B, "peak_source": peak_src,
+                     "step_frac": (B / (ms.value / args.steps * 1e-3) / 1e9) / peak},
+        "cpu_baseline": cpu,
+        "parity": parity,
+    }
+    print(json.dumps(line))
+
+
 def _ref_worker(args_tuple):
     n, lo, hi, dt, steps, warm = args_tuple
     m, a0 = build_case(n, lo=lo, hi=hi, cut_as_wall=True)
@@ -412,6 +554,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="leveque", choices=["leveque", "kelvin", "dambreak"],
+                    help="leveque: BASELINE.json configs[1] (the headline); kelvin: configs[2] (--size 95 = 1.7 M polyhedral cells); "
+                         "dambreak: configs[3] substitute (--size 368 = 50 M cells)")
+    ap.add_argument("--develop-steps", type=int, default=40, help="kelvin/dambreak: untimed steps before the timed window")
     ap.add_argument("--late-steps", type=int, default=200, help="timed steps of the second window (0: skip it)")
     ap.add_argument("--late-time", type=float, default=1.5, help="flow time the interface is advanced to before the second window")
     ap.add_argument("--late-cpu-steps", type=int, default=2, help="oracle steps for the parity block of the second window")
@@ -428,6 +574,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "leveque" and args.gpus <= 1 and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        run_workload(args)
     else:
         run_ours(args)
 

@@ -54,6 +54,7 @@ struct svof_handle {
     int overlap = 0;       // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=1 / svof_set_option);
                            // off by default: measured slower at 256^3 (1.57 vs 1.31 ms/step), see DESIGN.md section 6
     int advectCount = 0;
+    int epochBumps = 0;     // how often the device-side bounding epoch was advanced (tags derive from it)
     int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
     std::vector<svof_patch> patches;
     svof_params prm;
@@ -103,6 +104,7 @@ struct svof_handle {
     size_t dstageSmem = 0;
     bool useStaged = false;
     DenseFast dfast;                 // owner-sorted connectivity of the streaming kernel (k_dense_update2)
+    bool un0Group = false;           // 8 lanes per cut cell for the interface speed (SVOF_UN0=thread: round-1 thread-per-cell kernel)
     int plicCtas = 0;                // "plic_ctas" option: cap on resident CTAs/SM of the plane-positioning kernel (0 = all that fit)
     int denseCtas = 0;               // "dense_ctas" option: cap on resident CTAs/SM of the streaming kernel (0 = no cap)
     int forkAt = 1;                  // "fork" option (overlap != 0): 1 = streaming kernel may start after the near sets, 2 = after plane positioning
@@ -126,6 +128,8 @@ struct svof_handle {
         int* ownedIdx = nullptr;
     } halo;
     bool haveAlpha = false, havePhi = false, haveU = false, bitsValid = false, advected = false;
+    bool anyInletOutlet = false;
+    bool uPartial = false;   // svof_step_host (sparse_io) uploaded only the rows of U near the interface: not a full field
     double lastDt = 0.0;
     long long launches = 0;
     // svof_step_device: one captured CUDA graph per (alpha buffer parity, patch-value buffer parity, mixed bitmap valid), valid for one dt
@@ -310,6 +314,7 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
             bPatch[p.start - nIF + k] = (int)pi;
         }
         pd[pi].start = p.start; pd[pi].size = p.size; pd[pi].kind = p.kind; pd[pi].bc = p.alpha_bc; pd[pi].value = p.alpha_value;
+        if (p.kind == SVOF_PATCH_GENERIC && p.alpha_bc == SVOF_BC_INLET_OUTLET && p.size > 0) h->anyInletOutlet = true;
         expect += p.size;
     }
     if (expect != nF) throw std::invalid_argument("svof_mesh: patches do not cover all boundary faces");
@@ -625,7 +630,7 @@ void allocFields(svof_handle* h)
     h->oobIdx = dalloc<int>(h, nC);
     {
         const size_t recBytes = (h->maxCF <= 8) ? sizeof(CellBound<8>) : (h->maxCF <= 16) ? sizeof(CellBound<16>) : sizeof(CellBound<64>);
-        h->capRec = (int)std::min<size_t>(nC, std::max<size_t>(65536, nC / 16));
+        h->capRec = (int)std::min<size_t>(nC, std::max<size_t>(65536, nC / 8));   // out-of-bounds cells per sweep; overflow raises SVERR_LIST (returned at the next sync point)
         h->boundRecs = dalloc<unsigned char>(h, recBytes * (size_t)h->capRec, false);
     }
     h->oobState = dalloc<unsigned char>(h, nC);
@@ -714,15 +719,6 @@ __global__ void k_ctl_reset_advect(Ctl* ctl)
     ctl->minNear0 = ctl->minNearF = ~0ull;
     ctl->maxNear0 = ctl->maxNearF = 0ull;
 }
-// everything the streaming kernel touches is reset BEFORE the near bitmaps are published (evNear)
-__global__ void k_ctl_reset_recon(Ctl* ctl)
-{
-    ctl->nNear2 = 0;
-    ctl->plicNext = 0;
-    ctl->minDense = ~0ull;
-    ctl->maxDense = 0ull;
-}
-
 __global__ void k_ctl_reset_dense(Ctl* ctl)
 {
     ctl->minDense = ~0ull;
@@ -954,18 +950,15 @@ void doReconstruct(svof_handle* h)
     const MeshDev& d = h->md;
     cudaStream_t s = h->stream;
     double* alpha = h->alphaBuf[h->cur];
-    const int g128 = sparseGrid(h, 128), g256 = sparseGrid(h, 256);
-    // A1: sparse zeroing of the previous interface data, mixed-cell list in ascending order
-    LAUNCH(h, k_clear_prev, g256, 256, h->mixedCells, h->ctl, h->iN, h->iD, h->iC, h->iS, h->cellSlot);
+    const int g128 = sparseGrid(h, 128);
+    // A1: the front -- sparse clears of the previous step, mixed-cell list in ascending order, near sets (3 launches)
     if (!h->bitsValid) LAUNCH(h, k_mixed_bits, cdiv(h->nC, 256), 256, alpha, h->nC, h->prm.mixed_cell_tol, h->mixedBits);
-    LAUNCH(h, k_count_bits, h->nScanBlocks, SV_SCAN_WORDS, h->mixedBits, h->nWords, h->blockSums);
-    LAUNCH(h, k_scan_blocks, 1, 1024, h->blockSums, h->nScanBlocks, h->ctl, h->capMixed);
-    LAUNCH(h, k_write_mixed, h->nScanBlocks, SV_SCAN_WORDS, h->mixedBits, h->nWords, h->blockSums, h->capMixed, h->mixedCells,
-           h->cellStatus, h->cellSlot);
-    CK(cudaMemsetAsync(h->near1, 0, sizeof(unsigned int) * h->nWords, s));
-    CK(cudaMemsetAsync(h->near2, 0, sizeof(unsigned int) * h->nWords, s));
-    LAUNCH(h, k_ctl_reset_recon, 1, 1, h->ctl);
-    LAUNCH(h, k_mark_near, g256, 256, d, h->mixedCells, h->ctl, h->near1, h->near2, h->near2List, h->capNear);
+    LAUNCH(h, k_front_count, h->nScanBlocks, SV_SCAN_WORDS, h->mixedBits, h->nWords, h->blockSums, h->mixedCells, h->near2List, h->capNear,
+           h->ctl, h->iN, h->iD, h->iC, h->iS, h->cellSlot, h->near1, h->near2);
+    LAUNCH(h, k_front_scan, 1, 1024, h->blockSums, h->nScanBlocks, h->ctl, h->capMixed);
+    LAUNCH(h, k_front_write, h->nScanBlocks, SV_SCAN_WORDS, d, h->mixedBits, h->nWords, h->blockSums, h->capMixed, h->mixedCells,
+           h->cellStatus, h->cellSlot, h->ctl, h->near1, h->near2, h->near2List, h->capNear);
+    h->epochBumps++;
     // the streaming kernel of the coming advect() only needs alpha.oldTime, phi and the near2 bitmap: with the two-stream
     // schedule it may start from here (fork 1) or once the plane-positioning kernel has been issued (fork 2)
     if (h->overlap && h->forkAt == 1) CK(cudaEventRecord(h->evNear, s));
@@ -1022,10 +1015,17 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     if (h->overlap) CK(cudaEventRecord(h->evDense, sD));
 
     // ---- sparse chain
-    LAUNCH(h, k_ctl_reset_advect, 1, 1, h->ctl);
+    if (!h->freshRecon) {   // advect() without a new reconstruct(): the resets k_front_scan would have done
+        LAUNCH(h, k_ctl_reset_advect, 1, 1, h->ctl);
+        h->epochBumps++;
+    }
     // A7-A9: geometric fluxes on the downwind faces of cut cells
-    LAUNCH(h, k_un0_worklist, g128, 128, d, h->mixedCells, h->cellStatus, h->ctl, h->iN, h->iC, h->U, h->Ub, h->phi, h->Un0, h->work,
-           h->capWork);
+    if (h->un0Group)
+        LAUNCH(h, k_un0_group, g128, 128, d, h->mixedCells, h->cellStatus, h->ctl, h->iN, h->iC, h->U, h->Ub, h->phi, h->Un0, h->work,
+               h->capWork);
+    else
+        LAUNCH(h, k_un0_worklist, g128, 128, d, h->mixedCells, h->cellStatus, h->ctl, h->iN, h->iC, h->U, h->Ub, h->phi, h->Un0, h->work,
+               h->capWork);
     GEO(h, faceFlux, sS, g128, d, h->work, h->ctl, h->mixedCells, h->iN, h->iD, h->Un0, h->phi, dt, h->dVfGeo);
     // A10 for the near2 cells
     LAUNCH(h, k_near_update, g128, 128, d, h->near2List, h->near1, h->ctl, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->cellSlot,
@@ -1037,7 +1037,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     do {                                                                                                                     \
         LAUNCH(h, k_bound_deps<MB>, gB, 128, d, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, \
                dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList);           \
-        LAUNCH(h, k_bound_run<MB>, 2 * gB, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx, \
+        LAUNCH(h, k_bound_run<MB>, 16 * h->sms, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx, \
                (const CellBound<MB>*)h->boundRecs, h->capRec, dt, rDt);                                                      \
         LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs,               \
                h->oobList[(sidx + 1) & 1], h->oobState);                                                                     \
@@ -1060,12 +1060,13 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     h->advected = true;
     h->freshRecon = false;
     h->lastDt = dt;
-    if (++h->advectCount >= (1 << 25)) {  // tags would wrap: clear the tag arrays
+    ++h->advectCount;
+    if (h->epochBumps >= (1 << 25)) {  // tags would wrap: clear the tag arrays
         CK(cudaMemsetAsync(h->bs.tagV, 0, sizeof(int) * h->nF, sS));
         CK(cudaMemsetAsync(h->bs.tagR, 0, sizeof(int) * h->nF, sS));
         CK(cudaMemsetAsync(h->bs.affStamp, 0, sizeof(int) * h->nC, sS));
         CK(cudaMemsetAsync(&h->ctl->epoch, 0, sizeof(int), sS));
-        h->advectCount = 0;
+        h->epochBumps = 0;
     }
 }
 
@@ -1098,10 +1099,16 @@ bool parseBool(const char* v, int32_t* out)
     return false;
 }
 
+int deviceErr(svof_handle* h);
 int checkDeviceErr(svof_handle* h)
 {
     fetchCtl(h);
-    if (h->hctl->err) {
+    return h->hctl->err ? deviceErr(h) : (int)SVOF_OK;
+}
+// h->hctl holds a fresh copy of the control block with err != 0
+int deviceErr(svof_handle* h)
+{
+    {
         char b[256];
         snprintf(b, sizeof(b), "device capacity flag 0x%x (1 face verts, 2 cell faces, 4 cell points, 8 interface points, "
                  "16 LS stencil, 32 work list)", h->hctl->err);
@@ -1199,6 +1206,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         h->sms = prop.multiProcessorCount;
         h->overlap = getenv("SVOF_OVERLAP") ? atoi(getenv("SVOF_OVERLAP")) : 0;  // default off
         if (getenv("SVOF_FORK")) h->forkAt = atoi(getenv("SVOF_FORK"));
+        if (getenv("SVOF_UN0") && !strcmp(getenv("SVOF_UN0"), "group")) h->un0Group = true;   // measured 84 us against 77 us: opt-in
         if (getenv("SVOF_DENSE_CTAS")) h->denseCtas = atoi(getenv("SVOF_DENSE_CTAS"));
         h->prof = getenv("SVOF_PROFILE") && atoi(getenv("SVOF_PROFILE")) > 0;
         h->prm = *params;
@@ -1285,8 +1293,9 @@ int svof_set_phi(svof_handle* h, const double* phi)
     API_BEGIN
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
     h->havePhi = true;
+    if (h->anyInletOutlet && h->haveAlpha) alphaBC(h);   // inletOutlet patch values depend on the sign of phi
+    CK(cudaStreamSynchronize(h->stream));
     return SVOF_OK;
     API_END(h)
 }
@@ -1301,6 +1310,7 @@ int svof_set_U(svof_handle* h, const double* U, const double* Ub)
     else if (h->nBF) CK(cudaMemsetAsync(h->Ub, 0, sizeof(double) * 3 * h->nBF, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->haveU = true;
+    h->uPartial = false;
     return SVOF_OK;
     API_END(h)
 }
@@ -1397,6 +1407,7 @@ int svof_set_phi_device(svof_handle* h, const void* dphi)
     CK(cudaMemcpyAsync(h->phi, dphi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, h->stream));
     h->havePhi = true;
     h->inputsAfterNear = true;
+    if (h->anyInletOutlet && h->haveAlpha) alphaBC(h);
     return SVOF_OK;
     API_END(h)
 }
@@ -1409,6 +1420,7 @@ int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb)
     CK(cudaMemcpyAsync(h->U, dU, sizeof(double) * 3 * h->nC, cudaMemcpyDeviceToDevice, h->stream));
     if (dUb && h->nBF) CK(cudaMemcpyAsync(h->Ub, dUb, sizeof(double) * 3 * h->nBF, cudaMemcpyDeviceToDevice, h->stream));
     h->haveU = true;
+    h->uPartial = false;
     return SVOF_OK;
     API_END(h)
 }
@@ -1431,6 +1443,7 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
 {
     if (!h || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
     if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_advect: alpha/phi/U not set");
+    if (h->uPartial) return fail(h, SVOF_ERR_STATE, "svof_advect: U on the device is the sparse upload of svof_step_host; call svof_set_U first");
     API_BEGIN
     CK(cudaSetDevice(h->device));
     const double *dSp = nullptr, *dSu = nullptr;
@@ -1454,7 +1467,8 @@ int svof_step_device(svof_handle* h, double dt)
 {
     if (!h || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
     if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_step_device: alpha/phi/U not set");
-    if (h->prof || h->advectCount >= (1 << 25) - 2) {   // instrumented runs: plain launches
+    if (h->uPartial) return fail(h, SVOF_ERR_STATE, "svof_step_device: U on the device is the sparse upload of svof_step_host; call svof_set_U first");
+    if (h->prof || h->epochBumps >= (1 << 25) - 4) {   // instrumented runs / tag wrap imminent: plain launches
         const int rc = svof_reconstruct(h);
         return rc ? rc : svof_advect(h, dt, nullptr, nullptr);
     }
@@ -1620,6 +1634,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
                 h->d2hBytes += 4LL * nU + 4;
             }
             uDone = true;
+            h->uPartial = true;
         } else {
             CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * h->nWords, st));  // list overflowed: bits were left set
         }
@@ -1627,6 +1642,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     if (!uDone) {
         CK(cudaMemcpyAsync(h->U, U, sizeof(double) * 3 * h->nC, cudaMemcpyHostToDevice, st));
         h->h2dBytes += 24LL * h->nC;
+        h->uPartial = false;
     }
     h->haveU = true;
     h->inputsAfterNear = true;  // U landed after the near bitmaps were published
@@ -1656,9 +1672,11 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
         }
         h->hostAlphaPhiSynced = alpha_phi_out;
     }
+    CK(cudaMemcpyAsync(h->hctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     hostTick(h, "7 final sync");
     CK(cudaGetLastError());
+    if (h->hctl->err) return deviceErr(h);   // a work list or polyhedron cap overflowed: the fields just returned are not to be trusted
     return SVOF_OK;
     API_END(h)
 }
@@ -1703,7 +1721,9 @@ int64_t svof_get_field(svof_handle* h, int which, void* dst, int64_t capacity)
     }
     if (capacity < n) return fail(h, SVOF_ERR_INVALID_ARG, "svof_get_field: destination too small");
     if (n) CK(cudaMemcpyAsync(dst, src, (size_t)n * esz, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->hctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    if (h->hctl->err) return deviceErr(h);   // where the reference would FatalError: never hand out fields computed past a cap
     return n;
     API_END(h)
 }
@@ -1809,6 +1829,7 @@ int svof_device_touch(svof_handle* h, int which)
     h->haveAlpha = true;
     h->bitsValid = false;
     h->advected = false;
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;   // the caller's buffers no longer mirror the device
     return SVOF_OK;
     API_END(h)
 }
@@ -1824,6 +1845,7 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "fork")) { h->forkAt = value; return SVOF_OK; }
     if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; return SVOF_OK; }
     if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; return SVOF_OK; }
+    if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
     if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");

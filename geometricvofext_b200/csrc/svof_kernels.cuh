@@ -170,20 +170,6 @@ __global__ void k_flatness_tetbase(MeshDev m, double* flat, unsigned char* tetBa
 }
 
 // ==================================================================== reconstruct ====
-// sparse replacement of the reference's dense zero-fill of interfaceN/D/C/S (reconstruction.C:636-641)
-__global__ void k_clear_prev(const int* mixedPrev, Ctl* ctl, double* iN, double* iD, double* iC, double* iS, int* cellSlot)
-{
-    const int n = ctl->nMixed;  // still the previous reconstruct's count and list
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int c = mixedPrev[i];
-        st3(iN, c, zero3());
-        st3(iC, c, zero3());
-        st3(iS, c, zero3());
-        iD[c] = 0.0;
-        cellSlot[c] = -1;
-    }
-}
-
 // A1 (reconstruction.C:665-672, reconstruction.H:281-288): one bit per cell, one coalesced word per warp
 __global__ void k_mixed_bits(const double* __restrict__ alpha, int nCells, double tol, unsigned int* bits)
 {
@@ -214,9 +200,20 @@ __global__ void k_scatter_alpha(const int* __restrict__ idx, const double* __res
     }
 }
 
-// ordered compaction of a bitmap into an ascending list (keeps mixedCells_ bit-exact in ORDER too)
+// ---- the front of reconstruct(): three launches ------------------------------------------------------------------
+//   k_front_count : popcount of the mixed-cell bitmap per 1024-word block  +  the sparse clears of the previous step
+//                   (interfaceN/D/C/S and cellSlot of the previous mixed cells: the reference zero-fills 80 B/cell,
+//                   reconstruction.C:636-641; the near1/near2 bitmap words of the previous near2 list instead of two
+//                   field-sized memsets)
+//   k_front_scan  : exclusive scan of the block sums (one CTA) + every per-step reset of the control block
+//   k_front_write : ordered compaction (ascending list => mixedCells_ bit-exact in ORDER too), then each CTA marks the
+//                   near sets of the list segment it just wrote
+// (round 1: seven launches and two memsets)
 #define SV_SCAN_WORDS 1024  // words per block
-__global__ void k_count_bits(const unsigned int* bits, int nWords, unsigned int* blockSums)
+__global__ void __launch_bounds__(SV_SCAN_WORDS) k_front_count(const unsigned int* bits, int nWords, unsigned int* blockSums,
+                                                               const int* mixedPrev, const int* near2Prev, int capNear, const Ctl* ctl,
+                                                               double* iN, double* iD, double* iC, double* iS, int* cellSlot,
+                                                               unsigned int* near1, unsigned int* near2)
 {
     __shared__ unsigned int red[32];
     const int w = blockIdx.x * SV_SCAN_WORDS + threadIdx.x;
@@ -229,8 +226,25 @@ __global__ void k_count_bits(const unsigned int* bits, int nWords, unsigned int*
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if (threadIdx.x == 0) blockSums[blockIdx.x] = v;
     }
+    // the previous reconstruct's lists (their counts are still in the control block: k_front_scan resets them)
+    const int nM = ctl->nMixed, nN = min(ctl->nNear2, capNear);
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nM; i += stride) {
+        const int c = mixedPrev[i];
+        st3(iN, c, zero3());
+        st3(iC, c, zero3());
+        st3(iS, c, zero3());
+        iD[c] = 0.0;
+        cellSlot[c] = -1;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nN; i += stride) {
+        const int c = near2Prev[i];
+        near1[c >> 5] = 0u;
+        near2[c >> 5] = 0u;
+    }
 }
-__global__ void k_scan_blocks(unsigned int* blockSums, int nBlocks, Ctl* ctl, int capacity)
+
+__global__ void k_front_scan(unsigned int* blockSums, int nBlocks, Ctl* ctl, int capacity)
 {
     // single CTA, exclusive scan in place; total -> ctl->nMixed
     __shared__ unsigned int warpTot[32];
@@ -269,12 +283,49 @@ __global__ void k_scan_blocks(unsigned int* blockSums, int nBlocks, Ctl* ctl, in
             n = capacity;
         }
         ctl->nMixed = n;
+        // per-step resets: what reconstruct() and the advect() that follows it start from
+        ctl->nNear2 = 0;
+        ctl->plicNext = 0;
+        ctl->minDense = ~0ull;
+        ctl->maxDense = 0ull;
+        ctl->nWork = 0;
+        ctl->epoch++;
+        ctl->nOob[0] = ctl->nOob[1] = 0;
+        for (int s = 0; s <= SV_MAX_SWEEPS; ++s) ctl->nPend[s] = ctl->nAff[s] = ctl->nearOob[s] = 0;
+        ctl->minNear0 = ctl->minNearF = ~0ull;
+        ctl->maxNear0 = ctl->maxNearF = 0ull;
     }
 }
-__global__ void k_write_mixed(const unsigned int* bits, int nWords, const unsigned int* blockSums, int capacity,
-                              int* mixedCells, int* cellStatus, int* cellSlot)
+
+// near1 = mixed U face-neighbours (== needBounding of advectionTemplates.C:138-141 via
+// advection.C:54-82); near2 = near1 U face-neighbours (cells a bounding correction can touch).
+// Bits are set with atomicOr; the thread that flips a near2 bit appends the cell to the list,
+// so the list is a duplicate-free SET (its order is irrelevant: every consumer is per-cell).
+// Most marks are duplicates (43 per mixed cell, ~3 of them new), and atomics on the same bitmap word serialise in L2:
+// a plain L2 read filters the duplicates first (a stale read only costs a redundant atomic).  8 lanes per mixed cell,
+// one face-neighbour (and its own neighbours) per lane.
+__device__ __forceinline__ void markNear2(int c, unsigned int* near2, int* near2List, Ctl* ctl, int cap)
+{
+    const unsigned int bit = 1u << (c & 31);
+    if (__ldcg(&near2[c >> 5]) & bit) return;
+    const unsigned int old = atomicOr(&near2[c >> 5], bit);
+    if (!(old & bit)) {
+        const int pos = atomicAdd(&ctl->nNear2, 1);
+        if (pos < cap) near2List[pos] = c; else atomicOr(&ctl->err, SVERR_LIST);
+    }
+}
+__device__ __forceinline__ void markNear1(int c, unsigned int* near1)
+{
+    const unsigned int bit = 1u << (c & 31);
+    if (!(__ldcg(&near1[c >> 5]) & bit)) atomicOr(&near1[c >> 5], bit);
+}
+
+__global__ void __launch_bounds__(SV_SCAN_WORDS) k_front_write(MeshDev m, const unsigned int* bits, int nWords, const unsigned int* blockSums,
+                                                               int capacity, int* mixedCells, int* cellStatus, int* cellSlot, Ctl* ctl,
+                                                               unsigned int* near1, unsigned int* near2, int* near2List, int capNear)
 {
     __shared__ unsigned int warpTot[32];
+    __shared__ unsigned int blockTotal;
     const int w = blockIdx.x * SV_SCAN_WORDS + threadIdx.x;
     const unsigned int word = (w < nWords) ? bits[w] : 0;
     const unsigned int v = __popc(word);
@@ -292,9 +343,11 @@ __global__ void k_write_mixed(const unsigned int* bits, int nWords, const unsign
             if (threadIdx.x >= o) ti += u;
         }
         warpTot[threadIdx.x] = ti - t;
+        if (threadIdx.x == 31) blockTotal = ti;
     }
     __syncthreads();
-    unsigned int pos = blockSums[blockIdx.x] + warpTot[threadIdx.x >> 5] + inc - v;
+    const unsigned int segBegin = blockSums[blockIdx.x];
+    unsigned int pos = segBegin + warpTot[threadIdx.x >> 5] + inc - v;
     unsigned int rem = word;
     while (rem) {
         const int b = __ffs(rem) - 1;
@@ -307,51 +360,24 @@ __global__ void k_write_mixed(const unsigned int* bits, int nWords, const unsign
         }
         ++pos;
     }
-}
-
-// near1 = mixed U face-neighbours (== needBounding of advectionTemplates.C:138-141 via
-// advection.C:54-82); near2 = near1 U face-neighbours (cells a bounding correction can touch).
-// Bits are set with atomicOr; the thread that flips a near2 bit appends the cell to the list,
-// so the list is a duplicate-free SET (its order is irrelevant: every consumer is per-cell).
-// Most marks are duplicates (43 per mixed cell, ~3 of them new), and atomics on the same bitmap word serialise in L2:
-// a plain L2 read filters the duplicates first (a stale read only costs a redundant atomic).  8 lanes per mixed cell,
-// one face-neighbour (and its own neighbours) per lane.  Measured at 256^3: 38 us (thread per cell, every mark an
-// atomic) -> see DESIGN.md; firing a lane's atomics back to back instead made it slower (59 us): the limit is
-// same-address atomic throughput, not the length of the dependent chain.
-__device__ __forceinline__ void markNear2(int c, unsigned int* near2, int* near2List, Ctl* ctl, int cap)
-{
-    const unsigned int bit = 1u << (c & 31);
-    if (__ldcg(&near2[c >> 5]) & bit) return;
-    const unsigned int old = atomicOr(&near2[c >> 5], bit);
-    if (!(old & bit)) {
-        const int pos = atomicAdd(&ctl->nNear2, 1);
-        if (pos < cap) near2List[pos] = c; else atomicOr(&ctl->err, SVERR_LIST);
-    }
-}
-__device__ __forceinline__ void markNear1(int c, unsigned int* near1)
-{
-    const unsigned int bit = 1u << (c & 31);
-    if (!(__ldcg(&near1[c >> 5]) & bit)) atomicOr(&near1[c >> 5], bit);
-}
-__global__ void k_mark_near(MeshDev m, const int* mixedCells, Ctl* ctl, unsigned int* near1, unsigned int* near2,
-                            int* near2List, int cap)
-{
-    const int n = ctl->nMixed;
+    __syncthreads();
+    // the near sets of this CTA's list segment, 8 lanes per mixed cell
+    const int segEnd = min((int)(segBegin + blockTotal), capacity);
     const int lane = threadIdx.x & 7;
-    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n; i += (gridDim.x * blockDim.x) >> 3) {
+    for (int i = (int)segBegin + (threadIdx.x >> 3); i < segEnd; i += SV_SCAN_WORDS >> 3) {
         const int c = mixedCells[i];
         if (lane == 0) {
             markNear1(c, near1);
-            markNear2(c, near2, near2List, ctl, cap);
+            markNear2(c, near2, near2List, ctl, capNear);
         }
         for (int k = m.cellOff[c] + lane; k < m.cellOff[c + 1]; k += 8) {
             const int y = m.cellAsc[k].y;
             if (y < 0) continue;
             markNear1(y, near1);
-            markNear2(y, near2, near2List, ctl, cap);
+            markNear2(y, near2, near2List, ctl, capNear);
             for (int q = m.cellOff[y]; q < m.cellOff[y + 1]; ++q) {
                 const int z = m.cellAsc[q].y;
-                if (z >= 0) markNear2(z, near2, near2List, ctl, cap);
+                if (z >= 0) markNear2(z, near2, near2List, ctl, capNear);
             }
         }
     }
@@ -666,6 +692,166 @@ __global__ void __launch_bounds__(128) k_un0_worklist(MeshDev m, const int* mixe
             const int pos = atomicAdd(&ctl->nWork, cnt);
             for (int q = 0; q < cnt; ++q) {
                 if (pos + q < capWork) work[pos + q] = make_int2(i, loc[q]); else atomicOr(&ctl->err, SVERR_LIST);
+            }
+        }
+    }
+}
+
+// A7 first half (advection.C:112-175) with 8 lanes per cut cell: interface speed Un0 = U_interp(interfaceC) . n and the
+// compacted work list of (cut cell, downwind face) pairs.  interpolationCellPoint::interpolate (OF, recalled) walks the
+// cell's tets in order (cells() face order, tet index ascending) until one contains the point: here lane g tests the
+// tets of faces g, g+8, ... and the group takes the first hit in that order (ballot, lowest lane of the first round
+// with a hit); the inverse-distance point values of the three tet vertices are formed with one (point, cell) pair per
+// lane and the ORDERED sums redone by every lane from shared memory -- same operands, same order, same bits as the
+// thread-per-cell form, a quarter of its dependent chain.  (Round 1's lane-cooperative attempt passed everything through
+// shuffles and was instruction bound; this one stages through shared memory.)  Each face has exactly one upwind cell,
+// so the work list is duplicate free and the flux kernel's writes are conflict free.
+#define SV_UG_CELLS 16   // cut cells per 128-thread CTA
+struct Un0Shared {
+    double inv[8];
+    double term[8][3];
+};
+__device__ __forceinline__ d3 pointUGroup(const MeshDev& m, int p, const double* __restrict__ U, const double* __restrict__ Ub, int g,
+                                          unsigned gmask, int grpLane0, Un0Shared& sh)
+{
+    if (m.isPatchPoint[p] || (m.ptCellOff[p + 1] - m.ptCellOff[p]) > 8) {   // boundary points / many cells: one lane, in order
+        d3 v = zero3();
+        if (g == 0) v = pointU(m, p, U, Ub);
+        v.x = __shfl_sync(gmask, v.x, grpLane0);
+        v.y = __shfl_sync(gmask, v.y, grpLane0);
+        v.z = __shfl_sync(gmask, v.z, grpLane0);
+        return v;
+    }
+    const int j0 = m.ptCellOff[p], n = m.ptCellOff[p + 1] - j0;
+    const d3 pt = ld3(m.points, p);
+    int c = -1;
+    double inv = 0.0;
+    if (g < n) {
+        c = m.ptCells[j0 + g];
+        inv = 1.0 / mag(pt - ld3(m.C, c));
+        sh.inv[g] = inv;
+    }
+    __syncwarp(gmask);
+    double sumW = 0.0;
+    for (int q = 0; q < n; ++q) sumW += sh.inv[q];
+    if (g < n) {
+        const double pw = inv / sumW;
+        const d3 t = pw * ld3(U, c);
+        sh.term[g][0] = t.x;
+        sh.term[g][1] = t.y;
+        sh.term[g][2] = t.z;
+    }
+    __syncwarp(gmask);
+    d3 val = zero3();
+    for (int q = 0; q < n; ++q) val += mk3(sh.term[q][0], sh.term[q][1], sh.term[q][2]);
+    __syncwarp(gmask);   // the slots are reused by the next point
+    return val;
+}
+
+__global__ void __launch_bounds__(128) k_un0_group(MeshDev m, const int* mixedCells, const int* cellStatus, Ctl* ctl, const double* iN,
+                                                   const double* iC, const double* __restrict__ U, const double* __restrict__ Ub,
+                                                   const double* __restrict__ phi, double* Un0, int2* work, int capWork)
+{
+    __shared__ Un0Shared shAll[SV_UG_CELLS];
+    const int n = ctl->nMixed;
+    const int lane = threadIdx.x & 31, g = lane & 7, grp = lane >> 3;
+    const unsigned gmask = 0xFFu << (grp * 8);
+    const int grpLane0 = grp * 8;
+    Un0Shared& sh = shAll[threadIdx.x >> 3];
+    const int groupsTotal = (gridDim.x * blockDim.x) >> 3;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n; i += groupsTotal) {
+        if (cellStatus[i] != 0) {
+            if (g == 0) Un0[i] = 0.0;
+            continue;
+        }
+        const int celli = mixedCells[i];
+        const d3 position = ld3(iC, celli);
+        const double tol = SV_SMALL;
+        const double cellVolume = m.V[celli];
+        const d3 cc = ld3(m.C, celli);
+        const int c0 = m.cellOff[celli], c1 = m.cellOff[celli + 1];
+        // ---- the tet that contains the interface centre: first hit in (face, tet) order
+        double w[4] = {0.25, 0.25, 0.25, 0.25};
+        int tri[3] = {0, 0, 0};
+        bool found = false;
+        for (int k0 = c0; k0 < c1 && !found; k0 += 8) {
+            bool hit = false;
+            const int k = k0 + g;
+            if (k < c1) {
+                const int f = m.cellFaces[k];
+                const int nv = m.faceOff[f + 1] - m.faceOff[f];
+                for (int tetPt = 1; tetPt < nv - 1 && !hit; ++tetPt) {
+                    tetTri(m, f, tetPt, celli, tri);
+                    const double det = pointToBarycentric(cc, ld3(m.points, tri[0]), ld3(m.points, tri[1]), ld3(m.points, tri[2]), position, w);
+                    if (fabs(det / cellVolume) > tol) {
+                        const double u = w[0], v = w[1], ww = w[2];
+                        if ((u + tol > 0) && (v + tol > 0) && (ww + tol > 0) && (u + v + ww < 1 + tol)) hit = true;
+                    }
+                }
+            }
+            const unsigned b = __ballot_sync(gmask, hit) & gmask;
+            if (b) {
+                const int src = __ffs(b) - 1;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) tri[q] = __shfl_sync(gmask, tri[q], src);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) w[q] = __shfl_sync(gmask, w[q], src);
+                found = true;
+            }
+        }
+        if (!found) {  // least-violated tet (the interface centre lies inside its cell; safety net): one lane, in order
+            if (g == 0) {
+                double best = SV_VGREAT;
+                for (int q = 0; q < 4; ++q) w[q] = 0.25;
+                tri[0] = tri[1] = tri[2] = 0;
+                for (int k = c0; k < c1; ++k) {
+                    const int f = m.cellFaces[k];
+                    const int nv = m.faceOff[f + 1] - m.faceOff[f];
+                    for (int tetPt = 1; tetPt < nv - 1; ++tetPt) {
+                        int t3[3];
+                        double tw[4];
+                        tetTri(m, f, tetPt, celli, t3);
+                        pointToBarycentric(cc, ld3(m.points, t3[0]), ld3(m.points, t3[1]), ld3(m.points, t3[2]), position, tw);
+                        double viol = 0;
+                        for (int q = 0; q < 4; ++q) viol += (tw[q] < 0) ? -tw[q] : 0;
+                        if (viol < best) {
+                            best = viol;
+                            for (int q = 0; q < 3; ++q) tri[q] = t3[q];
+                            for (int q = 0; q < 4; ++q) w[q] = tw[q];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 3; ++q) tri[q] = __shfl_sync(gmask, tri[q], grpLane0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[q] = __shfl_sync(gmask, w[q], grpLane0);
+        }
+        // ---- cell value + the three point values, in the reference's order
+        d3 t = ld3(U, celli) * w[0];
+        t += pointUGroup(m, tri[0], U, Ub, g, gmask, grpLane0, sh) * w[1];
+        t += pointUGroup(m, tri[1], U, Ub, g, gmask, grpLane0, sh) * w[2];
+        t += pointUGroup(m, tri[2], U, Ub, g, gmask, grpLane0, sh) * w[3];
+        if (g == 0) Un0[i] = dot(t, ld3(iN, celli));
+        // ---- downwind faces of this cut cell -> work list (advection.C:134-151,192-197)
+        for (int k0 = c0; k0 < c1; k0 += 8) {
+            const int k = k0 + g;
+            bool down = false;
+            int f = 0;
+            if (k < c1) {
+                f = m.cellFaces[k];
+                if (f < m.nIF) down = (m.owner[f] == celli) ? (phi[f] >= 0.0) : (phi[f] < 0.0);
+                else down = (m.bKind[f - m.nIF] != 1) && (phi[f] >= 0.0);
+            }
+            const unsigned b = __ballot_sync(gmask, down) & gmask;
+            if (b) {
+                int pos = 0;
+                if (g == 0) pos = atomicAdd(&ctl->nWork, __popc(b));
+                pos = __shfl_sync(gmask, pos, grpLane0);
+                if (down) {
+                    const int slot = pos + __popc(b & ((1u << lane) - 1u));
+                    if (slot < capWork) work[slot] = make_int2(i, f); else atomicOr(&ctl->err, SVERR_LIST);
+                }
             }
         }
     }
@@ -1437,7 +1623,12 @@ __global__ void __launch_bounds__(64) k_bound_run(Ctl* ctl, int s, const int* oo
 {
     const int n = min(ctl->nOob[s & 1], capRec);
     const int tag = boundTag(ctl, s);
-    for (int i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += gridDim.x * blockDim.x) {
+    // ONE chain walker per WARP (lane 0): with a walker in every lane the 32 chains of a warp sit at different stages of
+    // the load / bound / release cycle and the SIMT serialisation of those divergent sections cost 8.3k cycles of "compute"
+    // per cell for one inner iteration (SV_BOUND_STATS, round 2: 4.6k with this form); the work is a few thousand cells,
+    // so warps are not scarce
+    if (threadIdx.x & 31) return;
+    for (int i0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i0 < n; i0 += (gridDim.x * blockDim.x) >> 5) {
         int c = oobList[i0];
         if (depInit[c] != 0) continue;  // released later by whoever finishes its last predecessor
         int i = i0;

@@ -343,6 +343,7 @@ def run_plic_vof_advection(case, lib=None, end_time=None, renumber=False, alpha0
     while drv.t < t_end - 1e-12:
         stop = min(t_end, next_write) if by_time else t_end
         drv.step(end_time=stop)
+        s.synchronize()          # device capacity flags (the reference would FatalError) surface here, once per step
         vols.append(s.volume())
         due = (by_time and drv.t >= next_write - 1e-12) or (not by_time and drv.steps % max(1, int(w_int)) == 0) or drv.t >= t_end - 1e-12
         if due:

@@ -332,6 +332,81 @@ def kelvin_mesh(n):
     return m
 
 
+def kelvin_mesh_fast(n):
+    """kelvin_mesh(n) built with numpy (2 n^3 cells in seconds instead of Python loops): the same cells and faces
+    with a different -- but deterministic and OpenFOAM-conforming -- point numbering (ascending lattice key) and the
+    internal faces in upper-triangular order.  n = 95 gives the 1.7 M polyhedral cells of BASELINE.json configs[2]."""
+    import itertools
+    verts = sorted({p for perm in itertools.permutations((0, 1, 2)) for p in
+                    itertools.product(*[(v, -v) if v else (0,) for v in perm])})
+    V = np.array(verts, dtype=np.int64)
+    normals = [np.array(e) * sgn for e in ((1, 0, 0), (0, 1, 0), (0, 0, 1)) for sgn in (1, -1)]
+    normals += [np.array(sg) for sg in itertools.product((1, -1), repeat=3)]
+    faces, fcentre = [], []
+    for nrm in normals:
+        d = 2 if np.abs(nrm).sum() == 1 else 3
+        on = np.nonzero(V @ nrm == d)[0]
+        fc = V[on].mean(axis=0)
+        u = (V[on[0]] - fc).astype(np.float64)
+        u /= np.linalg.norm(u)
+        w = np.cross(nrm / np.linalg.norm(nrm), u)
+        ang = np.arctan2((V[on] - fc) @ w, (V[on] - fc) @ u)
+        faces.append(np.array([int(i) for i in on[np.argsort(ang)]]))
+        fcentre.append(np.rint(fc).astype(np.int64))          # integer lattice point (2,0,0)- or (1,1,1)-type
+    g = np.arange(n, dtype=np.int64)
+    K, J, I = np.meshgrid(g, g, g, indexing="ij")
+    base = np.stack([I.reshape(-1), J.reshape(-1), K.reshape(-1)], axis=1) * 4
+    centres = np.concatenate([base, base + 2])                  # same cell order as kelvin_mesh
+    nC = centres.shape[0]
+    M = 4 * n + 8
+
+    def key(xyz):                                               # lattice coordinates (>= -2) -> unique integer
+        q = xyz + 2
+        return q[..., 0] + M * (q[..., 1] + M * q[..., 2])
+
+    # points
+    pk = key(centres[:, None, :] + V[None, :, :])               # [nC, 24]
+    uniq, inv = np.unique(pk.reshape(-1), return_inverse=True)
+    cell_pts = inv.reshape(nC, 24).astype(np.int32)
+    z, rem = np.divmod(uniq, M * M)
+    y, x = np.divmod(rem, M)
+    P = (np.stack([x, y, z], axis=1).astype(np.float64) - 2.0 + 2.0) / (4.0 * n + 2.0)
+    # faces: (cell, local face) records, matched through the lattice key of the face centre
+    recs = []
+    for lf, (fl, fc) in enumerate(zip(faces, fcentre)):
+        recs.append((key(centres + fc[None, :]), np.arange(nC, dtype=np.int64), np.full(nC, lf, np.int64)))
+    fkey = np.concatenate([r[0] for r in recs])
+    fcell = np.concatenate([r[1] for r in recs])
+    floc = np.concatenate([r[2] for r in recs])
+    order = np.lexsort((fcell, fkey))                           # by key, lower cell first
+    fkey, fcell, floc = fkey[order], fcell[order], floc[order]
+    same_next = np.concatenate([fkey[1:] == fkey[:-1], [False]])
+    same_prev = np.concatenate([[False], fkey[1:] == fkey[:-1]])
+    int_first = np.nonzero(same_next)[0]                        # owner side of an internal face
+    bnd = np.nonzero(~same_next & ~same_prev)[0]
+    own_i, nei_i, loc_i = fcell[int_first], fcell[int_first + 1], floc[int_first]
+    o2 = np.lexsort((nei_i, own_i))                             # upper-triangular order
+    own_i, nei_i, loc_i = own_i[o2], nei_i[o2], loc_i[o2]
+    own_b, loc_b = fcell[bnd], floc[bnd]
+    o3 = np.argsort(own_b, kind="stable")
+    own_b, loc_b = own_b[o3], loc_b[o3]
+    owner = np.concatenate([own_i, own_b])
+    loc = np.concatenate([loc_i, loc_b])
+    nv = np.array([len(f) for f in faces], dtype=np.int64)[loc]
+    face_offsets = np.concatenate([[0], np.cumsum(nv)])
+    face_points = np.empty(int(face_offsets[-1]), dtype=np.int32)
+    for lf, fl in enumerate(faces):
+        sel = np.nonzero(loc == lf)[0]
+        if sel.size:
+            dst = face_offsets[sel][:, None] + np.arange(len(fl))[None, :]
+            face_points[dst.reshape(-1)] = cell_pts[owner[sel]][:, fl].reshape(-1)
+    nIF = own_i.shape[0]
+    m = PolyMesh(points=P, face_offsets=face_offsets.astype(np.int32), face_points=face_points, owner=owner.astype(np.int32),
+                 neighbour=nei_i.astype(np.int32), patches=[Patch("walls", nIF, int(own_b.shape[0]))], n_cells=nC,
+                 meta={"kind": "kelvin", "cell_volume": 32.0 / (4.0 * n + 2.0) ** 3, "n": n})
+    return m
+
+
 def refined_interface_mesh(n):
     """2:1 refinement interface (what dynamicRefineFvMesh produces in the reference's AMR cases): the half
     x < 0.5 is meshed with n^3/2 coarse hexes, the half x > 0.5 with 8x finer ones; the coarse cells on the
