@@ -104,6 +104,7 @@ struct svof_handle {
     size_t dstageSmem = 0;
     bool useStaged = false;
     DenseFast dfast;                 // owner-sorted connectivity of the streaming kernel (k_dense_update2)
+    bool boundLanes = true;          // k_bound_run8 (SVOF_BOUND_LANES=0: the sequential walker)
     bool un0Group = false;           // 8 lanes per cut cell for the interface speed (SVOF_UN0=thread: round-1 thread-per-cell kernel)
     int plicCtas = 0;                // "plic_ctas" option: cap on resident CTAs/SM of the plane-positioning kernel (0 = all that fit)
     int denseCtas = 0;               // "dense_ctas" option: cap on resident CTAs/SM of the streaming kernel (0 = no cap)
@@ -1042,7 +1043,14 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs,               \
                h->oobList[(sidx + 1) & 1], h->oobState);                                                                     \
     } while (0)
-        if (h->maxCF <= 8) BOUND_SWEEP(8);
+        if (h->maxCF <= 8 && h->boundLanes) {   // eight faces in eight lanes of the chain walker's warp
+            LAUNCH(h, k_bound_deps<8>, gB, 128, d, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, dSu, h->bs,
+                   h->depInit, h->depLeft, h->oobIdx, (CellBound<8>*)h->boundRecs, h->capRec, h->affList);
+            LAUNCH(h, k_bound_run8, 16 * h->sms, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx,
+                   (const CellBound<8>*)h->boundRecs, h->capRec, dt, rDt);
+            LAUNCH(h, k_bound_apply<8>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs, h->oobList[(sidx + 1) & 1],
+                   h->oobState);
+        } else if (h->maxCF <= 8) BOUND_SWEEP(8);
         else if (h->maxCF <= 16) BOUND_SWEEP(16);
         else BOUND_SWEEP(64);
     }
@@ -1206,6 +1214,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         h->sms = prop.multiProcessorCount;
         h->overlap = getenv("SVOF_OVERLAP") ? atoi(getenv("SVOF_OVERLAP")) : 0;  // default off
         if (getenv("SVOF_FORK")) h->forkAt = atoi(getenv("SVOF_FORK"));
+        if (getenv("SVOF_BOUND_LANES")) h->boundLanes = atoi(getenv("SVOF_BOUND_LANES")) != 0;
         if (getenv("SVOF_UN0") && !strcmp(getenv("SVOF_UN0"), "group")) h->un0Group = true;   // measured 84 us against 77 us: opt-in
         if (getenv("SVOF_DENSE_CTAS")) h->denseCtas = atoi(getenv("SVOF_DENSE_CTAS"));
         h->prof = getenv("SVOF_PROFILE") && atoi(getenv("SVOF_PROFILE")) > 0;
@@ -1846,6 +1855,7 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; return SVOF_OK; }
     if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; return SVOF_OK; }
     if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "bound_lanes")) { h->boundLanes = value != 0; for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
     if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");
