@@ -123,10 +123,12 @@ solveVofEqu::solveVofEqu(volScalarField& alpha1, const surfaceScalarField& phi, 
     nInternalDev_(0),
     alphaOnDevice_(false),
     alphaPhi_("alphaPhi", mesh_, 0.0),
+    mapAlphaFieldOn_(false),
     reconstructor_(alpha1, *this)
 {
     svof_params p;
     readControls(p);
+    mapAlphaFieldOn_ = p.map_alpha_field != 0;
     if (Pstream::parRun()) createParallel(p); else createSerial(p);
     double fmin, fmax, favg;
     svof_get_info(h_, SVOF_I_FLATNESS_MIN, &fmin);
@@ -419,8 +421,52 @@ void solveVofEqu::advectFlat(const double* Sp, const double* Su)
 
 void solveVofEqu::mapAlphaField()
 {
-    if (!mesh_.changing()) return;                   // reconstruction.C:727-730: dynamicRefineFvMesh only
-    FatalErrorInFunction << "mapAlphaField on a changing mesh needs svof_update_mesh (not built)" << abort(FatalError);
+    if (!mesh_.changing() || !mapAlphaFieldOn_) return;       // reconstruction.C:727-732
+    if (sub_)
+    {
+        FatalErrorInFunction << "mapAlphaField in a decomposed run: re-run svof_decompose on the refined global mesh (not wired)"
+            << abort(FatalError);
+    }
+    // the mesh under us was refined: rebuild every mesh table of the handle, then hand over the fields OpenFOAM mapped
+    labelList faceOff, facePts;
+    flattenFaces(mesh_.faces(), faceOff, facePts);
+    List<svof_patch> patches(patchTable(mesh_, alpha1_));
+    svof_mesh m;
+    std::memset(&m, 0, sizeof(m));
+    m.n_points = mesh_.nPoints();
+    m.n_faces = mesh_.nFaces();
+    m.n_internal_faces = mesh_.nInternalFaces();
+    m.n_cells = mesh_.nCells();
+    m.n_patches = patches.size();
+    m.points = reinterpret_cast<const double*>(mesh_.points().cdata());
+    m.face_offsets = faceOff.cdata();
+    m.face_points = facePts.cdata();
+    m.owner = mesh_.faceOwner().cdata();
+    m.neighbour = mesh_.faceNeighbour().cdata();
+    m.patches = patches.cdata();
+    m.Cf = reinterpret_cast<const double*>(mesh_.faceCentres().cdata());
+    m.Sf = reinterpret_cast<const double*>(mesh_.faceAreas().cdata());
+    m.C = reinterpret_cast<const double*>(mesh_.cellCentres().cdata());
+    m.V = mesh_.cellVolumes().cdata();
+    check(svof_update_mesh(h_, &m), h_, "svof_update_mesh");
+    nCellsDev_ = m.n_cells;
+    nFacesDev_ = m.n_faces;
+    nInternalDev_ = m.n_internal_faces;
+    if (label(interfaceNMapped_.size()) != mesh_.nCells() || label(interfaceDMapped_.size()) != mesh_.nCells())
+    {
+        FatalErrorInFunction << "interfaceN/interfaceD were not mapped onto the refined mesh" << abort(FatalError);
+    }
+    pushAlpha();
+    check(svof_set_interface(h_, reinterpret_cast<const double*>(interfaceNMapped_.cdata()), interfaceDMapped_.cdata()), h_, "svof_set_interface");
+    const dictionary& refineDict = mesh_.dynamicRefineCoeffs();             // dynamicMeshDict.dynamicRefineFvMeshCoeffs
+    const scalar lower = std::stod(entryText(refineDict, "lowerRefineLevel"));
+    const scalar upper = std::stod(entryText(refineDict, "upperRefineLevel"));
+    check(svof_map_alpha_field(h_, lower, upper), h_, "svof_map_alpha_field");
+    alphaFlat_.setSize(nCellsDev_);
+    check(int(svof_get_field(h_, SVOF_F_ALPHA, alphaFlat_.data(), nCellsDev_) < 0 ? -1 : 0), h_, "svof_get_field(alpha)");
+    scalarField& a = alpha1_.primitiveFieldRef();
+    forAll(a, i) a[i] = alphaFlat_[i];
+    alpha1_.correctBoundaryConditions();                                    // alpha1_.oldTime() = alpha1_ is the caller's storage
 }
 
 tmp<surfaceScalarField> solveVofEqu::getRhoPhi(const dimensionedScalar rho1, const dimensionedScalar rho2) const
@@ -482,6 +528,11 @@ void reconstruction::reconstruct()
     svof_get_info(owner_.h_, SVOF_I_N_MIXED, &nMixed);
     Info<< "SimPLIC::reconstruction: Number of mixed cells = "
         << returnReduce(label(nMixed), sumOp<label>()) << endl;                     // reconstruction.C:675
+    if (owner_.mapAlphaFieldOn_)
+    {
+        owner_.interfaceNMapped_ = interfaceN();
+        owner_.interfaceDMapped_ = interfaceD();
+    }
 }
 
 plicSurface reconstruction::interface()

@@ -95,6 +95,11 @@ SYMBOLS = [
                                    c_double_p, c_double_p]),
     ("svof_plic_surface", C.c_int, [_H, C.c_int64, C.c_int64, c_double_p, c_int32_p, c_int32_p, C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int64)]),
+    # changing meshes
+    ("svof_update_points", C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    ("svof_update_mesh", C.c_int, [_H, C.POINTER(SvofMesh)]),
+    ("svof_set_interface", C.c_int, [_H, c_double_p, c_double_p]),
+    ("svof_map_alpha_field", C.c_int, [_H, C.c_double, C.c_double]),
     # decomposed runs
     ("svof_partition_rcb", C.c_int, [C.POINTER(SvofMesh), c_double_p, C.c_int32, c_int32_p]),
     ("svof_decompose", C.c_int, [C.POINTER(SvofMesh), c_int32_p, C.c_int32, C.c_int32, C.POINTER(_H)]),

@@ -51,8 +51,8 @@ struct svof_handle {
     bool inputsAfterNear = false, freshRecon = false;
     std::map<std::string, double> hostAcc;  // profile: host wall time per phase of svof_step_host (ms)
     std::chrono::steady_clock::time_point hostT;
-    int overlap = 0;       // run the streaming kernel on its own stream, concurrently with the sparse chain (SVOF_OVERLAP=1 / svof_set_option);
-                           // off by default: measured slower at 256^3 (1.57 vs 1.31 ms/step), see DESIGN.md section 6
+    int overlap = 1;       // run the streaming kernel on its own low-priority stream, concurrently with the interface kernels
+                           // (SVOF_OVERLAP / svof_set_option "overlap"); bitwise the same result, see DESIGN.md section 5
     int advectCount = 0;
     int epochBumps = 0;     // how often the device-side bounding epoch was advanced (tags derive from it)
     int nP = 0, nF = 0, nIF = 0, nC = 0, nBF = 0;
@@ -130,6 +130,8 @@ struct svof_handle {
     } halo;
     bool haveAlpha = false, havePhi = false, haveU = false, bitsValid = false, advected = false;
     bool anyInletOutlet = false;
+    bool interfaceDense = false;   // interfaceN/D were set for all cells (svof_set_interface): clear them densely once
+    double mapTime = 0;            // alphaMappingTime (reconstruction.C:782)
     bool uPartial = false;   // svof_step_host (sparse_io) uploaded only the rows of U near the interface: not a full field
     double lastDt = 0.0;
     long long launches = 0;
@@ -266,6 +268,66 @@ void profPrint(svof_handle* h)
     for (auto& kv : h->profAcc)
         fprintf(stderr, "  %-24s %10.3f ms %8ld  %9.2f us  %5.1f%%\n", kv.first.c_str(), kv.second.first, kv.second.second,
                 1e3 * kv.second.first / std::max(1L, kv.second.second), 100.0 * kv.second.first / std::max(tot, 1e-30));
+}
+
+// Face / cell geometry, face flatness (reconstruction::updateFaceFlatness, reconstruction.C:408-473), tet base points and
+// polyMesh::geometricD from the points on the device: at create and again whenever the points move (svof_update_points).
+void computeGeometry(svof_handle* h, const double* hCf, const double* hSf, const double* hC, const double* hV)
+{
+    const MeshDev& d = h->md;
+    const int nF = h->nF, nC = h->nC;
+    double *Cf = const_cast<double*>(d.Cf), *Sf = const_cast<double*>(d.Sf), *magSf = const_cast<double*>(d.magSf);
+    double *C = const_cast<double*>(d.C), *V = const_cast<double*>(d.V), *flat = const_cast<double*>(d.flat);
+    unsigned char* tetBase = const_cast<unsigned char*>(d.tetBase);
+    const int haveFaceGeom = (hCf && hSf) ? 1 : 0;
+    if (haveFaceGeom) {
+        CK(cudaMemcpyAsync(Cf, hCf, sizeof(double) * 3 * nF, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(Sf, hSf, sizeof(double) * 3 * nF, cudaMemcpyHostToDevice, h->stream));
+    }
+    LAUNCH(h, k_face_geom, cdiv(nF, 256), 256, d, Cf, Sf, magSf, haveFaceGeom);
+    if (hC && hV) {
+        CK(cudaMemcpyAsync(C, hC, sizeof(double) * 3 * nC, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(V, hV, sizeof(double) * nC, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        LAUNCH(h, k_cell_geom, cdiv(nC, 256), 256, d, C, V);
+    }
+    LAUNCH(h, k_flatness_tetbase, cdiv(nF, 256), 256, d, flat, tetBase);
+    CK(cudaStreamSynchronize(h->stream));
+
+    // "SimPLIC::Mesh face flatness: min/max/avg" (reconstruction.C:442-447)
+    {
+        std::vector<double> hf(nF), hm(nF);
+        CK(cudaMemcpy(hf.data(), flat, sizeof(double) * nF, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hm.data(), magSf, sizeof(double) * nF, cudaMemcpyDeviceToHost));
+        double mn = SV_VGREAT, mx = -SV_VGREAT, sfa = 0, sa = 0;
+        for (int f = 0; f < nF; ++f) {
+            mn = std::min(mn, hf[f]); mx = std::max(mx, hf[f]);
+            sfa += hf[f] * hm[f]; sa += hm[f];
+        }
+        h->flatMin = mn; h->flatMax = mx; h->flatAvg = sfa / sa;
+    }
+
+    // polyMesh::geometricD(): directions normal to empty patches are excluded (OF, recalled)
+    h->sp.geomD[0] = h->sp.geomD[1] = h->sp.geomD[2] = 1;
+    {
+        bool anyEmpty = false;
+        for (const svof_patch& p : h->patches) anyEmpty |= (p.kind == SVOF_PATCH_EMPTY && p.size > 0);
+        if (anyEmpty) {
+            std::vector<double> hs((size_t)3 * nF);
+            CK(cudaMemcpy(hs.data(), Sf, sizeof(double) * 3 * nF, cudaMemcpyDeviceToHost));
+            double e[3] = {0, 0, 0};
+            for (const svof_patch& p : h->patches) {
+                if (p.kind != SVOF_PATCH_EMPTY) continue;
+                for (int k = 0; k < p.size; ++k) {
+                    const double* s = &hs[(size_t)3 * (p.start + k)];
+                    const double ms = std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+                    if (ms > 0) for (int q = 0; q < 3; ++q) e[q] += std::fabs(s[q] / ms);
+                }
+            }
+            const double me = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+            if (me > 0) for (int q = 0; q < 3; ++q) h->sp.geomD[q] = (e[q] / me > 1e-6) ? -1 : 1;
+        }
+    }
 }
 
 void buildMesh(svof_handle* h, const svof_mesh& m)
@@ -520,63 +582,15 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
         h->dfast.slowBits = dupload(h, dfSlow.data(), dfSlow.size());
     }
 
-    double* Cf = dalloc<double>(h, (size_t)3 * nF);
-    double* Sf = dalloc<double>(h, (size_t)3 * nF);
-    double* magSf = dalloc<double>(h, nF);
-    double* C = dalloc<double>(h, (size_t)3 * nC);
-    double* V = dalloc<double>(h, nC);
-    double* flat = dalloc<double>(h, nF);
-    unsigned char* tetBase = dalloc<unsigned char>(h, nF);
-    const int haveFaceGeom = (m.Cf && m.Sf) ? 1 : 0;
-    if (haveFaceGeom) {
-        CK(cudaMemcpyAsync(Cf, m.Cf, sizeof(double) * 3 * nF, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(Sf, m.Sf, sizeof(double) * 3 * nF, cudaMemcpyHostToDevice, h->stream));
-    }
-    d.Cf = Cf; d.Sf = Sf; d.magSf = magSf; d.C = C; d.V = V; d.flat = flat; d.tetBase = tetBase;
-    LAUNCH(h, k_face_geom, cdiv(nF, 256), 256, d, Cf, Sf, magSf, haveFaceGeom);
-    if (m.C && m.V) {
-        CK(cudaMemcpyAsync(C, m.C, sizeof(double) * 3 * nC, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(V, m.V, sizeof(double) * nC, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        LAUNCH(h, k_cell_geom, cdiv(nC, 256), 256, d, C, V);
-    }
-    LAUNCH(h, k_flatness_tetbase, cdiv(nF, 256), 256, d, flat, tetBase);
+    d.Cf = dalloc<double>(h, (size_t)3 * nF);
+    d.Sf = dalloc<double>(h, (size_t)3 * nF);
+    d.magSf = dalloc<double>(h, nF);
+    d.C = dalloc<double>(h, (size_t)3 * nC);
+    d.V = dalloc<double>(h, nC);
+    d.flat = dalloc<double>(h, nF);
+    d.tetBase = dalloc<unsigned char>(h, nF);
     CK(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
-
-    // "SimPLIC::Mesh face flatness: min/max/avg" (reconstruction.C:442-447)
-    {
-        std::vector<double> hf(nF), hm(nF);
-        CK(cudaMemcpy(hf.data(), flat, sizeof(double) * nF, cudaMemcpyDeviceToHost));
-        CK(cudaMemcpy(hm.data(), magSf, sizeof(double) * nF, cudaMemcpyDeviceToHost));
-        double mn = SV_VGREAT, mx = -SV_VGREAT, sfa = 0, sa = 0;
-        for (int f = 0; f < nF; ++f) {
-            mn = std::min(mn, hf[f]); mx = std::max(mx, hf[f]);
-            sfa += hf[f] * hm[f]; sa += hm[f];
-        }
-        h->flatMin = mn; h->flatMax = mx; h->flatAvg = sfa / sa;
-    }
-
-    // polyMesh::geometricD(): directions normal to empty patches are excluded (OF, recalled)
-    h->sp.geomD[0] = h->sp.geomD[1] = h->sp.geomD[2] = 1;
-    {
-        bool anyEmpty = false;
-        for (const svof_patch& p : h->patches) anyEmpty |= (p.kind == SVOF_PATCH_EMPTY && p.size > 0);
-        if (anyEmpty) {
-            std::vector<double> hs((size_t)3 * nF);
-            CK(cudaMemcpy(hs.data(), Sf, sizeof(double) * 3 * nF, cudaMemcpyDeviceToHost));
-            double e[3] = {0, 0, 0};
-            for (const svof_patch& p : h->patches) {
-                if (p.kind != SVOF_PATCH_EMPTY) continue;
-                for (int k = 0; k < p.size; ++k) {
-                    const double* s = &hs[(size_t)3 * (p.start + k)];
-                    const double ms = std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
-                    if (ms > 0) for (int q = 0; q < 3; ++q) e[q] += std::fabs(s[q] / ms);
-                }
-            }
-            const double me = std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
-            if (me > 0) for (int q = 0; q < 3; ++q) h->sp.geomD[q] = (e[q] / me > 1e-6) ? -1 : 1;
-        }
-    }
+    computeGeometry(h, m.Cf, m.Sf, m.C, m.V);
 
     // work-list capacities
     h->capMixed = nC;
@@ -652,6 +666,7 @@ void allocFields(svof_handle* h)
     CK(cudaMallocHost((void**)&h->hctl, sizeof(Ctl)));
     CK(cudaMallocHost((void**)&h->hpartial, 1024 * sizeof(double)));
     memset(h->hctl, 0, sizeof(Ctl));
+    if (h->evNear) return;   // svof_update_mesh: the events of the handle are kept
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->marks[i]));
     CK(cudaEventCreateWithFlags(&h->evNear, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evDense, cudaEventDisableTiming));
@@ -953,6 +968,11 @@ void doReconstruct(svof_handle* h)
     double* alpha = h->alphaBuf[h->cur];
     const int g128 = sparseGrid(h, 128);
     // A1: the front -- sparse clears of the previous step, mixed-cell list in ascending order, near sets (3 launches)
+    if (h->interfaceDense) {   // mapped fields from svof_set_interface: the reference's dense zero-fill (reconstruction.C:636-641), once
+        CK(cudaMemsetAsync(h->iN, 0, sizeof(double) * 3 * h->nC, s));
+        CK(cudaMemsetAsync(h->iD, 0, sizeof(double) * h->nC, s));
+        h->interfaceDense = false;
+    }
     if (!h->bitsValid) LAUNCH(h, k_mixed_bits, cdiv(h->nC, 256), 256, alpha, h->nC, h->prm.mixed_cell_tol, h->mixedBits);
     LAUNCH(h, k_front_count, h->nScanBlocks, SV_SCAN_WORDS, h->mixedBits, h->nWords, h->blockSums, h->mixedCells, h->near2List, h->capNear,
            h->ctl, h->iN, h->iD, h->iC, h->iS, h->cellSlot, h->near1, h->near2);
@@ -1212,7 +1232,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
-        h->overlap = getenv("SVOF_OVERLAP") ? atoi(getenv("SVOF_OVERLAP")) : 0;  // default off
+        h->overlap = getenv("SVOF_OVERLAP") ? atoi(getenv("SVOF_OVERLAP")) : 1;  // default on (round 2: 1.173 vs 1.206 ms/step at 256^3)
         if (getenv("SVOF_FORK")) h->forkAt = atoi(getenv("SVOF_FORK"));
         if (getenv("SVOF_BOUND_LANES")) h->boundLanes = atoi(getenv("SVOF_BOUND_LANES")) != 0;
         if (getenv("SVOF_UN0") && !strcmp(getenv("SVOF_UN0"), "group")) h->un0Group = true;   // measured 84 us against 77 us: opt-in
@@ -1339,6 +1359,100 @@ int svof_scatter_alpha_device(svof_handle* h, const int32_t* d_idx, const double
     API_END(h)
 }
 
+
+// ---- changing meshes ------------------------------------------------------------------------------------
+int svof_update_points(svof_handle* h, const double* points, const double* Cf, const double* Sf, const double* C, const double* V)
+{
+    if (!h || !points) return SVOF_ERR_INVALID_ARG;
+    if ((Cf || Sf || C || V) && !(Cf && Sf && C && V)) return fail(h, SVOF_ERR_INVALID_ARG, "svof_update_points: give all of Cf, Sf, C, V or none");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->streamD));
+    CK(cudaMemcpyAsync(const_cast<double*>(h->md.points), points, sizeof(double) * 3 * h->nP, cudaMemcpyHostToDevice, h->stream));
+    computeGeometry(h, Cf, Sf, C, V);   // reconstruction.C:643-647: flatness follows the mesh
+    h->advected = false;
+    return SVOF_OK;
+    API_END(h)
+}
+
+namespace {
+void releaseMeshState(svof_handle* h)
+{
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->streamD) cudaStreamSynchronize(h->streamD);
+    for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    for (void* p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    h->bytes = 0;
+    auto freeHost = [](auto*& p) { if (p) cudaFreeHost(p); p = nullptr; };
+    freeHost(h->hctl); freeHost(h->hpartial); freeHost(h->hUList); freeHost(h->hUPacked); freeHost(h->hIdx); freeHost(h->hVal);
+    harvestEvents(h, true);
+    h->halo = svof_handle::Halo();
+    h->dfast = DenseFast();
+    h->haveAlpha = h->havePhi = h->haveU = h->bitsValid = h->advected = h->uPartial = false;
+    h->freshRecon = h->inputsAfterNear = false;
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;
+    h->cur = h->cb = 0;
+    h->epochBumps = 0;
+}
+}  // namespace
+
+int svof_update_mesh(svof_handle* h, const svof_mesh* mesh)
+{
+    if (!h || !mesh) return SVOF_ERR_INVALID_ARG;
+    int rc = SVOF_OK;
+    try {
+        CK(cudaSetDevice(h->device));
+        releaseMeshState(h);
+        buildMesh(h, *mesh);
+        allocFields(h);
+        CK(cudaStreamSynchronize(h->stream));
+    } catch (const Unsupported& e) { h->err = e.what(); rc = SVOF_ERR_UNSUPPORTED; }
+    catch (const std::invalid_argument& e) { h->err = e.what(); rc = SVOF_ERR_BAD_MESH; }
+    catch (const std::length_error& e) { h->err = e.what(); rc = SVOF_ERR_CAPACITY; }
+    catch (const std::exception& e) { h->err = e.what(); rc = SVOF_ERR_CUDA; }
+    return rc;
+}
+
+int svof_set_interface(svof_handle* h, const double* interfaceN, const double* interfaceD)
+{
+    if (!h || !interfaceN || !interfaceD) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->iN, interfaceN, sizeof(double) * 3 * h->nC, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->iD, interfaceD, sizeof(double) * h->nC, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->interfaceDense = true;   // the next reconstruct() must clear the whole fields, not just the previous mixed cells
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_map_alpha_field(svof_handle* h, double lower, double upper)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    if (!h->haveAlpha) return fail(h, SVOF_ERR_STATE, "svof_map_alpha_field: alpha not set");
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    double* alpha = h->alphaBuf[h->cur];
+    const int v = (h->variant >= 3) ? 2 : h->variant;   // the non-split capacity variant of this mesh (reconstruction.C:768)
+    if (h->prof) profBegin(h, "mapAlpha", h->stream);
+    switch (v) {
+        case 0: GeoLaunch<CapsHex>::mapAlpha(h->stream, h->md, h->iN, h->iD, lower, upper, alpha, h->ctl); break;
+        case 1: GeoLaunch<CapsSmall>::mapAlpha(h->stream, h->md, h->iN, h->iD, lower, upper, alpha, h->ctl); break;
+        default: GeoLaunch<CapsPoly>::mapAlpha(h->stream, h->md, h->iN, h->iD, lower, upper, alpha, h->ctl); break;
+    }
+    if (h->prof) profEnd(h, h->stream);
+    h->launches++;
+    alphaBC(h);                 // alpha1_.correctBoundaryConditions(); alpha1_.oldTime() = alpha1_ (the old-time buffer is the current one)
+    h->bitsValid = false;
+    h->advected = false;
+    h->hostAlphaSynced = nullptr;
+    CK(cudaStreamSynchronize(h->stream));
+    h->mapTime += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return checkDeviceErr(h);
+    API_END(h)
+}
 
 // ---- decomposed runs: NCCL bootstrap and the ghost-refresh plan --------------------------------------
 int svof_comm_unique_id(void* id128)
@@ -1768,7 +1882,7 @@ int svof_get_info(svof_handle* h, int which, double* out)
         case SVOF_I_N_BOUND_SWEEPS: *out = nSweeps(); return SVOF_OK;
         case SVOF_I_RECONSTRUCTION_TIME: harvestEvents(h, true); *out = h->reconTime; return SVOF_OK;
         case SVOF_I_ADVECTION_TIME: harvestEvents(h, true); *out = h->advTime; return SVOF_OK;
-        case SVOF_I_ALPHA_MAPPING_TIME: *out = 0; return SVOF_OK;
+        case SVOF_I_ALPHA_MAPPING_TIME: *out = h->mapTime; return SVOF_OK;
         case SVOF_I_VOLUME: {
             LAUNCH(h, k_volume_partial, 1024, 256, h->alphaBuf[h->cur], h->md.V, h->nC, h->partial);
             CK(cudaMemcpyAsync(h->hpartial, h->partial, 1024 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

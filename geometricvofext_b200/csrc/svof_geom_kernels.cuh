@@ -33,6 +33,8 @@ struct GeoLaunch {
     static int maxPolyPoints() { return CP::MAXEP; }
     static void plicPolygons(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
                              double* polyPts, int* polyCount);
+    // reconstruction::mapAlphaField: alpha <- calcSubCell(cell, interfaceN, interfaceD).VOF where lower <= alpha <= upper
+    static void mapAlpha(cudaStream_t st, MeshDev m, const double* iN, const double* iD, double lower, double upper, double* alpha, Ctl* ctl);
 };
 
 #ifdef SV_VARIANT
@@ -155,6 +157,21 @@ __global__ void __launch_bounds__(128) k_plic_polygons(MeshDev m, const int* mix
         if (err) atomicOr(&ctl->err, err);
     }
 }
+// reconstruction::mapAlphaField (reconstruction.C:751-768): thread per cell, the cut is evaluated WITHOUT splitWarpedFace
+template <class CP>
+__global__ void __launch_bounds__(128) k_map_alpha(MeshDev m, const double* iN, const double* iD, double lower, double upper, double* alpha,
+                                                   Ctl* ctl)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.nCells) return;
+    const double a = alpha[c];
+    if (!(a >= lower && a <= upper)) return;
+    SubCellOut sc;
+    int err = 0;
+    subCell<CP>(m, c, ld3(iN, c), iD[c], false, sc, err);
+    alpha[c] = sc.VOF;
+    if (err) atomicOr(&ctl->err, err);
+}
 template <class CP>
 __global__ void k_find_distance(MeshDev m, int n, const int* cells, const double* alphas, const double* normals, int split,
                                 int* status, double* dists, double* ic, double* ia, int* errOut)
@@ -270,6 +287,11 @@ void GeoLaunch<CP>::plicPolygons(cudaStream_t st, int grid, MeshDev m, const int
                                  double* polyPts, int* polyCount)
 {
     k_plic_polygons<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, iN, iD, polyPts, polyCount);
+}
+template <class CP>
+void GeoLaunch<CP>::mapAlpha(cudaStream_t st, MeshDev m, const double* iN, const double* iD, double lower, double upper, double* alpha, Ctl* ctl)
+{
+    k_map_alpha<CP><<<(m.nCells + 127) / 128, 128, 0, st>>>(m, iN, iD, lower, upper, alpha, ctl);
 }
 template <class CP>
 void GeoLaunch<CP>::findDistance(cudaStream_t st, MeshDev m, int n, const int* cells, const double* alphas, const double* normals,

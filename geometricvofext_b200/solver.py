@@ -116,10 +116,30 @@ class SolveVofEqu:
         self._chk(self.lib.svof_step_host(self._h, float(dt), capi.dptr(phi), capi.dptr(U), capi.dptr(ub),
                                           capi.dptr(alpha_out), capi.dptr(alpha_phi_out)))
 
-    def mapAlphaField(self):
-        """solveVofEqu::mapAlphaField(): a no-op unless the mesh is a dynamicRefineFvMesh
-        (reconstruction.C:727-730); static meshes only in this build."""
-        return None
+    def mapAlphaField(self, lower=0.01, upper=0.99):
+        """solveVofEqu::mapAlphaField() (reconstruction.C:725-784): after a refinement step, alpha in the cells whose
+        value lies within the refinement levels is re-derived from the mapped PLIC plane.  The caller decides when
+        (mesh.changing() && mapAlphaField) and maps interfaceN/D first (setInterface)."""
+        self._chk(self.lib.svof_map_alpha_field(self._h, float(lower), float(upper)))
+
+    def setInterface(self, N, D):
+        n, d = capi.f64(N, (self.nC, 3)), capi.f64(D, (self.nC,))
+        self._chk(self.lib.svof_set_interface(self._h, capi.dptr(n), capi.dptr(d)))
+
+    def updatePoints(self, points):
+        """mesh.moving(): new point positions, same topology"""
+        p = capi.f64(points, (self.mesh.n_points, 3))
+        self._chk(self.lib.svof_update_points(self._h, capi.dptr(p), None, None, None, None))
+        self.mesh.points = p
+
+    def updateMesh(self, mesh):
+        """mesh.topoChanging(): rebuild the handle's mesh tables for `mesh`; fields must be set again"""
+        cm, keep = mesh.to_c()
+        self._chk(self.lib.svof_update_mesh(self._h, C.byref(cm)))
+        del keep
+        self.mesh = mesh
+        self.nC, self.nF, self.nIF = mesh.n_cells, mesh.n_faces, mesh.n_internal_faces
+        self.nBF = self.nF - self.nIF
 
     def alpha(self):
         return self.field(capi.F_ALPHA)

@@ -331,6 +331,32 @@ int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const doub
 int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, double* points, int32_t* face_offsets,
                       int32_t* cells, int64_t* n_points, int64_t* n_faces);
 
+/* ---- changing meshes (moving points, refinement) ------------------------------
+ * The hooks the reference gets from OpenFOAM's mesh.changing()/moving()/topoChanging(). */
+
+/* Mesh motion without topology change (mesh.moving()): new point positions [3*n_points].  Face/cell geometry, the face
+ * flatness (reconstruction::updateFaceFlatness on mesh.changing(), reconstruction.C:643-647) and the tet base points are
+ * recomputed; Cf/Sf/C/V may be handed over as in svof_mesh (all four, or all NULL).  The moving-mesh volume scaling of
+ * advectionTemplates.C:377-380 acts on a field the update overwrites (alpha1 is recomputed from alpha1.oldTime()), so the
+ * new volumes are all the step needs; phi is then the mesh-relative flux, as in the reference's solvers. */
+int svof_update_points(svof_handle* h, const double* points, const double* Cf, const double* Sf, const double* C, const double* V);
+
+/* Topology change (dynamicRefineFvMesh refinement / unrefinement; the reference re-does setProcessorPatches on
+ * topoChanging, advectionTemplates.C:359-362): every mesh-dependent table of the handle is rebuilt for the new mesh, the
+ * parameters are kept.  Fields are NOT mapped here -- OpenFOAM maps its registered fields itself: set alpha (and, for
+ * mapAlphaField, the mapped interfaceN/D) afterwards.  Decomposed runs call svof_halo_setup again. */
+int svof_update_mesh(svof_handle* h, const svof_mesh* mesh);
+
+/* interfaceN [3*n_cells] and interfaceD [n_cells] as mapped onto the new mesh (the fields `interfaceN`/`interfaceD` the
+ * reference registers, reconstruction.C:518-560), for svof_map_alpha_field. */
+int svof_set_interface(svof_handle* h, const double* interfaceN, const double* interfaceD);
+
+/* reconstruction::mapAlphaField (reconstruction.C:725-784): in every cell with lower <= alpha <= upper (the
+ * dynamicRefineFvMeshCoeffs refinement levels) alpha becomes the volume fraction its (mapped) PLIC plane cuts off,
+ * cutCell::calcSubCell without splitWarpedFace; alpha.oldTime() follows.  The caller decides whether to call it
+ * (mesh.changing() && mapAlphaField, reconstruction.C:732). */
+int svof_map_alpha_field(svof_handle* h, double lower_refine_level, double upper_refine_level);
+
 /* ---- decomposed runs ----------------------------------------------------------
  * Replaces what the reference does across processor patches: the zoneDistribute stencil
  * exchange (reconstruction.C:97-107), syncProcPatches (advection.C:311-393, called once

@@ -54,6 +54,8 @@ struct Mesh {
     bool isInternalFace(label f) const { return f < nInternalFaces; }
 
     void build(const svof_mesh& m);
+    // mesh.moving(): new point positions, same topology -- geometry, flatness (reconstruction.C:643-647) and tet base points follow
+    void movePoints(const double* pts, const double* hCf, const double* hSf, const double* hC, const double* hV);
 
    private:
     void calcFaceCentresAndAreas();
@@ -222,6 +224,28 @@ inline void Mesh::calcTetBasePts()
         // tetIndices::faceTriIs falls back to 0 when no base point qualifies
         tetBasePt[f] = (found < 0) ? 0 : found;
     }
+}
+
+inline void Mesh::movePoints(const double* pts, const double* hCf, const double* hSf, const double* hC, const double* hV)
+{
+    for (label i = 0; i < nPoints; ++i) points[i] = point(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    if (hCf && hSf) {
+        for (label f = 0; f < nFaces; ++f) {
+            Cf[f] = vec(hCf[3 * f], hCf[3 * f + 1], hCf[3 * f + 2]);
+            Sf[f] = vec(hSf[3 * f], hSf[3 * f + 1], hSf[3 * f + 2]);
+        }
+    } else {
+        calcFaceCentresAndAreas();
+    }
+    for (label f = 0; f < nFaces; ++f) magSf[f] = mag(Sf[f]);
+    if (hC && hV) {
+        V.assign(hV, hV + nCells);
+        for (label c = 0; c < nCells; ++c) C[c] = vec(hC[3 * c], hC[3 * c + 1], hC[3 * c + 2]);
+    } else {
+        calcCellCentresAndVols();
+    }
+    calcFaceFlatness();
+    calcTetBasePts();
 }
 
 inline void Mesh::build(const svof_mesh& m)

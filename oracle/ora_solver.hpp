@@ -317,6 +317,20 @@ struct Solver {
     }
 
     // -------------------------------------------------------------- A3-A5 ---
+    // reconstruction::mapAlphaField (reconstruction.C:725-784), the part below the mesh.changing() && mapAlphaField_ test
+    double alphaMappingTime = 0;
+    void mapAlphaField(scalar lowerRefineLevel, scalar upperRefineLevel)
+    {
+        for (label celli = 0; celli < mesh.nCells; ++celli) {
+            if (alpha[celli] >= lowerRefineLevel && alpha[celli] <= upperRefineLevel) {
+                cutCell_->calcSubCell(celli, interfaceN[celli], interfaceD[celli], false);
+                alpha[celli] = cutCell_->volumeOfFluid();
+            }
+        }
+        correctAlphaBCs();
+        alphaOld = alpha;
+    }
+
     void reconstruct()  // reconstruction.C:680-722
     {
         initialize();

@@ -256,7 +256,7 @@ int svof_get_info(svof_handle* h, int which, double* out)
         case SVOF_I_N_BOUND_SWEEPS: *out = s.nSweeps; return SVOF_OK;
         case SVOF_I_RECONSTRUCTION_TIME: *out = s.reconstructionTime; return SVOF_OK;
         case SVOF_I_ADVECTION_TIME: *out = s.advectionTime; return SVOF_OK;
-        case SVOF_I_ALPHA_MAPPING_TIME: *out = 0; return SVOF_OK;
+        case SVOF_I_ALPHA_MAPPING_TIME: *out = h->s.alphaMappingTime; return SVOF_OK;
         case SVOF_I_VOLUME: *out = s.volume(); return SVOF_OK;
         case SVOF_I_GPU_LAUNCHES: *out = 0; return SVOF_OK;
         case SVOF_I_FLATNESS_MIN: *out = s.mesh.flatMin; return SVOF_OK;
@@ -412,6 +412,51 @@ int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const doub
                                            phi[i], h->s.mesh.magSf[f]);
     }
     return SVOF_OK;
+}
+
+// ---- changing meshes ------------------------------------------------------------------------------------
+int svof_update_points(svof_handle* h, const double* points, const double* Cf, const double* Sf, const double* C, const double* V)
+{
+    if (!h || !points) return SVOF_ERR_INVALID_ARG;
+    if ((Cf || Sf || C || V) && !(Cf && Sf && C && V)) return SVOF_ERR_INVALID_ARG;
+    ORA_TRY(h)
+    h->s.mesh.movePoints(points, Cf, Sf, C, V);
+    return SVOF_OK;
+    ORA_CATCH(h, SVOF_ERR_BAD_MESH)
+}
+
+int svof_update_mesh(svof_handle* h, const svof_mesh* mesh)
+{
+    if (!h || !mesh) return SVOF_ERR_INVALID_ARG;
+    ORA_TRY(h)
+    const svof_params p = h->s.prm;
+    h->s.~Solver();
+    new (&h->s) Solver();
+    h->s.init(*mesh, p);
+    return SVOF_OK;
+    ORA_CATCH(h, SVOF_ERR_BAD_MESH)
+}
+
+int svof_set_interface(svof_handle* h, const double* N, const double* D)
+{
+    if (!h || !N || !D) return SVOF_ERR_INVALID_ARG;
+    for (label c = 0; c < h->s.mesh.nCells; ++c) {
+        h->s.interfaceN[c] = vec(N[3 * c], N[3 * c + 1], N[3 * c + 2]);
+        h->s.interfaceD[c] = D[c];
+    }
+    return SVOF_OK;
+}
+
+int svof_map_alpha_field(svof_handle* h, double lower, double upper)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    if (!h->s.haveAlpha) { h->err = "svof_map_alpha_field: alpha not set"; return SVOF_ERR_STATE; }
+    ORA_TRY(h)
+    const double t0 = nowSec();
+    h->s.mapAlphaField(lower, upper);
+    h->s.alphaMappingTime += nowSec() - t0;
+    return SVOF_OK;
+    ORA_CATCH(h, SVOF_ERR_INVALID_ARG)
 }
 
 // decomposed runs: the CPU oracle is single-domain.  Sub-domain extraction and partitioning are host utilities of the
