@@ -468,13 +468,13 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
             for (int f = nIF; f < nF; ++f) dfSlow[own[f] >> 5] |= 1u << (own[f] & 31);        // cells with boundary faces: generic rows
         }
     }
-    // cellPoints ascending; pointCells ascending
+    // cellPoints ascending; pointCells ascending.  The per-cell sort/unique is the slowest host loop of the build
+    // (21-27 s of set-up at 256^3 in round 1): host threads over cell ranges, counts first, then the fill.
     std::vector<int> cellPtOff(nC + 1, 0), cellPts;
-    cellPts.reserve((size_t)nC * 8);
     int maxCP = 0;
     {
-        std::vector<int> tmp;
-        for (int c = 0; c < nC; ++c) {
+        const unsigned nT = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        auto uniquePts = [&](int c, std::vector<int>& tmp) {
             tmp.clear();
             for (int k = cellOff[c]; k < cellOff[c + 1]; ++k) {
                 const int f = cellFaces[k];
@@ -482,10 +482,34 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
             }
             std::sort(tmp.begin(), tmp.end());
             tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-            cellPts.insert(cellPts.end(), tmp.begin(), tmp.end());
-            cellPtOff[c + 1] = (int)cellPts.size();
-            maxCP = std::max(maxCP, (int)tmp.size());
-        }
+        };
+        auto forRanges = [&](auto&& body) {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nT; ++t) {
+                const int c0 = (int)((long long)nC * t / nT), c1 = (int)((long long)nC * (t + 1) / nT);
+                th.emplace_back([&, c0, c1, t]() { body(c0, c1, t); });
+            }
+            for (auto& x : th) x.join();
+        };
+        std::vector<int> maxPer(nT, 0);
+        forRanges([&](int c0, int c1, unsigned t) {
+            std::vector<int> tmp;
+            for (int c = c0; c < c1; ++c) {
+                uniquePts(c, tmp);
+                cellPtOff[c + 1] = (int)tmp.size();
+                maxPer[t] = std::max(maxPer[t], (int)tmp.size());
+            }
+        });
+        for (unsigned t = 0; t < nT; ++t) maxCP = std::max(maxCP, maxPer[t]);
+        for (int c = 0; c < nC; ++c) cellPtOff[c + 1] += cellPtOff[c];
+        cellPts.resize((size_t)cellPtOff[nC]);
+        forRanges([&](int c0, int c1, unsigned) {
+            std::vector<int> tmp;
+            for (int c = c0; c < c1; ++c) {
+                uniquePts(c, tmp);
+                std::copy(tmp.begin(), tmp.end(), cellPts.begin() + cellPtOff[c]);
+            }
+        });
     }
     std::vector<int> ptCellOff(nP + 1, 0);
     for (int p : cellPts) ptCellOff[p + 1]++;

@@ -355,9 +355,23 @@ def bench(args, controls, metric, unit):
     if not dist.is_initialized():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     strong = args.scaling == "strong"
+    workload_name = getattr(args, "workload", "leveque")
+    if workload_name == "dambreak":
+        # BASELINE.json configs[3] substitute: the damBreakWithObstacle box and alpha controls, 8-way
+        import bench as _bench
+        controls = dict(_bench.DAMBREAK_CONTROLS)
+        strong = True
     layers = args.layers if args.layers > 0 else default_layers(controls)
     t0 = time.perf_counter()
-    if strong:
+    if workload_name == "dambreak":
+        n = args.n
+        dec = BoxDecomposition(n, world, layers, boxes=box_rcb(n, world, None))
+        centre = None
+        dt = 0.2 / n
+        workload = ("damBreakWithObstacle substitute, advection only: %d^3 hex box (%.1f M cells), water box (0.6 x 0.1875 x 0.75), clip true / "
+                    "snapTol 1e-12 / mixedCellTol 1e-10, inletOutlet top patch, prescribed 3-D deformation velocity, split over %d ranks "
+                    "(BASELINE.json configs[3])" % (n, n ** 3 / 1e6, world))
+    elif strong:
         n = args.strong_n
         wfn = sphere_plane_weights(n, args.mixed_weight) if args.mixed_weight > 0 else None
         boxes = box_rcb(n, world, wfn)
@@ -376,9 +390,19 @@ def bench(args, controls, metric, unit):
         workload = ("LeVeque 3-D deformation tiled %dx%dx%d: one unit cube (%d^3 cubic hex cells, sphere r=0.15) per GPU" %
                     (grid[0], grid[1], grid[2], args.n))
     sub, maps = dec.rank_mesh(rank)
+    if workload_name == "dambreak":
+        from .mesh import cell_centres_hex
+        for p_ in sub.patches:
+            if p_.name == "top":
+                p_.alpha_bc, p_.alpha_value = capi.BC_INLET_OUTLET, 0.0
     ds = DecomposedSolveVofEqu(sub, maps, controls, rank, world, device=local)
     s = ds.s
-    a0 = fields.sphere_alpha_quadrature(sub, centre=centre)
+    if workload_name == "dambreak":
+        Cc = cell_centres_hex(sub)
+        a0 = ((Cc[:, 0] < 0.6) & (Cc[:, 1] < 0.1875) & (Cc[:, 2] < 0.75)).astype(np.float64)
+        del Cc
+    else:
+        a0 = fields.sphere_alpha_quadrature(sub, centre=centre)
     C_, Cf, Sf = s.field(capi.F_C), s.field(capi.F_CF), s.field(capi.F_SF)
     f = fields.u_factor(dt, dt, 6.0)
     U = fields.leveque_velocity(C_) * f
@@ -393,7 +417,7 @@ def bench(args, controls, metric, unit):
     ds.exchange_alpha()
     setup_s = time.perf_counter() - t0
 
-    for _ in range(2 + max(3, args.warmup)):
+    for _ in range(2 + max(3, args.warmup) + (getattr(args, "develop_steps", 0) if workload_name == "dambreak" else 0)):
         ds.step(dt)
     s.synchronize()
     l0 = s.info(capi.I_GPU_LAUNCHES)
@@ -441,7 +465,7 @@ def bench(args, controls, metric, unit):
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "multi-GPU leg is device resident (no host copies declared); the host-buffer end-to-end number is measured at N=1"},
         }
-        if strong:
+        if strong and workload_name != "dambreak":
             base = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "strong_base_%d.json" % args.strong_n)
             if os.path.exists(base):
                 try:
