@@ -95,6 +95,8 @@ SYMBOLS = [
                                    c_double_p, c_double_p]),
     ("svof_plic_surface", C.c_int, [_H, C.c_int64, C.c_int64, c_double_p, c_int32_p, c_int32_p, C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int64)]),
+    ("svof_subcell_faces", C.c_int, [_H, C.c_int64, C.c_int64, C.c_int64, c_double_p, c_int32_p, c_int32_p, c_int32_p,
+                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     # changing meshes
     ("svof_update_points", C.c_int, [_H, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     ("svof_update_mesh", C.c_int, [_H, C.POINTER(SvofMesh)]),

@@ -2257,4 +2257,139 @@ int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, dou
     API_END(h)
 }
 
+
+// reconstruction::subCellFaces() (reconstruction.C:838-891).  The polygons come from k_subcell_faces; the point merge and
+// the orientation fix of cutCell::updateSubCellPointsandFaces (cutCell.C:239-290) are list surgery on a few thousand small
+// polygons and run here on the host (post-processing for the reconstructedSubcellFaces sampler, not part of the step).
+int svof_subcell_faces(svof_handle* h, int64_t cap_points, int64_t cap_faces, int64_t cap_face_points, double* points,
+                       int32_t* face_offsets, int32_t* face_points, int32_t* face_cell, int64_t* n_points, int64_t* n_faces,
+                       int64_t* n_face_points)
+{
+    if (!h || !n_points || !n_faces || !n_face_points) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    PRIM_PROLOGUE
+    (void)down;
+    (void)dErr;
+    fetchCtl(h);
+    const int nM = h->hctl->nMixed;
+    const int maxFaces = h->maxCF + 1;
+    const int maxPts = h->maxCF * 2 * h->md.maxFV + 2 * h->maxCF + 8;
+    double* dPts = (double*)up(nullptr, sizeof(double) * 3 * (size_t)std::max(nM, 1) * maxPts);
+    int* dFs = (int*)up(nullptr, sizeof(int) * (size_t)std::max(nM, 1) * maxFaces);
+    int* dNf = (int*)up(nullptr, sizeof(int) * (size_t)std::max(nM, 1));
+    double* dCen = (double*)up(nullptr, sizeof(double) * 3 * (size_t)std::max(nM, 1));
+    std::vector<double> pts((size_t)3 * nM * maxPts), cen((size_t)3 * nM);
+    std::vector<int> fs((size_t)nM * maxFaces), nf(nM), mixed(nM);
+    if (nM) {
+        const int v = (h->variant >= 3) ? 2 : h->variant;   // evaluated without splitWarpedFace (reconstruction.C:856)
+        const int grid = sparseGrid(h, 128);
+        switch (v) {
+            case 0: GeoLaunch<CapsHex>::subCellFaces(h->stream, grid, h->md, h->mixedCells, h->ctl, h->iN, h->iD, maxFaces, maxPts, dPts, dFs, dNf, dCen); break;
+            case 1: GeoLaunch<CapsSmall>::subCellFaces(h->stream, grid, h->md, h->mixedCells, h->ctl, h->iN, h->iD, maxFaces, maxPts, dPts, dFs, dNf, dCen); break;
+            default: GeoLaunch<CapsPoly>::subCellFaces(h->stream, grid, h->md, h->mixedCells, h->ctl, h->iN, h->iD, maxFaces, maxPts, dPts, dFs, dNf, dCen); break;
+        }
+        h->launches++;
+        CK(cudaMemcpyAsync(pts.data(), dPts, sizeof(double) * pts.size(), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(cen.data(), dCen, sizeof(double) * cen.size(), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(fs.data(), dFs, sizeof(int) * fs.size(), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(nf.data(), dNf, sizeof(int) * nM, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(mixed.data(), h->mixedCells, sizeof(int) * nM, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    for (void* q : tmp) cudaFree(q);
+    fetchCtl(h);
+    if (h->hctl->err) return deviceErr(h);
+    auto P = [&](const std::vector<d3>& v, int i) -> const d3& { return v[(size_t)i]; };
+    // face::centre / face::areaNormal (OF, recalled) on a host polygon, as svof_geom.cuh does on the device
+    auto polyCentre = [&](const std::vector<d3>& p) {
+        const int n = (int)p.size();
+        if (n == 3) return (1.0 / 3.0) * (p[0] + p[1] + p[2]);
+        d3 cp = zero3();
+        for (int i = 0; i < n; ++i) cp += p[i];
+        cp /= double(n);
+        double sumA = 0;
+        d3 sumAc = zero3();
+        for (int i = 0; i < n; ++i) {
+            const d3 nx = p[(i + 1 == n) ? 0 : i + 1];
+            const d3 ttc = p[i] + nx + cp;
+            const double ta = mag(cross(p[i] - cp, nx - cp));
+            sumA += ta;
+            sumAc += ta * ttc;
+        }
+        if (sumA > SV_VSMALL) return sumAc / (3.0 * sumA);
+        return cp;
+    };
+    auto polyArea = [&](const std::vector<d3>& p) {
+        const int n = (int)p.size();
+        if (n == 3) return 0.5 * cross(p[1] - p[0], p[2] - p[0]);
+        d3 cp = zero3();
+        for (int i = 0; i < n; ++i) cp += p[i];
+        cp /= double(n);
+        d3 a = zero3();
+        for (int i = 0; i < n; ++i) {
+            const d3 nx = (i < n - 1) ? p[i + 1] : p[0];
+            a += 0.5 * cross(nx - p[i], cp - p[i]);
+        }
+        return a;
+    };
+    (void)P;
+    std::vector<double> outPts;
+    std::vector<int32_t> off(1, 0), fpts, fcell;
+    for (int i = 0; i < nM; ++i) {
+        if (nf[i] <= 0) continue;
+        const double* cp = pts.data() + (size_t)3 * i * maxPts;
+        const d3 centre = mk3(cen[3 * (size_t)i], cen[3 * (size_t)i + 1], cen[3 * (size_t)i + 2]);
+        // merge duplicate points (first occurrence kept, 10*SMALL), as the oracle does
+        std::vector<d3> uniq;
+        std::vector<int> toUnique;
+        int np = 0;
+        for (int k = 0; k < nf[i]; ++k) np += fs[(size_t)i * maxFaces + k];
+        toUnique.resize(np);
+        for (int q = 0; q < np; ++q) {
+            const d3 x = mk3(cp[3 * q], cp[3 * q + 1], cp[3 * q + 2]);
+            int found = -1;
+            for (size_t j = 0; j < uniq.size() && found < 0; ++j)
+                if (mag(x - uniq[j]) <= 10.0 * SV_SMALL) found = (int)j;
+            if (found < 0) {
+                found = (int)uniq.size();
+                uniq.push_back(x);
+            }
+            toUnique[q] = found;
+        }
+        const int32_t base = (int32_t)(outPts.size() / 3);
+        int q0 = 0;
+        for (int k = 0; k < nf[i]; ++k) {
+            const int cnt = fs[(size_t)i * maxFaces + k];
+            std::vector<int> f(cnt);
+            std::vector<d3> fp(cnt);
+            for (int q = 0; q < cnt; ++q) {
+                f[q] = toUnique[q0 + q];
+                fp[q] = uniq[f[q]];
+            }
+            q0 += cnt;
+            if (dot(polyCentre(fp) - centre, polyArea(fp)) < 0.0) std::reverse(f.begin() + 1, f.end());  // face::reverseFace keeps vertex 0
+            for (int v : f) fpts.push_back(base + v);
+            off.push_back((int32_t)fpts.size());
+            fcell.push_back(mixed[i]);
+        }
+        for (const d3& x : uniq) {
+            outPts.push_back(x.x);
+            outPts.push_back(x.y);
+            outPts.push_back(x.z);
+        }
+    }
+    *n_points = (int64_t)(outPts.size() / 3);
+    *n_faces = (int64_t)fcell.size();
+    *n_face_points = (int64_t)fpts.size();
+    if (!points) return SVOF_OK;
+    if (cap_points < *n_points || cap_faces < *n_faces || cap_face_points < *n_face_points || !face_offsets || !face_points || !face_cell)
+        return fail(h, SVOF_ERR_CAPACITY, "svof_subcell_faces: output arrays too small");
+    std::copy(outPts.begin(), outPts.end(), points);
+    std::copy(off.begin(), off.end(), face_offsets);
+    std::copy(fpts.begin(), fpts.end(), face_points);
+    std::copy(fcell.begin(), fcell.end(), face_cell);
+    return SVOF_OK;
+    API_END(h)
+}
+
 }  // extern "C"

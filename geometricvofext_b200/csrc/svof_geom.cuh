@@ -131,7 +131,8 @@ __device__ __forceinline__ void subFaceCentreAndArea(const d3* sp, int np, d3& c
 
 // cutFace::calcSubFace (cutFace.C:136-259).  ip/nip: interface points (valid for status 0).
 template <class CP>
-__device__ __noinline__ int clipFace(const d3* fp, int nv, const d3& n, double D, d3& centre, d3& area, d3* ip, int& nip, int& err)
+__device__ __noinline__ int clipFace(const d3* fp, int nv, const d3& n, double D, d3& centre, d3& area, d3* ip, int& nip, int& err,
+                                     d3* spOut = nullptr, int* npOut = nullptr)
 {
     double s[CP::MAXFV];
     int nSub = 0, first = -1;
@@ -173,6 +174,10 @@ __device__ __noinline__ int clipFace(const d3* fp, int nv, const d3& n, double D
     if (nip > CP::MAXIP) nip = CP::MAXIP;
     if (np >= 3) {
         subFaceCentreAndArea(sp, np, centre, area);
+        if (spOut) {  // cutFace::subFacePoints(), for reconstruction::subCellFaces()
+            for (int q = 0; q < np; ++q) spOut[q] = sp[q];
+            *npOut = np;
+        }
         return 0;
     }
     centre = faceCentreOF(fp, nv);
@@ -340,6 +345,9 @@ struct SubCellOut {
     // optional: the interface edge points of a cut cell (cutCell::interfaceEdges_, flattened), for surface extraction
     d3* epOut = nullptr;
     int nEp = 0;
+    // optional: cutCell::subCellCentre_ (calcSubCellCentreAndVolume, cutCell.C:103-137), only consumed by subCellFaces()
+    bool wantCentre = false;
+    d3 subCentre;
 };
 
 // face::reverseFace keeps vertex 0 and reverses the rest (cutCell.C:189,211,232)
@@ -483,6 +491,16 @@ __device__ __noinline__ void subCell(const MeshDev& m, int cell, const d3& n, do
         cEst /= double(nCut);
         double vol = 0.0;
         for (int q = 0; q < nCut; ++q) vol += dmax(fabs(dot(cfa[q], cfc[q] - cEst)), SV_VSMALL);
+        if (out.wantCentre) {
+            d3 sc = zero3();
+            for (int q = 0; q < nCut; ++q) {
+                const double pyr3Vol = dmax(fabs(dot(cfa[q], cfc[q] - cEst)), SV_VSMALL);
+                const d3 pc = 0.75 * cfc[q] + 0.25 * cEst;
+                sc += pyr3Vol * pc;
+            }
+            sc /= vol;
+            out.subCentre = sc;
+        }
         vol /= 3.0;
         out.subVol = vol;
         out.VOF = vol / __ldg(m.V + cell);

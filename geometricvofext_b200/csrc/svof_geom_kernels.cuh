@@ -33,6 +33,9 @@ struct GeoLaunch {
     static int maxPolyPoints() { return CP::MAXEP; }
     static void plicPolygons(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
                              double* polyPts, int* polyCount);
+    // reconstruction::subCellFaces(): raw polygons of the submerged sub-cell per mixed cell (fixed strides), merged on the host
+    static void subCellFaces(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
+                             int maxFaces, int maxPts, double* pts, int* faceSize, int* nFaces, double* centre);
     // reconstruction::mapAlphaField: alpha <- calcSubCell(cell, interfaceN, interfaceD).VOF where lower <= alpha <= upper
     static void mapAlpha(cudaStream_t st, MeshDev m, const double* iN, const double* iD, double lower, double upper, double* alpha, Ctl* ctl);
 };
@@ -113,6 +116,40 @@ __global__ void k_cut_cells(MeshDev m, int n, const int* cells, const double* no
 // cell; the cut is re-evaluated WITHOUT splitWarpedFace (as the reference does), the interface edge points are sorted
 // by angle about the interface centre in the plane of the interface (stable, ascending) and points within 1e-8 rad of
 // their predecessor are dropped.
+// cutCell::interfacePoints (cutCell.C:545-608): the interface edge points sorted by angle about the interface centre in the
+// plane of the interface (stable, ascending); points within 1e-8 rad of their predecessor are dropped.  Returns the count.
+template <class CP>
+__device__ __forceinline__ int interfacePolygonDev(const SubCellOut& sc, const d3* ep, double* out)
+{
+    int cnt = 0;
+    const d3 zhat = sc.iS / mag(sc.iS);
+    d3 xhat = ep[0] - sc.iC;
+    xhat = xhat - dot(xhat, zhat) * zhat;
+    xhat /= mag(xhat);
+    d3 yhat = cross(zhat, xhat);
+    yhat /= mag(yhat);
+    double ang[CP::MAXEP];
+    short ord[CP::MAXEP];
+    for (int q = 0; q < sc.nEp; ++q) {
+        const d3 d = ep[q] - sc.iC;
+        const double a = atan2(dot(d, yhat), dot(d, xhat));
+        int j = q - 1;  // stable insertion: equal angles keep their original order
+        while (j >= 0 && ang[j] > a) {
+            ang[j + 1] = ang[j];
+            ord[j + 1] = ord[j];
+            --j;
+        }
+        ang[j + 1] = a;
+        ord[j + 1] = (short)q;
+    }
+    for (int pi = 0; pi < sc.nEp; ++pi) {
+        if (pi > 0 && !(fabs(ang[pi] - ang[pi - 1]) > 1e-8)) continue;
+        st3(out, cnt, ep[ord[pi]]);
+        cnt++;
+    }
+    return cnt;
+}
+
 template <class CP>
 __global__ void __launch_bounds__(128) k_plic_polygons(MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
                                                        double* polyPts, int* polyCount)
@@ -125,38 +162,62 @@ __global__ void __launch_bounds__(128) k_plic_polygons(MeshDev m, const int* mix
         sc.epOut = ep;
         int err = 0, cnt = 0;
         subCell<CP>(m, c, ld3(iN, c), iD[c], false, sc, err);
-        if (sc.status == 0 && sc.nEp > 0) {
-            const d3 zhat = sc.iS / mag(sc.iS);
-            d3 xhat = ep[0] - sc.iC;
-            xhat = xhat - dot(xhat, zhat) * zhat;
-            xhat /= mag(xhat);
-            d3 yhat = cross(zhat, xhat);
-            yhat /= mag(yhat);
-            double ang[CP::MAXEP];
-            short ord[CP::MAXEP];
-            for (int q = 0; q < sc.nEp; ++q) {
-                const d3 d = ep[q] - sc.iC;
-                const double a = atan2(dot(d, yhat), dot(d, xhat));
-                int j = q - 1;  // stable insertion: equal angles keep their original order
-                while (j >= 0 && ang[j] > a) {
-                    ang[j + 1] = ang[j];
-                    ord[j + 1] = ord[j];
-                    --j;
-                }
-                ang[j + 1] = a;
-                ord[j + 1] = (short)q;
-            }
-            double* out = polyPts + 3 * (size_t)i * CP::MAXEP;
-            for (int pi = 0; pi < sc.nEp; ++pi) {
-                if (pi > 0 && !(fabs(ang[pi] - ang[pi - 1]) > 1e-8)) continue;
-                st3(out, cnt, ep[ord[pi]]);
-                cnt++;
-            }
-        }
+        if (sc.status == 0 && sc.nEp > 0) cnt = interfacePolygonDev<CP>(sc, ep, polyPts + 3 * (size_t)i * CP::MAXEP);
         polyCount[i] = cnt;
         if (err) atomicOr(&ctl->err, err);
     }
 }
+
+// reconstruction::subCellFaces() (reconstruction.C:838-891) + the collecting half of cutCell::calcSubCell (cutCell.C:443-475):
+// thread per mixed cell; per cut cell the clipped polygon of every cut face, every fully submerged face as it is, then the
+// interface polygon, into fixed-stride buffers (faceSize[i*maxFaces + k] points each, consecutive in pts[i*maxPts ...]).
+// The point merge and the orientation fix of updateSubCellPointsandFaces (cutCell.C:239-290) run on the host.
+template <class CP>
+__global__ void __launch_bounds__(128) k_subcell_faces(MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
+                                                       int maxFaces, int maxPts, double* pts, int* faceSize, int* nFaces, double* centre)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = mixedCells[i];
+        const d3 nn = ld3(iN, c);
+        const double D = iD[c];
+        d3 ep[CP::MAXEP];
+        SubCellOut sc;
+        sc.epOut = ep;
+        sc.wantCentre = true;
+        int err = 0, nf = 0, np = 0;
+        subCell<CP>(m, c, nn, D, false, sc, err);
+        if (sc.status == 0) {
+            double* out = pts + 3 * (size_t)i * maxPts;
+            int* fs = faceSize + (size_t)i * maxFaces;
+            const int c0 = __ldg(m.cellOff + c), c1 = __ldg(m.cellOff + c + 1);
+            for (int k = c0; k < c1; ++k) {
+                d3 fp[CP::MAXFV], sp[2 * CP::MAXFV], fc, fa, ip[CP::MAXIP];
+                int nip, nsp = 0;
+                const int nv = loadFace<CP>(m, __ldg(m.cellFaces + k), fp, err);
+                const int st = clipFace<CP>(fp, nv, nn, D, fc, fa, ip, nip, err, sp, &nsp);
+                if (st > 0) continue;
+                const d3* src = (st == 0) ? sp : fp;
+                const int cnt = (st == 0) ? nsp : nv;
+                if (nf >= maxFaces || np + cnt > maxPts) { err |= SVERR_CELL_FACES; break; }
+                for (int q = 0; q < cnt; ++q) st3(out, np + q, src[q]);
+                fs[nf++] = cnt;
+                np += cnt;
+            }
+            if (sc.nEp > 0 && nf < maxFaces && np + sc.nEp <= maxPts) {
+                const int cnt = interfacePolygonDev<CP>(sc, ep, out + 3 * (size_t)np);
+                if (cnt > 0) {
+                    fs[nf++] = cnt;
+                    np += cnt;
+                }
+            }
+            st3(centre, i, sc.subCentre);
+        }
+        nFaces[i] = nf;
+        if (err) atomicOr(&ctl->err, err);
+    }
+}
+
 // reconstruction::mapAlphaField (reconstruction.C:751-768): thread per cell, the cut is evaluated WITHOUT splitWarpedFace
 template <class CP>
 __global__ void __launch_bounds__(128) k_map_alpha(MeshDev m, const double* iN, const double* iD, double lower, double upper, double* alpha,
@@ -287,6 +348,12 @@ void GeoLaunch<CP>::plicPolygons(cudaStream_t st, int grid, MeshDev m, const int
                                  double* polyPts, int* polyCount)
 {
     k_plic_polygons<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, iN, iD, polyPts, polyCount);
+}
+template <class CP>
+void GeoLaunch<CP>::subCellFaces(cudaStream_t st, int grid, MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, const double* iD,
+                                 int maxFaces, int maxPts, double* pts, int* faceSize, int* nFaces, double* centre)
+{
+    k_subcell_faces<CP><<<grid, 128, 0, st>>>(m, mixedCells, ctl, iN, iD, maxFaces, maxPts, pts, faceSize, nFaces, centre);
 }
 template <class CP>
 void GeoLaunch<CP>::mapAlpha(cudaStream_t st, MeshDev m, const double* iN, const double* iD, double lower, double upper, double* alpha, Ctl* ctl)

@@ -200,6 +200,17 @@ class SolveVofEqu:
                                              C.byref(nP), C.byref(nFc)))
         return pts, off, cells
 
+    def subCellFaces(self):
+        """reconstruction::subCellFaces() (reconstruction.C:838-891): faces of the submerged sub-cells of the cut cells of the
+        last reconstruct() as (points [nP,3], face_offsets [nF+1], face_points, face_cell [nF])."""
+        nP, nF, nFP = C.c_int64(), C.c_int64(), C.c_int64()
+        self._chk(self.lib.svof_subcell_faces(self._h, 0, 0, 0, None, None, None, None, C.byref(nP), C.byref(nF), C.byref(nFP)))
+        pts = np.empty((nP.value, 3))
+        off, fp, fc = np.zeros(nF.value + 1, np.int32), np.empty(nFP.value, np.int32), np.empty(nF.value, np.int32)
+        self._chk(self.lib.svof_subcell_faces(self._h, nP.value, nF.value, nFP.value, capi.dptr(pts), capi.iptr(off), capi.iptr(fp),
+                                              capi.iptr(fc), C.byref(nP), C.byref(nF), C.byref(nFP)))
+        return pts, off, fp, fc
+
     # -- generic access ---------------------------------------------------------------
     _SHAPES = {
         capi.F_ALPHA: ("nC", 1, np.float64), capi.F_ALPHA_PHI: ("nF", 1, np.float64),

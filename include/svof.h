@@ -331,6 +331,16 @@ int svof_face_fluxes(svof_handle* h, int32_t n, const int32_t* faces, const doub
 int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, double* points, int32_t* face_offsets,
                       int32_t* cells, int64_t* n_points, int64_t* n_faces);
 
+/* reconstruction::subCellFaces() (reconstruction.C:838-891): the faces of the SUBMERGED sub-cell of every cut cell of the
+ * last svof_reconstruct -- the clipped cell faces, the fully submerged faces and the interface polygon
+ * (cutCell::updateSubCellPointsandFaces, cutCell.C:239-290: duplicate points merged at 1e-14, faces oriented away from
+ * the sub-cell centre).  Face i is face_points[face_offsets[i] .. face_offsets[i+1]) into points[] and belongs to mesh
+ * cell face_cell[i]; cells ascend.  Sizes are always returned; arrays are filled when points != NULL and the capacities
+ * suffice.  This is what the reconstructedSubcellFaces sampler reads (sampledReconstructedSubcellFaces.C:97-100). */
+int svof_subcell_faces(svof_handle* h, int64_t cap_points, int64_t cap_faces, int64_t cap_face_points, double* points,
+                       int32_t* face_offsets, int32_t* face_points, int32_t* face_cell, int64_t* n_points, int64_t* n_faces,
+                       int64_t* n_face_points);
+
 /* ---- changing meshes (moving points, refinement) ------------------------------
  * The hooks the reference gets from OpenFOAM's mesh.changing()/moving()/topoChanging(). */
 

@@ -452,6 +452,10 @@ class cutCell {
     }
 
    public:
+    bool collectSubCell_ = false;
+    std::vector<point> subCellPoints_;
+    std::vector<std::vector<label>> subCellFaces_;
+
     explicit cutCell(const Mesh& mesh)
         : mesh_(mesh), cutFace_(mesh), cellStatus_(-1), subCellVolume_(0), VOF_(0), cellI_(-1)
     {
@@ -508,7 +512,19 @@ class cutCell {
             }
         } else {
             const label* c = mesh_.cells.row(cellI);
-            for (label fi = 0; fi < mesh_.cells.size(cellI); ++fi) account(cutFace_.calcSubFace(c[fi], normal, distance));
+            subCellPoints_.clear();
+            subCellFaces_.clear();
+            for (label fi = 0; fi < mesh_.cells.size(cellI); ++fi) {
+                const label st = cutFace_.calcSubFace(c[fi], normal, distance);
+                account(st);
+                if (collectSubCell_ && st <= 0) {  // cutCell.C:443-454 (cut face), :464-475 (fully submerged face)
+                    const std::vector<point> fp = (st == 0) ? cutFace_.subFacePoints() : cutFace_.facePoints(c[fi]);
+                    std::vector<label> f(fp.size());
+                    for (size_t k = 0; k < fp.size(); ++k) f[k] = label(subCellPoints_.size() + k);
+                    subCellFaces_.push_back(f);
+                    subCellPoints_.insert(subCellPoints_.end(), fp.begin(), fp.end());
+                }
+            }
         }
 
         if (!fullySubmerged && !fullyEmpty) {
@@ -677,6 +693,44 @@ class cutCell {
     }
     const vec& interfaceArea() const { return interfaceArea_; }
     label cellStatus() const { return cellStatus_; }
+
+    // cutCell::updateSubCellPointsandFaces (cutCell.C:239-290) for the last calcSubCell (status 0, collectSubCell(true)):
+    // the submerged sub-faces plus the interface polygon, duplicate points merged (inplaceMergePoints, 10*SMALL; kept in
+    // order of first occurrence -- OF's internal order is not recalled), every face oriented away from the sub-cell centre.
+    void collectSubCell(bool on) { collectSubCell_ = on; }
+    void subCellPointsAndFaces(std::vector<point>& pts, std::vector<std::vector<label>>& faces) const
+    {
+        std::vector<point> all(subCellPoints_);
+        faces = subCellFaces_;
+        std::vector<point> poly;
+        interfacePolygon(poly);
+        if (!poly.empty()) {
+            std::vector<label> f(poly.size());
+            for (size_t k = 0; k < poly.size(); ++k) f[k] = label(all.size() + k);
+            faces.push_back(f);
+            all.insert(all.end(), poly.begin(), poly.end());
+        }
+        std::vector<label> toUnique(all.size());
+        pts.clear();
+        for (size_t i = 0; i < all.size(); ++i) {
+            label found = -1;
+            for (size_t j = 0; j < pts.size() && found < 0; ++j)
+                if (mag(all[i] - pts[j]) <= 10.0 * SMALL) found = label(j);
+            if (found < 0) {
+                found = label(pts.size());
+                pts.push_back(all[i]);
+            }
+            toUnique[i] = found;
+        }
+        for (std::vector<label>& f : faces) {
+            for (label& v : f) v = toUnique[v];
+            std::vector<point> fp(f.size());
+            for (size_t k = 0; k < f.size(); ++k) fp[k] = pts[f[k]];
+            const point fc = faceCentreOF(fp);
+            const vec fn = faceAreaNormalOF(fp);
+            if (((fc - subCellCentre_) & fn) < 0.0) std::reverse(f.begin() + 1, f.end());  // face::reverseFace keeps vertex 0
+        }
+    }
     cutFace& faceCutter() { return cutFace_; }
 };
 

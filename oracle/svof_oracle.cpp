@@ -382,6 +382,43 @@ int svof_plic_surface(svof_handle* h, int64_t cap_points, int64_t cap_faces, dou
     return SVOF_OK;
 }
 
+// reconstruction::subCellFaces() (reconstruction.C:838-891)
+int svof_subcell_faces(svof_handle* h, int64_t cap_points, int64_t cap_faces, int64_t cap_face_points, double* points,
+                       int32_t* face_offsets, int32_t* face_points, int32_t* face_cell, int64_t* n_points, int64_t* n_faces,
+                       int64_t* n_face_points)
+{
+    if (!h || !n_points || !n_faces || !n_face_points) return SVOF_ERR_INVALID_ARG;
+    Solver& s = h->s;
+    cutCell cc(s.mesh);
+    cc.collectSubCell(true);
+    std::vector<point> pts, cp;
+    std::vector<std::vector<label>> cf;
+    std::vector<int32_t> off(1, 0), fpts, fcell;
+    for (size_t i = 0; i < s.mixedCells.size(); ++i) {
+        const label c = s.mixedCells[i];
+        if (cc.calcSubCell(c, s.interfaceN[c], s.interfaceD[c], false) != 0) continue;
+        cc.subCellPointsAndFaces(cp, cf);
+        const int32_t base = int32_t(pts.size());
+        for (const std::vector<label>& f : cf) {
+            for (label v : f) fpts.push_back(base + v);
+            off.push_back(int32_t(fpts.size()));
+            fcell.push_back(c);
+        }
+        pts.insert(pts.end(), cp.begin(), cp.end());
+    }
+    *n_points = int64_t(pts.size());
+    *n_faces = int64_t(fcell.size());
+    *n_face_points = int64_t(fpts.size());
+    if (!points) return SVOF_OK;
+    if (cap_points < *n_points || cap_faces < *n_faces || cap_face_points < *n_face_points || !face_offsets || !face_points || !face_cell)
+        return SVOF_ERR_CAPACITY;
+    for (size_t i = 0; i < pts.size(); ++i) { points[3 * i] = pts[i].x; points[3 * i + 1] = pts[i].y; points[3 * i + 2] = pts[i].z; }
+    std::copy(off.begin(), off.end(), face_offsets);
+    std::copy(fpts.begin(), fpts.end(), face_points);
+    std::copy(fcell.begin(), fcell.end(), face_cell);
+    return SVOF_OK;
+}
+
 int svof_find_signed_distance(svof_handle* h, int32_t n, const int32_t* cells, const double* alphas, const double* normals,
                               int32_t* status, double* dists, double* ic, double* ia)
 {

@@ -4,7 +4,7 @@ import os
 import numpy as np
 import pytest
 
-from common import LEVEQUE_CONTROLS, SolveVofEqu, capi, exact_sphere_alpha, meshmod, oracle_lib
+from common import LEVEQUE_CONTROLS, SolveVofEqu, capi, exact_sphere_alpha, fields, meshmod, oracle_lib
 from geometricvofext_b200 import foamfile
 
 
@@ -78,3 +78,70 @@ def test_gpu_surface_matches_oracle(case):
     assert np.abs(po - pg).max() < 1e-13      # atan2 tie-breaks between coincident points: round-off, not bitwise (svof.h)
     so.close()
     sg.close()
+
+
+# ---- reconstruction::subCellFaces() (reconstruction.C:838-891) ------------------------------------------------------
+def _subcell_checks(s, m):
+    """every cut cell's sub-cell faces form a closed, outward-oriented polyhedron whose volume is alpha*V"""
+    pts, off, fp, fc = s.subCellFaces()
+    assert len(off) == len(fc) + 1 and off[-1] == len(fp)
+    alpha, V = s.alpha(), s.field(capi.F_V)
+    mixed, status = s.mixedCells(), s.cellStatus()
+    assert np.array_equal(np.unique(fc), mixed[status == 0]), "one sub-cell per cut cell, ascending"
+    worst = 0.0
+    for c in np.unique(fc)[:400]:
+        faces = [fp[off[i]:off[i + 1]] for i in np.nonzero(fc == c)[0]]
+        edges = {}
+        vol = 0.0
+        for f in faces:
+            assert len(f) >= 3
+            p = pts[f]
+            for a, b in zip(f, np.roll(f, -1)):
+                edges[(a, b)] = edges.get((a, b), 0) + 1
+            # divergence theorem with a fan about the first vertex: V = 1/6 sum (p0 . (pi x pi+1))
+            for i in range(1, len(f) - 1):
+                vol += np.dot(p[0], np.cross(p[i], p[i + 1])) / 6.0
+        for (a, b), k in edges.items():
+            assert k == 1 and edges.get((b, a), 0) == 1, "closed surface: every edge is shared by two faces, in opposite directions"
+        assert vol > 0, "outward orientation"
+        worst = max(worst, abs(vol - alpha[c] * V[c]) / V[c])
+    assert worst <= 5e-12, "sub-cell volume differs from alpha*V by %g V" % worst
+    return pts, off, fp, fc
+
+
+def test_subcell_faces_oracle_closed_polyhedra(oracle):
+    m = meshmod.hex_block(10)
+    s = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=oracle)
+    s.setAlpha(fields.sphere_alpha_quadrature(m))
+    s.reconstruct()
+    pts, off, fp, fc = _subcell_checks(s, m)
+    assert len(fc) > 100
+
+
+def test_subcell_faces_oracle_polyhedral_cells(oracle):
+    m = meshmod.kelvin_mesh(5)
+    s = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=oracle)
+    C_, V = s.field(capi.F_C), s.field(capi.F_V)
+    s.setAlpha(np.clip(0.5 - (np.linalg.norm(C_ - np.array([0.5, 0.55, 0.5]), axis=1) - 0.22) / np.cbrt(V), 0.0, 1.0))
+    s.reconstruct()
+    _subcell_checks(s, m)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hex", "kelvin"])
+def test_subcell_faces_gpu_parity(oracle, product, kind):
+    m = meshmod.hex_block(16) if kind == "hex" else meshmod.kelvin_mesh(6)
+    out = []
+    for lib in (oracle, product):
+        s = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=lib)
+        if kind == "hex":
+            a0 = fields.sphere_alpha_quadrature(m)
+        else:
+            C_, V = s.field(capi.F_C), s.field(capi.F_V)
+            a0 = np.clip(0.5 - (np.linalg.norm(C_ - np.array([0.5, 0.55, 0.5]), axis=1) - 0.22) / np.cbrt(V), 0.0, 1.0)
+        s.setAlpha(a0)
+        s.reconstruct()
+        out.append(_subcell_checks(s, m) if lib is product else s.subCellFaces())
+    (po, oo, fo, co), (pg, og, fg, cg) = out
+    assert np.array_equal(oo, og) and np.array_equal(fo, fg) and np.array_equal(co, cg), "same topology"
+    assert np.abs(po - pg).max() <= 1e-13
