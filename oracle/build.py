@@ -6,6 +6,12 @@
                                       Eigen compiled from /root/reference (only
                                       when that tree is present, i.e. in the build
                                       container; the GPU box uses the prebuilt file).
+  oracle/_ref/libref_cut.so        -- the reference's own cutFace.{H,C} and cutCell.{H,C}
+                                      (src/SimPLIC/cut), compiled UNMODIFIED from
+                                      /root/reference against oracle/of_stub/ (a stand-in
+                                      for the few OpenFOAM types they use) + ref_cut.cpp
+                                      (C entry points).  Pins the oracle's restatement of
+                                      the geometric core to the reference's statements.
 
 Both directories are git-ignored and are NOT gpurun-ignored.
 """
@@ -17,6 +23,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_APP = "/root/reference/applications/test/calcExactVofFieldForSphericalShapeInHexMesh"
 ORACLE_SO = os.path.join(HERE, "_build", "libsvof_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_overlap.so")
+REF_CUT = "/root/reference/src/SimPLIC/cut"
+REF_CUT_SO = os.path.join(HERE, "_ref", "libref_cut.so")
 
 
 def _stale(target, sources):
@@ -50,6 +58,23 @@ def build_ref(force=False):
     return REF_SO
 
 
+def build_ref_cut(force=False):
+    """Compile the reference's cutFace.C / cutCell.C where they lie, against the OpenFOAM stand-in; path or None."""
+    if not os.path.isdir(REF_CUT):
+        return REF_CUT_SO if os.path.exists(REF_CUT_SO) else None
+    wrapper = os.path.join(HERE, "ref_cut.cpp")
+    stub = os.path.join(HERE, "of_stub", "OpenFOAMCutStub.H")
+    ref_srcs = [os.path.join(REF_CUT, "cutFace", "cutFace.C"), os.path.join(REF_CUT, "cutCell", "cutCell.C")]
+    if force or _stale(REF_CUT_SO, [wrapper, stub, os.path.join(HERE, "..", "include", "svof.h")] + ref_srcs):
+        os.makedirs(os.path.dirname(REF_CUT_SO), exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w",
+               "-I", os.path.join(HERE, "of_stub"), "-I", os.path.join(REF_CUT, "cutFace"), "-I", os.path.join(REF_CUT, "cutCell"),
+               "-o", REF_CUT_SO, wrapper] + ref_srcs
+        subprocess.check_call(cmd)
+    return REF_CUT_SO
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
+    print(build_ref_cut(force="--force" in sys.argv))

@@ -46,6 +46,92 @@ def ref_overlap_lib():
     return _ref
 
 
+class RefCut:
+    """The REFERENCE's own cutFace / cutCell classes (src/SimPLIC/cut, compiled unmodified into oracle/_ref/libref_cut.so
+    against the OpenFOAM stand-in oracle/of_stub/), on a mesh.  Geometry and flatness come from `geom` (a SolveVofEqu of
+    the same mesh): they are OpenFOAM / reconstruction.C quantities, outside those four files."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            p = oracle_build.build_ref_cut()
+            if p is None:
+                return None
+            L = C.CDLL(p)
+            dp, ip = capi.c_double_p, capi.c_int32_p
+            L.ref_cut_create.restype = C.c_void_p
+            L.ref_cut_create.argtypes = [C.POINTER(capi.SvofMesh), dp, dp, dp, dp, dp]
+            L.ref_cut_destroy.argtypes = [C.c_void_p]
+            L.ref_cut_faces.argtypes = [C.c_void_p, C.c_int32, C.c_int32, dp, dp, dp, ip, dp, dp]
+            L.ref_cut_cells.argtypes = [C.c_void_p, C.c_int32, ip, dp, dp, ip, dp, dp, dp, dp]
+            L.ref_find_signed_distance.argtypes = [C.c_void_p, C.c_int32, ip, dp, dp, C.c_int32, ip, dp, dp, dp]
+            L.ref_face_fluxes.argtypes = [C.c_void_p, C.c_int32, ip, dp, dp, dp, C.c_double, dp, dp]
+            L.ref_interface_points.argtypes = [C.c_void_p, C.c_int32, dp, C.c_double, C.c_int32, dp]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, m, geom, split=False):
+        self.L = self.lib()
+        if self.L is None:
+            raise RuntimeError("oracle/_ref/libref_cut.so unavailable")
+        self.split = int(bool(split))
+        self._cm, self._keep = m.to_c()
+        Cf, Sf = geom.field(capi.F_CF), geom.field(capi.F_SF)
+        self._g = [capi.f64(Cf), capi.f64(geom.field(capi.F_C)), capi.f64(geom.field(capi.F_V)),
+                   capi.f64(np.sqrt(Sf[:, 0] * Sf[:, 0] + Sf[:, 1] * Sf[:, 1] + Sf[:, 2] * Sf[:, 2])),
+                   capi.f64(geom.faceFlatness())]
+        self._h = self.L.ref_cut_create(C.byref(self._cm), *[capi.dptr(a) for a in self._g])
+        assert self._h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_cut_destroy(self._h)
+            self._h = None
+
+    def cutFaces(self, pts, normals, dists):
+        pts = capi.f64(pts)
+        n, nv = pts.shape[0], pts.shape[1]
+        normals, dists = capi.f64(normals, (n, 3)), capi.f64(dists, (n,))
+        st, ce, ar = np.empty(n, np.int32), np.empty((n, 3)), np.empty((n, 3))
+        self.L.ref_cut_faces(self._h, n, nv, capi.dptr(pts), capi.dptr(normals), capi.dptr(dists), capi.iptr(st), capi.dptr(ce),
+                             capi.dptr(ar))
+        return st, ce, ar
+
+    def cutCells(self, cells, normals, dists):
+        cells = capi.i32(cells)
+        n = cells.shape[0]
+        normals, dists = capi.f64(normals, (n, 3)), capi.f64(dists, (n,))
+        st, vof, sv, ic, ia = np.empty(n, np.int32), np.empty(n), np.empty(n), np.empty((n, 3)), np.empty((n, 3))
+        self.L.ref_cut_cells(self._h, n, capi.iptr(cells), capi.dptr(normals), capi.dptr(dists), capi.iptr(st), capi.dptr(vof),
+                             capi.dptr(sv), capi.dptr(ic), capi.dptr(ia))
+        return st, vof, sv, ic, ia
+
+    def findSignedDistance(self, cells, alphas, normals):
+        cells = capi.i32(cells)
+        n = cells.shape[0]
+        alphas, normals = capi.f64(alphas, (n,)), capi.f64(normals, (n, 3))
+        st, D, ic, ia = np.empty(n, np.int32), np.empty(n), np.empty((n, 3)), np.empty((n, 3))
+        self.L.ref_find_signed_distance(self._h, n, capi.iptr(cells), capi.dptr(alphas), capi.dptr(normals), self.split,
+                                        capi.iptr(st), capi.dptr(D), capi.dptr(ic), capi.dptr(ia))
+        return st, D, ic, ia
+
+    def faceFluxes(self, faces, normals, dists, Un0, dt, phi):
+        faces = capi.i32(faces)
+        n = faces.shape[0]
+        normals, dists, Un0, phi = capi.f64(normals, (n, 3)), capi.f64(dists, (n,)), capi.f64(Un0, (n,)), capi.f64(phi, (n,))
+        out = np.empty(n)
+        self.L.ref_face_fluxes(self._h, n, capi.iptr(faces), capi.dptr(normals), capi.dptr(dists), capi.dptr(Un0), float(dt),
+                               capi.dptr(phi), capi.dptr(out))
+        return out
+
+    def interfacePoints(self, cell, normal, dist, cap=64):
+        out = np.empty((cap, 3))
+        n = self.L.ref_interface_points(self._h, int(cell), capi.dptr(capi.f64(normal, (3,))), float(dist), cap, capi.dptr(out))
+        return out[:n].copy()
+
+
 def exact_sphere_alpha(m, centre=(0.35, 0.35, 0.35), radius=0.15):
     """Exact sphere/hex volume fractions on a hex_block mesh via the reference's
     overlap library (calcExactVofFieldForSphericalShapeInHexMesh/functions.H:1-27)."""
