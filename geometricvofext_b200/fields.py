@@ -79,8 +79,10 @@ class AdvectionDriver:
     """
 
     def __init__(self, solver, velocity=leveque_velocity, period=6.0, max_co=0.5, max_alpha_co=0.5,
-                 max_delta_t=0.2, delta_t0=0.001, fixed_dt=None):
+                 max_delta_t=0.2, delta_t0=0.001, fixed_dt=None, write_interval=None, start_time=0.0):
         self.s = solver
+        # writeControl adjustableRunTime: Time::adjustDeltaT spreads the time to the next write over equal steps
+        self.write_interval, self.start_time, self.write_index, self.write_now = write_interval, start_time, 0, False
         self.period, self.max_co, self.max_alpha_co = period, max_co, max_alpha_co
         self.max_delta_t, self.fixed_dt = max_delta_t, fixed_dt
         self.t, self.dt = 0.0, (fixed_dt if fixed_dt else delta_t0)
@@ -117,13 +119,36 @@ class AdvectionDriver:
         f = min(self.max_co / (co + SMALL), self.max_alpha_co / (aco + SMALL))
         fact = min(min(f, 1.0 + 0.1 * f), 1.2)
         self.dt = min(fact * self.dt, self.max_delta_t)
+        self.adjust_delta_t()
+
+    def adjust_delta_t(self):
+        """Time::adjustDeltaT (OpenFOAM Time.C, called by Time::setDeltaT(dt, adjust = true) from setDeltaT.H:50):
+        the remaining time to the next write is covered by round(timeToNextWrite/deltaT) equal steps; the step may grow
+        by at most a factor 2 and shrink by at most a factor 5."""
+        if not self.write_interval:
+            return
+        to_next = max(0.0, (self.write_index + 1) * self.write_interval - (self.t - self.start_time))
+        n_steps = to_next / self.dt
+        if n_steps < 2 ** 31 - 1:
+            n = max(1, int(np.floor(n_steps + 0.5)))      # label(round(nSteps)), at least 1
+            new_dt = to_next / n
+            self.dt = min(new_dt, 2.0 * self.dt) if new_dt >= self.dt else max(new_dt, 0.2 * self.dt)
+
+    def running(self, end_time):
+        """Time::run(): value() < endTime - 0.5*deltaT."""
+        return self.t < end_time - 0.5 * self.dt
 
     def step(self, end_time=None):
         alpha = self.s.alpha() if not self.fixed_dt else None
         self.set_delta_t(alpha)
-        if end_time is not None and self.t + self.dt > end_time - 1e-12:
+        if end_time is not None and not self.write_interval and self.t + self.dt > end_time - 1e-12:
             self.dt = end_time - self.t
         self.t += self.dt                       # ++runTime
+        self.write_now = False
+        if self.write_interval:                 # Time::operator++: writeTime when the write index advances
+            wi = int(((self.t - self.start_time) + 0.5 * self.dt) / self.write_interval)
+            if wi > self.write_index:
+                self.write_now, self.write_index = True, wi
         f = u_factor(self.t, self.dt, self.period)   # updateU.H uses the NEW time value
         self.phi = self.phi0 * f
         self.s.setPhi(self.phi)

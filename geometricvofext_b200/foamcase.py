@@ -330,22 +330,25 @@ def run_plic_vof_advection(case, lib=None, end_time=None, renumber=False, alpha0
         s, period=float(controls.get("period", 0.0)), max_co=float(cd.get("maxCo", 1.0)),
         max_alpha_co=float(cd.get("maxAlphaCo", 1.0)), max_delta_t=float(cd.get("maxDeltaT", 1e30)),
         delta_t0=float(cd.get("deltaT", 1e-3)), fixed_dt=None if adjust else float(cd.get("deltaT", 1e-3)))
-    drv.t = float(cd.get("startTime", 0.0))
+    drv.t = drv.start_time = float(cd.get("startTime", 0.0))
     t_end = float(end_time if end_time is not None else cd.get("endTime"))
     w_int = float(cd.get("writeInterval", t_end))
     by_time = str(cd.get("writeControl", "adjustableRunTime")) in ("adjustableRunTime", "runTime")
+    adjustable = adjust and str(cd.get("writeControl", "adjustableRunTime")) == "adjustableRunTime"
+    if adjustable:
+        drv.write_interval = w_int        # Time::adjustDeltaT: equal steps up to each write time
     s.reconstruct()                       # plicVof.H:8-9: interface at the initial time, function objects executed
     surfaces = plic_surface_functions(cd) if write else []
     write_plic = write and str(controls.get("writePlicFields", "false")).lower() in ("true", "yes", "on", "1")
     _write_surfaces(case, s, _time_name(drv.t), surfaces)
     written, vols = [], []
     next_write = drv.t + w_int if by_time else None
-    while drv.t < t_end - 1e-12:
+    while (drv.running(t_end) if adjustable else drv.t < t_end - 1e-12):
         stop = min(t_end, next_write) if by_time else t_end
         drv.step(end_time=stop)
         s.synchronize()          # device capacity flags (the reference would FatalError) surface here, once per step
         vols.append(s.volume())
-        due = (by_time and drv.t >= next_write - 1e-12) or (not by_time and drv.steps % max(1, int(w_int)) == 0) or drv.t >= t_end - 1e-12
+        due = (drv.write_now or not drv.running(t_end)) if adjustable else ((by_time and drv.t >= next_write - 1e-12) or (not by_time and drv.steps % max(1, int(w_int)) == 0) or drv.t >= t_end - 1e-12)
         if due:
             name = _time_name(drv.t)
             if write:

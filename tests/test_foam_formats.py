@@ -188,11 +188,14 @@ def test_case_run_matches_direct_driver_and_writes_openfoam_fields(tmp_path):
     # the same loop driven directly
     s = SolveVofEqu(meshmod.hex_block(16), case.alpha_controls(), lib=oracle_lib())
     s.setAlpha(a0)
-    drv = fields.AdvectionDriver(s)
+    drv = fields.AdvectionDriver(s, write_interval=0.002)   # adjustableRunTime: Time::adjustDeltaT lands on the write times
     s.reconstruct()
     for te in (0.002, 0.004):
-        while drv.t < te - 1e-12:
-            drv.step(end_time=te)
+        while True:
+            drv.step()
+            if drv.write_now:
+                break
+        assert abs(drv.t - te) < 1e-12
     assert drv.steps == out["steps"]
     # writePlicFields true: the four reconstruction fields next to alpha, as OpenFOAM fields
     fN = foamfile.read_field(os.path.join(case.dir, "0.004", "interfaceN"))

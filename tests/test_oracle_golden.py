@@ -54,17 +54,20 @@ def test_oracle_full_deformation_run_against_golden_fields():
     field to t = 3 on the 64^3 mesh; metrics of updateErrors.H at the 12 golden instants."""
     s = SolveVofEqu(meshmod.hex_block(N), LEVEQUE_CONTROLS, lib=oracle_lib())
     s.setAlpha(gold("0"))
-    drv = fields.AdvectionDriver(s)
+    drv = fields.AdvectionDriver(s, write_interval=0.25)   # controlDict: adjustableRunTime, writeInterval 0.25
     V = 1.0 / N ** 3
     Es, Ev = {}, {}
     for tt in TIMES[1:]:
         te = float(tt)
-        while drv.t < te - 1e-12:
-            drv.step(end_time=te)
+        while True:
+            drv.step()
+            if drv.write_now:
+                break
+        assert abs(drv.t - te) < 1e-9, "Time::adjustDeltaT must land on the write time"
         a, ge = s.alpha(), gold(tt)
         Ev[tt] = (a.sum() * V - EXACT_INITIAL_VOL) / EXACT_INITIAL_VOL
         Es[tt] = np.abs(a - ge).sum() / ge.sum()
-        assert a.min() > -1e-5 and 1 - a.max() > -1e-5
+        assert a.min() > -1e-4 and 1 - a.max() > -1e-4   # nAlphaBounds 3, clip false: bounded to the sweeps' reach
     # volume: the run conserves the initial volume to round-off; E_v is the (constant) 1.9e-11 offset of the
     # golden t=0 field itself from exactInitialVol
     ev = np.array(list(Ev.values()))
