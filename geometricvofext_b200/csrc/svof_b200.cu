@@ -9,6 +9,9 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xcompiler -fPIC -shared
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +42,59 @@ struct EventPair {
     cudaEvent_t a = nullptr, b = nullptr;
     int kind = -1;  // 0 reconstruct, 1 advect
     bool pending = false;
+};
+
+// A few persistent host threads for the gather/scatter loops of svof_step_host (random accesses into field-sized host
+// arrays): created once per handle on first use, instead of spawning std::threads in every call.
+class HostPool {
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cvWork_, cvDone_;
+    std::function<void(int)> fn_;
+    int nTasks_ = 0, next_ = 0, pending_ = 0;
+    bool stop_ = false;
+    void loop()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cvWork_.wait(lk, [&] { return stop_ || next_ < nTasks_; });
+            if (stop_) return;
+            const int t = next_++;
+            lk.unlock();
+            fn_(t);
+            lk.lock();
+            if (--pending_ == 0) cvDone_.notify_one();
+        }
+    }
+
+public:
+    explicit HostPool(int n)
+    {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cvWork_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return (int)th_.size(); }
+    // run fn(0..n-1) on the pool's threads; returns when all are done
+    void run(int n, std::function<void(int)> fn)
+    {
+        if (n <= 0) return;
+        std::unique_lock<std::mutex> lk(m_);
+        fn_ = std::move(fn);
+        nTasks_ = n;
+        next_ = 0;
+        pending_ = n;
+        cvWork_.notify_all();
+        cvDone_.wait(lk, [&] { return pending_ == 0; });
+        nTasks_ = 0;
+    }
 };
 
 }  // namespace
@@ -97,6 +153,18 @@ struct svof_handle {
     int *dIdx = nullptr, *hIdx = nullptr;
     double *dVal = nullptr, *hVal = nullptr;
     int capDelta = 0;
+    // sparse phi upload (svof_step_host): bitmap over faces of the entries the step can depend on, host gather, device scatter
+    int lastNU = 0, lastCntA = 0, lastCntF = 0;   // sizes of the previous step's lists: the speculative read-back sizes
+    bool sparsePhi = true;           // "sparse_phi" option (only with sparse_io)
+    bool phiBitsReady = false;       // the face bitmap of the CURRENT alpha is already on the host (prefetched by the previous svof_step_host)
+    bool phiPartial = false;         // device phi holds stale values on faces between exactly empty cells: not a full field
+    int nWordsF = 0, nPhiBlocks = 0;
+    size_t capPhiPacked = 0;
+    unsigned int *phiBits = nullptr, *hPhiBits = nullptr;
+    int *phiBlockOff = nullptr, *hPhiBlockOff = nullptr;
+    double *phiPacked = nullptr, *hPhiPacked = nullptr;
+    cudaEvent_t evBits = nullptr;
+    HostPool* pool = nullptr;
     const double* hostAlphaSynced = nullptr;     // caller buffers known to hold the previous step's results
     const double* hostAlphaPhiSynced = nullptr;
     long long h2dBytes = 0, d2hBytes = 0;        // bytes actually moved by the last svof_step_host
@@ -1306,6 +1374,11 @@ int svof_destroy(svof_handle* h)
     if (h->hUPacked) cudaFreeHost(h->hUPacked);
     if (h->hIdx) cudaFreeHost(h->hIdx);
     if (h->hVal) cudaFreeHost(h->hVal);
+    if (h->hPhiBits) cudaFreeHost(h->hPhiBits);
+    if (h->hPhiBlockOff) cudaFreeHost(h->hPhiBlockOff);
+    if (h->hPhiPacked) cudaFreeHost(h->hPhiPacked);
+    if (h->evBits) cudaEventDestroy(h->evBits);
+    delete h->pool;
     for (EventPair& e : h->events) {
         if (e.a) cudaEventDestroy(e.a);
         if (e.b) cudaEventDestroy(e.b);
@@ -1335,7 +1408,7 @@ int svof_set_alpha(svof_handle* h, const double* alpha)
     h->haveAlpha = true;
     h->bitsValid = false;
     h->advected = false;
-    h->hostAlphaSynced = nullptr;
+    h->hostAlphaSynced = nullptr; h->phiBitsReady = false;
     return SVOF_OK;
     API_END(h)
 }
@@ -1347,6 +1420,7 @@ int svof_set_phi(svof_handle* h, const double* phi)
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->stream));
     h->havePhi = true;
+    h->phiPartial = false;
     if (h->anyInletOutlet && h->haveAlpha) alphaBC(h);   // inletOutlet patch values depend on the sign of phi
     CK(cudaStreamSynchronize(h->stream));
     return SVOF_OK;
@@ -1378,7 +1452,7 @@ int svof_scatter_alpha_device(svof_handle* h, const int32_t* d_idx, const double
                   h->mixedBits, h->bitsValid ? 1 : 0);
     alphaBC(h);
     h->advected = false;
-    h->hostAlphaSynced = nullptr;
+    h->hostAlphaSynced = nullptr; h->phiBitsReady = false;
     return SVOF_OK;
     API_END(h)
 }
@@ -1410,12 +1484,14 @@ void releaseMeshState(svof_handle* h)
     h->bytes = 0;
     auto freeHost = [](auto*& p) { if (p) cudaFreeHost(p); p = nullptr; };
     freeHost(h->hctl); freeHost(h->hpartial); freeHost(h->hUList); freeHost(h->hUPacked); freeHost(h->hIdx); freeHost(h->hVal);
+    freeHost(h->hPhiBits); freeHost(h->hPhiBlockOff); freeHost(h->hPhiPacked);
+    h->phiBits = nullptr; h->phiBlockOff = nullptr; h->phiPacked = nullptr; h->phiPartial = false;
     harvestEvents(h, true);
     h->halo = svof_handle::Halo();
     h->dfast = DenseFast();
-    h->haveAlpha = h->havePhi = h->haveU = h->bitsValid = h->advected = h->uPartial = false;
+    h->haveAlpha = h->havePhi = h->haveU = h->bitsValid = h->advected = h->uPartial = h->phiPartial = false;
     h->freshRecon = h->inputsAfterNear = false;
-    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; h->phiBitsReady = false;
     h->cur = h->cb = 0;
     h->epochBumps = 0;
 }
@@ -1471,7 +1547,7 @@ int svof_map_alpha_field(svof_handle* h, double lower, double upper)
     alphaBC(h);                 // alpha1_.correctBoundaryConditions(); alpha1_.oldTime() = alpha1_ (the old-time buffer is the current one)
     h->bitsValid = false;
     h->advected = false;
-    h->hostAlphaSynced = nullptr;
+    h->hostAlphaSynced = nullptr; h->phiBitsReady = false;
     CK(cudaStreamSynchronize(h->stream));
     h->mapTime += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return checkDeviceErr(h);
@@ -1541,7 +1617,7 @@ int svof_halo_exchange(svof_handle* h)
     CK(cudaSetDevice(h->device));
     haloExchange(h);
     alphaBC(h);
-    h->hostAlphaSynced = nullptr;
+    h->hostAlphaSynced = nullptr; h->phiBitsReady = false;
     return SVOF_OK;
     API_END(h)
 }
@@ -1553,6 +1629,7 @@ int svof_set_phi_device(svof_handle* h, const void* dphi)
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync(h->phi, dphi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, h->stream));
     h->havePhi = true;
+    h->phiPartial = false;
     h->inputsAfterNear = true;
     if (h->anyInletOutlet && h->haveAlpha) alphaBC(h);
     return SVOF_OK;
@@ -1591,6 +1668,7 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
     if (!h || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
     if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_advect: alpha/phi/U not set");
     if (h->uPartial) return fail(h, SVOF_ERR_STATE, "svof_advect: U on the device is the sparse upload of svof_step_host; call svof_set_U first");
+    if (h->phiPartial) return fail(h, SVOF_ERR_STATE, "svof_advect: phi on the device is the sparse upload of svof_step_host; call svof_set_phi first");
     API_BEGIN
     CK(cudaSetDevice(h->device));
     const double *dSp = nullptr, *dSu = nullptr;
@@ -1599,7 +1677,7 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
     EventPair& e = beginTimed(h, 1);
     doAdvect(h, dt, dSp, dSu);
     endTimed(h, e);
-    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;  // the caller's buffers no longer mirror the device
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; h->phiBitsReady = false;  // the caller's buffers no longer mirror the device
     CK(cudaGetLastError());
     if (Sp || Su) CK(cudaStreamSynchronize(h->stream));  // caller's buffers may be pageable
     return SVOF_OK;
@@ -1615,6 +1693,7 @@ int svof_step_device(svof_handle* h, double dt)
     if (!h || !(dt > 0)) return SVOF_ERR_INVALID_ARG;
     if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_step_device: alpha/phi/U not set");
     if (h->uPartial) return fail(h, SVOF_ERR_STATE, "svof_step_device: U on the device is the sparse upload of svof_step_host; call svof_set_U first");
+    if (h->phiPartial) return fail(h, SVOF_ERR_STATE, "svof_step_device: phi on the device is the sparse upload of svof_step_host; call svof_set_phi first");
     if (h->prof || h->epochBumps >= (1 << 25) - 4) {   // instrumented runs / tag wrap imminent: plain launches
         const int rc = svof_reconstruct(h);
         return rc ? rc : svof_advect(h, dt, nullptr, nullptr);
@@ -1677,7 +1756,7 @@ int svof_step_device(svof_handle* h, double dt)
     h->inputsAfterNear = false;
     h->lastDt = dt;
     h->advectCount++;
-    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; h->phiBitsReady = false;
     return SVOF_OK;
     API_END(h)
 }
@@ -1693,38 +1772,106 @@ inline void hostTick(svof_handle* h, const char* name)
 
 
 namespace {
-// (index, value) read-back of the entries of `cur` that differ bitwise from what the host buffer holds
-bool deltaReadback(svof_handle* h, const double* cur, double* prevDev, const double* refDev, long long n, int* counter, double* hostOut)
+HostPool& hostPool(svof_handle* h)
 {
-    CK(cudaMemsetAsync(counter, 0, sizeof(int), h->stream));
-    LAUNCH(h, k_delta, cdiv(n, 256), 256, cur, prevDev, refDev, n, counter, h->dIdx, h->dVal, h->capDelta);
-    int cnt = 0;
-    CK(cudaMemcpyAsync(&cnt, counter, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    hostTick(h, "4 wait: GPU step + k_delta + count");
-    h->d2hBytes += sizeof(int);
-    if (cnt > h->capDelta) return false;  // too many changes: the caller falls back to a full copy
-    if (cnt) {
-        CK(cudaMemcpyAsync(h->hIdx, h->dIdx, sizeof(int) * cnt, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->hVal, h->dVal, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        hostTick(h, "5 delta D2H");
-        h->d2hBytes += 12LL * cnt;
-        // scatter into the caller's buffer; a few host threads (random writes into a field-sized array)
-        const int nT = cnt > (1 << 16) ? 8 : 1;
-        auto work = [&](int t) {
-            const int lo = (int)((long long)cnt * t / nT), hi = (int)((long long)cnt * (t + 1) / nT);
-            for (int i = lo; i < hi; ++i) hostOut[h->hIdx[i]] = h->hVal[i];
-        };
-        if (nT == 1) work(0);
-        else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nT; ++t) th.emplace_back(work, t);
-            for (auto& x : th) x.join();
-        }
-        hostTick(h, "6 host scatter");
+    if (!h->pool) h->pool = new HostPool((int)std::max(1u, std::min(std::thread::hardware_concurrency(), 8u)));
+    return *h->pool;
+}
+
+// phi of this step, sparse form: enqueue the face bitmap (streamD) and its read-back; see k_phi_need_bits.
+void sparsePhiBegin(svof_handle* h)
+{
+    if (!h->phiBits) {
+        h->nWordsF = cdiv(h->nF, 32);
+        h->nPhiBlocks = cdiv(h->nWordsF, 32);
+        h->capPhiPacked = std::max<size_t>(1 << 20, (size_t)h->nF / 4);   // more marked faces than this: the full copy is cheaper
+        h->phiBits = dalloc<unsigned int>(h, (size_t)h->nPhiBlocks * 32);
+        h->phiBlockOff = dalloc<int>(h, (size_t)h->nPhiBlocks + 1);
+        h->phiPacked = dalloc<double>(h, h->capPhiPacked, false);
+        CK(cudaMallocHost((void**)&h->hPhiBits, sizeof(unsigned int) * (size_t)h->nPhiBlocks * 32));
+        CK(cudaMallocHost((void**)&h->hPhiBlockOff, sizeof(int) * ((size_t)h->nPhiBlocks + 1)));
+        CK(cudaMallocHost((void**)&h->hPhiPacked, sizeof(double) * h->capPhiPacked));
+        memset(h->hPhiBits, 0, sizeof(unsigned int) * (size_t)h->nPhiBlocks * 32);
+        if (!h->evBits) CK(cudaEventCreateWithFlags(&h->evBits, cudaEventDisableTiming));
+        CK(cudaStreamSynchronize(h->stream));   // the zero fills above are ordered on the main stream
     }
+    if (h->phiBitsReady) return;   // prefetched at the end of the previous call
+    k_phi_need_bits<<<cdiv((long long)h->nWordsF * 32, 256), 256, 0, h->streamD>>>(h->md, h->alphaBuf[h->cur], h->phiBits, h->nWordsF);
+    h->launches++;
+    CK(cudaMemcpyAsync(h->hPhiBits, h->phiBits, sizeof(unsigned int) * h->nWordsF, cudaMemcpyDeviceToHost, h->streamD));
+    CK(cudaEventRecord(h->evBits, h->streamD));
+}
+
+// ... gather the marked entries of the caller's phi (host threads), copy them up and scatter them (streamD).
+// Returns false when too many faces are marked: the caller copies the full field instead.
+bool sparsePhiFinish(svof_handle* h, const double* phi)
+{
+    if (!h->phiBitsReady) {
+        CK(cudaEventSynchronize(h->evBits));
+        hostTick(h, "0a wait: phi face bitmap D2H");
+    }
+    h->phiBitsReady = false;
+    h->d2hBytes += 4LL * h->nWordsF;
+    HostPool& pool = hostPool(h);
+    const int nB = h->nPhiBlocks, nT = pool.size();
+    const unsigned int* bits = h->hPhiBits;
+    int* off = h->hPhiBlockOff;
+    // marked faces per block of 32 bitmap words (= 1024 faces), then the exclusive prefix sum
+    pool.run(nT, [&](int t) {
+        const int b0 = (int)((long long)nB * t / nT), b1 = (int)((long long)nB * (t + 1) / nT);
+        for (int b = b0; b < b1; ++b) {
+            int c = 0;
+            for (int w = 32 * b; w < 32 * b + 32; ++w) c += __builtin_popcount(bits[w]);
+            off[b + 1] = c;
+        }
+    });
+    hostTick(h, "0b host: marked faces per 1024-face block");
+    off[0] = 0;
+    long long total = 0;
+    for (int b = 0; b < nB; ++b) {
+        total += off[b + 1];
+        if (total > (long long)h->capPhiPacked) return false;
+        off[b + 1] = (int)total;
+    }
+    double* packed = h->hPhiPacked;
+    pool.run(nT, [&](int t) {
+        const int b0 = (int)((long long)nB * t / nT), b1 = (int)((long long)nB * (t + 1) / nT);
+        size_t pos = (size_t)off[b0];
+        for (int w = 32 * b0; w < 32 * b1; ++w) {
+            unsigned int x = bits[w];
+            const double* src = phi + ((size_t)w << 5);
+            while (x) {
+                packed[pos++] = src[__builtin_ctz(x)];
+                x &= x - 1;
+            }
+        }
+    });
+    hostTick(h, "0c host gather of the marked phi entries");
+    if (h->prof) {
+        static int once = 0;
+        if (!once++) fprintf(stderr, "[svof profile] sparse phi: %lld of %d faces marked, %d host threads\n", total, h->nF, nT);
+    }
+    CK(cudaMemcpyAsync(h->phiBlockOff, off, sizeof(int) * ((size_t)nB + 1), cudaMemcpyHostToDevice, h->streamD));
+    if (total) CK(cudaMemcpyAsync(h->phiPacked, packed, sizeof(double) * (size_t)total, cudaMemcpyHostToDevice, h->streamD));
+    k_phi_scatter<<<cdiv(h->nWordsF, 256), 256, 0, h->streamD>>>(h->phiBits, h->phiBlockOff, h->nWordsF, h->phiPacked, h->phi);
+    h->launches++;
+    h->h2dBytes += 8LL * total + 4LL * (nB + 1);
     return true;
+}
+// host side of the delta read-back: out[idx[i]] = val[i] (random writes into a field-sized array)
+void scatterDeltas(svof_handle* h, const int* idx, const double* val, int cnt, double* out)
+{
+    if (cnt <= 0) return;
+    if (cnt < (1 << 14)) {
+        for (int i = 0; i < cnt; ++i) out[idx[i]] = val[i];
+        return;
+    }
+    HostPool& pool = hostPool(h);
+    const int nT = pool.size();
+    pool.run(nT, [&](int t) {
+        const int lo = (int)((long long)cnt * t / nT), hi = (int)((long long)cnt * (t + 1) / nT);
+        for (int i = lo; i < hi; ++i) out[idx[i]] = val[i];
+    });
 }
 }  // namespace
 
@@ -1742,17 +1889,40 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     // sparse-U round trip run on the main one
     CK(cudaEventRecord(h->evInputs, st));
     CK(cudaStreamWaitEvent(h->streamD, h->evInputs, 0));  // previous step's readers of phi/Ub are done
-    CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
-    h->h2dBytes += 8LL * h->nF;
+    // phi goes up on the second stream while reconstruct() and the sparse-U round trip run on the main one.  Sparse form
+    // (default): only the faces whose value can matter (k_phi_need_bits); the device's other entries keep older values,
+    // which multiply an exactly zero alpha.  Otherwise the full field (nF doubles) crosses PCIe.
+    const bool trySparsePhi = h->sparseIO && h->sparsePhi;   // the device's phi starts zero-filled: stale entries are finite
+    if (trySparsePhi) sparsePhiBegin(h);
+    else {
+        CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
+        h->h2dBytes += 8LL * h->nF;
+        h->phiPartial = false;
+    }
     if (Ub && h->nBF) {
         CK(cudaMemcpyAsync(h->Ub, Ub, sizeof(double) * 3 * h->nBF, cudaMemcpyHostToDevice, h->streamD));
         h->h2dBytes += 24LL * h->nBF;
     }
-    CK(cudaEventRecord(h->evCopy, h->streamD));
-    h->havePhi = true;
+    if (h->anyInletOutlet && h->nBF) {
+        // inletOutlet patch values of alpha.oldTime follow the sign of the NEW phi (what svof_set_phi does for the split
+        // calls) and the LS normals read them: the boundary part of phi goes up first, on the main stream
+        CK(cudaMemcpyAsync(h->phi + h->nIF, phi + h->nIF, sizeof(double) * h->nBF, cudaMemcpyHostToDevice, st));
+        h->h2dBytes += 8LL * h->nBF;
+        alphaBC(h);
+    }
     EventPair& e0 = beginTimed(h, 0);
     doReconstruct(h);
     endTimed(h, e0);
+    if (trySparsePhi) {   // host work below overlaps the reconstruct kernels just enqueued
+        if (sparsePhiFinish(h, phi)) h->phiPartial = true;
+        else {
+            CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
+            h->h2dBytes += 8LL * h->nF;
+            h->phiPartial = false;
+        }
+    }
+    CK(cudaEventRecord(h->evCopy, h->streamD));
+    h->havePhi = true;
     // U: only the rows the interface-velocity interpolation reads
     bool uDone = false;
     if (h->sparseIO) {
@@ -1760,25 +1930,36 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
         LAUNCH(h, k_clear_u_bits, g256, 256, h->uList, h->ctl, h->uBits, h->capU);
         CK(cudaMemsetAsync(&h->ctl->nUCells, 0, sizeof(int), st));
         LAUNCH(h, k_mark_u_cells, g256, 256, h->md, h->mixedCells, h->cellStatus, h->ctl, h->uBits, h->uList, h->capU);
-        int nU = 0;
-        CK(cudaMemcpyAsync(&nU, &h->ctl->nUCells, sizeof(int), cudaMemcpyDeviceToHost, st));
+        // count and a speculative prefix of the list in ONE round trip (sized from the previous step; the rest, if any, follows)
+        const int estU = std::min(h->capU, std::max(1 << 14, h->lastNU + h->lastNU / 4));
+        CK(cudaMemcpyAsync(&h->hctl->nUCells, &h->ctl->nUCells, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->hUList, h->uList, sizeof(int) * estU, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        hostTick(h, "1 wait: reconstruct + U-row marking");
+        hostTick(h, "1 wait: reconstruct + U-row marking + list D2H");
+        const int nU = h->hctl->nUCells;
+        h->lastNU = nU;
         if (nU <= h->capU) {
-            if (nU) {
-                CK(cudaMemcpyAsync(h->hUList, h->uList, sizeof(int) * nU, cudaMemcpyDeviceToHost, st));
+            if (nU > estU) {
+                CK(cudaMemcpyAsync(h->hUList + estU, h->uList + estU, sizeof(int) * (nU - estU), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
-                hostTick(h, "2 U-row list D2H");
-                for (int i = 0; i < nU; ++i) {
-                    const double* src = U + 3 * (size_t)h->hUList[i];
-                    double* dst = h->hUPacked + 3 * (size_t)i;
-                    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
-                }
+                hostTick(h, "2 U-row list D2H (remainder)");
+            }
+            if (nU) {
+                const int nT = nU > (1 << 15) ? hostPool(h).size() : 1;
+                auto gather = [&](int t) {
+                    const int lo = (int)((long long)nU * t / nT), hi = (int)((long long)nU * (t + 1) / nT);
+                    for (int i = lo; i < hi; ++i) {
+                        const double* src = U + 3 * (size_t)h->hUList[i];
+                        double* dst = h->hUPacked + 3 * (size_t)i;
+                        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+                    }
+                };
+                if (nT == 1) gather(0); else hostPool(h).run(nT, gather);
                 hostTick(h, "3 host gather of U rows");
                 CK(cudaMemcpyAsync(h->uPacked, h->hUPacked, sizeof(double) * 3 * nU, cudaMemcpyHostToDevice, st));
                 LAUNCH(h, k_scatter_u, cdiv(nU, 256), 256, h->uList, nU, h->uPacked, h->U);
                 h->h2dBytes += 24LL * nU;
-                h->d2hBytes += 4LL * nU + 4;
+                h->d2hBytes += 4LL * std::max(nU, estU) + 4;
             }
             uDone = true;
             h->uPartial = true;
@@ -1797,31 +1978,86 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     EventPair& e1 = beginTimed(h, 1);
     doAdvect(h, dt, nullptr, nullptr);
     endTimed(h, e1);
-    // results: deltas against what the caller's buffers already hold, else full copies
-    if (alpha_out) {
-        bool done = false;
-        if (h->sparseIO && h->hostAlphaSynced == alpha_out)
-            done = deltaReadback(h, h->alphaBuf[h->cur], nullptr, h->alphaBuf[h->cur ^ 1], h->nC, &h->ctl->nDeltaA, alpha_out);
-        if (!done) {
-            CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, st));
-            h->d2hBytes += 8LL * h->nC;
-        }
-        h->hostAlphaSynced = alpha_out;
-    }
-    if (alpha_phi_out) {
-        bool done = false;
-        if (h->sparseIO && h->hostAlphaPhiSynced == alpha_phi_out)
-            done = deltaReadback(h, h->alphaPhi, h->alphaPhiPrev, nullptr, h->nF, &h->ctl->nDeltaF, alpha_phi_out);
-        if (!done) {
-            CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
-            if (h->sparseIO) CK(cudaMemcpyAsync(h->alphaPhiPrev, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, st));
-            h->d2hBytes += 8LL * h->nF;
-        }
-        h->hostAlphaPhiSynced = alpha_phi_out;
+    // results: deltas against what the caller's buffers already hold, else full copies.  Both delta kernels, the control
+    // block (with the two counts) and a speculative prefix of each (index, value) list -- sized from the previous step --
+    // are enqueued together and waited for ONCE; a list that turned out longer gets its remainder in a second copy.
+    const int capA = h->capDelta / 4, capF = h->capDelta - capA;   // alpha deltas in [0, capA), alphaPhi deltas behind them
+    const bool deltaA = alpha_out && h->sparseIO && h->hostAlphaSynced == alpha_out;
+    const bool deltaF = alpha_phi_out && h->sparseIO && h->hostAlphaPhiSynced == alpha_phi_out;
+    int estA = 0, estF = 0;
+    if (deltaA || deltaF) CK(cudaMemsetAsync(&h->ctl->nDeltaA, 0, 2 * sizeof(int), st));
+    if (deltaA)
+        LAUNCH(h, k_delta, cdiv(h->nC, 256), 256, h->alphaBuf[h->cur], (double*)nullptr, h->alphaBuf[h->cur ^ 1], (long long)h->nC,
+               &h->ctl->nDeltaA, h->dIdx, h->dVal, capA);
+    if (deltaF)
+        LAUNCH(h, k_delta, cdiv(h->nF, 256), 256, h->alphaPhi, h->alphaPhiPrev, (const double*)nullptr, (long long)h->nF, &h->ctl->nDeltaF,
+               h->dIdx + capA, h->dVal + capA, capF);
+    // the next call's phi face bitmap (of the alpha just computed) rides along with this call's read-back
+    const bool prefetchBits = trySparsePhi && h->phiPartial;
+    if (prefetchBits) {
+        LAUNCH(h, k_phi_need_bits, cdiv((long long)h->nWordsF * 32, 256), 256, h->md, h->alphaBuf[h->cur], h->phiBits, h->nWordsF);
+        CK(cudaMemcpyAsync(h->hPhiBits, h->phiBits, sizeof(unsigned int) * h->nWordsF, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaMemcpyAsync(h->hctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    if (deltaA) {
+        estA = std::min(capA, std::max(1 << 14, h->lastCntA + h->lastCntA / 4));
+        CK(cudaMemcpyAsync(h->hIdx, h->dIdx, sizeof(int) * estA, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->hVal, h->dVal, sizeof(double) * estA, cudaMemcpyDeviceToHost, st));
+    } else if (alpha_out) {
+        CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, st));
+        h->d2hBytes += 8LL * h->nC;
+    }
+    if (deltaF) {
+        estF = std::min(capF, std::max(1 << 14, h->lastCntF + h->lastCntF / 4));
+        CK(cudaMemcpyAsync(h->hIdx + capA, h->dIdx + capA, sizeof(int) * estF, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h->hVal + capA, h->dVal + capA, sizeof(double) * estF, cudaMemcpyDeviceToHost, st));
+    } else if (alpha_phi_out) {
+        CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
+        if (h->sparseIO) CK(cudaMemcpyAsync(h->alphaPhiPrev, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, st));
+        h->d2hBytes += 8LL * h->nF;
+    }
     CK(cudaStreamSynchronize(st));
-    hostTick(h, "7 final sync");
+    hostTick(h, "4 wait: GPU step + delta kernels + D2H");
+    h->d2hBytes += sizeof(Ctl);
+    const int cntA = deltaA ? h->hctl->nDeltaA : 0, cntF = deltaF ? h->hctl->nDeltaF : 0;
+    bool again = false;
+    if (deltaA) {
+        h->lastCntA = std::min(cntA, capA);
+        if (cntA > capA) {   // too many changes for the list: full copy
+            CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, st));
+            h->d2hBytes += 8LL * h->nC;
+            again = true;
+        } else if (cntA > estA) {
+            CK(cudaMemcpyAsync(h->hIdx + estA, h->dIdx + estA, sizeof(int) * (cntA - estA), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->hVal + estA, h->dVal + estA, sizeof(double) * (cntA - estA), cudaMemcpyDeviceToHost, st));
+            again = true;
+        }
+        h->d2hBytes += 12LL * std::max(estA, std::min(cntA, capA));
+    }
+    if (deltaF) {
+        h->lastCntF = std::min(cntF, capF);
+        if (cntF > capF) {
+            CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->alphaPhiPrev, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, st));
+            h->d2hBytes += 8LL * h->nF;
+            again = true;
+        } else if (cntF > estF) {
+            CK(cudaMemcpyAsync(h->hIdx + capA + estF, h->dIdx + capA + estF, sizeof(int) * (cntF - estF), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(h->hVal + capA + estF, h->dVal + capA + estF, sizeof(double) * (cntF - estF), cudaMemcpyDeviceToHost, st));
+            again = true;
+        }
+        h->d2hBytes += 12LL * std::max(estF, std::min(cntF, capF));
+    }
+    if (again) {
+        CK(cudaStreamSynchronize(st));
+        hostTick(h, "5 D2H of list remainders / full fields");
+    }
+    if (deltaA && cntA <= capA) scatterDeltas(h, h->hIdx, h->hVal, cntA, alpha_out);
+    if (deltaF && cntF <= capF) scatterDeltas(h, h->hIdx + capA, h->hVal + capA, cntF, alpha_phi_out);
+    hostTick(h, "6 host scatter");
+    if (alpha_out) h->hostAlphaSynced = alpha_out;
+    if (alpha_phi_out) h->hostAlphaPhiSynced = alpha_phi_out;
+    h->phiBitsReady = prefetchBits;   // valid until anything else changes alpha
     CK(cudaGetLastError());
     if (h->hctl->err) return deviceErr(h);   // a work list or polyhedron cap overflowed: the fields just returned are not to be trusted
     return SVOF_OK;
@@ -1976,7 +2212,7 @@ int svof_device_touch(svof_handle* h, int which)
     h->haveAlpha = true;
     h->bitsValid = false;
     h->advected = false;
-    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;   // the caller's buffers no longer mirror the device
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; h->phiBitsReady = false;   // the caller's buffers no longer mirror the device
     return SVOF_OK;
     API_END(h)
 }
@@ -1995,7 +2231,8 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
     if (!strcmp(name, "bound_lanes")) { h->boundLanes = value != 0; for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
-    if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; return SVOF_OK; }
+    if (!strcmp(name, "sparse_phi")) { h->sparsePhi = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; h->phiBitsReady = false; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");
     API_END(h)
 }

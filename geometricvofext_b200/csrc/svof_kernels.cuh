@@ -2013,6 +2013,44 @@ __global__ void k_scatter_u(const int* uList, int n, const double* packed, doubl
     U[3 * (size_t)c + 1] = packed[3 * (size_t)i + 1];
     U[3 * (size_t)c + 2] = packed[3 * (size_t)i + 2];
 }
+//  * phi enters the step only as a factor of an alpha (upwind transport phi*alpha_up, geometric flux of cut cells, the
+//    bounding of out-of-bounds cells, the downwind test of cut cells) or on a boundary face (inletOutlet patch values):
+//    on an internal face with alpha == 0 exactly on BOTH sides its value cannot change any result (the product is a signed
+//    zero, alphaPhi compares equal), so only the other faces have to cross PCIe.  k_phi_need_bits publishes them as a bitmap
+//    over faces; the host gathers the marked entries of the caller's phi in face order and k_phi_scatter puts them back.
+__global__ void k_phi_need_bits(MeshDev m, const double* __restrict__ alpha, unsigned int* bits, int nWordsF)
+{
+    const long long fl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false;
+    if (fl < m.nFaces) {
+        const int f = (int)fl;
+        need = (f >= m.nIF) || (__ldg(alpha + __ldg(m.owner + f)) != 0.0) || (__ldg(alpha + __ldg(m.neighbour + f)) != 0.0);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, need);
+    if ((threadIdx.x & 31) == 0 && (fl >> 5) < nWordsF) bits[fl >> 5] = w;
+}
+// blockOff[b] = number of marked faces before bitmap word 32*b (host prefix sum); one thread per bitmap word
+__global__ void k_phi_scatter(const unsigned int* __restrict__ bits, const int* __restrict__ blockOff, int nWordsF,
+                              const double* __restrict__ packed, double* phi)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned int word = (w < nWordsF) ? bits[w] : 0u;
+    const int cnt = __popc(word);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (!word) return;
+    int pos = blockOff[w >> 5] + incl - cnt;
+    while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        phi[((size_t)w << 5) + b] = packed[pos++];
+    }
+}
 // entries whose bit pattern changed: (index, value) appended with warp-aggregated atomics; if prev != nullptr
 // it is brought up to date at the same time
 __global__ void k_delta(const double* __restrict__ cur, double* prev, const double* __restrict__ ref, long long n, int* counter,

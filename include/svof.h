@@ -264,13 +264,18 @@ int svof_scatter_alpha_device(svof_handle* h, const int32_t* d_idx, const double
  * device-to-device (CUDA library only). */
 int svof_set_phi_device(svof_handle* h, const void* dphi);
 int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
-/* Runtime switches: "overlap" (default 0; 1: run the streaming kernel on a second stream concurrently with
- * the whole sparse interface chain, 2: only with the tail of reconstruct() -- bitwise the same result either way;
- * both measured slower on B200), "profile" (0/1: CUDA events around every launch, printed at destroy),
+/* Runtime switches: "overlap" (default 1: the streaming kernel runs on a second stream beside the interface
+ * kernels; 0: one stream -- bitwise the same result either way), "fork", "plic_ctas", "dense_ctas" (tuning of that
+ * schedule), "profile" (0/1: CUDA events around every launch, printed at destroy),
  * "sparse_io" (0/1, default 1: svof_step_host uploads only the rows of U the interface-velocity interpolation
  * reads and reads alpha/alphaPhi back as (index,value) deltas against what the SAME caller buffers received
  * from the previous svof_step_host; a caller that modifies those buffers in between must call svof_set_alpha
- * or pass 0). */
+ * or pass 0),
+ * "sparse_phi" (0/1, default 1, with sparse_io: svof_step_host copies up only the phi entries the step can depend
+ * on -- every boundary face and every internal face with alpha != 0 in at least one of its two cells; on the other
+ * faces phi multiplies an exactly zero alpha, so the device keeps whatever it held.  The caller's phi buffer is read
+ * afresh in every call.  After such a call the device's phi is not a full field: svof_advect / svof_step_device
+ * return SVOF_ERR_STATE until svof_set_phi / svof_set_phi_device). */
 int svof_set_option(svof_handle* h, const char* name, int value);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is ordered on, so a caller that
  * lives on the GPU (halo exchange in multigpu.py) can enqueue its own work in order without a host sync. */

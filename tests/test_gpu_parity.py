@@ -175,6 +175,62 @@ def test_step_host_matches_split_calls(oracle, product):
     assert s1.info(capi.I_GPU_LAUNCHES) > 0
 
 
+@pytest.mark.parametrize("case", ["sphere in an empty box", "half-filled box with inflow/outflow patches"])
+def test_step_host_sparse_phi_upload_is_bitwise_the_full_upload(product, case):
+    """svof_step_host uploads only the phi entries the step can depend on (faces next to a cell with alpha != 0, and all
+    boundary faces); phi changes on EVERY face between calls, including its sign.  Results must be bitwise those of the
+    split calls with full fields, and of svof_step_host with sparse_phi off."""
+    N = 16
+    m = meshmod.hex_block(N)
+    if case.startswith("half"):
+        for p in m.patches:
+            if p.name == "back":
+                p.alpha_bc, p.alpha_value = capi.BC_FIXED_VALUE, 1.0
+            if p.name == "front":
+                p.alpha_bc, p.alpha_value = capi.BC_INLET_OUTLET, 1.0
+    ctl = dict(LEVEQUE_CONTROLS, clip=True, snapTol=1e-12) if case.startswith("half") else LEVEQUE_CONTROLS
+    s1, s2, s3 = (SolveVofEqu(m, ctl, lib=product) for _ in range(3))
+    C, Cf, Sf = s1.field(capi.F_C), s1.field(capi.F_CF), s1.field(capi.F_SF)
+    if case.startswith("half"):
+        a0 = (C[:, 2] < 0.5).astype(np.float64)
+        vel = lambda x: np.tile(np.array([1.0, 0.2, 0.1]), (len(x), 1))
+        U0, phi0 = vel(C), fields.face_flux(Cf, Sf, vel)
+        Ub = vel(Cf[m.n_internal_faces:])
+    else:
+        a0 = exact_sphere_alpha(m)
+        U0, phi0 = fields.leveque_velocity(C), fields.face_flux(Cf, Sf)
+        Ub = np.zeros((s1.nBF, 3))
+    for s in (s1, s2, s3):
+        s.setAlpha(a0)
+    s3.setOption("sparse_phi", 0)
+    out2, aphi2, out3, aphi3 = np.empty(m.n_cells), np.empty(m.n_faces), np.empty(m.n_cells), np.empty(m.n_faces)
+    rng = np.random.default_rng(5)
+    full = 8 * (m.n_faces + 3 * m.n_cells + 3 * s1.nBF)
+    for k, f in enumerate((1.0, 0.7, -0.4, -1.0, 0.3, 0.9)):
+        phi = phi0 * f + 1e-9 * rng.normal(size=phi0.shape) * np.abs(phi0).max()   # every face changes every step
+        U = U0 * f
+        s1.setPhi(phi)
+        s1.setU(U, Ub * f)
+        s1.reconstruct()
+        s1.advect(0.01)
+        s2.step_host(0.01, phi, U, Ub * f, out2, aphi2)
+        s3.step_host(0.01, phi, U, Ub * f, out3, aphi3)
+        assert np.array_equal(s1.alpha(), out2), "step %d: alpha differs (sparse phi)" % k
+        assert np.array_equal(s1.alphaPhi(), aphi2), "step %d: alphaPhi differs (sparse phi)" % k
+        assert np.array_equal(out3, out2) and np.array_equal(aphi3, aphi2)
+        assert np.array_equal(s1.field(capi.F_ALPHA_BOUNDARY), s2.field(capi.F_ALPHA_BOUNDARY))
+        if not case.startswith("half"):
+            assert s2.info(capi.I_H2D_BYTES) < 0.5 * full < s3.info(capi.I_H2D_BYTES)
+    # the device's phi is not a full field after the sparse upload: the split calls refuse it until svof_set_phi
+    with pytest.raises(capi.SvofError):
+        s2.advect(0.01)
+    s2.setPhi(phi0)
+    s2.setU(U0, Ub)
+    s2.reconstruct()
+    s2.advect(0.01)
+    assert s2.info(capi.I_ERROR_FLAGS) == 0
+
+
 def _smeared_sphere(C_, V, centre=(0.5, 0.62, 0.5), radius=0.15):
     """A sphere-like field on ANY mesh: one layer of mixed cells (parity input, not an exact shape)."""
     h = np.cbrt(V)
