@@ -8,6 +8,7 @@
 // Build (see geometricvofext_b200/build.py):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xcompiler -fPIC -shared
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
@@ -51,19 +52,36 @@ class HostPool {
     std::mutex m_;
     std::condition_variable cvWork_, cvDone_;
     std::function<void(int)> fn_;
+    std::atomic<unsigned long long> gen_{0};
     int nTasks_ = 0, next_ = 0, pending_ = 0;
     bool stop_ = false;
-    void loop()
+    // take and run tasks of the current batch until none is left (lock held on entry and on return)
+    void drain(std::unique_lock<std::mutex>& lk)
     {
-        std::unique_lock<std::mutex> lk(m_);
-        for (;;) {
-            cvWork_.wait(lk, [&] { return stop_ || next_ < nTasks_; });
-            if (stop_) return;
+        while (next_ < nTasks_) {
             const int t = next_++;
             lk.unlock();
             fn_(t);
             lk.lock();
-            if (--pending_ == 0) cvDone_.notify_one();
+            if (--pending_ == 0) cvDone_.notify_all();
+        }
+    }
+    void loop()
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            // the phases of one svof_step_host follow each other within microseconds: spin briefly before sleeping, a
+            // condition-variable wake-up costs more than the work of a phase
+            for (int i = 0; i < 40000 && gen_.load(std::memory_order_acquire) == seen; ++i) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            std::unique_lock<std::mutex> lk(m_);
+            cvWork_.wait(lk, [&] { return stop_ || next_ < nTasks_ || gen_.load(std::memory_order_relaxed) != seen; });
+            if (stop_) return;
+            seen = gen_.load(std::memory_order_relaxed);
+            drain(lk);
         }
     }
 
@@ -77,12 +95,13 @@ public:
         {
             std::lock_guard<std::mutex> lk(m_);
             stop_ = true;
+            gen_.fetch_add(1, std::memory_order_release);
         }
         cvWork_.notify_all();
         for (auto& t : th_) t.join();
     }
-    int size() const { return (int)th_.size(); }
-    // run fn(0..n-1) on the pool's threads; returns when all are done
+    int size() const { return (int)th_.size() + 1; }   // the calling thread works too
+    // run fn(0..n-1) on the pool's threads and the caller; returns when all are done
     void run(int n, std::function<void(int)> fn)
     {
         if (n <= 0) return;
@@ -91,7 +110,9 @@ public:
         nTasks_ = n;
         next_ = 0;
         pending_ = n;
+        gen_.fetch_add(1, std::memory_order_release);
         cvWork_.notify_all();
+        drain(lk);
         cvDone_.wait(lk, [&] { return pending_ == 0; });
         nTasks_ = 0;
     }
@@ -1774,8 +1795,18 @@ inline void hostTick(svof_handle* h, const char* name)
 namespace {
 HostPool& hostPool(svof_handle* h)
 {
-    if (!h->pool) h->pool = new HostPool((int)std::max(1u, std::min(std::thread::hardware_concurrency(), 8u)));
+    if (!h->pool) h->pool = new HostPool((int)std::max(1u, std::min(std::thread::hardware_concurrency(), 8u)) - 1);
     return *h->pool;
+}
+
+// face bitmap of the current alpha + marked faces per 1024-face block, and their read-back, on stream s
+void enqueuePhiBits(svof_handle* h, cudaStream_t s)
+{
+    CK(cudaMemsetAsync(h->phiBlockOff, 0, sizeof(int) * ((size_t)h->nPhiBlocks + 1), s));
+    k_phi_need_bits<<<cdiv((long long)h->nWordsF * 32, 256), 256, 0, s>>>(h->md, h->alphaBuf[h->cur], h->phiBits, h->nWordsF, h->phiBlockOff);
+    h->launches++;
+    CK(cudaMemcpyAsync(h->hPhiBits, h->phiBits, sizeof(unsigned int) * h->nWordsF, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hPhiBlockOff, h->phiBlockOff, sizeof(int) * ((size_t)h->nPhiBlocks + 1), cudaMemcpyDeviceToHost, s));
 }
 
 // phi of this step, sparse form: enqueue the face bitmap (streamD) and its read-back; see k_phi_need_bits.
@@ -1796,9 +1827,7 @@ void sparsePhiBegin(svof_handle* h)
         CK(cudaStreamSynchronize(h->stream));   // the zero fills above are ordered on the main stream
     }
     if (h->phiBitsReady) return;   // prefetched at the end of the previous call
-    k_phi_need_bits<<<cdiv((long long)h->nWordsF * 32, 256), 256, 0, h->streamD>>>(h->md, h->alphaBuf[h->cur], h->phiBits, h->nWordsF);
-    h->launches++;
-    CK(cudaMemcpyAsync(h->hPhiBits, h->phiBits, sizeof(unsigned int) * h->nWordsF, cudaMemcpyDeviceToHost, h->streamD));
+    enqueuePhiBits(h, h->streamD);
     CK(cudaEventRecord(h->evBits, h->streamD));
 }
 
@@ -1811,21 +1840,11 @@ bool sparsePhiFinish(svof_handle* h, const double* phi)
         hostTick(h, "0a wait: phi face bitmap D2H");
     }
     h->phiBitsReady = false;
-    h->d2hBytes += 4LL * h->nWordsF;
+    h->d2hBytes += 4LL * h->nWordsF + 4LL * (h->nPhiBlocks + 1);
     HostPool& pool = hostPool(h);
     const int nB = h->nPhiBlocks, nT = pool.size();
     const unsigned int* bits = h->hPhiBits;
-    int* off = h->hPhiBlockOff;
-    // marked faces per block of 32 bitmap words (= 1024 faces), then the exclusive prefix sum
-    pool.run(nT, [&](int t) {
-        const int b0 = (int)((long long)nB * t / nT), b1 = (int)((long long)nB * (t + 1) / nT);
-        for (int b = b0; b < b1; ++b) {
-            int c = 0;
-            for (int w = 32 * b; w < 32 * b + 32; ++w) c += __builtin_popcount(bits[w]);
-            off[b + 1] = c;
-        }
-    });
-    hostTick(h, "0b host: marked faces per 1024-face block");
+    int* off = h->hPhiBlockOff;   // arrives as counts in off[1 + b]: exclusive prefix sum in place
     off[0] = 0;
     long long total = 0;
     for (int b = 0; b < nB; ++b) {
@@ -1833,13 +1852,26 @@ bool sparsePhiFinish(svof_handle* h, const double* phi)
         if (total > (long long)h->capPhiPacked) return false;
         off[b + 1] = (int)total;
     }
+    // equal shares of MARKED faces per thread (the marked faces cluster where the liquid is): block boundaries from the prefix sums
+    std::vector<int> cut(nT + 1, nB);
+    cut[0] = 0;
+    for (int t = 1; t < nT; ++t) cut[t] = (int)(std::lower_bound(off, off + nB + 1, (int)(total * t / nT)) - off);
+    for (int t = 1; t <= nT; ++t) cut[t] = std::max(cut[t], cut[t - 1]);
+    cut[nT] = nB;
     double* packed = h->hPhiPacked;
+    const int nWordsF = h->nWordsF;
     pool.run(nT, [&](int t) {
-        const int b0 = (int)((long long)nB * t / nT), b1 = (int)((long long)nB * (t + 1) / nT);
+        const int b0 = std::min(cut[t], nB), b1 = std::min(cut[t + 1], nB);
         size_t pos = (size_t)off[b0];
-        for (int w = 32 * b0; w < 32 * b1; ++w) {
+        const int w1 = std::min(32 * b1, nWordsF);
+        for (int w = 32 * b0; w < w1; ++w) {
             unsigned int x = bits[w];
             const double* src = phi + ((size_t)w << 5);
+            if (x == 0xffffffffu) {   // the marked faces come in long runs (faces of consecutive cells)
+                memcpy(packed + pos, src, 32 * sizeof(double));
+                pos += 32;
+                continue;
+            }
             while (x) {
                 packed[pos++] = src[__builtin_ctz(x)];
                 x &= x - 1;
@@ -1913,16 +1945,19 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     EventPair& e0 = beginTimed(h, 0);
     doReconstruct(h);
     endTimed(h, e0);
-    if (trySparsePhi) {   // host work below overlaps the reconstruct kernels just enqueued
-        if (sparsePhiFinish(h, phi)) h->phiPartial = true;
-        else {
-            CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
-            h->h2dBytes += 8LL * h->nF;
-            h->phiPartial = false;
+    auto finishPhi = [&]() {   // host work that overlaps the reconstruct / U-marking kernels already enqueued
+        if (trySparsePhi) {
+            if (sparsePhiFinish(h, phi)) h->phiPartial = true;
+            else {
+                CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
+                h->h2dBytes += 8LL * h->nF;
+                h->phiPartial = false;
+            }
         }
-    }
-    CK(cudaEventRecord(h->evCopy, h->streamD));
-    h->havePhi = true;
+        CK(cudaEventRecord(h->evCopy, h->streamD));
+        h->havePhi = true;
+    };
+    if (!h->sparseIO) finishPhi();
     // U: only the rows the interface-velocity interpolation reads
     bool uDone = false;
     if (h->sparseIO) {
@@ -1934,6 +1969,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
         const int estU = std::min(h->capU, std::max(1 << 14, h->lastNU + h->lastNU / 4));
         CK(cudaMemcpyAsync(&h->hctl->nUCells, &h->ctl->nUCells, sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h->hUList, h->uList, sizeof(int) * estU, cudaMemcpyDeviceToHost, st));
+        finishPhi();
         CK(cudaStreamSynchronize(st));
         hostTick(h, "1 wait: reconstruct + U-row marking + list D2H");
         const int nU = h->hctl->nUCells;
@@ -1995,8 +2031,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     // the next call's phi face bitmap (of the alpha just computed) rides along with this call's read-back
     const bool prefetchBits = trySparsePhi && h->phiPartial;
     if (prefetchBits) {
-        LAUNCH(h, k_phi_need_bits, cdiv((long long)h->nWordsF * 32, 256), 256, h->md, h->alphaBuf[h->cur], h->phiBits, h->nWordsF);
-        CK(cudaMemcpyAsync(h->hPhiBits, h->phiBits, sizeof(unsigned int) * h->nWordsF, cudaMemcpyDeviceToHost, st));
+        enqueuePhiBits(h, st);
     }
     CK(cudaMemcpyAsync(h->hctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     if (deltaA) {

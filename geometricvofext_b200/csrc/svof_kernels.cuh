@@ -2018,7 +2018,8 @@ __global__ void k_scatter_u(const int* uList, int n, const double* packed, doubl
 //    on an internal face with alpha == 0 exactly on BOTH sides its value cannot change any result (the product is a signed
 //    zero, alphaPhi compares equal), so only the other faces have to cross PCIe.  k_phi_need_bits publishes them as a bitmap
 //    over faces; the host gathers the marked entries of the caller's phi in face order and k_phi_scatter puts them back.
-__global__ void k_phi_need_bits(MeshDev m, const double* __restrict__ alpha, unsigned int* bits, int nWordsF)
+// blockCnt[1 + b] += marked faces of the 1024-face block b (zeroed by the caller; the host turns it into the prefix sum)
+__global__ void k_phi_need_bits(MeshDev m, const double* __restrict__ alpha, unsigned int* bits, int nWordsF, int* blockCnt)
 {
     const long long fl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool need = false;
@@ -2027,7 +2028,10 @@ __global__ void k_phi_need_bits(MeshDev m, const double* __restrict__ alpha, uns
         need = (f >= m.nIF) || (__ldg(alpha + __ldg(m.owner + f)) != 0.0) || (__ldg(alpha + __ldg(m.neighbour + f)) != 0.0);
     }
     const unsigned int w = __ballot_sync(0xffffffffu, need);
-    if ((threadIdx.x & 31) == 0 && (fl >> 5) < nWordsF) bits[fl >> 5] = w;
+    if ((threadIdx.x & 31) == 0 && (fl >> 5) < nWordsF) {
+        bits[fl >> 5] = w;
+        if (w) atomicAdd(blockCnt + 1 + (fl >> 10), __popc(w));
+    }
 }
 // blockOff[b] = number of marked faces before bitmap word 32*b (host prefix sum); one thread per bitmap word
 __global__ void k_phi_scatter(const unsigned int* __restrict__ bits, const int* __restrict__ blockOff, int nWordsF,
