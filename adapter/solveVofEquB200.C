@@ -555,6 +555,28 @@ plicSurface reconstruction::interface()
     return s;
 }
 
+plicSurface reconstruction::subCellFaces()
+{
+    plicSurface s;
+    int64_t nP = 0, nF = 0, nFP = 0;
+    solveVofEqu::check(svof_subcell_faces(owner_.h_, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, &nP, &nF, &nFP), owner_.h_,
+                       "svof_subcell_faces");
+    scalarField pts(3*label(nP));
+    labelList off(label(nF) + 1, 0), fpts(label(nFP), 0), cells(label(nF), 0);
+    solveVofEqu::check(svof_subcell_faces(owner_.h_, nP, nF, nFP, pts.data(), off.data(), fpts.data(), cells.data(), &nP, &nF, &nFP),
+                       owner_.h_, "svof_subcell_faces");
+    s.points.setSize(label(nP));
+    forAll(s.points, i) s.points[i] = point(pts[3*i], pts[3*i + 1], pts[3*i + 2]);
+    s.faces.setSize(label(nF));
+    s.meshCells = cells;
+    forAll(s.faces, i)
+    {
+        s.faces[i].setSize(off[i + 1] - off[i]);
+        forAll(s.faces[i], k) s.faces[i][k] = fpts[off[i] + k];
+    }
+    return s;
+}
+
 static labelList labelField(svof_handle* h, int which, label cap)
 {
     labelList l(cap, 0);

@@ -101,6 +101,11 @@ int main(int argc, char** argv)
     Info<< "plicSurface: " << surf.faces.size() << " polygons, " << surf.points.size() << " points; reconstructionTime "
         << plicVofSolver.reconstructionTime() << " s, advectionTime " << plicVofSolver.advectionTime() << " s" << endl;
 
+    // the second sampler's source (sampledReconstructedSubcellFaces.C:97-100)
+    geometricVofExt::SimPLIC::plicSurface sub =
+        mesh.lookupObjectRef<geometricVofExt::SimPLIC::reconstruction>("reconstruction").subCellFaces();
+    Info<< "subCellFaces: " << sub.faces.size() << " faces, " << sub.points.size() << " points" << endl;
+
     FILE* o = fopen(argv[2], "wb");
     fwrite(alpha1.primitiveField().cdata(), sizeof(double), size_t(nC), o);
     fwrite(plicVofSolver.alphaPhi().primitiveField().cdata(), sizeof(double), size_t(nIF), o);
@@ -108,6 +113,8 @@ int main(int argc, char** argv)
     fwrite(rhoPhi2().primitiveField().cdata(), sizeof(double), size_t(nIF), o);
     const int32_t nPoly = int32_t(surf.faces.size());
     fwrite(&nPoly, sizeof(int32_t), 1, o);
+    const int32_t nSub = int32_t(sub.faces.size());
+    fwrite(&nSub, sizeof(int32_t), 1, o);
     fclose(o);
     return 0;
 }

@@ -85,6 +85,45 @@ def test_step_parity_leveque(oracle, product, N, steps):
     assert sg.info(capi.I_ERROR_FLAGS) == 0
 
 
+def test_step_parity_64_from_the_golden_t15_field(oracle, product):
+    """The reference's own 64^3 case at its hardest instant: the golden exact field at t = 1.5 (maximum deformation,
+    6 094 interface cells in thin sheets -- where boundFlux chains, sliver sub-cells and < 3-point sub-faces occur),
+    advanced 40 steps with the driver's adaptive dt (maxCo = maxAlphaCo = 0.5) and phi(t), U(t) of updateU.H.
+    Every step: interface-cell list, cut status, N/D/C/S, Un0, alpha, alphaPhi, dVf and the bounding log bitwise."""
+    import os
+    N = 64
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "exact_alpha_64.npz"))
+    a0 = np.zeros(N ** 3)
+    a0[G["full_idx_1.5"]] = 1.0
+    a0[G["part_idx_1.5"]] = G["part_val_1.5"]
+    assert int(((a0 > 1e-8) & (a0 < 1 - 1e-8)).sum()) == 6094
+    m = meshmod.hex_block(N)
+    so, sg = _pair(m, LEVEQUE_CONTROLS, oracle, product)
+    drivers = []
+    for s in (so, sg):
+        s.setAlpha(a0)
+        d = fields.AdvectionDriver(s)
+        d.t, d.dt = 1.5, 2.0e-3
+        d.phi = d.phi0 * fields.u_factor(1.5, d.dt, 6.0)
+        drivers.append(d)
+    n_sweeps = 0
+    for k in range(40):
+        for d in drivers:
+            d.step()
+        assert drivers[0].dt == drivers[1].dt, "step %d: the two drivers chose different time steps" % k
+        assert np.array_equal(so.mixedCells(), sg.mixedCells()), "step %d: interface-cell set differs" % k
+        assert np.array_equal(so.cellStatus(), sg.cellStatus()), "step %d: cut status differs" % k
+        for name, f in (("N", capi.F_INTERFACE_N), ("D", capi.F_INTERFACE_D), ("C", capi.F_INTERFACE_C), ("S", capi.F_INTERFACE_S),
+                        ("Un0", capi.F_UN0), ("alpha", capi.F_ALPHA), ("alphaPhi", capi.F_ALPHA_PHI), ("dVf", capi.F_DVF)):
+            assert np.array_equal(so.field(f), sg.field(f)), "step %d: %s differs" % (k, name)
+        assert so.info(capi.I_N_BOUND_SWEEPS) == sg.info(capi.I_N_BOUND_SWEEPS)
+        n_sweeps += int(sg.info(capi.I_N_BOUND_SWEEPS))
+        for i in (capi.I_MIN_ALPHA_BEFORE, capi.I_MAX_ALPHA_M1_BEFORE, capi.I_MIN_ALPHA_AFTER, capi.I_MAX_ALPHA_M1_AFTER):
+            assert so.info(i) == sg.info(i)
+    assert len(sg.mixedCells()) > 5000 and n_sweeps > 0
+    assert sg.info(capi.I_ERROR_FLAGS) == 0
+
+
 def test_step_parity_clip_snap_sources(oracle, product):
     """damBreak-style controls (clip true, snapTol 1e-12, mixedCellTol 1e-10, nAlphaBounds 5:
     tutorials/solvers/interPlicFoam/damBreakWithObstacle/system/fvSolution) and non-zero Sp/Su
