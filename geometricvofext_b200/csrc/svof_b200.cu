@@ -175,6 +175,14 @@ struct svof_handle {
     double *dVal = nullptr, *hVal = nullptr;
     int capDelta = 0;
     // sparse phi upload (svof_step_host): bitmap over faces of the entries the step can depend on, host gather, device scatter
+    // orientationMethod isoRDF (lazily allocated): RDF field, zone bitmap/list, per-mixed-cell work arrays
+    double *rdf = nullptr, *rdfB = nullptr, *rdfNormal = nullptr, *rdfRes = nullptr, *rdfAng = nullptr, *rdfSave = nullptr;
+    unsigned int* rdfBits = nullptr;
+    int* rdfList = nullptr;
+    unsigned char* rdfCoarse = nullptr;
+    int capRdfList = 0, capRdfMixed = 0, nRdfPrev = 0, rdfIterations = 0;
+    std::vector<double> hRdfRes, hRdfAng;
+    std::vector<unsigned char> hRdfCoarse;
     int lastNU = 0, lastCntA = 0, lastCntF = 0;   // sizes of the previous step's lists: the speculative read-back sizes
     bool sparsePhi = true;           // "sparse_phi" option (only with sparse_io)
     bool phiBitsReady = false;       // the face bitmap of the CURRENT alpha is already on the host (prefetched by the previous svof_step_host)
@@ -1074,6 +1082,91 @@ void alphaBC(svof_handle* h)
         LAUNCH(h, k_alpha_bc, cdiv(h->nBF, 256), 256, h->md, h->dPatches, h->bPatch, h->alphaBuf[h->cur], h->phi, h->alphaBBuf[h->cb]);
 }
 
+void fetchCtl(svof_handle* h);
+// reconstruction::calcInterfaceNFromIsoRDF (reconstruction.C:196-405), driven from the host: the convergence test sums the
+// residuals of the mixed cells in list order (avgRes, avgNormRes), so they are read back and summed here each iteration.
+void rdfNormals(svof_handle* h, double* alpha)
+{
+    const MeshDev& d = h->md;
+    cudaStream_t s = h->stream;
+    if (h->capturing) throw std::runtime_error("isoRDF cannot be captured into a CUDA graph (host-side convergence test)");
+    const int g128 = sparseGrid(h, 128);
+    fetchCtl(h);
+    const int nMixed = h->hctl->nMixed;
+    h->rdfIterations = 0;
+    if (nMixed == 0) return;
+    if (!h->rdf) {
+        h->rdf = dalloc<double>(h, h->nC);
+        h->rdfB = dalloc<double>(h, std::max(h->nBF, 1));
+        h->rdfBits = dalloc<unsigned int>(h, h->nWords + 1);
+        h->capRdfList = h->nC;
+        h->rdfList = dalloc<int>(h, h->capRdfList, false);
+    }
+    if (nMixed > h->capRdfMixed) {   // per-mixed-cell arrays grow with the interface (the old ones stay in the handle's pool)
+        h->capRdfMixed = std::max(nMixed + nMixed / 2, 1 << 16);
+        h->rdfNormal = dalloc<double>(h, 3 * (size_t)h->capRdfMixed, false);
+        h->rdfRes = dalloc<double>(h, h->capRdfMixed, false);
+        h->rdfAng = dalloc<double>(h, h->capRdfMixed, false);
+        h->rdfSave = dalloc<double>(h, 8 * (size_t)h->capRdfMixed, false);
+        h->rdfCoarse = dalloc<unsigned char>(h, h->capRdfMixed, false);
+    }
+    // zone = mixed cells + point neighbours; a fresh RDF per call
+    if (h->nRdfPrev) LAUNCH(h, k_rdf_reset, g128, 128, d, h->rdfList, h->nRdfPrev, h->rdfBits, h->rdf, h->rdfB, 1);
+    CK(cudaMemsetAsync(&h->ctl->nRdf, 0, sizeof(int), s));
+    LAUNCH(h, k_rdf_mark, g128, 128, d, h->mixedCells, h->ctl, h->rdfBits, h->rdfList, h->capRdfList);
+    fetchCtl(h);
+    const int nRdf = std::min(h->hctl->nRdf, h->capRdfList);
+    h->nRdfPrev = nRdf;
+    LAUNCH(h, k_rdf_reset, g128, 128, d, h->rdfList, nRdf, h->rdfBits, h->rdf, h->rdfB, 0);
+    LAUNCH(h, k_rdf_grad, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->rdfNormal);   // :219
+    h->hRdfCoarse.assign(nMixed, 0);
+    h->hRdfRes.resize(nMixed);
+    h->hRdfAng.resize(nMixed);
+    CK(cudaMemsetAsync(h->rdfCoarse, 0, nMixed, s));
+    const double tol = h->prm.rdf_tol, relTol = h->prm.rdf_rel_tol;
+    const int iterations = h->prm.rdf_iterations;
+    for (int iter = 0; iter < iterations; ++iter) {
+        h->rdfIterations++;
+        LAUNCH(h, k_rdf_set_normals, g128, 128, h->mixedCells, h->ctl, h->rdfNormal, h->iN, h->rdfCoarse, h->cellStatus, h->iD, h->iC, h->iS,
+               h->rdfSave);
+        CK(cudaMemsetAsync(&h->ctl->plicNext, 0, sizeof(int), s));   // the batch counter of the persistent plane-positioning kernel
+        GEO(h, plic, s, h->plicCtas, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
+        LAUNCH(h, k_rdf_restore, g128, 128, h->mixedCells, h->ctl, h->rdfCoarse, h->cellStatus, h->iD, h->iC, h->iS, h->rdfSave);
+        LAUNCH(h, k_rdf_construct, g128, 128, d, h->rdfList, h->ctl, h->iN, h->iC, h->rdf, h->rdfB);
+        LAUNCH(h, k_rdf_grad, g128, 128, d, h->mixedCells, h->ctl, h->rdf, h->rdfB, h->sp, h->rdfNormal);                // :268
+        LAUNCH(h, k_rdf_residual, g128, 128, d, h->mixedCells, h->ctl, h->iN, h->rdfNormal, h->rdfRes, h->rdfAng);
+        CK(cudaMemcpyAsync(h->hRdfRes.data(), h->rdfRes, sizeof(double) * nMixed, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(h->hRdfAng.data(), h->rdfAng, sizeof(double) * nMixed, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        int resCounter = 0;
+        double avgRes = 0, avgNormRes = 0;
+        bool coarseChanged = false;
+        for (int i = 0; i < nMixed; ++i) {
+            const double normalRes = h->hRdfRes[i], avgA = h->hRdfAng[i];
+            if (avgA > 0.26 && iter > 0) {   // 15 deg
+                if (!h->hRdfCoarse[i]) coarseChanged = true;
+                h->hRdfCoarse[i] = 1;
+            } else {
+                avgRes += normalRes;
+                double normRes = 0;
+                const double discreteError = 0.01 * (avgA * avgA);
+                if (discreteError != 0) normRes = normalRes / std::max(discreteError, tol);
+                else normRes = normalRes / tol;
+                avgNormRes += normRes;
+                resCounter++;
+            }
+        }
+        if (resCounter == 0) {
+            resCounter = 1;
+            avgRes = 0;
+            avgNormRes = 0;
+        }
+        if (((avgNormRes / resCounter < relTol || avgRes / resCounter < tol) && iter >= 1) || iter + 1 == iterations) break;
+        if (coarseChanged) CK(cudaMemcpyAsync(h->rdfCoarse, h->hRdfCoarse.data(), nMixed, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemsetAsync(&h->ctl->plicNext, 0, sizeof(int), s));   // for the plane positioning of reconstruct() that follows
+}
+
 void doReconstruct(svof_handle* h)
 {
     const MeshDev& d = h->md;
@@ -1099,7 +1192,9 @@ void doReconstruct(svof_handle* h)
     h->inputsAfterNear = false;
     h->freshRecon = true;
     // A2: LS normals; A3-A5: plane positions
-    if (h->prm.orientation_method == SVOF_ORIENT_ALPHA_GRAD)
+    if (h->prm.orientation_method == SVOF_ORIENT_ISO_RDF)
+        rdfNormals(h, alpha);
+    else if (h->prm.orientation_method == SVOF_ORIENT_ALPHA_GRAD)
         LAUNCH(h, k_alpha_grad_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->iN);
     else
         LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
@@ -1321,8 +1416,8 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         if (!comm->nccl_unique_id) { g_createError = "svof_comm: world_size > 1 needs nccl_unique_id (svof_comm_unique_id on one rank, broadcast)"; return SVOF_ERR_INVALID_ARG; }
         if (!ncclApi().ok) { g_createError = "NCCL unavailable: " + ncclApi().why; return SVOF_ERR_COMM; }
     }
-    if (params->orientation_method == SVOF_ORIENT_ISO_RDF) {
-        g_createError = "orientationMethod isoRDF is not implemented (needs OpenFOAM's reconstructedDistanceFunction; SURVEY.md 8f)";
+    if (params->orientation_method == SVOF_ORIENT_ISO_RDF && comm && comm->world_size > 1) {
+        g_createError = "orientationMethod isoRDF in a decomposed run: the convergence sums (reconstruction.C:369-371) are not reduced across ranks yet";
         return SVOF_ERR_UNSUPPORTED;
     }
     if (params->n_alpha_bounds > SV_MAX_SWEEPS) { g_createError = "nAlphaBounds exceeds 32"; return SVOF_ERR_INVALID_ARG; }
@@ -1507,6 +1602,7 @@ void releaseMeshState(svof_handle* h)
     freeHost(h->hctl); freeHost(h->hpartial); freeHost(h->hUList); freeHost(h->hUPacked); freeHost(h->hIdx); freeHost(h->hVal);
     freeHost(h->hPhiBits); freeHost(h->hPhiBlockOff); freeHost(h->hPhiPacked);
     h->phiBits = nullptr; h->phiBlockOff = nullptr; h->phiPacked = nullptr; h->phiPartial = false;
+    h->rdf = nullptr; h->capRdfMixed = 0; h->nRdfPrev = 0;   // isoRDF buffers are re-created for the new mesh
     harvestEvents(h, true);
     h->halo = svof_handle::Halo();
     h->dfast = DenseFast();
@@ -1715,7 +1811,8 @@ int svof_step_device(svof_handle* h, double dt)
     if (!h->haveAlpha || !h->havePhi || !h->haveU) return fail(h, SVOF_ERR_STATE, "svof_step_device: alpha/phi/U not set");
     if (h->uPartial) return fail(h, SVOF_ERR_STATE, "svof_step_device: U on the device is the sparse upload of svof_step_host; call svof_set_U first");
     if (h->phiPartial) return fail(h, SVOF_ERR_STATE, "svof_step_device: phi on the device is the sparse upload of svof_step_host; call svof_set_phi first");
-    if (h->prof || h->epochBumps >= (1 << 25) - 4) {   // instrumented runs / tag wrap imminent: plain launches
+    if (h->prof || h->epochBumps >= (1 << 25) - 4 || h->prm.orientation_method == SVOF_ORIENT_ISO_RDF) {
+        // instrumented runs / tag wrap imminent / isoRDF (host-side convergence test): plain launches
         const int rc = svof_reconstruct(h);
         return rc ? rc : svof_advect(h, dt, nullptr, nullptr);
     }
@@ -2203,6 +2300,7 @@ int svof_get_info(svof_handle* h, int which, double* out)
             return SVOF_OK;
         }
         case SVOF_I_HALO_BYTES: *out = 8.0 * h->halo.cells.nRecv; return SVOF_OK;
+        case SVOF_I_RDF_ITERATIONS: *out = (double)h->rdfIterations; return SVOF_OK;
         case SVOF_I_GPU_LAUNCHES: *out = (double)h->launches; return SVOF_OK;
         case SVOF_I_FLATNESS_MIN: *out = h->flatMin; return SVOF_OK;
         case SVOF_I_FLATNESS_MAX: *out = h->flatMax; return SVOF_OK;

@@ -23,6 +23,7 @@ struct Ctl {
     int nMixed;   // mixedCells_.size()
     int nNear2;   // |near2|
     int nWork;    // (cut cell, downwind face) work items
+    int nRdf;     // cells of the isoRDF zone (mixed cells + their point neighbours)
     int nUCells;  // cells whose U the interface-velocity interpolation reads (end-to-end path)
     int plicNext; // batch counter of the persistent plane-positioning kernel
     int epoch;    // advect() counter kept on the DEVICE (a captured CUDA graph replays correctly): bounding tags derive from it
@@ -400,6 +401,67 @@ __device__ __forceinline__ bool sortedInsert(int* a, int& n, int cap, int v)
     ++n;
     return true;
 }
+// zoneCPCStencil of celli without the cell itself: cells sharing a vertex (ascending label) and valid boundary faces at its
+// vertices (ascending), in thread-local lists
+__device__ __forceinline__ void cpcStencilDev(const MeshDev& m, int celli, int* st, int& ns, int* sb, int& nb, int& err)
+{
+    ns = 0;
+    nb = 0;
+    for (int k = m.cellPtOff[celli]; k < m.cellPtOff[celli + 1]; ++k) {
+        const int p = m.cellPts[k];
+        for (int j = m.ptCellOff[p]; j < m.ptCellOff[p + 1]; ++j) {
+            const int c = m.ptCells[j];
+            if (c != celli && !sortedInsert(st, ns, SV_MAXST, c)) err |= SVERR_STENCIL;
+        }
+        for (int j = m.ptBFOff[p]; j < m.ptBFOff[p + 1]; ++j) {
+            const int bf = m.ptBFaces[j];
+            if (m.bKind[bf] == 0 && !sortedInsert(sb, nb, SV_MAXSB, bf)) err |= SVERR_STENCIL;
+        }
+    }
+}
+// leastSquareGrad<scalar>("polyDegree1", geometricD).grad over {celli} + stencil: cell values / boundary-face values
+__device__ __forceinline__ d3 lsGradDev(const MeshDev& m, const StepParams& sp, int celli, const int* st, int ns, const int* sb, int nb,
+                                        const double* __restrict__ cellVal, const double* __restrict__ bVal)
+{
+    int dims[3], nDims = 0;
+    for (int d = 0; d < 3; ++d)
+        if (sp.geomD[d] == 1) dims[nDims++] = d;
+    const int nTerms = 1 + nDims;
+    double A[4][4], src[4];
+    for (int r = 0; r < 4; ++r) {
+        src[r] = 0.0;
+        for (int q = 0; q < 4; ++q) A[r][q] = 0.0;
+    }
+    const d3 Ci = ld3(m.C, celli);
+    for (int s = -1; s < ns + nb; ++s) {
+        d3 pos;
+        double val;
+        if (s < 0) {
+            pos = Ci;
+            val = cellVal[celli];
+        } else if (s < ns) {
+            pos = ld3(m.C, st[s]);
+            val = cellVal[st[s]];
+        } else {
+            const int bf = sb[s - ns];
+            pos = ld3(m.Cf, m.nIF + bf);
+            val = bVal[bf];
+        }
+        pos -= Ci;
+        const double comp[3] = {pos.x, pos.y, pos.z};
+        double terms[4];
+        terms[0] = 1.0;
+        for (int d = 0; d < nDims; ++d) terms[d + 1] = comp[dims[d]];
+        for (int r = 0; r < nTerms; ++r) {
+            src[r] += terms[r] * val;
+            for (int q = 0; q < nTerms; ++q) A[r][q] += terms[r] * terms[q];
+        }
+    }
+    luSolve4(A, src, nTerms);
+    double g[3] = {0.0, 0.0, 0.0};
+    for (int d = 0; d < nDims; ++d) g[dims[d]] = src[d + 1];
+    return mk3(g[0], g[1], g[2]);
+}
 __global__ void __launch_bounds__(128) k_ls_normals(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
                                                     const double* __restrict__ alphaB, StepParams sp, double* iN)
 {
@@ -408,58 +470,204 @@ __global__ void __launch_bounds__(128) k_ls_normals(MeshDev m, const int* mixedC
         const int celli = mixedCells[i];
         int st[SV_MAXST], sb[SV_MAXSB];
         int ns = 0, nb = 0, err = 0;
-        for (int k = m.cellPtOff[celli]; k < m.cellPtOff[celli + 1]; ++k) {
-            const int p = m.cellPts[k];
-            for (int j = m.ptCellOff[p]; j < m.ptCellOff[p + 1]; ++j) {
-                const int c = m.ptCells[j];
-                if (c != celli && !sortedInsert(st, ns, SV_MAXST, c)) err |= SVERR_STENCIL;
-            }
-            for (int j = m.ptBFOff[p]; j < m.ptBFOff[p + 1]; ++j) {
-                const int bf = m.ptBFaces[j];
-                if (m.bKind[bf] == 0 && !sortedInsert(sb, nb, SV_MAXSB, bf)) err |= SVERR_STENCIL;
-            }
-        }
+        cpcStencilDev(m, celli, st, ns, sb, nb, err);
         if (err) atomicOr(&ctl->err, err);
-        int dims[3], nDims = 0;
-        for (int d = 0; d < 3; ++d)
-            if (sp.geomD[d] == 1) dims[nDims++] = d;
-        const int nTerms = 1 + nDims;
-        double A[4][4], src[4];
-        for (int r = 0; r < 4; ++r) {
-            src[r] = 0.0;
-            for (int q = 0; q < 4; ++q) A[r][q] = 0.0;
-        }
-        const d3 Ci = ld3(m.C, celli);
-        for (int s = -1; s < ns + nb; ++s) {
-            d3 pos;
-            double val;
-            if (s < 0) {
-                pos = Ci;
-                val = alpha[celli];
-            } else if (s < ns) {
-                pos = ld3(m.C, st[s]);
-                val = alpha[st[s]];
-            } else {
-                const int bf = sb[s - ns];
-                pos = ld3(m.Cf, m.nIF + bf);
-                val = alphaB[bf];
-            }
-            pos -= Ci;
-            const double comp[3] = {pos.x, pos.y, pos.z};
-            double terms[4];
-            terms[0] = 1.0;
-            for (int d = 0; d < nDims; ++d) terms[d + 1] = comp[dims[d]];
-            for (int r = 0; r < nTerms; ++r) {
-                src[r] += terms[r] * val;
-                for (int q = 0; q < nTerms; ++q) A[r][q] += terms[r] * terms[q];
-            }
-        }
-        luSolve4(A, src, nTerms);
-        double g[3] = {0.0, 0.0, 0.0};
-        for (int d = 0; d < nDims; ++d) g[dims[d]] = src[d + 1];
-        d3 nn = -mk3(g[0], g[1], g[2]);
+        d3 nn = -lsGradDev(m, sp, celli, st, ns, sb, nb, alpha, alphaB);
         nn /= (mag(nn) + SV_SMALL);
         st3(iN, celli, nn);
+    }
+}
+
+// ---- orientationMethod isoRDF (reconstruction::calcInterfaceNFromIsoRDF, reconstruction.C:196-405) ---------------------
+// The iteration is driven from the host (svof_b200.cu:rdfNormals): its convergence test needs sums over the mixed cells
+// in list order.  Not a hot path: no shipped case selects it; thread per item.
+
+// reconstructedDistanceFunction::markCellsNearSurf(isMixedCell, 1) (OF, recalled): the mixed cells and every cell sharing
+// a vertex with one, as bitmap + list
+__global__ void k_rdf_mark(MeshDev m, const int* mixedCells, Ctl* ctl, unsigned int* bits, int* list, int cap)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = mixedCells[i];
+        for (int k = m.cellPtOff[c]; k < m.cellPtOff[c + 1]; ++k) {
+            const int p = m.cellPts[k];
+            for (int j = m.ptCellOff[p]; j < m.ptCellOff[p + 1]; ++j) {   // the cell's own vertices list the cell itself
+                const int y = m.ptCells[j];
+                const unsigned int bit = 1u << (y & 31);
+                if (bits[y >> 5] & bit) continue;
+                const unsigned int old = atomicOr(&bits[y >> 5], bit);
+                if (!(old & bit)) {
+                    const int pos = atomicAdd(&ctl->nRdf, 1);
+                    if (pos < cap) list[pos] = y; else atomicOr(&ctl->err, SVERR_LIST);
+                }
+            }
+        }
+    }
+}
+// a fresh RDF object per call (reconstruction.C:204): zero where this call will read; forget the previous call's marks
+__global__ void k_rdf_reset(MeshDev m, const int* list, int n, unsigned int* bits, double* RDF, double* RDFb, int clearBits)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = list[i];
+        if (clearBits) { bits[c >> 5] = 0u; continue; }
+        RDF[c] = 0.0;
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int f = m.cellFaces[k];
+            if (f >= m.nIF) RDFb[f - m.nIF] = 0.0;
+        }
+    }
+}
+// isoInterfaceGrad (reconstruction.C:144-192): interfaceNormal[i] = LS gradient of a field (alpha, then the RDF)
+__global__ void __launch_bounds__(128) k_rdf_grad(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ cellVal,
+                                                  const double* __restrict__ bVal, StepParams sp, double* iNormal)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int celli = mixedCells[i];
+        int st[SV_MAXST], sb[SV_MAXSB];
+        int ns = 0, nb = 0, err = 0;
+        cpcStencilDev(m, celli, st, ns, sb, nb, err);
+        if (err) atomicOr(&ctl->err, err);
+        st3(iNormal, i, lsGradDev(m, sp, celli, st, ns, sb, nb, cellVal, bVal));
+    }
+}
+// Vector::normalise(tol) (OF, recalled), in place
+__device__ __forceinline__ d3 normaliseOF(d3 v, double tol)
+{
+    const double s = mag(v);
+    if (s < tol) return zero3();
+    v /= s;
+    return v;
+}
+// reconstruction.C:234-235: interfaceN = -interfaceNormal[i].normalise(SMALL) (the normalisation stays in interfaceNormal);
+// cells flagged too coarse keep D/C/S/status of their last evaluation: saved here, put back by k_rdf_restore after the
+// plane-positioning kernel has run over ALL mixed cells
+__global__ void k_rdf_set_normals(const int* mixedCells, Ctl* ctl, double* iNormal, double* iN, const unsigned char* coarse,
+                                  const int* cellStatus, const double* iD, const double* iC, const double* iS, double* save)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = mixedCells[i];
+        const d3 v = normaliseOF(ld3(iNormal, i), SV_SMALL);
+        st3(iNormal, i, v);
+        st3(iN, c, -v);
+        if (coarse[i]) {
+            double* s = save + 8 * (size_t)i;
+            s[0] = iD[c];
+            s[1] = iC[3 * (size_t)c]; s[2] = iC[3 * (size_t)c + 1]; s[3] = iC[3 * (size_t)c + 2];
+            s[4] = iS[3 * (size_t)c]; s[5] = iS[3 * (size_t)c + 1]; s[6] = iS[3 * (size_t)c + 2];
+            s[7] = (double)cellStatus[i];
+        }
+    }
+}
+__global__ void k_rdf_restore(const int* mixedCells, Ctl* ctl, const unsigned char* coarse, int* cellStatus, double* iD, double* iC,
+                              double* iS, const double* save)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (!coarse[i]) continue;
+        const int c = mixedCells[i];
+        const double* s = save + 8 * (size_t)i;
+        iD[c] = s[0];
+        iC[3 * (size_t)c] = s[1]; iC[3 * (size_t)c + 1] = s[2]; iC[3 * (size_t)c + 2] = s[3];
+        iS[3 * (size_t)c] = s[4]; iS[3 * (size_t)c + 1] = s[5]; iS[3 * (size_t)c + 2] = s[6];
+        cellStatus[i] = (int)s[7];
+    }
+}
+// reconstructedDistanceFunction::constructRDF (OF v2312, recalled; reconstruction.C:257-264 with centre = interfaceC,
+// normal = -interfaceN): weighted average of the distances to the planes of the stencil cells
+__device__ __forceinline__ void rdfAverage(const MeshDev& m, const d3& p, int celli, const int* st, int ns, const double* iN,
+                                           const double* iC, double& averageDist, double& avgWeight)
+{
+    averageDist = 0.0;
+    avgWeight = 0.0;
+    for (int s = -1; s < ns; ++s) {   // the cell itself first, then its point neighbours ascending; patch values of interfaceN are zero
+        const int g = (s < 0) ? celli : st[s];
+        d3 n = ld3(iN, g);
+        if (mag(n) != 0.0) {
+            n /= mag(n);
+            d3 d = ld3(iC, g) - p;
+            const double distToSurf = dot(d, n);
+            double weight;
+            if (mag(d) != 0.0) {
+                d /= mag(d);
+                const double a = fabs(dot(d, n));
+                weight = a * a;
+            } else {
+                weight = 1.0;
+            }
+            averageDist += distToSurf * weight;
+            avgWeight += weight;
+        }
+    }
+}
+__global__ void __launch_bounds__(128) k_rdf_construct(MeshDev m, const int* list, Ctl* ctl, const double* iN, const double* iC, double* RDF,
+                                                       double* RDFb)
+{
+    const int n = ctl->nRdf;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int celli = list[i];
+        int st[SV_MAXST], sb[SV_MAXSB];
+        int ns = 0, nb = 0, err = 0;
+        bool haveSt = false;
+        const d3 nI = ld3(iN, celli);
+        if (mag(nI) != 0.0) {   // interface cell: the distance of its own plane
+            const d3 nn = nI / mag(nI);
+            RDF[celli] = dot(ld3(iC, celli) - ld3(m.C, celli), nn);
+        } else {
+            cpcStencilDev(m, celli, st, ns, sb, nb, err);
+            haveSt = true;
+            double ad, aw;
+            rdfAverage(m, ld3(m.C, celli), celli, st, ns, iN, iC, ad, aw);
+            if (aw != 0.0) RDF[celli] = ad / aw;
+        }
+        for (int k = m.cellOff[celli]; k < m.cellOff[celli + 1]; ++k) {   // calculated patches: the same average at the face centre
+            const int f = m.cellFaces[k];
+            if (f < m.nIF || m.bKind[f - m.nIF] != 0) continue;
+            if (!haveSt) {
+                cpcStencilDev(m, celli, st, ns, sb, nb, err);
+                haveSt = true;
+            }
+            double ad, aw;
+            rdfAverage(m, ld3(m.Cf, f), celli, st, ns, iN, iC, ad, aw);
+            RDFb[f - m.nIF] = (aw != 0.0) ? ad / aw : 0.0;
+        }
+        if (err) atomicOr(&ctl->err, err);
+    }
+}
+// reconstruction.C:277-340: per mixed cell the normal residual and the mean angle to the normals of its stencil
+__global__ void __launch_bounds__(128) k_rdf_residual(MeshDev m, const int* mixedCells, Ctl* ctl, const double* iN, double* iNormal,
+                                                      double* normalRes, double* avgAngle)
+{
+    const int n = ctl->nMixed;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int celli = mixedCells[i];
+        int st[SV_MAXST], sb[SV_MAXSB];
+        int ns = 0, nb = 0, err = 0;
+        cpcStencilDev(m, celli, st, ns, sb, nb, err);
+        if (err) atomicOr(&ctl->err, err);
+        const d3 cellNormal = ld3(iN, celli);
+        d3 v = ld3(iNormal, i);
+        // `mag(N) < TSMALL or mag(interfaceNormal.normalise(SMALL)) < TSMALL`: the second operand (and its in-place
+        // normalisation) is only evaluated when the first is false
+        if (!(mag(cellNormal) < SV_TSMALL)) v = normaliseOF(v, SV_SMALL);
+        double avgDiffNormal = 0.0, maxDiffNormal = SV_GREAT, weight = 0.0;
+        for (int s = 0; s < ns; ++s) {   // j != 0: the cell itself is skipped; patch values of interfaceN are zero
+            const d3 normal = ld3(iN, st[s]);
+            const double mg = mag(normal);
+            if (mg >= SV_TSMALL) {
+                const d3 nn = normal / mg;
+                const double cosAngle = dmax(dmin(dot(cellNormal, nn), 1.0), -1.0);
+                avgDiffNormal += acos(cosAngle) * mg;
+                weight += mg;
+                if (cosAngle < maxDiffNormal) maxDiffNormal = cosAngle;
+            }
+        }
+        if (weight != 0.0) avgDiffNormal /= weight; else avgDiffNormal = 0.0;
+        v = normaliseOF(v, SV_SMALL);
+        st3(iNormal, i, v);
+        normalRes[i] = 1.0 - dot(cellNormal, -v);
+        avgAngle[i] = avgDiffNormal;
     }
 }
 

@@ -244,6 +244,7 @@ typedef enum {
     SVOF_I_D2H_BYTES = 20,       /* ... and device->host                          */
     SVOF_I_VOLUME_OWNED = 21,    /* sum(alpha*V) over the cells this rank owns (== VOLUME without ghosts) */
     SVOF_I_HALO_BYTES = 22,      /* bytes this rank receives per ghost refresh    */
+    SVOF_I_RDF_ITERATIONS = 23,  /* isoRDF: iterations the last reconstruct ran (reconstruction.C:228-399) */
     SVOF_I_COUNT_
 } svof_info;
 

@@ -122,8 +122,6 @@ struct Solver {
         for (const svof_patch& pt : mesh.patches)
             if (pt.kind == SVOF_PATCH_PROCESSOR && pt.size > 0)
                 throw std::invalid_argument("the CPU oracle is single-domain: processor patches are not supported");
-        if (prm.orientation_method == SVOF_ORIENT_ISO_RDF)
-            throw std::invalid_argument("orientationMethod isoRDF needs OpenFOAM's reconstructedDistanceFunction (not in the tree): not restated");
         const label nC = mesh.nCells, nF = mesh.nFaces;
         alpha.assign(nC, 0);
         alphaOld.assign(nC, 0);
@@ -273,47 +271,209 @@ struct Solver {
         }
     }
 
-    void calcInterfaceNFromIsoAlphaGrad()  // reconstruction.C:85-141
+    // leastSquareGrad<scalar>("polyDegree1", geometricD).grad(positions - C[celli], values) over the stencil st
+    // (multiDimPolyFitter::fitData: resetMatrix, fillMatrix per sample, LUsolve); cell values / boundary-face values
+    vec lsGrad(label celli, const std::vector<label>& st, const std::vector<scalar>& cellVal, const std::vector<scalar>& bVal) const
     {
         int nDims = 0;
         for (int d = 0; d < 3; ++d) nDims += (geomD[d] == 1);
         const int nTerms = 1 + nDims;
+        scalar A[4][4] = {{0}}, src[4] = {0};
+        for (label g : st) {
+            vec pos;
+            scalar val;
+            if (g < mesh.nCells) {
+                pos = mesh.C[g];
+                val = cellVal[g];
+            } else {
+                pos = mesh.Cf[mesh.nInternalFaces + (g - mesh.nCells)];
+                val = bVal[g - mesh.nCells];
+            }
+            pos -= mesh.C[celli];  // cellCentre -= mesh_.C()[celli]  (:133)
+            const scalar comp[3] = {pos.x, pos.y, pos.z};
+            scalar terms[4];
+            terms[0] = 1;  // polyDegree1::termValues
+            int dimCounter = 0;
+            for (int d = 0; d < 3; ++d)
+                if (geomD[d] == 1) terms[++dimCounter] = comp[d];
+            for (int r = 0; r < nTerms; ++r) {
+                src[r] += terms[r] * val;
+                for (int q = 0; q < nTerms; ++q) A[r][q] += terms[r] * terms[q];
+            }
+        }
+        LUsolve(A, src, nTerms);
+        scalar g3[3] = {0, 0, 0};
+        int dimCounter = 0;
+        for (int d = 0; d < 3; ++d)
+            if (geomD[d] == 1) g3[d] = src[++dimCounter];
+        return vec(g3[0], g3[1], g3[2]);
+    }
+
+    void calcInterfaceNFromIsoAlphaGrad()  // reconstruction.C:85-141
+    {
         std::vector<label> st;
         for (size_t i = 0; i < mixedCells.size(); ++i) {
             const label celli = mixedCells[i];
             cpcStencil(celli, st);
-            // multiDimPolyFitter::fitData: resetMatrix, fillMatrix per sample, LUsolve
-            scalar A[4][4] = {{0}}, src[4] = {0};
-            for (label g : st) {
-                vec pos;
-                scalar val;
-                if (g < mesh.nCells) {
-                    pos = mesh.C[g];
-                    val = alpha[g];
-                } else {
-                    pos = mesh.Cf[mesh.nInternalFaces + (g - mesh.nCells)];
-                    val = alphaB[g - mesh.nCells];
-                }
-                pos -= mesh.C[celli];  // cellCentre -= mesh_.C()[celli]  (:133)
-                const scalar comp[3] = {pos.x, pos.y, pos.z};
-                scalar terms[4];
-                terms[0] = 1;  // polyDegree1::termValues
-                int dimCounter = 0;
-                for (int d = 0; d < 3; ++d)
-                    if (geomD[d] == 1) terms[++dimCounter] = comp[d];
-                for (int r = 0; r < nTerms; ++r) {
-                    src[r] += terms[r] * val;
-                    for (int q = 0; q < nTerms; ++q) A[r][q] += terms[r] * terms[q];
-                }
-            }
-            LUsolve(A, src, nTerms);
-            scalar g3[3] = {0, 0, 0};
-            int dimCounter = 0;
-            for (int d = 0; d < 3; ++d)
-                if (geomD[d] == 1) g3[d] = src[++dimCounter];
-            interfaceN[celli] = -vec(g3[0], g3[1], g3[2]);  // :135
+            interfaceN[celli] = -lsGrad(celli, st, alpha, alphaB);  // :135
         }
         for (label c = 0; c < mesh.nCells; ++c) interfaceN[c] /= (mag(interfaceN[c]) + SMALL);  // :138
+    }
+
+    // Vector::normalise(tol) (OF, recalled): s = mag; s < tol ? Zero : v / s, in place
+    static vec& normalise(vec& v, scalar tol)
+    {
+        const scalar s = mag(v);
+        if (s < tol) v = vec(); else v /= s;
+        return v;
+    }
+
+    // reconstructedDistanceFunction::constructRDF (OF v2312 src/transportModels/geometricVoF/reconstructedDistanceFunction,
+    // recalled; called at reconstruction.C:257-264 with centre = interfaceC, normal = -interfaceN, updateStencil = false):
+    // interface cells get the signed distance of their own plane, the other cells of the zone a weighted average of the
+    // distances to the planes of their stencil cells, weight = cos^2 of the angle between the connection and the normal;
+    // calculated patches get the same average at their face centres.
+    void constructRDF(const std::vector<char>& nextToInterface, std::vector<scalar>& RDF, std::vector<scalar>& RDFb) const
+    {
+        std::vector<label> st;
+        auto average = [&](const vec& p, const std::vector<label>& stc, scalar& averageDist, scalar& avgWeight) {
+            averageDist = 0;
+            avgWeight = 0;
+            for (label g : stc) {
+                if (g >= mesh.nCells) continue;  // boundary values of interfaceN are zero (calculated patches of a zero field)
+                vec n = interfaceN[g];           // -(-interfaceN)
+                if (mag(n) != 0) {
+                    n /= mag(n);
+                    const vec c = interfaceC[g];
+                    vec distanceToIntSeg = c - p;
+                    const scalar distToSurf = distanceToIntSeg & n;
+                    scalar weight = 0;
+                    if (mag(distanceToIntSeg) != 0) {
+                        distanceToIntSeg /= mag(distanceToIntSeg);
+                        const scalar m_ = std::fabs(distanceToIntSeg & n);
+                        weight = m_ * m_;
+                    } else {
+                        weight = 1;
+                    }
+                    averageDist += distToSurf * weight;
+                    avgWeight += weight;
+                }
+            }
+        };
+        for (label celli = 0; celli < mesh.nCells; ++celli) {
+            if (!nextToInterface[celli]) {
+                RDF[celli] = 0;
+                continue;
+            }
+            if (mag(interfaceN[celli]) != 0) {  // interface cell
+                const vec n = interfaceN[celli] / mag(interfaceN[celli]);
+                RDF[celli] = (interfaceC[celli] - mesh.C[celli]) & n;
+            } else {
+                cpcStencil(celli, st);
+                scalar averageDist, avgWeight;
+                average(mesh.C[celli], st, averageDist, avgWeight);
+                if (avgWeight != 0) RDF[celli] = averageDist / avgWeight;
+            }
+        }
+        for (label bf = 0; bf < mesh.nBoundaryFaces(); ++bf) {
+            if (!mesh.isPatchFace[bf]) continue;  // calculated patches only (empty / coupled keep their constraint type)
+            const label pCellI = mesh.owner[mesh.nInternalFaces + bf];
+            if (!nextToInterface[pCellI]) {
+                RDFb[bf] = 0;
+                continue;
+            }
+            cpcStencil(pCellI, st);
+            scalar averageDist, avgWeight;
+            average(mesh.Cf[mesh.nInternalFaces + bf], st, averageDist, avgWeight);
+            RDFb[bf] = (avgWeight != 0) ? averageDist / avgWeight : 0;
+        }
+    }
+
+    label isoRDFIterationsDone = 0;   // for tests: iterations the last calcInterfaceNFromIsoRDF executed
+    void calcInterfaceNFromIsoRDF()  // reconstruction.C:196-405
+    {
+        const scalar TSMALL = 10.0 * SMALL;
+        const size_t nMixed = mixedCells.size();
+        std::vector<vec> interfaceNormal(nMixed);
+        std::vector<char> isMixedCell(mesh.nCells, 0), nextToInterface(mesh.nCells, 0);
+        for (label c : mixedCells) isMixedCell[c] = 1;
+        // reconstructedDistanceFunction::markCellsNearSurf(isMixedCell, 1) (OF, recalled): the interface cells and
+        // every cell sharing a vertex with one
+        for (label c : mixedCells) {
+            nextToInterface[c] = 1;
+            for (label k = 0; k < mesh.cellPoints.size(c); ++k) {
+                const label p = mesh.cellPoints.row(c)[k];
+                for (label j = 0; j < mesh.pointCells.size(p); ++j) nextToInterface[mesh.pointCells.row(p)[j]] = 1;
+            }
+        }
+        std::vector<std::vector<label>> stencil(nMixed);
+        for (size_t i = 0; i < nMixed; ++i) cpcStencil(mixedCells[i], stencil[i]);
+        for (size_t i = 0; i < nMixed; ++i) interfaceNormal[i] = lsGrad(mixedCells[i], stencil[i], alpha, alphaB);  // :219
+        // interfaceC_, interfaceN_ = Zero (:223-224): already zero after initialize()
+        std::vector<char> tooCoarse(mesh.nCells, 0);
+        std::vector<scalar> RDF(mesh.nCells, 0.0), RDFb(mesh.nBoundaryFaces(), 0.0);   // a fresh RDF object per call (:204)
+        std::vector<scalar> normalResNormalResidual(nMixed), normalResAvgAngle(nMixed);
+        isoRDFIterationsDone = 0;
+        for (label iter = 0; iter < prm.rdf_iterations; ++iter) {
+            ++isoRDFIterationsDone;
+            for (size_t i = 0; i < nMixed; ++i) {
+                const label celli = mixedCells[i];
+                interfaceN[celli] = -normalise(interfaceNormal[i], SMALL);
+                if (tooCoarse[celli]) continue;
+                cellStatus[i] = cutCell_->findSignedDistance(celli, alpha[celli], interfaceN[celli], prm.split_warped_face != 0,
+                                                             interfaceD[celli], interfaceC[celli], interfaceS[celli]);
+            }
+            constructRDF(nextToInterface, RDF, RDFb);   // updateContactAngle (:266): no contact-angle patches on this path
+            for (size_t i = 0; i < nMixed; ++i) interfaceNormal[i] = lsGrad(mixedCells[i], stencil[i], RDF, RDFb);  // :268
+            for (size_t i = 0; i < nMixed; ++i) {
+                const label celli = mixedCells[i];
+                if (mag(interfaceN[celli]) < TSMALL || mag(normalise(interfaceNormal[i], SMALL)) < TSMALL) {
+                    normalResNormalResidual[i] = 0.0;   // (:283-292 -- no `continue` in the reference: overwritten below)
+                    normalResAvgAngle[i] = 0.0;
+                }
+                scalar avgDiffNormal = 0, maxDiffNormal = GREAT, weight = 0;
+                const vec cellNormal = interfaceN[celli];
+                for (size_t j = 0; j < stencil[i].size(); ++j) {
+                    const label g = stencil[i][j];
+                    const vec normal = (g < mesh.nCells) ? interfaceN[g] : vec();
+                    if (mag(normal) >= TSMALL && j != 0) {
+                        const vec n = normal / mag(normal);
+                        const scalar cosAngle = std::max(std::min((cellNormal & n), 1.0), -1.0);
+                        avgDiffNormal += std::acos(cosAngle) * mag(normal);
+                        weight += mag(normal);
+                        if (cosAngle < maxDiffNormal) maxDiffNormal = cosAngle;
+                    }
+                }
+                if (weight != 0) avgDiffNormal /= weight; else avgDiffNormal = 0;
+                const vec newCellNormal = -normalise(interfaceNormal[i], SMALL);
+                normalResNormalResidual[i] = 1.0 - (cellNormal & newCellNormal);
+                normalResAvgAngle[i] = avgDiffNormal;
+            }
+            label resCounter = 0;
+            scalar avgRes = 0, avgNormRes = 0;
+            for (size_t i = 0; i < nMixed; ++i) {
+                const scalar normalRes = normalResNormalResidual[i], avgA = normalResAvgAngle[i];
+                if (avgA > 0.26 && iter > 0) {  // 15 deg
+                    tooCoarse[mixedCells[i]] = 1;
+                } else {
+                    avgRes += normalRes;
+                    scalar normRes = 0;
+                    const scalar discreteError = 0.01 * (avgA * avgA);
+                    if (discreteError != 0) normRes = normalRes / std::max(discreteError, prm.rdf_tol);
+                    else normRes = normalRes / prm.rdf_tol;
+                    avgNormRes += normRes;
+                    resCounter++;
+                }
+            }
+            if (resCounter == 0) {
+                resCounter = 1;
+                avgRes = 0;
+                avgNormRes = 0;
+            }
+            if (((avgNormRes / resCounter < prm.rdf_rel_tol || avgRes / resCounter < prm.rdf_tol) && iter >= 1) ||
+                iter + 1 == prm.rdf_iterations)
+                break;
+        }
     }
 
     // -------------------------------------------------------------- A3-A5 ---
@@ -337,6 +497,7 @@ struct Solver {
         Un0.assign(mixedCells.size(), 0.0);
         if (mixedCells.empty()) return;
         if (prm.orientation_method == SVOF_ORIENT_ALPHA_GRAD) calcInterfaceNFromRegAlphaGrad();  // reconstruction.C:694-713
+        else if (prm.orientation_method == SVOF_ORIENT_ISO_RDF) calcInterfaceNFromIsoRDF();
         else calcInterfaceNFromIsoAlphaGrad();
         for (size_t i = 0; i < mixedCells.size(); ++i) {
             const label c = mixedCells[i];

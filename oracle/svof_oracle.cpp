@@ -269,6 +269,7 @@ int svof_get_info(svof_handle* h, int which, double* out)
         case SVOF_I_N_NEAR: *out = 0; return SVOF_OK;
         case SVOF_I_H2D_BYTES: *out = 0; return SVOF_OK;
         case SVOF_I_D2H_BYTES: *out = 0; return SVOF_OK;
+        case SVOF_I_RDF_ITERATIONS: *out = double(s.isoRDFIterationsDone); return SVOF_OK;
     }
     return SVOF_ERR_INVALID_ARG;
 }

@@ -283,6 +283,10 @@ _POLY_CASES = {
     "warped hexes": (lambda: meshmod.perturb_points(meshmod.hex_block(12), 0.2, 3), {}),
     "warped hexes, splitWarpedFace": (lambda: meshmod.perturb_points(meshmod.hex_block(12), 0.2, 3), {"splitWarpedFace": True}),
     "Kelvin cells (14 faces, 24 points: polyDualMesh population)": (lambda: meshmod.kelvin_mesh(10), {}),
+    # orientationMethod isoRDF (reconstruction.C:196-405): host-driven iteration on the device, bitwise the oracle's
+    "hexes, isoRDF": (lambda: meshmod.hex_block(20), {"orientationMethod": "isoRDF"}),
+    "warped hexes, isoRDF": (lambda: meshmod.perturb_points(meshmod.hex_block(12), 0.2, 3), {"orientationMethod": "isoRDF"}),
+    "Kelvin cells, isoRDF, one iteration": (lambda: meshmod.kelvin_mesh(8), {"orientationMethod": "RDF", "iterations": 1}),
     # orientationMethod alphaGrad (reconstruction.C:74-82) on hexes and on polyhedra with non-orthogonal faces
     "hexes, alphaGrad": (lambda: meshmod.hex_block(14), {"orientationMethod": "alphaGrad"}),
     "refinement-interface polyhedra, alphaGrad": (lambda: meshmod.refined_interface_mesh(8), {"orientationMethod": "alphaGrad"}),
@@ -326,6 +330,7 @@ def test_step_parity_polyhedral(oracle, product, case):
         assert np.array_equal(ao, ag), "step %d: alpha not bitwise equal (max %g)" % (k, np.abs(ao - ag).max())
         assert np.array_equal(so.alphaPhi(), sg.alphaPhi())
         assert so.info(capi.I_N_BOUND_SWEEPS) == sg.info(capi.I_N_BOUND_SWEEPS)
+        assert so.info(capi.I_RDF_ITERATIONS) == sg.info(capi.I_RDF_ITERATIONS)
         n_mixed = max(n_mixed, len(sg.mixedCells()))
     assert n_mixed > 50
     assert abs(sg.volume() - v0) <= 1e-12 * abs(v0)   # rotation keeps the shape inside the domain
