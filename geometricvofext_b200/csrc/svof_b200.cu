@@ -200,6 +200,9 @@ struct svof_handle {
     DenseStage dstage;
     size_t dstageSmem = 0;
     bool useStaged = false;
+    DenseSliced dsliced;             // sliced, transposed rows of the streaming kernel (k_dense_update4); SVOF_DENSE_V4 / "dense_v4"
+    bool denseV4 = false;
+    bool denseV3 = false;            // k_dense_update3 (batched loads); SVOF_DENSE_V3 / option "dense_v3"
     DenseFast dfast;                 // owner-sorted connectivity of the streaming kernel (k_dense_update2)
     bool boundLanes = true;          // k_bound_run8 (SVOF_BOUND_LANES=0: the sequential walker)
     bool un0Group = false;           // 8 lanes per cut cell for the interface speed (SVOF_UN0=thread: round-1 thread-per-cell kernel)
@@ -693,6 +696,29 @@ void buildMesh(svof_handle* h, const svof_mesh& m)
     h->dstageSmem = (size_t)(h->dstage.rowCap + 2) * 8 + (size_t)(h->dstage.phiCap + 2) * 8;
     // measured (profiles/r1l_*): 0.431 ms for the CSR kernel vs 0.556 ms staged -> staged is opt-in (SVOF_DENSE_STAGED=1)
     h->useStaged = getenv("SVOF_DENSE_STAGED") && atoi(getenv("SVOF_DENSE_STAGED")) > 0;
+    h->denseV3 = getenv("SVOF_DENSE_V3") && atoi(getenv("SVOF_DENSE_V3")) > 0;
+    h->denseV4 = getenv("SVOF_DENSE_V4") && atoi(getenv("SVOF_DENSE_V4")) > 0;
+    h->dsliced.enabled = 0;
+    if (h->denseV4) {   // sliced, transposed rows: per 32 consecutive cells, entry q of all 32 rows contiguous, padded to the widest row
+        // measured at 256^3 (profiles/r2w_dense_variants.txt): 504 us against 426 us for the strided int2 rows -- the strided rows
+        // act as a prefetch (one DRAM access brings the lines of the next five iterations into L1) -> opt-in, built on request only
+        const int nSl = (nC + 31) / 32;
+        std::vector<int> sliceOff(nSl + 1, 0);
+        for (int sl = 0; sl < nSl; ++sl) {
+            int w = 0;
+            for (int c = sl * 32; c < std::min(nC, sl * 32 + 32); ++c) w = std::max(w, cellOff[c + 1] - cellOff[c]);
+            sliceOff[sl + 1] = sliceOff[sl] + w;
+        }
+        std::vector<int2> rowsT((size_t)sliceOff[nSl] * 32, make_int2(SV_ROW_PAD, SV_ROW_PAD));
+        for (int c = 0; c < nC; ++c) {
+            const size_t base = (size_t)sliceOff[c >> 5] * 32 + (c & 31);
+            for (int k = cellOff[c]; k < cellOff[c + 1]; ++k) rowsT[base + (size_t)(k - cellOff[c]) * 32] = cellAsc[k];
+        }
+        h->dsliced.rowsT = dupload(h, rowsT.data(), rowsT.size());
+        h->dsliced.sliceOff = dupload(h, sliceOff.data(), sliceOff.size());
+        h->dsliced.enabled = 1;
+        CK(cudaStreamSynchronize(h->stream));
+    }
     CK(cudaFuncSetAttribute(k_dense_update_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dstageSmem));
     h->bPatch = dupload(h, bPatch.data(), bPatch.size());
     h->dfast.enabled = dfOk ? 1 : 0;
@@ -1231,6 +1257,12 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         if (h->useStaged)
             k_dense_update_staged<<<nTiles, 256, h->dstageSmem, sD>>>(d, h->dstage, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi,
                                                                     h->near2, h->mixedBits, dt, rDt, dSp, dSu, h->sp, h->ctl);
+        else if (h->denseV4 && h->dsliced.enabled)
+            k_dense_update4<<<nTiles, 256, 0, sD>>>(d, h->dsliced, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
+                                                    dt, rDt, dSp, dSu, h->sp, h->ctl);
+        else if (h->denseV3)
+            k_dense_update3<<<nTiles, 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits, dt, rDt,
+                                                    dSp, dSu, h->sp, h->ctl);
         else if (h->dfast.enabled)
             k_dense_update2<<<grid, 256, 0, sD>>>(d, h->dfast, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
                                                   dt, rDt, dSp, dSu, h->sp, h->ctl, nTiles);
@@ -2364,6 +2396,8 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
     if (!strcmp(name, "bound_lanes")) { h->boundLanes = value != 0; for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "dense_v4")) { h->denseV4 = value != 0 && h->dsliced.enabled; for (auto& g : h->graphs) g.sched = -1; return SVOF_OK; }
+    if (!strcmp(name, "dense_v3")) { h->denseV3 = value != 0; for (auto& g : h->graphs) g.sched = -1; return SVOF_OK; }
     if (!strcmp(name, "sparse_phi")) { h->sparsePhi = value != 0; return SVOF_OK; }
     if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; h->phiBitsReady = false; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");

@@ -1389,6 +1389,190 @@ __global__ void __launch_bounds__(256, SV_DMINB) k_dense_update2(MeshDev m, Dens
   blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
 }
 
+// K7, batched variant (round 2).  Same rows, arithmetic, summation order and outputs as k_dense_update; what changes is the
+// shape of the memory traffic.  ncu of k_dense_update: 456 executed instructions per cell, issue slots 50 % busy, one or two
+// loads in flight per thread (row entry -> phi -> alpha is a dependent chain walked face by face through a branchy loop).
+// Here a cell with six faces and a 16-byte aligned row (every cell of a hexahedral mesh) loads its whole row with three
+// 16-byte requests, then issues the six phi gathers back to back, then the (predicated) alpha gathers, and only then does
+// the arithmetic in ascending face order: up to six independent loads in flight per thread and no loop-carried branches.
+// Other cells take the generic loop.
+#ifndef SV_D3MINB
+#define SV_D3MINB 5
+#endif
+__global__ void __launch_bounds__(256, SV_D3MINB) k_dense_update3(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                                                  const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                                                  double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
+                                                                  unsigned int* __restrict__ mixedNext, double dt, double rDt,
+                                                                  const double* __restrict__ Sp, const double* __restrict__ Su, StepParams sp,
+                                                                  Ctl* ctl)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    bool mixed = false;
+    if (c < m.nCells && !bitTest(near2, c)) {
+        const int k0 = __ldg(m.cellOff + c), k1 = __ldg(m.cellOff + c + 1);
+        const double aC = __ldg(aOld + c);
+        double sum = 0.0;
+        if (k1 - k0 == 6 && (k0 & 1) == 0) {
+            int ex[6], ey[6];
+            {
+                const int4* row = reinterpret_cast<const int4*>(m.cellAsc + k0);
+                const int4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2);
+                ex[0] = r0.x; ey[0] = r0.y; ex[1] = r0.z; ey[1] = r0.w;
+                ex[2] = r1.x; ey[2] = r1.y; ex[3] = r1.z; ey[3] = r1.w;
+                ex[4] = r2.x; ey[4] = r2.y; ex[5] = r2.z; ey[5] = r2.w;
+            }
+            double ph[6], aUp[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) ph[q] = __ldg(phi + (ex[q] & 0x7fffffff));
+            bool skip[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const bool flip = ex[q] < 0;
+                skip[q] = false;
+                if (ey[q] >= 0) {
+                    const bool selfUp = flip ? (ph[q] < 0) : (ph[q] >= 0);
+                    aUp[q] = aC;
+                    if (!selfUp) aUp[q] = __ldg(aOld + ey[q]);
+                } else {
+                    const int bf = -1 - ey[q];
+                    skip[q] = (__ldg(m.bKind + bf) == 1);   // empty patch: no field
+                    aUp[q] = __ldg(alphaB + bf);
+                }
+            }
+            double dvf[6];
+            bool anyNZ = false;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                dvf[q] = (ph[q] * aUp[q]) * dt;
+                anyNZ |= (!skip[q] && dvf[q] != 0.0);
+            }
+            const bool warpNZ = __any_sync(__activemask(), anyNZ);   // x/dt == x bitwise for x = +-0: skip the divides where the warp is empty
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                if (skip[q]) continue;
+                if (ex[q] >= 0) {
+                    sum += dvf[q];
+                    double ap = dvf[q];
+                    if (warpNZ) ap = (ap == 0.0) ? ap : ap / dt;
+                    alphaPhi[ex[q]] = ap;
+                } else {
+                    sum -= dvf[q];
+                }
+            }
+        } else {
+            for (int k = k0; k < k1; ++k) {
+                const int2 e = __ldg(m.cellAsc + k);
+                const int f = e.x & 0x7fffffff;
+                const bool flip = e.x < 0;
+                const double p = __ldg(phi + f);
+                double a;
+                if (e.y >= 0) {
+                    const bool selfUp = flip ? (p < 0) : (p >= 0);
+                    a = selfUp ? aC : __ldg(aOld + e.y);
+                } else {
+                    const int bf = -1 - e.y;
+                    if (__ldg(m.bKind + bf) == 1) continue;
+                    a = __ldg(alphaB + bf);
+                }
+                const double d = (p * a) * dt;
+                if (!flip) {
+                    sum += d;
+                    alphaPhi[f] = divz(d, dt);
+                } else {
+                    sum -= d;
+                }
+            }
+        }
+        const double ivf = divz(sum, __ldg(m.V + c));
+        double num = aC * rDt;
+        if (Su) num = num + Su[c];
+        num = num - ivf * rDt;
+        double a = divz(num, (Sp ? (rDt - Sp[c]) : rDt));
+        mn = a;
+        mx = a;
+        a = snapClip(a, sp.snapTol, sp.clip);
+        aNew[c] = a;
+        mixed = (sp.mixedTol < a) && (a < 1.0 - sp.mixedTol);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, mixed);
+    if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
+    blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
+}
+
+// K7 over a sliced, transposed copy of the rows (round 2).  k_dense_update reads its int2 rows with a 48-byte stride between
+// the lanes of a warp: every load instruction touches 12 lines for 256 useful bytes and relies on L1 to keep them for the
+// next five iterations (ncu: 63 % of the L2->L1 sectors "excessive", L1 hit rate 52 %).  Here the rows of each group of 32
+// consecutive cells are stored entry-major -- entry q of the 32 cells contiguous -- so each row load is one fully used
+// 256-byte request and L1 is left to the phi / alpha gathers.  Same arithmetic, summation order and outputs; the loop trip
+// count is the widest row of the slice (warp uniform), shorter rows are padded with a sentinel.
+#define SV_ROW_PAD ((int)0x80000000)   // {PAD, PAD}: e.y == INT_MIN is no cell and no boundary face
+struct DenseSliced {
+    const int2* rowsT;     // [sliceOff[nSlices] * 32]
+    const int* sliceOff;   // [nSlices + 1], in units of 32 entries
+    int enabled;
+};
+__global__ void __launch_bounds__(256, 8) k_dense_update4(MeshDev m, DenseSliced ds, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                                          const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                                          double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
+                                                          unsigned int* __restrict__ mixedNext, double dt, double rDt,
+                                                          const double* __restrict__ Sp, const double* __restrict__ Su, StepParams sp,
+                                                          Ctl* ctl)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    bool mixed = false;
+    const bool inRange = c < m.nCells;
+    const int slice = c >> 5;
+    int b0 = 0, b1 = 0;
+    if (((slice << 5) < m.nCells)) {
+        b0 = __ldg(ds.sliceOff + slice);
+        b1 = __ldg(ds.sliceOff + slice + 1);
+    }
+    const bool work = inRange && !bitTest(near2, c);
+    const double aC = inRange ? __ldg(aOld + c) : 0.0;
+    double sum = 0.0;
+    for (int q = b0; q < b1; ++q) {
+        const int2 e = __ldg(ds.rowsT + ((size_t)q << 5) + lane);
+        if (!work || (e.x == SV_ROW_PAD && e.y == SV_ROW_PAD)) continue;
+        const int f = e.x & 0x7fffffff;
+        const bool flip = e.x < 0;
+        const double ph = __ldg(phi + f);
+        double aUp;
+        if (e.y >= 0) {
+            const bool selfUp = flip ? (ph < 0) : (ph >= 0);
+            aUp = selfUp ? aC : __ldg(aOld + e.y);
+        } else {
+            const int bf = -1 - e.y;
+            if (__ldg(m.bKind + bf) == 1) continue;  // empty patch: no field
+            aUp = __ldg(alphaB + bf);
+        }
+        const double dvf = (ph * aUp) * dt;
+        if (!flip) {
+            sum += dvf;
+            alphaPhi[f] = divz(dvf, dt);
+        } else {
+            sum -= dvf;
+        }
+    }
+    if (work) {
+        const double ivf = divz(sum, __ldg(m.V + c));
+        double num = aC * rDt;
+        if (Su) num = num + Su[c];
+        num = num - ivf * rDt;
+        double a = divz(num, (Sp ? (rDt - Sp[c]) : rDt));
+        mn = a;
+        mx = a;
+        a = snapClip(a, sp.snapTol, sp.clip);
+        aNew[c] = a;
+        mixed = (sp.mixedTol < a) && (a < 1.0 - sp.mixedTol);
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, mixed);
+    if (lane == 0 && inRange) mixedNext[c >> 5] = w;
+    blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
+}
+
 // K7, staged variant: the same arithmetic as k_dense_update, but the CTA first copies (cp.async, 16-byte
 // requests, no registers) its contiguous slab of cell->face rows and the phi values of the faces its cells
 // OWN (contiguous too: OpenFOAM orders internal faces by owner) into shared memory.  That turns the two
