@@ -1,7 +1,7 @@
 """Per-kernel summary of one step from an ncu launch list:
     ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file L.csv python bench.py --steps 2 --warmup 3 ...
     python scripts/launch_summary.py L.csv > profiles/<round>_launch_summary.txt
-The LAST complete step in the list (k_clear_prev .. k_alpha_bc) is summarised; ncu times are serialised and cold-cache."""
+The LAST complete step in the list (k_front_count .. k_alpha_bc) is summarised; ncu times are serialised and cold-cache."""
 import csv, re, sys
 from collections import OrderedDict
 
@@ -17,7 +17,7 @@ for r in csv.DictReader(lines):
             v *= 1e3
         name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("svof::", "")
         rows.append((name, v))
-starts = [i for i, (n, _) in enumerate(rows) if n.startswith("k_clear_prev")]
+starts = [i for i, (n, _) in enumerate(rows) if n.startswith("k_front_count") or n.startswith("k_clear_prev")]
 ends = [i for i, (n, _) in enumerate(rows) if n.startswith("k_alpha_bc")]
 ends = [e for e in ends if any(s < e for s in starts)]
 step = None
