@@ -337,11 +337,14 @@ def run_ours(args):
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "full_field_bytes_per_step": {"h2d": 8 * (s.nF + 3 * s.nC + 3 * s.nBF), "d2h": 8 * (s.nC + s.nF)},
                 "note": "svof_step_host with pinned host buffers for phi, U, Ub in and alpha, alphaPhi out; phi and U are rescaled on "
-                        "the host between calls (every entry changes), only the calls are timed.  The library copies up the phi "
-                        "entries of faces next to a cell with alpha != 0 plus all boundary faces (the others multiply an exactly zero "
-                        "alpha) and the rows of U next to cut cells, and reads back alpha/alphaPhi as deltas; the caller's output "
-                        "buffers hold the complete new fields after every call (bitwise equal to full-field calls: "
-                        "tests/test_gpu_parity.py::test_step_host_sparse_phi_upload_is_bitwise_the_full_upload)"},
+                        "the host between calls (every entry changes), only the calls are timed.  With pinned caller buffers the "
+                        "kernels read the caller's phi / U and write its alpha / alphaPhi directly over PCIe (zero copy, one host "
+                        "wait per call): phi on boundary faces and on internal faces with alpha != 0 in one of the two cells (the "
+                        "others multiply an exactly zero alpha), the rows of U next to cut cells, the alpha cells whose bits "
+                        "changed and alphaPhi on the marked faces; the caller's output buffers hold the complete new fields after "
+                        "every call (bitwise equal to full-field calls: "
+                        "tests/test_gpu_parity.py::test_step_host_sparse_phi_upload_is_bitwise_the_full_upload).  The byte counts "
+                        "are those of the last timed call: with snapTol 0 the support of alpha grows by one cell layer per step."},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "k_dense_update", "kernel_ms": dense_ms,

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -185,12 +186,25 @@ struct svof_handle {
     std::vector<unsigned char> hRdfCoarse;
     int lastNU = 0, lastCntA = 0, lastCntF = 0;   // sizes of the previous step's lists: the speculative read-back sizes
     bool sparsePhi = true;           // "sparse_phi" option (only with sparse_io)
+    double sparsePhiTol = 0.0;       // "sparse_phi_exp" option e > 0: cells with |alpha| <= 10^-e count as empty for the phi upload (0: exact)
+    // zero-copy host path (svof_step_host with pinned caller buffers): two device face bitmaps (this step's and the previous one's)
+    bool zeroCopy = true;            // "zero_copy" option
+    unsigned int* zcBits[2] = {nullptr, nullptr};
+    int zcCur = 0;
+    bool zcPrevValid = false;        // zcBits[zcCur] describes the alphaPhi the caller's buffer holds
+    std::map<const void*, void*> pinnedCache;   // caller pointer -> device pointer (nullptr: not device-accessible host memory)
+    const unsigned int* boundPhiBits = nullptr;   // set by svof_step_host around its doAdvect: see k_bound_apply
     bool phiBitsReady = false;       // the face bitmap of the CURRENT alpha is already on the host (prefetched by the previous svof_step_host)
     bool phiPartial = false;         // device phi holds stale values on faces between exactly empty cells: not a full field
     int nWordsF = 0, nPhiBlocks = 0;
     size_t capPhiPacked = 0;
-    unsigned int *phiBits = nullptr, *hPhiBits = nullptr;
-    int *phiBlockOff = nullptr, *hPhiBlockOff = nullptr;
+    unsigned int *phiBits = nullptr, *hPhiBits2[2] = {nullptr, nullptr};   // host bitmaps double-buffered: this call's and the
+    int *phiBlockOff = nullptr, *hPhiBlockOff2[2] = {nullptr, nullptr};    // previous call's / the prefetched next one
+    int pb = 0;                      // host buffer holding the bitmap of the current (or last) call
+    bool phiPrevBitsValid = false;   // the other host buffer holds the bitmap of the previous sparse call (alphaPhi read-back)
+    bool alphaPhiPrevValid = false;  // alphaPhiPrev mirrors the caller's alphaPhi buffer (delta read-back)
+    long long phiTotal = 0;          // marked faces of the current bitmap
+    std::vector<int> phiCut;         // block boundaries of the equal-share split of the marked faces over the host threads
     double *phiPacked = nullptr, *hPhiPacked = nullptr;
     cudaEvent_t evBits = nullptr;
     HostPool* pool = nullptr;
@@ -1297,19 +1311,19 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
 #define BOUND_SWEEP(MB)                                                                                                       \
     do {                                                                                                                     \
         LAUNCH(h, k_bound_deps<MB>, gB, 128, d, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, \
-               dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList);           \
+               dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList, h->boundPhiBits); \
         LAUNCH(h, k_bound_run<MB>, 16 * h->sms, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx, \
                (const CellBound<MB>*)h->boundRecs, h->capRec, dt, rDt);                                                      \
         LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs,               \
-               h->oobList[(sidx + 1) & 1], h->oobState);                                                                     \
+               h->oobList[(sidx + 1) & 1], h->oobState, h->boundPhiBits);                                                                     \
     } while (0)
         if (h->maxCF <= 8 && h->boundLanes) {   // eight faces in eight lanes of the chain walker's warp
             LAUNCH(h, k_bound_deps<8>, gB, 128, d, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, dSu, h->bs,
-                   h->depInit, h->depLeft, h->oobIdx, (CellBound<8>*)h->boundRecs, h->capRec, h->affList);
+                   h->depInit, h->depLeft, h->oobIdx, (CellBound<8>*)h->boundRecs, h->capRec, h->affList, h->boundPhiBits);
             LAUNCH(h, k_bound_run8, 16 * h->sms, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx,
                    (const CellBound<8>*)h->boundRecs, h->capRec, dt, rDt);
             LAUNCH(h, k_bound_apply<8>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs, h->oobList[(sidx + 1) & 1],
-                   h->oobState);
+                   h->oobState, h->boundPhiBits);
         } else if (h->maxCF <= 8) BOUND_SWEEP(8);
         else if (h->maxCF <= 16) BOUND_SWEEP(16);
         else BOUND_SWEEP(64);
@@ -1522,8 +1536,10 @@ int svof_destroy(svof_handle* h)
     if (h->hUPacked) cudaFreeHost(h->hUPacked);
     if (h->hIdx) cudaFreeHost(h->hIdx);
     if (h->hVal) cudaFreeHost(h->hVal);
-    if (h->hPhiBits) cudaFreeHost(h->hPhiBits);
-    if (h->hPhiBlockOff) cudaFreeHost(h->hPhiBlockOff);
+    for (int i = 0; i < 2; ++i) {
+        if (h->hPhiBits2[i]) cudaFreeHost(h->hPhiBits2[i]);
+        if (h->hPhiBlockOff2[i]) cudaFreeHost(h->hPhiBlockOff2[i]);
+    }
     if (h->hPhiPacked) cudaFreeHost(h->hPhiPacked);
     if (h->evBits) cudaEventDestroy(h->evBits);
     delete h->pool;
@@ -1632,9 +1648,12 @@ void releaseMeshState(svof_handle* h)
     h->bytes = 0;
     auto freeHost = [](auto*& p) { if (p) cudaFreeHost(p); p = nullptr; };
     freeHost(h->hctl); freeHost(h->hpartial); freeHost(h->hUList); freeHost(h->hUPacked); freeHost(h->hIdx); freeHost(h->hVal);
-    freeHost(h->hPhiBits); freeHost(h->hPhiBlockOff); freeHost(h->hPhiPacked);
+    for (int i = 0; i < 2; ++i) { freeHost(h->hPhiBits2[i]); freeHost(h->hPhiBlockOff2[i]); }
+    freeHost(h->hPhiPacked);
+    h->phiPrevBitsValid = h->alphaPhiPrevValid = false;
     h->phiBits = nullptr; h->phiBlockOff = nullptr; h->phiPacked = nullptr; h->phiPartial = false;
     h->rdf = nullptr; h->capRdfMixed = 0; h->nRdfPrev = 0;   // isoRDF buffers are re-created for the new mesh
+    h->zcBits[0] = h->zcBits[1] = nullptr; h->zcPrevValid = false;
     harvestEvents(h, true);
     h->halo = svof_handle::Halo();
     h->dfast = DenseFast();
@@ -1929,13 +1948,13 @@ HostPool& hostPool(svof_handle* h)
 }
 
 // face bitmap of the current alpha + marked faces per 1024-face block, and their read-back, on stream s
-void enqueuePhiBits(svof_handle* h, cudaStream_t s)
+void enqueuePhiBits(svof_handle* h, cudaStream_t s, int buf)
 {
     CK(cudaMemsetAsync(h->phiBlockOff, 0, sizeof(int) * ((size_t)h->nPhiBlocks + 1), s));
-    k_phi_need_bits<<<cdiv((long long)h->nWordsF * 32, 256), 256, 0, s>>>(h->md, h->alphaBuf[h->cur], h->phiBits, h->nWordsF, h->phiBlockOff);
+    k_phi_need_bits<<<cdiv((long long)h->nWordsF * 32, 256), 256, 0, s>>>(h->md, h->alphaBuf[h->cur], h->phiBits, h->nWordsF, h->phiBlockOff, h->sparsePhiTol);
     h->launches++;
-    CK(cudaMemcpyAsync(h->hPhiBits, h->phiBits, sizeof(unsigned int) * h->nWordsF, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(h->hPhiBlockOff, h->phiBlockOff, sizeof(int) * ((size_t)h->nPhiBlocks + 1), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hPhiBits2[buf], h->phiBits, sizeof(unsigned int) * h->nWordsF, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->hPhiBlockOff2[buf], h->phiBlockOff, sizeof(int) * ((size_t)h->nPhiBlocks + 1), cudaMemcpyDeviceToHost, s));
 }
 
 // phi of this step, sparse form: enqueue the face bitmap (streamD) and its read-back; see k_phi_need_bits.
@@ -1948,21 +1967,26 @@ void sparsePhiBegin(svof_handle* h)
         h->phiBits = dalloc<unsigned int>(h, (size_t)h->nPhiBlocks * 32);
         h->phiBlockOff = dalloc<int>(h, (size_t)h->nPhiBlocks + 1);
         h->phiPacked = dalloc<double>(h, h->capPhiPacked, false);
-        CK(cudaMallocHost((void**)&h->hPhiBits, sizeof(unsigned int) * (size_t)h->nPhiBlocks * 32));
-        CK(cudaMallocHost((void**)&h->hPhiBlockOff, sizeof(int) * ((size_t)h->nPhiBlocks + 1)));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaMallocHost((void**)&h->hPhiBits2[i], sizeof(unsigned int) * (size_t)h->nPhiBlocks * 32));
+            CK(cudaMallocHost((void**)&h->hPhiBlockOff2[i], sizeof(int) * ((size_t)h->nPhiBlocks + 1)));
+            memset(h->hPhiBits2[i], 0, sizeof(unsigned int) * (size_t)h->nPhiBlocks * 32);
+        }
         CK(cudaMallocHost((void**)&h->hPhiPacked, sizeof(double) * h->capPhiPacked));
-        memset(h->hPhiBits, 0, sizeof(unsigned int) * (size_t)h->nPhiBlocks * 32);
+        h->phiPrevBitsValid = false;
         if (!h->evBits) CK(cudaEventCreateWithFlags(&h->evBits, cudaEventDisableTiming));
         CK(cudaStreamSynchronize(h->stream));   // the zero fills above are ordered on the main stream
     }
-    if (h->phiBitsReady) return;   // prefetched at the end of the previous call
-    enqueuePhiBits(h, h->streamD);
+    h->pb ^= 1;                    // the bitmap of this call lives in the other host buffer: the previous call's stays readable
+    if (h->phiBitsReady) return;   // prefetched (into that buffer) at the end of the previous call
+    h->phiPrevBitsValid = false;   // alpha was changed behind the host path: the old bitmap describes nothing the caller holds
+    enqueuePhiBits(h, h->streamD, h->pb);
     CK(cudaEventRecord(h->evBits, h->streamD));
 }
 
 // ... gather the marked entries of the caller's phi (host threads), copy them up and scatter them (streamD).
 // Returns false when too many faces are marked: the caller copies the full field instead.
-bool sparsePhiFinish(svof_handle* h, const double* phi)
+bool sparsePhiFinish(svof_handle* h, const double* phi, double* zeroStaleIn)
 {
     if (!h->phiBitsReady) {
         CK(cudaEventSynchronize(h->evBits));
@@ -1972,8 +1996,8 @@ bool sparsePhiFinish(svof_handle* h, const double* phi)
     h->d2hBytes += 4LL * h->nWordsF + 4LL * (h->nPhiBlocks + 1);
     HostPool& pool = hostPool(h);
     const int nB = h->nPhiBlocks, nT = pool.size();
-    const unsigned int* bits = h->hPhiBits;
-    int* off = h->hPhiBlockOff;   // arrives as counts in off[1 + b]: exclusive prefix sum in place
+    const unsigned int* bits = h->hPhiBits2[h->pb];
+    int* off = h->hPhiBlockOff2[h->pb];   // arrives as counts in off[1 + b]: exclusive prefix sum in place
     off[0] = 0;
     long long total = 0;
     for (int b = 0; b < nB; ++b) {
@@ -1982,14 +2006,28 @@ bool sparsePhiFinish(svof_handle* h, const double* phi)
         off[b + 1] = (int)total;
     }
     // equal shares of MARKED faces per thread (the marked faces cluster where the liquid is): block boundaries from the prefix sums
-    std::vector<int> cut(nT + 1, nB);
+    h->phiTotal = total;
+    std::vector<int>& cut = h->phiCut;
+    cut.assign(nT + 1, nB);
     cut[0] = 0;
     for (int t = 1; t < nT; ++t) cut[t] = (int)(std::lower_bound(off, off + nB + 1, (int)(total * t / nT)) - off);
     for (int t = 1; t <= nT; ++t) cut[t] = std::max(cut[t], cut[t - 1]);
     cut[nT] = nB;
     double* packed = h->hPhiPacked;
     const int nWordsF = h->nWordsF;
+    const unsigned int* prevBits = (zeroStaleIn && h->phiPrevBitsValid) ? h->hPhiBits2[h->pb ^ 1] : nullptr;
     pool.run(nT, [&](int t) {
+        if (prevBits) {   // faces the previous call marked and this one does not: both cells are exactly empty now, their alphaPhi is zero
+            const int wa = (int)((long long)nWordsF * t / nT), wb = (int)((long long)nWordsF * (t + 1) / nT);
+            for (int w = wa; w < wb; ++w) {
+                unsigned int x = prevBits[w] & ~bits[w];
+                double* dst = zeroStaleIn + ((size_t)w << 5);
+                while (x) {
+                    dst[__builtin_ctz(x)] = 0.0;
+                    x &= x - 1;
+                }
+            }
+        }
         const int b0 = std::min(cut[t], nB), b1 = std::min(cut[t + 1], nB);
         size_t pos = (size_t)off[b0];
         const int w1 = std::min(32 * b1, nWordsF);
@@ -2034,6 +2072,159 @@ void scatterDeltas(svof_handle* h, const int* idx, const double* val, int cnt, d
         for (int i = lo; i < hi; ++i) out[idx[i]] = val[i];
     });
 }
+// host side of the packed alphaPhi read-back: out[f] = packed[k] over the marked faces of this call's bitmap, in face order
+void scatterPacked(svof_handle* h, double* out)
+{
+    HostPool& pool = hostPool(h);
+    const int nB = h->nPhiBlocks, nT = pool.size(), nWordsF = h->nWordsF;
+    const unsigned int* bits = h->hPhiBits2[h->pb];
+    const int* off = h->hPhiBlockOff2[h->pb];
+    const double* packed = h->hPhiPacked;
+    const std::vector<int>& cut = h->phiCut;
+    pool.run(nT, [&](int t) {
+        const int b0 = std::min(cut[t], nB), b1 = std::min(cut[t + 1], nB);
+        size_t pos = (size_t)off[b0];
+        const int w1 = std::min(32 * b1, nWordsF);
+        for (int w = 32 * b0; w < w1; ++w) {
+            unsigned int x = bits[w];
+            double* dst = out + ((size_t)w << 5);
+            if (x == 0xffffffffu) {
+                memcpy(dst, packed + pos, 32 * sizeof(double));
+                pos += 32;
+                continue;
+            }
+            while (x) {
+                dst[__builtin_ctz(x)] = packed[pos++];
+                x &= x - 1;
+            }
+        }
+    });
+}
+// device pointer of a caller buffer that is page-locked, device-accessible host memory (cudaMallocHost / svof_host_alloc /
+// cudaHostRegister), else nullptr
+void* devPtrOfPinned(svof_handle* h, const void* p)
+{
+    if (!p) return nullptr;
+    auto it = h->pinnedCache.find(p);
+    if (it != h->pinnedCache.end()) return it->second;
+    if (h->pinnedCache.size() > 64) h->pinnedCache.clear();
+    void* d = nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) == cudaSuccess) {
+        if (a.type == cudaMemoryTypeHost && a.devicePointer) d = a.devicePointer;
+    } else {
+        (void)cudaGetLastError();
+    }
+    h->pinnedCache[p] = d;
+    return d;
+}
+
+// svof_step_host when every caller buffer is pinned: nothing is staged and the host never waits inside the step.
+//   second stream : k_phi_pull (face bitmap of the entries that can matter + their values straight from the caller's phi), Ub
+//   main stream   : reconstruct -> U rows next to cut cells pulled from the caller's U -> advect ->
+//                   changed alpha cells and the marked alphaPhi faces written straight into the caller's buffers
+// One synchronisation at the end (control block: capacity flags and the byte counts).
+// An EMPTY cell went out of bounds (overfilled at Courant > 1), so the bounding read phi on faces the sparse upload had
+// skipped: rewind to alpha.oldTime (its buffer is intact) and redo the step with the full flux field and full read-backs.
+int redoStepWithFullPhi(svof_handle* h, double dt, const double* phi, const double* U, const double* Ub, double* alpha_out,
+                        double* alpha_phi_out)
+{
+    h->cur ^= 1;
+    h->cb ^= 1;
+    h->bitsValid = false;   // the mixed-cell bitmap on the device belongs to the discarded result
+    h->advected = false;
+    --h->advectCount;
+    h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr;
+    h->phiBitsReady = h->phiPrevBitsValid = h->alphaPhiPrevValid = h->zcPrevValid = false;
+    const bool sp = h->sparsePhi;
+    h->sparsePhi = false;
+    const int rc = svof_step_host(h, dt, phi, U, Ub, alpha_out, alpha_phi_out);
+    h->sparsePhi = sp;
+    return rc;
+}
+
+int stepHostZeroCopy(svof_handle* h, double dt, const double* phi, const double* phiD, const double* U, const double* UD, const double* Ub,
+                     double* alpha_out, double* alphaOutD, double* alpha_phi_out, double* alphaPhiOutD)
+{
+    cudaStream_t st = h->stream, sD = h->streamD;
+    h->h2dBytes = h->d2hBytes = 0;
+    hostTick(h, nullptr);
+    if (!h->zcBits[0]) {
+        h->nWordsF = cdiv(h->nF, 32);
+        h->zcBits[0] = dalloc<unsigned int>(h, (size_t)h->nWordsF + 1);
+        h->zcBits[1] = dalloc<unsigned int>(h, (size_t)h->nWordsF + 1);
+        h->zcPrevValid = false;
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaEventRecord(h->evInputs, st));
+    CK(cudaStreamWaitEvent(sD, h->evInputs, 0));   // previous step's readers of phi/Ub are done
+    const bool pushF = alpha_phi_out && h->hostAlphaPhiSynced == alpha_phi_out && h->zcPrevValid;
+    h->zcCur ^= 1;
+    unsigned int* bitsCur = h->zcBits[h->zcCur];
+    const unsigned int* bitsPrev = h->zcBits[h->zcCur ^ 1];
+    CK(cudaMemsetAsync(&h->ctl->nPhiPulled, 0, sizeof(int), sD));
+    k_phi_pull<<<cdiv((long long)h->nWordsF * 32, 256), 256, 0, sD>>>(h->md, h->alphaBuf[h->cur], h->sparsePhiTol, phiD, h->phi, bitsCur,
+                                                                     h->nWordsF, h->ctl);
+    h->launches++;
+    if (Ub && h->nBF) {
+        CK(cudaMemcpyAsync(h->Ub, Ub, sizeof(double) * 3 * h->nBF, cudaMemcpyHostToDevice, sD));
+        h->h2dBytes += 24LL * h->nBF;
+    }
+    CK(cudaEventRecord(h->evCopy, sD));
+    h->havePhi = true;
+    h->phiPartial = true;
+    if (h->anyInletOutlet && h->nBF) {   // as in the staged path: patch values follow the sign of the new boundary phi
+        CK(cudaMemcpyAsync(h->phi + h->nIF, phi + h->nIF, sizeof(double) * h->nBF, cudaMemcpyHostToDevice, st));
+        h->h2dBytes += 8LL * h->nBF;
+        alphaBC(h);
+    }
+    EventPair& e0 = beginTimed(h, 0);
+    doReconstruct(h);
+    endTimed(h, e0);
+    // U rows the interface-velocity interpolation reads: bitmap only (no list to overflow, nothing to read back)
+    CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), st));
+    CK(cudaMemsetAsync(&h->ctl->nUCells, 0, sizeof(int), st));
+    LAUNCH(h, k_mark_u_cells, sparseGrid(h, 256), 256, h->md, h->mixedCells, h->cellStatus, h->ctl, h->uBits, h->uList, 0);
+    LAUNCH(h, k_u_pull, cdiv(h->nC, 256), 256, h->uBits, h->nC, UD, h->U);
+    CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), st));   // leave the bitmap clean for the staged path
+    h->haveU = true;
+    h->uPartial = true;
+    h->inputsAfterNear = true;
+    CK(cudaStreamWaitEvent(st, h->evCopy, 0));
+    CK(cudaMemsetAsync(&h->ctl->packUnsafe, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(&h->ctl->phiUnsafe, 0, sizeof(int), st));
+    h->boundPhiBits = bitsCur;   // k_bound_deps / k_bound_apply flag an out-of-bounds cell with a face outside the bitmap
+    EventPair& e1 = beginTimed(h, 1);
+    doAdvect(h, dt, nullptr, nullptr);
+    endTimed(h, e1);
+    h->boundPhiBits = nullptr;
+    // results
+    const bool pushA = alpha_out && h->hostAlphaSynced == alpha_out;
+    CK(cudaMemsetAsync(&h->ctl->nDeltaA, 0, 2 * sizeof(int), st));
+    if (pushA) LAUNCH(h, k_alpha_push, cdiv(h->nC, 256), 256, h->alphaBuf[h->cur], h->alphaBuf[h->cur ^ 1], h->nC, alphaOutD, h->ctl);
+    else if (alpha_out) {
+        CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, st));
+        h->d2hBytes += 8LL * h->nC;
+    }
+    if (pushF) LAUNCH(h, k_alphaphi_push, cdiv(h->nF, 256), 256, bitsCur, bitsPrev, h->alphaPhi, alphaPhiOutD, h->nF, h->ctl);
+    else if (alpha_phi_out) {
+        CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
+        h->d2hBytes += 8LL * h->nF;
+    }
+    CK(cudaMemcpyAsync(h->hctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    hostTick(h, "zero-copy step: the one wait");
+    h->h2dBytes += 8LL * h->hctl->nPhiPulled + 24LL * std::max(h->hctl->nUCells, 0);
+    h->d2hBytes += sizeof(Ctl) + (pushA ? 8LL * h->hctl->nDeltaA : 0) + (pushF ? 8LL * h->hctl->nDeltaF : 0);
+    if (alpha_out) h->hostAlphaSynced = alpha_out;
+    if (alpha_phi_out) h->hostAlphaPhiSynced = alpha_phi_out;
+    h->zcPrevValid = alpha_phi_out != nullptr;
+    h->phiBitsReady = h->phiPrevBitsValid = h->alphaPhiPrevValid = false;   // the staged path's mirrors are stale now
+    CK(cudaGetLastError());
+    if (h->hctl->err) return deviceErr(h);
+    if (h->hctl->phiUnsafe) return redoStepWithFullPhi(h, dt, phi, U, Ub, alpha_out, alpha_phi_out);
+    return SVOF_OK;
+}
 }  // namespace
 
 int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U, const double* Ub, double* alpha_out,
@@ -2044,6 +2235,16 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     API_BEGIN
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
+    if (h->sparseIO && h->sparsePhi && h->zeroCopy) {   // every caller buffer pinned: no staging at all
+        void* phiD = devPtrOfPinned(h, phi);
+        void* UD = devPtrOfPinned(h, U);
+        void* aD = devPtrOfPinned(h, alpha_out);
+        void* apD = devPtrOfPinned(h, alpha_phi_out);
+        if (phiD && UD && (!alpha_out || aD) && (!alpha_phi_out || apD))
+            return stepHostZeroCopy(h, dt, phi, (const double*)phiD, U, (const double*)UD, Ub, alpha_out, (double*)aD, alpha_phi_out,
+                                    (double*)apD);
+    }
+    h->zcPrevValid = false;
     h->h2dBytes = h->d2hBytes = 0;
     hostTick(h, nullptr);
     // phi (the one field that has to cross PCIe in full) goes up on the second stream while reconstruct() and the
@@ -2074,9 +2275,12 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     EventPair& e0 = beginTimed(h, 0);
     doReconstruct(h);
     endTimed(h, e0);
+    bool packedF = false;   // alphaPhi read-back packed by the phi bitmap (set by finishPhi)
     auto finishPhi = [&]() {   // host work that overlaps the reconstruct / U-marking kernels already enqueued
         if (trySparsePhi) {
-            if (sparsePhiFinish(h, phi)) h->phiPartial = true;
+            // alphaPhi comes back packed by this call's bitmap when the caller's buffer mirrors the previous result
+            const bool packedBack = alpha_phi_out && h->hostAlphaPhiSynced == alpha_phi_out && h->phiPrevBitsValid;
+            if (sparsePhiFinish(h, phi, packedBack ? alpha_phi_out : nullptr)) { h->phiPartial = true; packedF = packedBack; }
             else {
                 CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
                 h->h2dBytes += 8LL * h->nF;
@@ -2140,15 +2344,23 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     h->haveU = true;
     h->inputsAfterNear = true;  // U landed after the near bitmaps were published
     CK(cudaStreamWaitEvent(st, h->evCopy, 0));  // phi/Ub are on the device
+    const bool sparsePhiUsed = trySparsePhi && h->phiPartial;
+    CK(cudaMemsetAsync(&h->ctl->phiUnsafe, 0, sizeof(int), st));
+    if (sparsePhiUsed) {
+        CK(cudaMemsetAsync(&h->ctl->packUnsafe, 0, sizeof(int), st));
+        h->boundPhiBits = h->phiBits;   // see k_bound_deps / k_bound_apply
+    }
     EventPair& e1 = beginTimed(h, 1);
     doAdvect(h, dt, nullptr, nullptr);
     endTimed(h, e1);
+    h->boundPhiBits = nullptr;
     // results: deltas against what the caller's buffers already hold, else full copies.  Both delta kernels, the control
     // block (with the two counts) and a speculative prefix of each (index, value) list -- sized from the previous step --
     // are enqueued together and waited for ONCE; a list that turned out longer gets its remainder in a second copy.
     const int capA = h->capDelta / 4, capF = h->capDelta - capA;   // alpha deltas in [0, capA), alphaPhi deltas behind them
     const bool deltaA = alpha_out && h->sparseIO && h->hostAlphaSynced == alpha_out;
-    const bool deltaF = alpha_phi_out && h->sparseIO && h->hostAlphaPhiSynced == alpha_phi_out;
+    // alphaPhi: packed by this call's phi bitmap when possible (packedF), else deltas against alphaPhiPrev, else the full field
+    const bool deltaF = !packedF && alpha_phi_out && h->sparseIO && h->hostAlphaPhiSynced == alpha_phi_out && h->alphaPhiPrevValid;
     int estA = 0, estF = 0;
     if (deltaA || deltaF) CK(cudaMemsetAsync(&h->ctl->nDeltaA, 0, 2 * sizeof(int), st));
     if (deltaA)
@@ -2157,10 +2369,16 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     if (deltaF)
         LAUNCH(h, k_delta, cdiv(h->nF, 256), 256, h->alphaPhi, h->alphaPhiPrev, (const double*)nullptr, (long long)h->nF, &h->ctl->nDeltaF,
                h->dIdx + capA, h->dVal + capA, capF);
-    // the next call's phi face bitmap (of the alpha just computed) rides along with this call's read-back
+    if (packedF) {   // before the device bitmap is overwritten below
+        LAUNCH(h, k_phi_pack, cdiv(h->nWordsF, 256), 256, h->phiBits, h->phiBlockOff, h->nWordsF, h->alphaPhi, h->phiPacked);
+        if (h->phiTotal) CK(cudaMemcpyAsync(h->hPhiPacked, h->phiPacked, sizeof(double) * (size_t)h->phiTotal, cudaMemcpyDeviceToHost, st));
+        h->d2hBytes += 8LL * h->phiTotal;
+    }
+    // the next call's phi face bitmap (of the alpha just computed) rides along with this call's read-back, into the host
+    // buffer this call does not use
     const bool prefetchBits = trySparsePhi && h->phiPartial;
     if (prefetchBits) {
-        enqueuePhiBits(h, st);
+        enqueuePhiBits(h, st, h->pb ^ 1);
     }
     CK(cudaMemcpyAsync(h->hctl, h->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, st));
     if (deltaA) {
@@ -2175,11 +2393,13 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
         estF = std::min(capF, std::max(1 << 14, h->lastCntF + h->lastCntF / 4));
         CK(cudaMemcpyAsync(h->hIdx + capA, h->dIdx + capA, sizeof(int) * estF, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(h->hVal + capA, h->dVal + capA, sizeof(double) * estF, cudaMemcpyDeviceToHost, st));
-    } else if (alpha_phi_out) {
+    } else if (alpha_phi_out && !packedF) {
         CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
         if (h->sparseIO) CK(cudaMemcpyAsync(h->alphaPhiPrev, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToDevice, st));
         h->d2hBytes += 8LL * h->nF;
+        h->alphaPhiPrevValid = h->sparseIO;
     }
+    if (packedF) h->alphaPhiPrevValid = false;   // alphaPhiPrev is not maintained by the packed read-back
     CK(cudaStreamSynchronize(st));
     hostTick(h, "4 wait: GPU step + delta kernels + D2H");
     h->d2hBytes += sizeof(Ctl);
@@ -2212,18 +2432,29 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
         }
         h->d2hBytes += 12LL * std::max(estF, std::min(cntF, capF));
     }
+    if (packedF && h->hctl->packUnsafe) {   // rare: see k_bound_apply
+        CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
+        h->d2hBytes += 8LL * h->nF;
+        packedF = false;
+        again = true;
+    }
     if (again) {
         CK(cudaStreamSynchronize(st));
         hostTick(h, "5 D2H of list remainders / full fields");
     }
     if (deltaA && cntA <= capA) scatterDeltas(h, h->hIdx, h->hVal, cntA, alpha_out);
     if (deltaF && cntF <= capF) scatterDeltas(h, h->hIdx + capA, h->hVal + capA, cntF, alpha_phi_out);
+    if (packedF) scatterPacked(h, alpha_phi_out);
     hostTick(h, "6 host scatter");
     if (alpha_out) h->hostAlphaSynced = alpha_out;
     if (alpha_phi_out) h->hostAlphaPhiSynced = alpha_phi_out;
     h->phiBitsReady = prefetchBits;   // valid until anything else changes alpha
+    // the bitmap of this call stays in hPhiBits2[pb]: the next call may zero the faces that leave it, provided this call
+    // left the caller's alphaPhi buffer complete
+    h->phiPrevBitsValid = trySparsePhi && h->phiPartial && alpha_phi_out != nullptr;
     CK(cudaGetLastError());
     if (h->hctl->err) return deviceErr(h);   // a work list or polyhedron cap overflowed: the fields just returned are not to be trusted
+    if (sparsePhiUsed && h->hctl->phiUnsafe) return redoStepWithFullPhi(h, dt, phi, U, Ub, alpha_out, alpha_phi_out);
     return SVOF_OK;
     API_END(h)
 }
@@ -2398,6 +2629,12 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
     if (!strcmp(name, "dense_v4")) { h->denseV4 = value != 0 && h->dsliced.enabled; for (auto& g : h->graphs) g.sched = -1; return SVOF_OK; }
     if (!strcmp(name, "dense_v3")) { h->denseV3 = value != 0; for (auto& g : h->graphs) g.sched = -1; return SVOF_OK; }
+    if (!strcmp(name, "zero_copy")) { h->zeroCopy = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "sparse_phi_exp")) {
+        h->sparsePhiTol = value > 0 ? pow(10.0, -(double)value) : 0.0;
+        h->phiBitsReady = false;
+        return SVOF_OK;
+    }
     if (!strcmp(name, "sparse_phi")) { h->sparsePhi = value != 0; return SVOF_OK; }
     if (!strcmp(name, "sparse_io")) { h->sparseIO = value != 0; h->hostAlphaSynced = h->hostAlphaPhiSynced = nullptr; h->phiBitsReady = false; return SVOF_OK; }
     return fail(h, SVOF_ERR_INVALID_ARG, "svof_set_option: unknown option");

@@ -23,6 +23,9 @@ struct Ctl {
     int nMixed;   // mixedCells_.size()
     int nNear2;   // |near2|
     int nWork;    // (cut cell, downwind face) work items
+    int nPhiPulled;  // zero-copy host path: phi entries read from the caller's pinned buffer in the last svof_step_host
+    int phiUnsafe;   // host path: an out-of-bounds cell owns a face outside the phi bitmap (an EMPTY cell overfilled, Courant > 1): the step is redone with the full phi
+    int packUnsafe;  // a bounding correction landed on a face outside the phi bitmap (host path: alphaPhi then comes back in full)
     int nRdf;     // cells of the isoRDF zone (mixed cells + their point neighbours)
     int nUCells;  // cells whose U the interface-velocity interpolation reads (end-to-end path)
     int plicNext; // batch counter of the persistent plane-positioning kernel
@@ -1955,7 +1958,8 @@ __global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, 
                                                     const unsigned char* oobState, const double* alpha, const double* aOld,
                                                     const double* __restrict__ phi, const double* dVf, const double* Sp,
                                                     const double* Su, BoundScratch b, int* depInit, int* depLeft, int* oobIdx,
-                                                    CellBound<SV_MAXBF>* recs, int capRec, int* affList)
+                                                    CellBound<SV_MAXBF>* recs, int capRec, int* affList,
+                                                    const unsigned int* __restrict__ phiBits = nullptr)
 {
     const int n = ctl->nOob[s & 1];
     const int tag = boundTag(ctl, s);
@@ -1963,6 +1967,10 @@ __global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, 
         const int c = oobList[i];
         CellBound<SV_MAXBF> cb;
         loadCellBound(m, c, phi, dVf, b, tag, cb);  // corrections of this sweep do not exist yet: fCorr == 0
+        if (phiBits) {   // svof_step_host uploaded phi only where a neighbouring cell held liquid: every face of this cell must be among them
+            for (int q = 0; q < cb.nf; ++q)
+                if (!((phiBits[cb.fId[q] >> 5] >> (cb.fId[q] & 31)) & 1u)) ctl->phiUnsafe = 1;
+        }
         cb.V = m.V[c];
         cb.alpha = alpha[c];
         cb.aOld = aOld[c];
@@ -2224,7 +2232,7 @@ __global__ void __launch_bounds__(64) k_bound_run8(Ctl* ctl, int s, const int* o
 template <int SV_MAXBF>
 __global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s, const int* affList, const unsigned int* near1,
                                                      double* alpha, double* dVf, BoundScratch b, int* oobListNext,
-                                                     unsigned char* oobState)
+                                                     unsigned char* oobState, const unsigned int* __restrict__ phiBits = nullptr)
 {
     const int n = ctl->nAff[s];
     const int tag = boundTag(ctl, s);
@@ -2293,6 +2301,9 @@ __global__ void __launch_bounds__(128) k_bound_apply(MeshDev m, Ctl* ctl, int s,
             if ((ownM >> x) & 1ull) {
                 a -= cvv[x] / Vc;
                 dVf[fl[x]] = dVf[fl[x]] + cvv[x];  // setFaceValue(dVf_, facei, corrVf): once, by the owner
+                // svof_step_host reads alphaPhi back on the faces its phi bitmap marks (a cell with liquid on one side): a
+                // correction elsewhere (an empty cell overfilled at Courant > 1) makes it fall back to the full field
+                if (phiBits && !((phiBits[fl[x] >> 5] >> (fl[x] & 31)) & 1u)) ctl->packUnsafe = 1;
             } else {
                 a += cvv[x] / Vc;
             }
@@ -2411,13 +2422,16 @@ __global__ void k_scatter_u(const int* uList, int n, const double* packed, doubl
 //    zero, alphaPhi compares equal), so only the other faces have to cross PCIe.  k_phi_need_bits publishes them as a bitmap
 //    over faces; the host gathers the marked entries of the caller's phi in face order and k_phi_scatter puts them back.
 // blockCnt[1 + b] += marked faces of the 1024-face block b (zeroed by the caller; the host turns it into the prefix sum)
-__global__ void k_phi_need_bits(MeshDev m, const double* __restrict__ alpha, unsigned int* bits, int nWordsF, int* blockCnt)
+// tol = 0: exact (alpha != 0).  tol > 0 (option "sparse_phi_exp"): cells with |alpha| <= tol count as empty -- with snapTol 0 the
+// support of alpha grows by one cell layer per step downstream (upwind transport of round-off-sized values), which this
+// keeps out of the bitmap at the price of an O(tol) difference from the full-field call.
+__global__ void k_phi_need_bits(MeshDev m, const double* __restrict__ alpha, unsigned int* bits, int nWordsF, int* blockCnt, double tol)
 {
     const long long fl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool need = false;
     if (fl < m.nFaces) {
         const int f = (int)fl;
-        need = (f >= m.nIF) || (__ldg(alpha + __ldg(m.owner + f)) != 0.0) || (__ldg(alpha + __ldg(m.neighbour + f)) != 0.0);
+        need = (f >= m.nIF) || (fabs(__ldg(alpha + __ldg(m.owner + f))) > tol) || (fabs(__ldg(alpha + __ldg(m.neighbour + f))) > tol);
     }
     const unsigned int w = __ballot_sync(0xffffffffu, need);
     if ((threadIdx.x & 31) == 0 && (fl >> 5) < nWordsF) {
@@ -2445,6 +2459,90 @@ __global__ void k_phi_scatter(const unsigned int* __restrict__ bits, const int* 
         const int b = __ffs(word) - 1;
         word &= word - 1;
         phi[((size_t)w << 5) + b] = packed[pos++];
+    }
+}
+// ---- svof_step_host with PINNED caller buffers: the kernels read the caller's phi / U and write its alpha / alphaPhi
+// directly over PCIe (zero copy), so the host neither gathers nor scatters and never waits inside the step.
+// k_phi_pull = k_phi_need_bits + the pull of the marked entries: lane b of a warp handles face 32 w + b, so the reads of
+// a fully marked word are one 256-byte request.
+__global__ void k_phi_pull(MeshDev m, const double* __restrict__ alpha, double tol, const double* phiHost, double* phiDev,
+                           unsigned int* bits, int nWordsF, Ctl* ctl)
+{
+    const long long fl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool need = false;
+    if (fl < m.nFaces) {
+        const int f = (int)fl;
+        need = (f >= m.nIF) || (fabs(__ldg(alpha + __ldg(m.owner + f))) > tol) || (fabs(__ldg(alpha + __ldg(m.neighbour + f))) > tol);
+        if (need) phiDev[f] = phiHost[f];
+    }
+    const unsigned int w = __ballot_sync(0xffffffffu, need);
+    if ((threadIdx.x & 31) == 0 && (fl >> 5) < nWordsF) {
+        bits[fl >> 5] = w;
+        if (w) atomicAdd(&ctl->nPhiPulled, __popc(w));
+    }
+}
+// rows of U next to cut cells (bitmap from k_mark_u_cells), straight from the caller's buffer
+__global__ void k_u_pull(const unsigned int* __restrict__ uBits, int nCells, const double* UHost, double* UDev)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells || !((uBits[c >> 5] >> (c & 31)) & 1u)) return;
+    UDev[3 * (size_t)c] = UHost[3 * (size_t)c];
+    UDev[3 * (size_t)c + 1] = UHost[3 * (size_t)c + 1];
+    UDev[3 * (size_t)c + 2] = UHost[3 * (size_t)c + 2];
+}
+// alpha cells whose bit pattern changed go straight into the caller's buffer (which holds the previous field)
+__global__ void k_alpha_push(const double* __restrict__ cur, const double* __restrict__ ref, int n, double* host, Ctl* ctl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool changed = false;
+    if (i < n) {
+        const double v = cur[i];
+        changed = __double_as_longlong(v) != __double_as_longlong(ref[i]);
+        if (changed) host[i] = v;
+    }
+    const unsigned int mk = __ballot_sync(0xffffffffu, changed);
+    if ((threadIdx.x & 31) == 0 && mk) atomicAdd(&ctl->nDeltaA, __popc(mk));
+}
+// alphaPhi can only be non-zero on the faces this step's bitmap marks: those are written; faces the previous step marked
+// and this one does not are zero now; if a bounding correction landed elsewhere (ctl->packUnsafe) every face is written
+__global__ void k_alphaphi_push(const unsigned int* __restrict__ bitsCur, const unsigned int* __restrict__ bitsPrev,
+                                const double* __restrict__ alphaPhi, double* host, int nFaces, Ctl* ctl)
+{
+    const long long fl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    if (fl >= nFaces) return;
+    const int w = (int)(fl >> 5);
+    const unsigned int bit = 1u << lane;
+    const bool all = ctl->packUnsafe != 0;
+    const unsigned int cur = bitsCur[w], prev = bitsPrev[w];
+    if (all || (cur & bit)) host[fl] = alphaPhi[fl];
+    else if (prev & bit) host[fl] = 0.0;
+    if (lane == 0) {
+        const int cnt = all ? 32 : __popc(cur | prev);
+        if (cnt) atomicAdd(&ctl->nDeltaF, cnt);
+    }
+}
+// the reverse of k_phi_scatter: packed[k] = field[f] for the marked faces in face order (alphaPhi read-back: alphaPhi can only
+// be non-zero on a face whose upwind cell held liquid, i.e. on the faces the step's phi bitmap marks)
+__global__ void k_phi_pack(const unsigned int* __restrict__ bits, const int* __restrict__ blockOff, int nWordsF,
+                           const double* __restrict__ field, double* __restrict__ packed)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    unsigned int word = (w < nWordsF) ? bits[w] : 0u;
+    const int cnt = __popc(word);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (!word) return;
+    int pos = blockOff[w >> 5] + incl - cnt;
+    while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        packed[pos++] = field[((size_t)w << 5) + b];
     }
 }
 // entries whose bit pattern changed: (index, value) appended with warp-aggregated atomics; if prev != nullptr

@@ -276,7 +276,11 @@ int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
  * on -- every boundary face and every internal face with alpha != 0 in at least one of its two cells; on the other
  * faces phi multiplies an exactly zero alpha, so the device keeps whatever it held.  The caller's phi buffer is read
  * afresh in every call.  After such a call the device's phi is not a full field: svof_advect / svof_step_device
- * return SVOF_ERR_STATE until svof_set_phi / svof_set_phi_device). */
+ * return SVOF_ERR_STATE until svof_set_phi / svof_set_phi_device),
+ * "sparse_phi_exp" (e > 0: for that upload, cells with |alpha| <= 10^-e count as empty.  With snapTol 0 the support of
+ * alpha grows one cell layer per step downstream -- round-off-sized values carried by the upwind flux -- until the sparse
+ * upload degenerates into the full one; the threshold keeps it tight at the price of an O(10^-e) difference from the
+ * full-field call.  Default 0: exact). */
 int svof_set_option(svof_handle* h, const char* name, int value);
 /* The CUDA stream (cudaStream_t) every kernel and copy of this handle is ordered on, so a caller that
  * lives on the GPU (halo exchange in multigpu.py) can enqueue its own work in order without a host sync. */

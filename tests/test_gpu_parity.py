@@ -214,12 +214,17 @@ def test_step_host_matches_split_calls(oracle, product):
     assert s1.info(capi.I_GPU_LAUNCHES) > 0
 
 
-@pytest.mark.parametrize("case", ["sphere in an empty box", "half-filled box with inflow/outflow patches"])
-def test_step_host_sparse_phi_upload_is_bitwise_the_full_upload(product, case):
+@pytest.mark.parametrize("pinned", [False, True], ids=["pageable caller buffers (staged)", "pinned caller buffers (zero copy)"])
+@pytest.mark.parametrize("case", ["sphere in an empty box", "half-filled box with inflow/outflow patches",
+                                  "sphere in an empty box, Courant number 2"])
+def test_step_host_sparse_phi_upload_is_bitwise_the_full_upload(product, case, pinned):
     """svof_step_host uploads only the phi entries the step can depend on (faces next to a cell with alpha != 0, and all
-    boundary faces); phi changes on EVERY face between calls, including its sign.  Results must be bitwise those of the
-    split calls with full fields, and of svof_step_host with sparse_phi off."""
+    boundary faces) and reads alphaPhi back packed by the same face bitmap; phi changes on EVERY face between calls,
+    including its sign.  Results must be bitwise those of the split calls with full fields, and of svof_step_host with
+    sparse_phi off.  At Courant 2 empty cells overfill and bounding corrections land on faces outside the bitmap: the
+    library must notice and return the full alphaPhi."""
     N = 16
+    dt = 0.06 if case.endswith("2") else 0.01
     m = meshmod.hex_block(N)
     if case.startswith("half"):
         for p in m.patches:
@@ -243,6 +248,10 @@ def test_step_host_sparse_phi_upload_is_bitwise_the_full_upload(product, case):
         s.setAlpha(a0)
     s3.setOption("sparse_phi", 0)
     out2, aphi2, out3, aphi3 = np.empty(m.n_cells), np.empty(m.n_faces), np.empty(m.n_cells), np.empty(m.n_faces)
+    if pinned:   # page-locked buffers: the kernels read phi / U and write alpha / alphaPhi in the caller's memory directly
+        out2, aphi2 = capi.pinned_array(product, (m.n_cells,)), capi.pinned_array(product, (m.n_faces,))
+        phi_p, U_p, Ub_p = (capi.pinned_array(product, (m.n_faces,)), capi.pinned_array(product, (m.n_cells, 3)),
+                            capi.pinned_array(product, (max(s1.nBF, 1), 3)))
     rng = np.random.default_rng(5)
     full = 8 * (m.n_faces + 3 * m.n_cells + 3 * s1.nBF)
     for k, f in enumerate((1.0, 0.7, -0.4, -1.0, 0.3, 0.9)):
@@ -251,22 +260,28 @@ def test_step_host_sparse_phi_upload_is_bitwise_the_full_upload(product, case):
         s1.setPhi(phi)
         s1.setU(U, Ub * f)
         s1.reconstruct()
-        s1.advect(0.01)
-        s2.step_host(0.01, phi, U, Ub * f, out2, aphi2)
-        s3.step_host(0.01, phi, U, Ub * f, out3, aphi3)
+        s1.advect(dt)
+        if pinned:
+            phi_p[:], U_p[:], Ub_p[:s1.nBF] = phi, U, Ub * f
+            s2.step_host(dt, phi_p, U_p, Ub_p, out2, aphi2)
+        else:
+            s2.step_host(dt, phi, U, Ub * f, out2, aphi2)
+        s3.step_host(dt, phi, U, Ub * f, out3, aphi3)
         assert np.array_equal(s1.alpha(), out2), "step %d: alpha differs (sparse phi)" % k
         assert np.array_equal(s1.alphaPhi(), aphi2), "step %d: alphaPhi differs (sparse phi)" % k
         assert np.array_equal(out3, out2) and np.array_equal(aphi3, aphi2)
         assert np.array_equal(s1.field(capi.F_ALPHA_BOUNDARY), s2.field(capi.F_ALPHA_BOUNDARY))
-        if not case.startswith("half"):
+        if case == "sphere in an empty box":
             assert s2.info(capi.I_H2D_BYTES) < 0.5 * full < s3.info(capi.I_H2D_BYTES)
+            if k >= 2:   # alphaPhi comes back on the marked faces only: less than the full fields
+                assert s2.info(capi.I_D2H_BYTES) < 8 * (m.n_cells + m.n_faces)
     # the device's phi is not a full field after the sparse upload: the split calls refuse it until svof_set_phi
     with pytest.raises(capi.SvofError):
-        s2.advect(0.01)
+        s2.advect(dt)
     s2.setPhi(phi0)
     s2.setU(U0, Ub)
     s2.reconstruct()
-    s2.advect(0.01)
+    s2.advect(dt)
     assert s2.info(capi.I_ERROR_FLAGS) == 0
 
 
