@@ -577,6 +577,7 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("SVOF_BENCH_N", "256")),
                     help="cells per axis (per GPU block when --gpus > 1)")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-multi", action="store_true", help="N > 1: also time svof_step_host per rank (host buffers in/out)")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="leveque", choices=["leveque", "kelvin", "dambreak"],

@@ -2235,7 +2235,9 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     API_BEGIN
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    if (h->sparseIO && h->sparsePhi && h->zeroCopy) {   // every caller buffer pinned: no staging at all
+    // decomposed runs: the sparse-phi forms may redo a step on ONE rank (redoStepWithFullPhi), which would unpair the ranks'
+    // NCCL ghost refreshes -- full flux field there
+    if (h->sparseIO && h->sparsePhi && h->zeroCopy && !h->halo.active) {   // every caller buffer pinned: no staging at all
         void* phiD = devPtrOfPinned(h, phi);
         void* UD = devPtrOfPinned(h, U);
         void* aD = devPtrOfPinned(h, alpha_out);
@@ -2254,7 +2256,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     // phi goes up on the second stream while reconstruct() and the sparse-U round trip run on the main one.  Sparse form
     // (default): only the faces whose value can matter (k_phi_need_bits); the device's other entries keep older values,
     // which multiply an exactly zero alpha.  Otherwise the full field (nF doubles) crosses PCIe.
-    const bool trySparsePhi = h->sparseIO && h->sparsePhi;   // the device's phi starts zero-filled: stale entries are finite
+    const bool trySparsePhi = h->sparseIO && h->sparsePhi && !h->halo.active;   // the device's phi starts zero-filled: stale entries are finite
     if (trySparsePhi) sparsePhiBegin(h);
     else {
         CK(cudaMemcpyAsync(h->phi, phi, sizeof(double) * h->nF, cudaMemcpyHostToDevice, h->streamD));
