@@ -192,7 +192,13 @@ int svof_step_device(svof_handle* h, double dt);
 
 /* Host-pointer convenience = set_phi + set_U + reconstruct + advect + read back
  * alpha (and alphaPhi if non-NULL): the end-to-end call bench.py times.  On return the caller's buffers
- * hold the complete new fields (see the "sparse_io" option for how few bytes that takes). */
+ * hold the complete new fields (see the "sparse_io" / "sparse_phi" / "zero_copy" options for how few bytes that takes).
+ * When phi, U, alpha_out and alpha_phi_out are page-locked, device-accessible host memory (svof_host_alloc, cudaMallocHost,
+ * cudaHostRegister) nothing is staged: the kernels read the entries of phi / rows of U they need and write the changed alpha
+ * cells and alphaPhi faces straight into the caller's buffers, and the call waits for the device once.  Pageable buffers
+ * take the staged path (face bitmap, host gather/scatter on a small thread pool, three round trips).  Either way the result
+ * is bitwise that of full-field copies; if an EMPTY cell goes out of bounds (possible only at Courant > 1) the library
+ * notices on the device and redoes the step with the full flux field. */
 int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U,
                    const double* Ub, double* alpha_out, double* alpha_phi_out);
 
@@ -277,6 +283,7 @@ int svof_set_U_device(svof_handle* h, const void* dU, const void* dUb);
  * faces phi multiplies an exactly zero alpha, so the device keeps whatever it held.  The caller's phi buffer is read
  * afresh in every call.  After such a call the device's phi is not a full field: svof_advect / svof_step_device
  * return SVOF_ERR_STATE until svof_set_phi / svof_set_phi_device),
+ * "zero_copy" (0/1, default 1: the pinned-buffer path of svof_step_host described there),
  * "sparse_phi_exp" (e > 0: for that upload, cells with |alpha| <= 10^-e count as empty.  With snapTol 0 the support of
  * alpha grows one cell layer per step downstream -- round-off-sized values carried by the upwind flux -- until the sparse
  * upload degenerates into the full one; the threshold keeps it tight at the price of an O(10^-e) difference from the
