@@ -222,6 +222,7 @@ struct svof_handle {
     bool un0Group = false;           // 8 lanes per cut cell for the interface speed (SVOF_UN0=thread: round-1 thread-per-cell kernel)
     int plicCtas = 0;                // "plic_ctas" option: cap on resident CTAs/SM of the plane-positioning kernel (0 = all that fit)
     int denseCtas = 0;               // "dense_ctas" option: cap on resident CTAs/SM of the streaming kernel (0 = no cap)
+    int denseThreads = 256;          // "dense_threads" option: threads per CTA of the capped streaming kernel (128 or 256)
     int forkAt = 1;                  // "fork" option (overlap != 0): 1 = streaming kernel may start after the near sets, 2 = after plane positioning
     int* bPatch = nullptr;
     double* partial = nullptr;
@@ -1280,7 +1281,13 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         else if (h->dfast.enabled)
             k_dense_update2<<<grid, 256, 0, sD>>>(d, h->dfast, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits,
                                                   dt, rDt, dSp, dSu, h->sp, h->ctl, nTiles);
-        else
+        else if (h->denseCtas > 0) {   // capped grid walking the tiles: a fixed share of every SM (see k_dense_update_capped)
+            const int thr = (h->denseThreads == 128) ? 128 : 256;
+            const int tiles = cdiv(h->nC, thr);
+            k_dense_update_capped<<<std::min(tiles, h->denseCtas * h->sms), thr, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb],
+                                                                                       h->alphaPhi, h->near2, h->mixedBits, dt, rDt, dSp,
+                                                                                       dSu, h->sp, h->ctl, tiles);
+        } else
             k_dense_update<<<nTiles, 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits, dt, rDt,
                                                    dSp, dSu, h->sp, h->ctl);
     }
@@ -1350,6 +1357,12 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         CK(cudaMemsetAsync(&h->ctl->epoch, 0, sizeof(int), sS));
         h->epochBumps = 0;
     }
+}
+
+// every run-time option that changes which kernels / grids a captured step contains
+int schedKey(const svof_handle* h)
+{
+    return (((h->overlap * 10 + h->forkAt) * 100 + h->plicCtas) * 100 + h->denseCtas) * 2 + (h->denseThreads == 128 ? 1 : 0);
 }
 
 void fetchCtl(svof_handle* h)
@@ -1870,7 +1883,7 @@ int svof_step_device(svof_handle* h, double dt)
     API_BEGIN
     CK(cudaSetDevice(h->device));
     svof_handle::StepGraph& g = h->graphs[h->cur * 4 + h->cb * 2 + (h->bitsValid ? 1 : 0)];
-    if (!g.exec || g.dt != dt || g.sched != h->overlap * 100000 + h->forkAt * 10000 + h->plicCtas * 100 + h->denseCtas) {
+    if (!g.exec || g.dt != dt || g.sched != schedKey(h)) {
         if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
         // run the first step of this kind with plain launches (warms every lazily initialised launcher), then capture
         const int cur0 = h->cur, cb0 = h->cb;
@@ -1907,7 +1920,7 @@ int svof_step_device(svof_handle* h, double dt)
         if (graph) cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { g.exec = nullptr; (void)cudaGetLastError(); }   // graphs unavailable: keep using plain launches
         g.dt = dt;
-        g.sched = h->overlap * 100000 + h->forkAt * 10000 + h->plicCtas * 100 + h->denseCtas;
+        g.sched = schedKey(h);
         return SVOF_OK;
     }
     CK(cudaGraphLaunch(g.exec, h->stream));
@@ -2625,6 +2638,7 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "overlap")) { h->overlap = value; return SVOF_OK; }
     if (!strcmp(name, "fork")) { h->forkAt = value; return SVOF_OK; }
     if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_threads")) { h->denseThreads = value; return SVOF_OK; }
     if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; return SVOF_OK; }
     if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
     if (!strcmp(name, "bound_lanes")) { h->boundLanes = value != 0; for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } return SVOF_OK; }

@@ -1180,15 +1180,13 @@ __device__ __forceinline__ void blockMinMaxFast(double mn, double mx, unsigned l
 #define SV_DENSE_UNROLL 1
 #endif
 constexpr int kDenseUnroll = SV_DENSE_UNROLL;
-__global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
-                                                      const double* __restrict__ phi, const double* __restrict__ alphaB,
-                                                      double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
-                                                      unsigned int* __restrict__ mixedNext, double dt, double rDt,
-                                                      const double* __restrict__ Sp, const double* __restrict__ Su, StepParams sp,
-                                                      Ctl* ctl)
+// the per-cell body of the streaming pass: returns whether the new value is a mixed cell; mn / mx take the unclipped value
+__device__ __forceinline__ bool denseCell(const MeshDev& m, int c, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                          const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                          double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2, double dt, double rDt,
+                                          const double* __restrict__ Sp, const double* __restrict__ Su, const StepParams& sp, double& mn,
+                                          double& mx)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    double mn = SV_VGREAT, mx = -SV_VGREAT;
     bool mixed = false;
     if (c < m.nCells && !bitTest(near2, c)) {
         const int k0 = __ldg(m.cellOff + c), k1 = __ldg(m.cellOff + c + 1);
@@ -1224,14 +1222,48 @@ __global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double
         if (Su) num = num + Su[c];
         num = num - ivf * rDt;
         double a = divz(num, (Sp ? (rDt - Sp[c]) : rDt));
-        mn = a;
-        mx = a;
+        mn = dmin(mn, a);
+        mx = dmax(mx, a);
         a = snapClip(a, sp.snapTol, sp.clip);
         aNew[c] = a;
         mixed = (sp.mixedTol < a) && (a < 1.0 - sp.mixedTol);
     }
+    return mixed;
+}
+
+__global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                                      const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                                      double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
+                                                      unsigned int* __restrict__ mixedNext, double dt, double rDt,
+                                                      const double* __restrict__ Sp, const double* __restrict__ Su, StepParams sp,
+                                                      Ctl* ctl)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    const bool mixed = denseCell(m, c, aOld, aNew, phi, alphaB, alphaPhi, near2, dt, rDt, Sp, Su, sp, mn, mx);
     const unsigned int w = __ballot_sync(0xffffffffu, mixed);
     if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
+    blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
+}
+
+// The same pass as a CAPPED grid ("dense_ctas" CTAs per SM, "dense_threads" threads each) whose CTAs walk the tiles
+// interleaved: a fixed share of every SM for the streaming pass for as long as the interface kernels run beside it on
+// the other stream, instead of 8 resident CTAs per SM that saturate DRAM (and every warp slot) for 0.43 ms and stretch
+// the latency-bound interface kernels.  Same per-cell code, same bits.
+__global__ void __launch_bounds__(256, 8) k_dense_update_capped(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                                             const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                                             double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
+                                                             unsigned int* __restrict__ mixedNext, double dt, double rDt,
+                                                             const double* __restrict__ Sp, const double* __restrict__ Su,
+                                                             StepParams sp, Ctl* ctl, int nTiles)
+{
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int c = tile * blockDim.x + threadIdx.x;
+        const bool mixed = denseCell(m, c, aOld, aNew, phi, alphaB, alphaPhi, near2, dt, rDt, Sp, Su, sp, mn, mx);
+        const unsigned int w = __ballot_sync(0xffffffffu, mixed);
+        if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
+    }
     blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
 }
 

@@ -13,6 +13,12 @@
                                       (C entry points).  Pins the oracle's restatement of
                                       the geometric core to the reference's statements.
 
+  oracle/_ref/libref_advect.so     -- the reference's own advection.{H,C} + advectionTemplates.C (src/SimPLIC/advection)
+                                      and cutFace.{H,C}, compiled UNMODIFIED from /root/reference against
+                                      oracle/of_stub_adv/ (a larger stand-in: GeometricField algebra, patches,
+                                      upwind, fvc::surfaceIntegrate, bitSet, zeroField ...) + ref_advect.cpp.
+                                      Pins the oracle's restatement of advect() to the reference's statements.
+
 Both directories are git-ignored and are NOT gpurun-ignored.
 """
 import os
@@ -25,6 +31,8 @@ ORACLE_SO = os.path.join(HERE, "_build", "libsvof_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libref_overlap.so")
 REF_CUT = "/root/reference/src/SimPLIC/cut"
 REF_CUT_SO = os.path.join(HERE, "_ref", "libref_cut.so")
+REF_ADV = "/root/reference/src/SimPLIC/advection"
+REF_ADV_SO = os.path.join(HERE, "_ref", "libref_advect.so")
 
 
 def _stale(target, sources):
@@ -74,7 +82,28 @@ def build_ref_cut(force=False):
     return REF_CUT_SO
 
 
+def build_ref_advect(force=False):
+    """Compile the reference's advection.C / advectionTemplates.C / cutFace.C where they lie, against the larger
+    OpenFOAM stand-in (oracle/of_stub_adv/); path or None."""
+    if not os.path.isdir(REF_ADV):
+        return REF_ADV_SO if os.path.exists(REF_ADV_SO) else None
+    wrapper = os.path.join(HERE, "ref_advect.cpp")
+    stubs = [os.path.join(HERE, "of_stub_adv", f) for f in ("OpenFOAMAdvectStub.H", "reconstruction.H")] + \
+            [os.path.join(HERE, "of_stub", "OpenFOAMCutStub.H")]
+    ora = [os.path.join(HERE, f) for f in ("ora_vec.hpp", "ora_mesh.hpp", "ora_cut.hpp", "ora_solver.hpp")]
+    ref_srcs = [os.path.join(REF_ADV, "advection.C"), os.path.join(REF_CUT, "cutFace", "cutFace.C")]
+    ref_hdrs = [os.path.join(REF_ADV, "advection.H"), os.path.join(REF_ADV, "advectionTemplates.C")]
+    if force or _stale(REF_ADV_SO, [wrapper, os.path.join(HERE, "..", "include", "svof.h")] + stubs + ora + ref_srcs + ref_hdrs):
+        os.makedirs(os.path.dirname(REF_ADV_SO), exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-DNoRepository",
+               "-I", os.path.join(HERE, "of_stub_adv"), "-I", REF_ADV, "-I", os.path.join(REF_CUT, "cutFace"),
+               "-I", os.path.join(REF_CUT, "cutCell"), "-I", HERE, "-o", REF_ADV_SO, wrapper] + ref_srcs
+        subprocess.check_call(cmd)
+    return REF_ADV_SO
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
     print(build_ref_cut(force="--force" in sys.argv))
+    print(build_ref_advect(force="--force" in sys.argv))

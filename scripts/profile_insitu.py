@@ -11,6 +11,8 @@ dt=0.2/n
 U, phi = bench.velocity_fields(s, dt, dt)
 s.setAlpha(a0); s.setPhi(phi); s.setU(U, np.zeros((s.nBF,3)))
 s.setOption("overlap", int(os.environ.get("OV","1")))
+s.setOption("dense_ctas", int(os.environ.get("DENSE_CTAS","0"))); s.setOption("dense_threads", int(os.environ.get("DENSE_THREADS","256")))
+s.setOption("plic_ctas", int(os.environ.get("PLIC_CTAS","0")))
 for _ in range(5): s.reconstruct(); s.advect(dt)
 s.synchronize()
 s.setOption("profile", 1)

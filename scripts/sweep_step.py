@@ -1,5 +1,5 @@
 """Schedule sweep at N^3 (default 256): device-resident graph step time for combinations of the run-time options
-(overlap, fork, plic_ctas, dense_ctas).  python scripts/sweep_step.py "ov,fork,plic,dense;ov,fork,plic,dense;..." [steps]"""
+(overlap, fork, plic_ctas, dense_ctas[, dense_threads]).  python scripts/sweep_step.py "ov,fork,plic,dense[,thr];..." [steps]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, numpy as np
@@ -14,9 +14,12 @@ dt = 0.2 / n
 U, phi = bench.velocity_fields(s, dt, dt)
 s.setPhi(phi); s.setU(U, np.zeros((s.nBF, 3)))
 ref = None
-for ov, fork, plic, dense in combos:
+for combo in combos:
+    ov, fork, plic, dense = combo[:4]
+    thr = combo[4] if len(combo) > 4 else 256
     s.setAlpha(a0)
     s.setOption("overlap", ov); s.setOption("fork", fork); s.setOption("plic_ctas", plic); s.setOption("dense_ctas", dense)
+    s.setOption("dense_threads", thr)
     for _ in range(6): s.step(dt)
     s.synchronize()
     s.lib.svof_mark(s._h, 0)
@@ -25,6 +28,6 @@ for ov, fork, plic, dense in combos:
     ms = C.c_double(); s.lib.svof_elapsed_ms(s._h, 0, 1, C.byref(ms)); s.synchronize()
     a = s.alpha()
     if ref is None: ref = a
-    print("overlap %d fork %d plic_ctas %d dense_ctas %d: %.4f ms/step  bitwise-same-as-first %s  err %d" %
-          (ov, fork, plic, dense, ms.value / steps, np.array_equal(a, ref), int(s.info(capi.I_ERROR_FLAGS))), flush=True)
+    print("overlap %d fork %d plic_ctas %d dense_ctas %d dense_threads %d: %.4f ms/step  bitwise-same-as-first %s  err %d" %
+          (ov, fork, plic, dense, thr, ms.value / steps, np.array_equal(a, ref), int(s.info(capi.I_ERROR_FLAGS))), flush=True)
 s.close()

@@ -132,6 +132,66 @@ class RefCut:
         return out[:n].copy()
 
 
+class RefAdvect:
+    """The REFERENCE's own advection class (src/SimPLIC/advection/advection.{H,C}, advectionTemplates.C, + cutFace.C,
+    compiled unmodified into oracle/_ref/libref_advect.so against the OpenFOAM stand-in oracle/of_stub_adv/), on a mesh.
+    One call = one advection::advect(Sp, Su) on the state handed in; the reconstruction it reads is an input."""
+
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            p = oracle_build.build_ref_advect()
+            if p is None:
+                return None
+            L = C.CDLL(p)
+            dp, ip = capi.c_double_p, capi.c_int32_p
+            L.ref_advect_create.restype = C.c_void_p
+            L.ref_advect_create.argtypes = [C.POINTER(capi.SvofMesh), C.POINTER(capi.SvofParams)]
+            L.ref_advect_destroy.argtypes = [C.c_void_p]
+            L.ref_advect_step.argtypes = [C.c_void_p, dp, dp, dp, dp, C.c_int32, ip, ip, dp, dp, dp, C.c_double, dp, dp, dp, dp, dp]
+            L.ref_advect_log.restype = C.c_char_p
+            L.ref_advect_log.argtypes = [C.c_void_p]
+            L.ref_advect_error.restype = C.c_char_p
+            L.ref_advect_error.argtypes = [C.c_void_p]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, m, params):
+        self.L = self.lib()
+        if self.L is None:
+            raise RuntimeError("oracle/_ref/libref_advect.so unavailable")
+        self.m = m
+        self._cm, self._keep = m.to_c()
+        self._h = self.L.ref_advect_create(C.byref(self._cm), C.byref(params))
+        assert self._h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self.L.ref_advect_destroy(self._h)
+            self._h = None
+
+    def step(self, alpha, phi, U, Ub, mixed, status, iN, iD, iC, dt, Sp=None, Su=None):
+        """-> alpha_new [nC], alphaPhi [nF], alpha boundary values [nBF], the Info lines of the step"""
+        m = self.m
+        nC, nF, nBF = m.n_cells, m.n_faces, m.n_faces - m.n_internal_faces
+        alpha, phi = capi.f64(alpha, (nC,)), capi.f64(phi, (nF,))
+        U, Ub = capi.f64(U, (nC, 3)), capi.f64(Ub, (nBF, 3))
+        mixed, status = capi.i32(mixed), capi.i32(status)
+        iN, iD, iC = capi.f64(iN, (nC, 3)), capi.f64(iD, (nC,)), capi.f64(iC, (nC, 3))
+        sp = capi.f64(Sp, (nC,)) if Sp is not None else None
+        su = capi.f64(Su, (nC,)) if Su is not None else None
+        a, ap, ab = np.empty(nC), np.empty(nF), np.empty(nBF)
+        rc = self.L.ref_advect_step(self._h, capi.dptr(alpha), capi.dptr(phi), capi.dptr(U), capi.dptr(Ub), len(mixed),
+                                    capi.iptr(mixed), capi.iptr(status), capi.dptr(iN), capi.dptr(iD), capi.dptr(iC), float(dt),
+                                    capi.dptr(sp) if sp is not None else None, capi.dptr(su) if su is not None else None,
+                                    capi.dptr(a), capi.dptr(ap), capi.dptr(ab))
+        if rc != 0:
+            raise RuntimeError("reference advect failed: %s" % self.L.ref_advect_error(self._h).decode())
+        return a, ap, ab, self.L.ref_advect_log(self._h).decode()
+
+
 def exact_sphere_alpha(m, centre=(0.35, 0.35, 0.35), radius=0.15):
     """Exact sphere/hex volume fractions on a hex_block mesh via the reference's
     overlap library (calcExactVofFieldForSphericalShapeInHexMesh/functions.H:1-27)."""
