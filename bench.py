@@ -593,6 +593,9 @@ def main():
     ap.add_argument("--scaling", default=os.environ.get("SVOF_BENCH_SCALING", "strong"), choices=["strong", "weak"])
     ap.add_argument("--strong-size", dest="strong_n", type=int, default=int(os.environ.get("SVOF_BENCH_STRONG_N", "512")))
     ap.add_argument("--layers", type=int, default=0, help="ghost layers (0: nAlphaBounds + 2)")
+    ap.add_argument("--partition", default=os.environ.get("SVOF_BENCH_PARTITION", "rcb"), choices=["interface", "rcb"],
+                    help="strong scaling on 4 / 8 ranks: 'interface' = the sphere on half of the ranks with few bulk cells, the other half "
+                         "streaming only (multigpu.interface_boxes); 'rcb' = weighted recursive bisection (--mixed-weight)")
     ap.add_argument("--mixed-weight", type=float, default=float(os.environ.get("SVOF_BENCH_MIXED_WEIGHT", "1000")),
                     help="partition weight of an interface cell relative to a bulk cell (strong scaling)")
     ap.add_argument("--overlap", type=int, default=-1, help="two-stream schedule (library option 'overlap'); -1: library default")

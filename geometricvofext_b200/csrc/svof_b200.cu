@@ -125,7 +125,7 @@ struct svof_handle {
     int device = 0;
     cudaStream_t stream = nullptr;   // main stream: copies, sparse kernels, timing events
     cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
-    cudaEvent_t evNear = nullptr, evDense = nullptr, evInputs = nullptr, evCopy = nullptr;
+    cudaEvent_t evNear = nullptr, evPlic = nullptr, evDense = nullptr, evInputs = nullptr, evCopy = nullptr;
     bool inputsAfterNear = false, freshRecon = false;
     std::map<std::string, double> hostAcc;  // profile: host wall time per phase of svof_step_host (ms)
     std::chrono::steady_clock::time_point hostT;
@@ -222,6 +222,8 @@ struct svof_handle {
     bool un0Group = false;           // 8 lanes per cut cell for the interface speed (SVOF_UN0=thread: round-1 thread-per-cell kernel)
     int plicCtas = 0;                // "plic_ctas" option: cap on resident CTAs/SM of the plane-positioning kernel (0 = all that fit)
     int denseCtas = 0;               // "dense_ctas" option: cap on resident CTAs/SM of the streaming kernel (0 = no cap)
+    int denseSplit = 0;              // "dense_split" option (with dense_ctas): percent of the tiles launched uncapped before plane positioning
+    int denseL2 = 0;                 // "dense_l2" option: 1 = L2 evict-first hints in the streaming kernel
     int denseThreads = 256;          // "dense_threads" option: threads per CTA of the capped streaming kernel (128 or 256)
     int forkAt = 1;                  // "fork" option (overlap != 0): 1 = streaming kernel may start after the near sets, 2 = after plane positioning
     int* bPatch = nullptr;
@@ -831,6 +833,7 @@ void allocFields(svof_handle* h)
     if (h->evNear) return;   // svof_update_mesh: the events of the handle are kept
     for (int i = 0; i < 8; ++i) CK(cudaEventCreate(&h->marks[i]));
     CK(cudaEventCreateWithFlags(&h->evNear, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evPlic, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evDense, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evInputs, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evCopy, cudaEventDisableTiming));
@@ -1241,6 +1244,7 @@ void doReconstruct(svof_handle* h)
         LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
     GEO(h, plic, s, h->plicCtas, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
     if (h->overlap && h->forkAt != 1) CK(cudaEventRecord(h->evNear, s));
+    if (h->overlap) CK(cudaEventRecord(h->evPlic, s));
     h->bitsValid = false;  // consumed
 }
 
@@ -1284,10 +1288,30 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
         else if (h->denseCtas > 0) {   // capped grid walking the tiles: a fixed share of every SM (see k_dense_update_capped)
             const int thr = (h->denseThreads == 128) ? 128 : 256;
             const int tiles = cdiv(h->nC, thr);
-            k_dense_update_capped<<<std::min(tiles, h->denseCtas * h->sms), thr, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb],
-                                                                                       h->alphaPhi, h->near2, h->mixedBits, dt, rDt, dSp,
-                                                                                       dSu, h->sp, h->ctl, tiles);
-        } else
+            int tile0 = 0;
+            if (h->overlap && h->denseSplit > 0 && h->freshRecon && !(h->inputsAfterNear || dSp || dSu)) {
+                // "dense_split" percent of the tiles at full occupancy right after the near sets (beside the normals kernel,
+                // until the plane-positioning kernel takes the registers), the rest capped once plane positioning is done
+                tile0 = (int)((long long)tiles * std::min(h->denseSplit, 100) / 100);
+                if (tile0 > 0)
+                    k_dense_update_capped<<<tile0, thr, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2,
+                                                                 h->mixedBits, dt, rDt, dSp, dSu, h->sp, h->ctl, 0, tile0);
+                CK(cudaStreamWaitEvent(sD, h->evPlic, 0));
+                h->launches++;
+            }
+            if (tile0 < tiles)
+                k_dense_update_capped<<<std::min(tiles - tile0, h->denseCtas * h->sms), thr, 0, sD>>>(
+                    d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits, dt, rDt, dSp, dSu, h->sp, h->ctl, tile0,
+                    tiles);
+        } else if (h->denseL2) {   // L2 evict-first hints on what the pass streams (see DenseMem)
+#define DENSE_EF(E) k_dense_update_hint<E><<<nTiles, 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, \
+                                                               h->mixedBits, dt, rDt, dSp, dSu, h->sp, h->ctl)
+            if (h->denseL2 == 1) DENSE_EF(1);
+            else if (h->denseL2 == 2) DENSE_EF(2);
+            else DENSE_EF(3);
+#undef DENSE_EF
+        }
+        else
             k_dense_update<<<nTiles, 256, 0, sD>>>(d, aOld, aNew, h->phi, h->alphaBBuf[h->cb], h->alphaPhi, h->near2, h->mixedBits, dt, rDt,
                                                    dSp, dSu, h->sp, h->ctl);
     }
@@ -1362,7 +1386,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
 // every run-time option that changes which kernels / grids a captured step contains
 int schedKey(const svof_handle* h)
 {
-    return (((h->overlap * 10 + h->forkAt) * 100 + h->plicCtas) * 100 + h->denseCtas) * 2 + (h->denseThreads == 128 ? 1 : 0);
+    return (((h->overlap * 10 + h->forkAt) * 100 + h->plicCtas) * 100 + h->denseCtas) * 8 + (h->denseThreads == 128 ? 1 : 0) + 2 * h->denseL2 + 1000000 * h->denseSplit;
 }
 
 void fetchCtl(svof_handle* h)
@@ -1563,6 +1587,7 @@ int svof_destroy(svof_handle* h)
     for (int i = 0; i < 8; ++i) if (h->marks[i]) cudaEventDestroy(h->marks[i]);
     for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->evNear) cudaEventDestroy(h->evNear);
+    if (h->evPlic) cudaEventDestroy(h->evPlic);
     if (h->evDense) cudaEventDestroy(h->evDense);
     if (h->evInputs) cudaEventDestroy(h->evInputs);
     if (h->evCopy) cudaEventDestroy(h->evCopy);
@@ -2639,6 +2664,8 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "fork")) { h->forkAt = value; return SVOF_OK; }
     if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; return SVOF_OK; }
     if (!strcmp(name, "dense_threads")) { h->denseThreads = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_l2")) { h->denseL2 = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_split")) { h->denseSplit = value; return SVOF_OK; }
     if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; return SVOF_OK; }
     if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
     if (!strcmp(name, "bound_lanes")) { h->boundLanes = value != 0; for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } return SVOF_OK; }

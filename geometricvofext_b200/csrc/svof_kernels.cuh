@@ -1180,29 +1180,73 @@ __device__ __forceinline__ void blockMinMaxFast(double mn, double mx, unsigned l
 #define SV_DENSE_UNROLL 1
 #endif
 constexpr int kDenseUnroll = SV_DENSE_UNROLL;
+// L2 eviction hints for the streaming pass (PTX createpolicy + .L2::cache_hint), "dense_l2" option: the lines the pass
+// streams (1.9 GB per launch through a 126 MB L2) become PREFERRED VICTIMS -- 1: connectivity rows, offsets, volumes and
+// the stores; 2: those loads only; 3: everything incl. phi and alpha (measured: 3 costs the pass its own L2 reuse of
+// phi / alpha, +0.09 ms) -- so the few MB the interface kernels on the other stream keep re-reading (mesh rows and fields next to the
+// interface, the lists one kernel hands to the next) stay resident while it runs beside them.
+template <bool EF> struct DenseMem;
+template <> struct DenseMem<false> {
+    __device__ __forceinline__ DenseMem() {}
+    __device__ __forceinline__ int ldi(const int* p) const { return __ldg(p); }
+    __device__ __forceinline__ int2 ldi2(const int2* p) const { return __ldg(p); }
+    __device__ __forceinline__ double ldd(const double* p) const { return __ldg(p); }
+    __device__ __forceinline__ void std_(double* p, double v) const { *p = v; }
+};
+template <> struct DenseMem<true> {
+    unsigned long long pol;
+    __device__ __forceinline__ DenseMem() { asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol)); }
+    __device__ __forceinline__ int ldi(const int* p) const
+    {
+        int v;
+        asm("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+        return v;
+    }
+    __device__ __forceinline__ int2 ldi2(const int2* p) const
+    {
+        int2 v;
+        asm("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+        return v;
+    }
+    __device__ __forceinline__ double ldd(const double* p) const
+    {
+        double v;
+        asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+        return v;
+    }
+    __device__ __forceinline__ void std_(double* p, double v) const
+    {
+        asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+    }
+};
+
 // the per-cell body of the streaming pass: returns whether the new value is a mixed cell; mn / mx take the unclipped value
+template <int EF>
 __device__ __forceinline__ bool denseCell(const MeshDev& m, int c, const double* __restrict__ aOld, double* __restrict__ aNew,
                                           const double* __restrict__ phi, const double* __restrict__ alphaB,
                                           double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2, double dt, double rDt,
                                           const double* __restrict__ Sp, const double* __restrict__ Su, const StepParams& sp, double& mn,
                                           double& mx)
 {
+    const DenseMem<(EF != 0)> mem;          // single-use streams: connectivity rows, offsets, volumes
+    const DenseMem<(EF == 3)> memR;         // streams with reuse in L2 (phi: read by both cells of a face; alpha: gathers)
+    const DenseMem<(EF == 1 || EF == 3)> memW;  // stores
     bool mixed = false;
     if (c < m.nCells && !bitTest(near2, c)) {
-        const int k0 = __ldg(m.cellOff + c), k1 = __ldg(m.cellOff + c + 1);
-        const double aC = __ldg(aOld + c);
+        const int k0 = mem.ldi(m.cellOff + c), k1 = mem.ldi(m.cellOff + c + 1);
+        const double aC = memR.ldd(aOld + c);
         double sum = 0.0;
 #pragma unroll kDenseUnroll
         for (int k = k0; k < k1; ++k) {
-            const int2 e = __ldg(m.cellAsc + k);
+            const int2 e = mem.ldi2(m.cellAsc + k);
             const int f = e.x & 0x7fffffff;
             const bool flip = e.x < 0;
-            const double ph = __ldg(phi + f);
+            const double ph = memR.ldd(phi + f);
             double aUp;
             if (e.y >= 0) {
                 // upwind cell: owner if phi >= 0 else neighbour; this cell's own value is in a register
                 const bool selfUp = flip ? (ph < 0) : (ph >= 0);
-                aUp = selfUp ? aC : __ldg(aOld + e.y);
+                aUp = selfUp ? aC : memR.ldd(aOld + e.y);
             } else {
                 const int bf = -1 - e.y;
                 const unsigned char kind = __ldg(m.bKind + bf);
@@ -1212,12 +1256,12 @@ __device__ __forceinline__ bool denseCell(const MeshDev& m, int c, const double*
             const double dvf = (ph * aUp) * dt;
             if (!flip) {
                 sum += dvf;
-                alphaPhi[f] = divz(dvf, dt);
+                memW.std_(alphaPhi + f, divz(dvf, dt));
             } else {
                 sum -= dvf;
             }
         }
-        const double ivf = divz(sum, __ldg(m.V + c));
+        const double ivf = divz(sum, mem.ldd(m.V + c));
         double num = aC * rDt;
         if (Su) num = num + Su[c];
         num = num - ivf * rDt;
@@ -1225,12 +1269,26 @@ __device__ __forceinline__ bool denseCell(const MeshDev& m, int c, const double*
         mn = dmin(mn, a);
         mx = dmax(mx, a);
         a = snapClip(a, sp.snapTol, sp.clip);
-        aNew[c] = a;
+        memW.std_(aNew + c, a);
         mixed = (sp.mixedTol < a) && (a < 1.0 - sp.mixedTol);
     }
     return mixed;
 }
 
+template <int EF>
+__device__ __forceinline__ void denseTile(const MeshDev& m, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                          const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                          double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
+                                          unsigned int* __restrict__ mixedNext, double dt, double rDt, const double* __restrict__ Sp,
+                                          const double* __restrict__ Su, const StepParams& sp, Ctl* ctl)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double mn = SV_VGREAT, mx = -SV_VGREAT;
+    const bool mixed = denseCell<EF>(m, c, aOld, aNew, phi, alphaB, alphaPhi, near2, dt, rDt, Sp, Su, sp, mn, mx);
+    const unsigned int w = __ballot_sync(0xffffffffu, mixed);
+    if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
+    blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
+}
 __global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
                                                       const double* __restrict__ phi, const double* __restrict__ alphaB,
                                                       double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
@@ -1238,12 +1296,18 @@ __global__ void __launch_bounds__(256, 8) k_dense_update(MeshDev m, const double
                                                       const double* __restrict__ Sp, const double* __restrict__ Su, StepParams sp,
                                                       Ctl* ctl)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    double mn = SV_VGREAT, mx = -SV_VGREAT;
-    const bool mixed = denseCell(m, c, aOld, aNew, phi, alphaB, alphaPhi, near2, dt, rDt, Sp, Su, sp, mn, mx);
-    const unsigned int w = __ballot_sync(0xffffffffu, mixed);
-    if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
-    blockMinMaxFast(mn, mx, &ctl->minDense, &ctl->maxDense);
+    denseTile<0>(m, aOld, aNew, phi, alphaB, alphaPhi, near2, mixedNext, dt, rDt, Sp, Su, sp, ctl);
+}
+// "dense_l2" variants (opt-in; all measured slower, profiles/r4f_sweep_dense_l2_hints.txt)
+template <int EF>
+__global__ void __launch_bounds__(256, 8) k_dense_update_hint(MeshDev m, const double* __restrict__ aOld, double* __restrict__ aNew,
+                                                           const double* __restrict__ phi, const double* __restrict__ alphaB,
+                                                           double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
+                                                           unsigned int* __restrict__ mixedNext, double dt, double rDt,
+                                                           const double* __restrict__ Sp, const double* __restrict__ Su, StepParams sp,
+                                                           Ctl* ctl)
+{
+    denseTile<EF>(m, aOld, aNew, phi, alphaB, alphaPhi, near2, mixedNext, dt, rDt, Sp, Su, sp, ctl);
 }
 
 // The same pass as a CAPPED grid ("dense_ctas" CTAs per SM, "dense_threads" threads each) whose CTAs walk the tiles
@@ -1255,12 +1319,12 @@ __global__ void __launch_bounds__(256, 8) k_dense_update_capped(MeshDev m, const
                                                              double* __restrict__ alphaPhi, const unsigned int* __restrict__ near2,
                                                              unsigned int* __restrict__ mixedNext, double dt, double rDt,
                                                              const double* __restrict__ Sp, const double* __restrict__ Su,
-                                                             StepParams sp, Ctl* ctl, int nTiles)
+                                                             StepParams sp, Ctl* ctl, int tile0, int nTiles)
 {
     double mn = SV_VGREAT, mx = -SV_VGREAT;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    for (int tile = tile0 + blockIdx.x; tile < nTiles; tile += gridDim.x) {
         const int c = tile * blockDim.x + threadIdx.x;
-        const bool mixed = denseCell(m, c, aOld, aNew, phi, alphaB, alphaPhi, near2, dt, rDt, Sp, Su, sp, mn, mx);
+        const bool mixed = denseCell<0>(m, c, aOld, aNew, phi, alphaB, alphaPhi, near2, dt, rDt, Sp, Su, sp, mn, mx);
         const unsigned int w = __ballot_sync(0xffffffffu, mixed);
         if ((threadIdx.x & 31) == 0 && c < m.nCells) mixedNext[c >> 5] = w;
     }

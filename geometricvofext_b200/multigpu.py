@@ -341,6 +341,56 @@ def sphere_plane_weights(n, mixed_weight, centre=(0.35, 0.35, 0.35), radius=0.15
     return fn
 
 
+def interface_boxes(n, world, centre=(0.35, 0.35, 0.35), radius=0.15, margin=3, k_bulk=25.7e-9, chain=(0.35, 17.2e-6), hide=0.76):
+    """Boxes for the strong-scaling run that put the INTERFACE on half of the ranks and give those ranks few bulk cells.
+
+    Cost model of one rank (fitted on the single-GPU profiles): the interface chain costs
+    chain[0] + chain[1] * interface cells [ms] however few cells the rank streams, and the streaming kernel k_bulk ms per
+    cell, of which `hide` still shows when both run on one GPU.  A bisection that balances (cells + w * interface cells)
+    hands every rank a piece of the sphere, so EVERY rank pays the chain on top of its share of the bulk.  Here the
+    corner region [0,qx) x [0,qy) x [0,qz) that contains the sphere is split, through the sphere's centre, over world/2
+    "interface ranks"; the rest of the box -- three slabs -- goes to the other ranks as pure streaming work:
+        world 8:  4 interface boxes (x, y split)  |  x >= qx in two halves, {x < qx, y >= qy}, {x < qx, y < qy, z >= qz}
+        world 4:  2 interface boxes (x split) of the column [0,qx) x [0,qy) x [0,n)  |  x >= qx, {x < qx, y >= qy}
+    qx, qy, qz >= the sphere's extent + margin are chosen to even out the bulk ranks.  Other rank counts: None (the caller
+    falls back to the weighted bisection).  Returns a list of (lo, hi) integer triples, box r for rank r."""
+    n = int(n)
+    qmin = int(np.ceil((max(centre) + radius) * n)) + margin
+    c = [int(round(x * n)) for x in centre]
+    if qmin >= n - 1:
+        return None
+    best = None
+    if world == 8:
+        for qz in range(qmin, n, max(1, n // 64)):
+            for qy in range(qmin, n, max(1, n // 64)):
+                for qx in range(qmin, n, max(1, n // 64)):
+                    A = (n - qx) * n * n / 2.0
+                    B = qx * (n - qy) * n
+                    Cc = qx * qy * (n - qz)
+                    R = qx * qy * qz / 4.0
+                    shell = 4 * np.pi * (radius * n) ** 2 * 1.5 / 4.0
+                    t = max(k_bulk * max(A, B, Cc), chain[0] + chain[1] * shell + hide * k_bulk * R)
+                    if best is None or t < best[0]:
+                        best = (t, qx, qy, qz)
+        _, qx, qy, qz = best
+        h = n // 2
+        return [((0, 0, 0), (c[0], c[1], qz)), ((c[0], 0, 0), (qx, c[1], qz)), ((0, c[1], 0), (c[0], qy, qz)), ((c[0], c[1], 0), (qx, qy, qz)),
+                ((qx, 0, 0), (n, h, n)), ((qx, h, 0), (n, n, n)), ((0, qy, 0), (qx, n, n)), ((0, 0, qz), (qx, qy, n))]
+    if world == 4:
+        for qy in range(qmin, n, max(1, n // 64)):
+            for qx in range(qmin, n, max(1, n // 64)):
+                A = (n - qx) * n * n
+                B = qx * (n - qy) * n
+                R = qx * qy * n / 2.0
+                shell = 4 * np.pi * (radius * n) ** 2 * 1.5 / 2.0
+                t = max(k_bulk * max(A, B), chain[0] + chain[1] * shell + hide * k_bulk * R)
+                if best is None or t < best[0]:
+                    best = (t, qx, qy)
+        _, qx, qy = best
+        return [((0, 0, 0), (c[0], qy, n)), ((c[0], 0, 0), (qx, qy, n)), ((qx, 0, 0), (n, n, n)), ((0, qy, 0), (qx, n, n))]
+    return None
+
+
 def bench(args, controls, metric, unit):
     """N-GPU leg of bench.py: STRONG scaling of one LeVeque problem (default 512^3, BASELINE.json configs[4]) over
     `world` ranks, or (--scaling weak) one 256^3 unit cube per GPU."""
@@ -374,12 +424,17 @@ def bench(args, controls, metric, unit):
     elif strong:
         n = args.strong_n
         wfn = sphere_plane_weights(n, args.mixed_weight) if args.mixed_weight > 0 else None
-        boxes = box_rcb(n, world, wfn)
+        # the margin keeps the sphere out of the GHOST layers of the bulk ranks too (a rank with any interface cell pays the chain)
+        boxes = interface_boxes(n, world, margin=layers + 2) if getattr(args, "partition", "rcb") == "interface" else None
+        how = "into interface boxes (the sphere on %d ranks with few bulk cells) and bulk boxes (streaming only)" % (world // 2)
+        if boxes is None:
+            boxes = box_rcb(n, world, wfn)
+            how = "by weighted recursive bisection into boxes (interface cells weigh %g)" % args.mixed_weight
         dec = BoxDecomposition(n, world, layers, boxes=boxes)
         centre = (0.35, 0.35, 0.35)
         dt = 0.2 / n
         workload = ("LeVeque 3-D deformation, sphere r=0.15, %d^3 hex blockMesh (BASELINE.json configs[4]), ONE problem split over "
-                    "%d ranks by weighted recursive bisection into boxes (interface cells weigh %g)" % (n, world, args.mixed_weight))
+                    "%d ranks %s" % (n, world, how))
     else:
         grid = np.array(block_grid(world))
         n_global = (args.n * grid).tolist()

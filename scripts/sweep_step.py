@@ -1,5 +1,5 @@
 """Schedule sweep at N^3 (default 256): device-resident graph step time for combinations of the run-time options
-(overlap, fork, plic_ctas, dense_ctas[, dense_threads]).  python scripts/sweep_step.py "ov,fork,plic,dense[,thr];..." [steps]"""
+(overlap, fork, plic_ctas, dense_ctas[, dense_threads]).  python scripts/sweep_step.py "ov,fork,plic,dense[,thr[,l2]];..." [steps]"""
 import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, numpy as np
@@ -17,6 +17,10 @@ ref = None
 for combo in combos:
     ov, fork, plic, dense = combo[:4]
     thr = combo[4] if len(combo) > 4 else 256
+    l2 = combo[5] if len(combo) > 5 else 0
+    s.setOption("dense_l2", l2)
+    split = combo[6] if len(combo) > 6 else 0
+    s.setOption("dense_split", split)
     s.setAlpha(a0)
     s.setOption("overlap", ov); s.setOption("fork", fork); s.setOption("plic_ctas", plic); s.setOption("dense_ctas", dense)
     s.setOption("dense_threads", thr)
@@ -28,6 +32,6 @@ for combo in combos:
     ms = C.c_double(); s.lib.svof_elapsed_ms(s._h, 0, 1, C.byref(ms)); s.synchronize()
     a = s.alpha()
     if ref is None: ref = a
-    print("overlap %d fork %d plic_ctas %d dense_ctas %d dense_threads %d: %.4f ms/step  bitwise-same-as-first %s  err %d" %
-          (ov, fork, plic, dense, thr, ms.value / steps, np.array_equal(a, ref), int(s.info(capi.I_ERROR_FLAGS))), flush=True)
+    print("overlap %d fork %d plic_ctas %d dense_ctas %d dense_threads %d dense_l2 %d dense_split %d: %.4f ms/step  bitwise-same-as-first %s  err %d" %
+          (ov, fork, plic, dense, thr, l2, split, ms.value / steps, np.array_equal(a, ref), int(s.info(capi.I_ERROR_FLAGS))), flush=True)
 s.close()

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def _case(kind, n):
     """mesh, controls, alpha0(C, V), velocity, dt -- the same on every rank and in the single-domain run"""
     from common import LEVEQUE_CONTROLS, fields, meshmod
-    if kind == "hex":
+    if kind in ("hex", "hexI"):   # hexI: the interface-aware boxes of the strong-scaling bench (multigpu.interface_boxes)
         m = meshmod.hex_block(n)
         return m, dict(LEVEQUE_CONTROLS), None, fields.leveque_velocity, 0.25 / n
     if kind == "hex10":   # default nAlphaBounds 10, Courant ~1: several effective bounding sweeps near the cuts
@@ -47,10 +47,12 @@ def _worker(rank, world, kind, n, steps, port, out_dir, layers):
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
     m, controls, _, velocity, dt = _case(kind, n)
     layers = layers or mg.default_layers(controls)
+    custom = mg.interface_boxes(n, world) if kind == "hexI" else None
+    assert kind != "hexI" or custom is not None
     if kind.startswith("hex") and rank % 2 == 0:
-        sub, maps = mg.BoxDecomposition(n, world, layers).rank_mesh(rank)      # box fast path (no global mesh)
+        sub, maps = mg.BoxDecomposition(n, world, layers, boxes=custom).rank_mesh(rank)      # box fast path (no global mesh)
     elif kind.startswith("hex"):
-        boxes = mg.BoxDecomposition(n, world, layers).boxes                     # the same boxes through svof_decompose
+        boxes = mg.BoxDecomposition(n, world, layers, boxes=custom).boxes                     # the same boxes through svof_decompose
         cr = np.empty(n ** 3, np.int32)
         for r, (lo, hi) in enumerate(boxes):
             k, j, i = np.meshgrid(np.arange(lo[2], hi[2]), np.arange(lo[1], hi[1]), np.arange(lo[0], hi[0]), indexing="ij")
@@ -150,10 +152,10 @@ def test_partition_and_decomposition_are_consistent():
 
 
 @pytest.mark.parametrize("kind,world,n,steps,layers", [("hex", 2, 20, 6, 0), ("hex", 4, 20, 6, 0), ("kelvin", 3, 6, 5, 0),
-                                                       ("hex10", 2, 24, 10, 0)])
+                                                       ("hex10", 2, 24, 10, 0), ("hexI", 4, 24, 6, 0), ("hexI", 8, 24, 6, 0)])
 def test_gloo_ranks_match_single_domain(tmp_path, kind, world, n, steps, layers):
     import torch.multiprocessing as mp
-    port = 29500 + (os.getpid() % 500) + world + (7 if kind != "hex" else 0) + (13 if kind == "hex10" else 0)
+    port = 29500 + (os.getpid() % 500) + world + (7 if kind != "hex" else 0) + (13 if kind == "hex10" else 0) + (23 if kind == "hexI" else 0)
     mp.spawn(_worker, args=(world, kind, n, steps, port, str(tmp_path), layers), nprocs=world, join=True)
     ref, vref, ncells, max_sweeps = _single(kind, n, steps)
     got = np.full(ncells, np.nan)
