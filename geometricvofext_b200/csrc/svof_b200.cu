@@ -193,7 +193,8 @@ struct svof_handle {
     int zcCur = 0;
     bool zcPrevValid = false;        // zcBits[zcCur] describes the alphaPhi the caller's buffer holds
     std::map<const void*, void*> pinnedCache;   // caller pointer -> device pointer (nullptr: not device-accessible host memory)
-    const unsigned int* boundPhiBits = nullptr;   // set by svof_step_host around its doAdvect: see k_bound_apply
+    unsigned int* boundPhiBits = nullptr;   // set by svof_step_host around its doAdvect: see k_bound_deps / k_bound_apply
+    const double* boundPhiHost = nullptr;   // zero-copy form: the caller's pinned phi (device address), see loadCellBound
     bool phiBitsReady = false;       // the face bitmap of the CURRENT alpha is already on the host (prefetched by the previous svof_step_host)
     bool phiPartial = false;         // device phi holds stale values on faces between exactly empty cells: not a full field
     int nWordsF = 0, nPhiBlocks = 0;
@@ -1342,7 +1343,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
 #define BOUND_SWEEP(MB)                                                                                                       \
     do {                                                                                                                     \
         LAUNCH(h, k_bound_deps<MB>, gB, 128, d, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, \
-               dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList, h->boundPhiBits); \
+               dSu, h->bs, h->depInit, h->depLeft, h->oobIdx, (CellBound<MB>*)h->boundRecs, h->capRec, h->affList, h->boundPhiBits, h->boundPhiHost); \
         LAUNCH(h, k_bound_run<MB>, 16 * h->sms, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx, \
                (const CellBound<MB>*)h->boundRecs, h->capRec, dt, rDt);                                                      \
         LAUNCH(h, k_bound_apply<MB>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs,               \
@@ -1350,7 +1351,7 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     } while (0)
         if (h->maxCF <= 8 && h->boundLanes) {   // eight faces in eight lanes of the chain walker's warp
             LAUNCH(h, k_bound_deps<8>, gB, 128, d, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, aNew, aOld, h->phi, h->dVf, dSp, dSu, h->bs,
-                   h->depInit, h->depLeft, h->oobIdx, (CellBound<8>*)h->boundRecs, h->capRec, h->affList, h->boundPhiBits);
+                   h->depInit, h->depLeft, h->oobIdx, (CellBound<8>*)h->boundRecs, h->capRec, h->affList, h->boundPhiBits, h->boundPhiHost);
             LAUNCH(h, k_bound_run8, 16 * h->sms, 64, h->ctl, sidx, h->oobList[sidx & 1], h->oobState, h->bs, h->depInit, h->depLeft, h->oobIdx,
                    (const CellBound<8>*)h->boundRecs, h->capRec, dt, rDt);
             LAUNCH(h, k_bound_apply<8>, gB, 128, d, h->ctl, sidx, h->affList, h->near1, aNew, h->dVf, h->bs, h->oobList[(sidx + 1) & 1],
@@ -2231,11 +2232,13 @@ int stepHostZeroCopy(svof_handle* h, double dt, const double* phi, const double*
     CK(cudaStreamWaitEvent(st, h->evCopy, 0));
     CK(cudaMemsetAsync(&h->ctl->packUnsafe, 0, sizeof(int), st));
     CK(cudaMemsetAsync(&h->ctl->phiUnsafe, 0, sizeof(int), st));
-    h->boundPhiBits = bitsCur;   // k_bound_deps / k_bound_apply flag an out-of-bounds cell with a face outside the bitmap
+    h->boundPhiBits = bitsCur;   // an out-of-bounds cell with a face outside the bitmap: k_bound_deps reads that entry from the caller's phi
+    h->boundPhiHost = phiD;
     EventPair& e1 = beginTimed(h, 1);
     doAdvect(h, dt, nullptr, nullptr);
     endTimed(h, e1);
     h->boundPhiBits = nullptr;
+    h->boundPhiHost = nullptr;
     // results
     const bool pushA = alpha_out && h->hostAlphaSynced == alpha_out;
     CK(cudaMemsetAsync(&h->ctl->nDeltaA, 0, 2 * sizeof(int), st));
@@ -2394,6 +2397,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     doAdvect(h, dt, nullptr, nullptr);
     endTimed(h, e1);
     h->boundPhiBits = nullptr;
+    h->boundPhiHost = nullptr;
     // results: deltas against what the caller's buffers already hold, else full copies.  Both delta kernels, the control
     // block (with the two counts) and a speculative prefix of each (index, value) list -- sized from the previous step --
     // are enqueued together and waited for ONCE; a list that turned out longer gets its remainder in a second copy.

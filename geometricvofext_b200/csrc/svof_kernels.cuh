@@ -1898,8 +1898,13 @@ struct __align__(16) CellBound {
 };
 
 template <int SV_MAXBF>
-__device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const double* __restrict__ phi, const double* dVf,
-                                              const BoundScratch& b, int tag, CellBound<SV_MAXBF>& cb)
+// phiBits / phiHost / phiDev (svof_step_host, zero-copy form): the device holds phi only on the faces its bitmap marks (a
+// cell with alpha != 0 on one side).  An out-of-bounds cell whose own alpha WAS zero -- it received a negative sliver from a
+// neighbour, or was overfilled at Courant > 1 -- has unmarked faces: their entries are read here straight from the caller's
+// pinned phi, stored and marked, so the sweep (and the alphaPhi read-back) sees exactly the full field.
+__device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const double* phi, const double* dVf,
+                                              const BoundScratch& b, int tag, CellBound<SV_MAXBF>& cb, unsigned int* phiBits = nullptr,
+                                              const double* phiHost = nullptr, double* phiDev = nullptr, Ctl* ctl = nullptr)
 {
     const int c0 = m.cellOff[celli];
     int nf = m.cellOff[celli + 1] - c0;
@@ -1918,7 +1923,15 @@ __device__ __forceinline__ void loadCellBound(const MeshDev& m, int celli, const
             if (ff[j] >= 0) {
                 const int f = ff[j];
                 ow[j] = m.owner[f];
-                ph[j] = phi[f];
+                if (phiHost && !((__ldcg(phiBits + (f >> 5)) >> (f & 31)) & 1u)) {
+                    ph[j] = *(const volatile double*)(phiHost + f);
+                    phiDev[f] = ph[j];
+                    __threadfence();   // whoever sees the bit sees the value
+                    atomicOr(phiBits + (f >> 5), 1u << (f & 31));
+                    atomicAdd(&ctl->nPhiPulled, 1);
+                } else {
+                    ph[j] = __ldcg(phi + f);
+                }
                 dv[j] = dVf[f];
                 tg[j] = __ldcg(b.tagV + f);  // L2 reads: written by other SMs during this kernel
                 cr[j] = __ldcg(b.corr + f);
@@ -2052,18 +2065,18 @@ __device__ bool boundCell(int celli, CellBound<SV_MAXBF>& cb, const BoundScratch
 template <int SV_MAXBF>
 __global__ void __launch_bounds__(128) k_bound_deps(MeshDev m, Ctl* ctl, int s, const int* oobList,
                                                     const unsigned char* oobState, const double* alpha, const double* aOld,
-                                                    const double* __restrict__ phi, const double* dVf, const double* Sp,
+                                                    double* phi, const double* dVf, const double* Sp,
                                                     const double* Su, BoundScratch b, int* depInit, int* depLeft, int* oobIdx,
                                                     CellBound<SV_MAXBF>* recs, int capRec, int* affList,
-                                                    const unsigned int* __restrict__ phiBits = nullptr)
+                                                    unsigned int* phiBits = nullptr, const double* phiHost = nullptr)
 {
     const int n = ctl->nOob[s & 1];
     const int tag = boundTag(ctl, s);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int c = oobList[i];
         CellBound<SV_MAXBF> cb;
-        loadCellBound(m, c, phi, dVf, b, tag, cb);  // corrections of this sweep do not exist yet: fCorr == 0
-        if (phiBits) {   // svof_step_host uploaded phi only where a neighbouring cell held liquid: every face of this cell must be among them
+        loadCellBound(m, c, phi, dVf, b, tag, cb, phiBits, phiHost, phi, ctl);  // corrections of this sweep do not exist yet: fCorr == 0
+        if (phiBits && !phiHost) {   // staged svof_step_host: phi was uploaded only where a neighbouring cell held liquid: every face of this cell must be among them
             for (int q = 0; q < cb.nf; ++q)
                 if (!((phiBits[cb.fId[q] >> 5] >> (cb.fId[q] & 31)) & 1u)) ctl->phiUnsafe = 1;
         }
