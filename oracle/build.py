@@ -19,6 +19,13 @@
                                       upwind, fvc::surfaceIntegrate, bitSet, zeroField ...) + ref_advect.cpp.
                                       Pins the oracle's restatement of advect() to the reference's statements.
 
+  oracle/_ref/libref_solver.so     -- the reference's WHOLE solveVofEqu class: solveVofEqu.{H,C} + solveVofEquTemplates.C,
+                                      reconstruction.{H,C}, advection.{H,C} + advectionTemplates.C, cutFace.{H,C},
+                                      cutCell.{H,C} (every file of src/SimPLIC outside sampling/), compiled UNMODIFIED from
+                                      /root/reference against oracle/of_stub_rec/ (+ leastSquareGrad, Gauss-linear fvc::grad,
+                                      zoneDistribute, reconstructedDistanceFunction, IOdictionary ...) + ref_solver.cpp.
+                                      Pins reconstruct() and the chained reconstruct + advect steps to the reference's statements.
+
 Both directories are git-ignored and are NOT gpurun-ignored.
 """
 import os
@@ -33,6 +40,9 @@ REF_CUT = "/root/reference/src/SimPLIC/cut"
 REF_CUT_SO = os.path.join(HERE, "_ref", "libref_cut.so")
 REF_ADV = "/root/reference/src/SimPLIC/advection"
 REF_ADV_SO = os.path.join(HERE, "_ref", "libref_advect.so")
+REF_REC = "/root/reference/src/SimPLIC/reconstruction"
+REF_SOLVER = "/root/reference/src/SimPLIC/solveVofEqu"
+REF_SOLVER_SO = os.path.join(HERE, "_ref", "libref_solver.so")
 
 
 def _stale(target, sources):
@@ -102,8 +112,35 @@ def build_ref_advect(force=False):
     return REF_ADV_SO
 
 
+def build_ref_solver(force=False):
+    """Compile the reference's solveVofEqu.C / reconstruction.C / advection.C / cutFace.C / cutCell.C where they lie, against
+    oracle/of_stub_rec/ (which builds on the two smaller stand-ins); path or None."""
+    if not os.path.isdir(REF_REC):
+        return REF_SOLVER_SO if os.path.exists(REF_SOLVER_SO) else None
+    wrapper = os.path.join(HERE, "ref_solver.cpp")
+    stubs = [os.path.join(HERE, "of_stub_rec", "OpenFOAMReconStub.H"), os.path.join(HERE, "of_stub_adv", "OpenFOAMAdvectStub.H"),
+             os.path.join(HERE, "of_stub", "OpenFOAMCutStub.H")]
+    ora = [os.path.join(HERE, f) for f in ("ora_vec.hpp", "ora_mesh.hpp", "ora_cut.hpp", "ora_solver.hpp")]
+    ref_srcs = [os.path.join(REF_SOLVER, "solveVofEqu.C"), os.path.join(REF_REC, "reconstruction.C"),
+                os.path.join(REF_ADV, "advection.C"), os.path.join(REF_CUT, "cutFace", "cutFace.C"),
+                os.path.join(REF_CUT, "cutCell", "cutCell.C")]
+    ref_hdrs = [os.path.join(REF_SOLVER, "solveVofEqu.H"), os.path.join(REF_SOLVER, "solveVofEquTemplates.C"),
+                os.path.join(REF_REC, "reconstruction.H"), os.path.join(REF_ADV, "advection.H"),
+                os.path.join(REF_ADV, "advectionTemplates.C")]
+    if force or _stale(REF_SOLVER_SO, [wrapper, os.path.join(HERE, "..", "include", "svof.h")] + stubs + ora + ref_srcs + ref_hdrs):
+        os.makedirs(os.path.dirname(REF_SOLVER_SO), exist_ok=True)
+        # the reference's own directories come first: reconstruction.H must be the real one
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-w", "-DNoRepository",
+               "-I", REF_REC, "-I", REF_SOLVER, "-I", REF_ADV, "-I", os.path.join(REF_CUT, "cutFace"),
+               "-I", os.path.join(REF_CUT, "cutCell"), "-I", os.path.join(HERE, "of_stub_rec"), "-I", HERE,
+               "-o", REF_SOLVER_SO, wrapper] + ref_srcs
+        subprocess.check_call(cmd)
+    return REF_SOLVER_SO
+
+
 if __name__ == "__main__":
     print(build_oracle(force="--force" in sys.argv))
     print(build_ref(force="--force" in sys.argv))
     print(build_ref_cut(force="--force" in sys.argv))
     print(build_ref_advect(force="--force" in sys.argv))
+    print(build_ref_solver(force="--force" in sys.argv))
