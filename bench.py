@@ -509,7 +509,9 @@ def run_workload(args):
 
 
 def _ref_worker(args_tuple):
-    n, lo, hi, dt, steps, warm = args_tuple
+    """One z-slab sub-domain, single-threaded: the reference's own solveVofEqu class (oracle/_ref/libref_solver.so) when it was
+    built, and the oracle port on the same slab and steps for comparison.  -> cells, seconds (reference class or None), seconds (port)"""
+    n, lo, hi, dt, steps, warm, want_class = args_tuple
     m, a0 = build_case(n, lo=lo, hi=hi, cut_as_wall=True)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import build as oracle_build
@@ -519,6 +521,22 @@ def _ref_worker(args_tuple):
     so.setAlpha(a0)
     so.setPhi(phi)
     so.setU(U)
+    t_class = None
+    if want_class:
+        from refsolver import RefSolver
+        if RefSolver.lib() is not None:
+            Cf = so.field(capi.F_CF)
+            ref = RefSolver(m, so._params)
+            ref.setState(a0, phi, U, fields.leveque_velocity(Cf[m.n_internal_faces:]) * fields.u_factor(dt, dt, PERIOD))
+            for _ in range(warm):
+                ref.reconstruct()
+                ref.advect(dt)
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                ref.reconstruct()
+                ref.advect(dt)
+            t_class = time.perf_counter() - t0
+            del ref
     for _ in range(warm):
         so.reconstruct()
         so.advect(dt)
@@ -526,14 +544,17 @@ def _ref_worker(args_tuple):
     for _ in range(steps):
         so.reconstruct()
         so.advect(dt)
-    return m.n_cells, time.perf_counter() - t0
+    return m.n_cells, t_class, time.perf_counter() - t0
 
 
 def run_reference(args):
-    """The reference's own CPU algorithm for the path on the box's host cores.  OpenFOAM v2312 cannot be
-    built here (no wmake/MPI), so this is the oracle port, run the way the reference runs in parallel:
-    P sub-domains (z-slabs of the same mesh), one single-threaded process each, no halo exchange
-    (cut faces are treated as walls, which only removes communication cost from the CPU side)."""
+    """The reference's own CPU implementation of the path on the box's host cores: its solveVofEqu class -- every file of
+    src/SimPLIC outside sampling/, compiled unmodified against an OpenFOAM stand-in into oracle/_ref/libref_solver.so
+    (OpenFOAM v2312 itself cannot be built here: no wmake/MPI) -- run the way the reference runs in parallel:
+    P sub-domains (z-slabs of the same mesh), one single-threaded process each, no halo exchange (cut faces are treated as
+    walls, which only removes communication cost from the CPU side).  The oracle port runs the same slabs and steps right
+    after it; its figure is reported beside the class's (cpu_baseline.port_value).  Without the prebuilt library the port is
+    the arm (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -545,24 +566,37 @@ def run_reference(args):
     dt = 0.2 / ns
     bounds = [(ns * p) // P for p in range(P + 1)]
     steps = max(1, args.steps)
-    jobs = [(ns, (0, 0, bounds[p]), (ns, ns, bounds[p + 1]), dt, steps, max(1, min(args.warmup, 1))) for p in range(P)]
+    want_class = args.ref_kind != "port"
+    jobs = [(ns, (0, 0, bounds[p]), (ns, ns, bounds[p + 1]), dt, steps, max(1, min(args.warmup, 1)), want_class) for p in range(P)]
     t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(P) as pool:
         res = pool.map(_ref_worker, jobs)
     wall = time.perf_counter() - t0
     cells = sum(r[0] for r in res)
-    tmax = max(r[1] for r in res)
+    t_port = max(r[2] for r in res)
+    have_class = all(r[1] is not None for r in res)
+    tmax = max(r[1] for r in res) if have_class else t_port
     value = cells * steps / tmax
+    if have_class:
+        cpu = {"value": value, "unit": UNIT, "cores": P, "kind": "reference",
+               "sample": "%d^3 LeVeque mesh split into %d z-slab sub-domains, one single-threaded process each running the "
+                         "reference's own solveVofEqu class (src/SimPLIC compiled unmodified against an OpenFOAM stand-in: "
+                         "oracle/_ref/libref_solver.so; OpenFOAM v2312/MPI not installable here), %d steps, slowest rank %.1f s"
+                         % (ns, P, steps, tmax),
+               "port_value": cells * steps / t_port,
+               "port_note": "the CPU restatement (oracle/) on the same slabs and steps, slowest rank %.1f s" % t_port}
+    else:
+        cpu = {"value": value, "unit": UNIT, "cores": P, "kind": "port",
+               "sample": "%d^3 LeVeque mesh split into %d z-slab sub-domains, one single-threaded process each "
+                         "(CPU restatement of the reference algorithm; oracle/_ref/libref_solver.so not built), "
+                         "%d steps, slowest rank %.1f s" % (ns, P, steps, tmax)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tmax / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "LeVeque 3-D deformation, sphere r=0.15, %d^3 hex blockMesh (BASELINE.json configs[1])" % n,
                    "sample_mesh": "%d^3 in %d z-slabs" % (ns, P), "dt": dt, "controls": CONTROLS, "wall_s": wall},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port",
-                         "sample": "%d^3 LeVeque mesh split into %d z-slab sub-domains, one single-threaded process each "
-                                   "(CPU restatement of the reference algorithm; OpenFOAM v2312/MPI not installable here), "
-                                   "%d steps, slowest rank %.1f s" % (ns, P, steps, tmax)},
+        "cpu_baseline": cpu,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -589,6 +623,9 @@ def main():
     ap.add_argument("--late-cpu-steps", type=int, default=2, help="oracle steps for the parity block of the second window")
     ap.add_argument("--ref-procs", type=int, default=0)
     ap.add_argument("--ref-size", dest="ref_n", type=int, default=0)
+    ap.add_argument("--ref-kind", default="reference", choices=["reference", "port"],
+                    help="--impl reference: the reference's own class from oracle/_ref/libref_solver.so (default; falls back to the "
+                         "port when the library is not there) or only the oracle port")
     # N > 1: strong scaling of ONE problem (BASELINE.json configs[4]) unless --scaling weak (one 256^3 unit cube per GPU)
     ap.add_argument("--scaling", default=os.environ.get("SVOF_BENCH_SCALING", "strong"), choices=["strong", "weak"])
     ap.add_argument("--strong-size", dest="strong_n", type=int, default=int(os.environ.get("SVOF_BENCH_STRONG_N", "512")))
