@@ -267,3 +267,95 @@ def test_oracle_surfaces_match_reference(kind):
 @pytest.mark.parametrize("kind", ["hexes", "Kelvin cells"])
 def test_gpu_surfaces_match_reference(kind, product):
     _surfaces_against_reference(product, {"hexes": lambda: meshmod.hex_block(14), "Kelvin cells": lambda: meshmod.kelvin_mesh(6)}[kind])
+
+
+# ---- the reference's test case as a whole: plicVofAdvectionFoam's time loop around the reference's own class ----------
+class _RefAsSolver:
+    """The few members fields.AdvectionDriver uses, served by the reference's solveVofEqu (geometry from `geom`)."""
+
+    def __init__(self, m, geom):
+        self.ref = RefSolver(m, geom._params)
+        self.mesh, self.nC, self.nF, self.nIF, self.nBF = m, geom.nC, geom.nF, geom.nIF, geom.nBF
+        self._geom = geom
+
+    def field(self, which):
+        return self._geom.field(which)
+
+    def alpha(self):
+        return self.ref.fields()[0]
+
+    def setAlpha(self, a):
+        self.ref.setState(alpha=a)
+
+    def setPhi(self, phi):
+        self.ref.setState(phi=phi)
+
+    def setU(self, U, Ub):
+        self.ref.setState(U=U, Ub=Ub)
+
+    def reconstruct(self):
+        self.ref.reconstruct()
+
+    def advect(self, dt):
+        self.ref.advect(dt)
+
+
+def _drive_both(m, lib, a0, t0, dt0, n_steps=None, end_time=None, what=""):
+    s = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=lib)
+    r = _RefAsSolver(m, s)
+    drivers = []
+    for x in (s, r):
+        x.setAlpha(a0)
+        d = fields.AdvectionDriver(x)
+        if t0 > 0:
+            d.t, d.dt = t0, dt0
+            d.phi = d.phi0 * fields.u_factor(t0, d.dt, 6.0)
+        drivers.append(d)
+    k = n_mixed = 0
+    while (k < n_steps) if n_steps is not None else drivers[0].running(end_time):
+        for d in drivers:
+            d.step(end_time)
+        assert drivers[0].dt == drivers[1].dt, "%s step %d: the two time loops chose different time steps" % (what, k)
+        mc, st, iN, iD, iC, iS = r.ref.recon()
+        assert np.array_equal(mc, s.mixedCells()) and np.array_equal(st, s.cellStatus()), "%s step %d: interface cells" % (what, k)
+        assert np.array_equal(iN[mc], s.interfaceN()[mc]) and np.array_equal(iD, s.interfaceD()), "%s step %d: planes" % (what, k)
+        ra, rap, _ = r.ref.fields()
+        assert np.array_equal(ra, s.alpha()), "%s step %d (t = %.4f): alpha differs from the reference's by %g" % (
+            what, k, drivers[0].t, np.abs(ra - s.alpha()).max())
+        assert np.array_equal(rap, s.alphaPhi()), "%s step %d: alphaPhi" % (what, k)
+        n_mixed = max(n_mixed, len(mc))
+        k += 1
+    flags = s.info(capi.I_ERROR_FLAGS)
+    s.close()
+    assert flags == 0
+    return k, n_mixed
+
+
+def test_oracle_full_deformation_run_32_equals_reference_class_every_step():
+    """The reference's test case (tutorials/test/plicVofAdvectionFoam: LeVeque deformation, period 6, maxCo = maxAlphaCo = 0.5,
+    adaptive dt) at 32^3 from t = 0 to maximum deformation and back (t = 3): under-resolved filaments, slivers, bounding
+    chains -- the oracle equals the reference's own solveVofEqu bitwise at every one of the ~300 steps."""
+    m = meshmod.hex_block(32)
+    steps, n_mixed = _drive_both(m, oracle_lib(), exact_sphere_alpha(m), 0.0, None, end_time=3.0, what="oracle 32^3")
+    assert steps > 250 and n_mixed > 1200
+
+
+@pytest.mark.gpu
+def test_gpu_64_from_the_golden_t15_field_equals_reference_class(product):
+    """CUDA library vs the reference's own class on the reference's 64^3 case at its hardest instant (golden exact field at
+    t = 1.5: 6 094 interface cells in thin sheets), 12 adaptive steps."""
+    import os
+    N = 64
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "exact_alpha_64.npz"))
+    a0 = np.zeros(N ** 3)
+    a0[G["full_idx_1.5"]] = 1.0
+    a0[G["part_idx_1.5"]] = G["part_val_1.5"]
+    steps, n_mixed = _drive_both(meshmod.hex_block(N), product, a0, 1.5, 2.0e-3, n_steps=12, what="CUDA 64^3")
+    assert n_mixed > 5000
+
+
+@pytest.mark.gpu
+def test_gpu_deformation_run_32_equals_reference_class(product):
+    m = meshmod.hex_block(32)
+    steps, n_mixed = _drive_both(m, product, exact_sphere_alpha(m), 0.0, None, n_steps=120, what="CUDA 32^3")
+    assert n_mixed > 500
