@@ -6,6 +6,7 @@
 
 #include <cstring>
 #include <sstream>
+#include <vector>
 
 namespace Foam
 {
@@ -398,6 +399,29 @@ const double* solveVofEqu::sourcePtr(const volScalarField::Internal& f, scalarFi
 void solveVofEqu::reconstruct()
 {
     reconstructor_.reconstruct();
+}
+
+void solveVofEqu::setCellTypes(const labelList& cellTypes)
+{
+    if (cellTypes.size() == 0)
+    {
+        check(svof_set_cell_types(h_, nullptr), h_, "svof_set_cell_types");
+        return;
+    }
+    if (sub_)
+    {
+        FatalErrorInFunction
+            << "overset cell types on a decomposed device mesh need the ghost cells' types as well: not supported"
+            << abort(FatalError);
+    }
+    if (cellTypes.size() != mesh_.nCells())
+    {
+        FatalErrorInFunction << "cellTypes has " << cellTypes.size() << " entries for " << mesh_.nCells() << " cells"
+            << abort(FatalError);
+    }
+    std::vector<int32_t> t(cellTypes.size());
+    forAll(cellTypes, c) t[c] = cellTypes[c];
+    check(svof_set_cell_types(h_, t.data()), h_, "svof_set_cell_types");
 }
 
 void solveVofEqu::advectFlat(const double* Sp, const double* Su)

@@ -116,5 +116,20 @@ int main(int argc, char** argv)
     const int32_t nSub = int32_t(sub.faces.size());
     fwrite(&nSub, sizeof(int32_t), 1, o);
     fclose(o);
+
+    // overset hook (reconstruction.C:649-662): with cell types set, only CALCULATED cells are listed
+    geometricVofExt::SimPLIC::reconstruction& rec = mesh.lookupObjectRef<geometricVofExt::SimPLIC::reconstruction>("reconstruction");
+    const label nAll = label(rec.mixedCells().size());
+    labelList types(nC, 0);
+    for (label c = 0; c < nC; c += 2) types[c] = 1;      // every other cell INTERPOLATED
+    plicVofSolver.setCellTypes(types);
+    plicVofSolver.reconstruct();
+    const labelList kept(rec.mixedCells());
+    bool onlyCalculated = true;
+    forAll(kept, i) onlyCalculated = onlyCalculated && (types[kept[i]] == 0);
+    plicVofSolver.setCellTypes(labelList());
+    plicVofSolver.reconstruct();
+    Info<< "overset filter: " << label(kept.size()) << " of " << nAll << " interface cells kept, CALCULATED only "
+        << (onlyCalculated ? "yes" : "no") << ", restored " << label(rec.mixedCells().size()) << endl;
     return 0;
 }

@@ -102,6 +102,7 @@ SYMBOLS = [
     ("svof_update_mesh", C.c_int, [_H, C.POINTER(SvofMesh)]),
     ("svof_set_interface", C.c_int, [_H, c_double_p, c_double_p]),
     ("svof_map_alpha_field", C.c_int, [_H, C.c_double, C.c_double]),
+    ("svof_set_cell_types", C.c_int, [_H, c_int32_p]),
     # decomposed runs
     ("svof_partition_rcb", C.c_int, [C.POINTER(SvofMesh), c_double_p, C.c_int32, c_int32_p]),
     ("svof_decompose", C.c_int, [C.POINTER(SvofMesh), c_int32_p, C.c_int32, C.c_int32, C.POINTER(_H)]),

@@ -248,6 +248,8 @@ struct svof_handle {
     } halo;
     bool haveAlpha = false, havePhi = false, haveU = false, bitsValid = false, advected = false;
     bool anyInletOutlet = false;
+    unsigned int* calcBitsStore = nullptr;
+    unsigned int* calcBits = nullptr;   // overset: one bit per CALCULATED cell (svof_set_cell_types), nullptr = no filter
     bool interfaceDense = false;   // interfaceN/D were set for all cells (svof_set_interface): clear them densely once
     double mapTime = 0;            // alphaMappingTime (reconstruction.C:782)
     bool uPartial = false;   // svof_step_host (sparse_io) uploaded only the rows of U near the interface: not a full field
@@ -1225,6 +1227,7 @@ void doReconstruct(svof_handle* h)
         h->interfaceDense = false;
     }
     if (!h->bitsValid) LAUNCH(h, k_mixed_bits, cdiv(h->nC, 256), 256, alpha, h->nC, h->prm.mixed_cell_tol, h->mixedBits);
+    if (h->calcBits) LAUNCH(h, k_and_bits, cdiv(h->nWords, 256), 256, h->mixedBits, h->calcBits, h->nWords);   // reconstruction.C:649-662
     LAUNCH(h, k_front_count, h->nScanBlocks, SV_SCAN_WORDS, h->mixedBits, h->nWords, h->blockSums, h->mixedCells, h->near2List, h->capNear,
            h->ctl, h->iN, h->iD, h->iC, h->iS, h->cellSlot, h->near1, h->near2);
     LAUNCH(h, k_front_scan, 1, 1024, h->blockSums, h->nScanBlocks, h->ctl, h->capMixed);
@@ -1692,6 +1695,7 @@ void releaseMeshState(svof_handle* h)
     h->phiPrevBitsValid = h->alphaPhiPrevValid = false;
     h->phiBits = nullptr; h->phiBlockOff = nullptr; h->phiPacked = nullptr; h->phiPartial = false;
     h->rdf = nullptr; h->capRdfMixed = 0; h->nRdfPrev = 0;   // isoRDF buffers are re-created for the new mesh
+    h->calcBits = h->calcBitsStore = nullptr;                // cell types belong to the old mesh
     h->zcBits[0] = h->zcBits[1] = nullptr; h->zcPrevValid = false;
     harvestEvents(h, true);
     h->halo = svof_handle::Halo();
@@ -1730,6 +1734,30 @@ int svof_set_interface(svof_handle* h, const double* interfaceN, const double* i
     CK(cudaMemcpyAsync(h->iD, interfaceD, sizeof(double) * h->nC, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->interfaceDense = true;   // the next reconstruct() must clear the whole fields, not just the previous mixed cells
+    return SVOF_OK;
+    API_END(h)
+}
+
+int svof_set_cell_types(svof_handle* h, const int32_t* cell_types)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    API_BEGIN
+    CK(cudaSetDevice(h->device));
+    const bool had = h->calcBits != nullptr;
+    if (!cell_types) {
+        h->calcBits = nullptr;   // the buffer stays with the handle's allocations; the filter is off
+    } else {
+        std::vector<unsigned int> bits((size_t)h->nWords, 0u);
+        for (int c = 0; c < h->nC; ++c)
+            if (cell_types[c] == 0) bits[(size_t)c >> 5] |= 1u << (c & 31);   // cellCellStencil::CALCULATED
+        if (!h->calcBitsStore) h->calcBitsStore = dalloc<unsigned int>(h, (size_t)h->nWords);
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(h->calcBitsStore, bits.data(), sizeof(unsigned int) * (size_t)h->nWords, cudaMemcpyHostToDevice));
+        h->calcBits = h->calcBitsStore;
+    }
+    // the launch list of reconstruct() changes with the filter: captured steps are re-captured
+    if (had != (h->calcBits != nullptr))
+        for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     return SVOF_OK;
     API_END(h)
 }

@@ -187,6 +187,14 @@ __global__ void k_mixed_bits(const double* __restrict__ alpha, int nCells, doubl
     if ((threadIdx.x & 31) == 0 && c < nCells) bits[c >> 5] = w;
 }
 
+// overset meshes (reconstruction.C:649-662): only CALCULATED cells may enter the interface-cell list; `calc` holds one bit
+// per CALCULATED cell (svof_set_cell_types)
+__global__ void k_and_bits(unsigned int* __restrict__ bits, const unsigned int* __restrict__ calc, int nWords)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < nWords) bits[w] &= calc[w];
+}
+
 // alpha[idx[i]] = vals[i] (halo cells refreshed from their owning rank) with the mixed-cell bitmap kept up to date,
 // so a decomposed run needs no dense bitmap pass after its halo swap
 __global__ void k_scatter_alpha(const int* __restrict__ idx, const double* __restrict__ vals, long long n, double tol, double* alpha,

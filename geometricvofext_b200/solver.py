@@ -122,6 +122,16 @@ class SolveVofEqu:
         (mesh.changing() && mapAlphaField) and maps interfaceN/D first (setInterface)."""
         self._chk(self.lib.svof_map_alpha_field(self._h, float(lower), float(upper)))
 
+    def setCellTypes(self, cell_types):
+        """dynamicOversetFvMesh: the overset stencil's cell types (0 = CALCULATED); interface cells are listed only among the
+        CALCULATED cells (reconstruction.C:649-662).  None switches the filter off.  phi must be the masked flux."""
+        if cell_types is None:
+            self._chk(self.lib.svof_set_cell_types(self._h, None))
+            return
+        t = capi.i32(cell_types)
+        assert t.shape == (self.nC,)
+        self._chk(self.lib.svof_set_cell_types(self._h, capi.iptr(t)))
+
     def setInterface(self, N, D):
         n, d = capi.f64(N, (self.nC, 3)), capi.f64(D, (self.nC,))
         self._chk(self.lib.svof_set_interface(self._h, capi.dptr(n), capi.dptr(d)))

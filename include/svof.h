@@ -384,6 +384,15 @@ int svof_set_interface(svof_handle* h, const double* interfaceN, const double* i
  * (mesh.changing() && mapAlphaField, reconstruction.C:732). */
 int svof_map_alpha_field(svof_handle* h, double lower_refine_level, double upper_refine_level);
 
+/* Overset meshes (dynamicOversetFvMesh).  cell_types [n_cells] are cellCellStencil::cellType values of the overset
+ * stencil (0 CALCULATED, 1 INTERPOLATED, 2 HOLE, ...): reconstruction::initialize() then lists an interface cell only
+ * where the type is CALCULATED (reconstruction.C:649-662).  NULL switches the filter off (any other mesh type).
+ * The second overset statement of the path, dVf_ *= faceMask (advectionTemplates.C:383-396, faceMask = the smaller
+ * cellMask of the two cells of a face), multiplies by exactly 0 or 1 and is an identity when phi is already masked --
+ * which the reference demands of its callers ("Make sure phi_ *= faceMask if overset mesh is used", :370) and its solvers
+ * do: pass the masked phi to svof_set_phi.  Call again after the stencil is updated (mesh motion). */
+int svof_set_cell_types(svof_handle* h, const int32_t* cell_types);
+
 /* ---- decomposed runs ----------------------------------------------------------
  * Replaces what the reference does across processor patches: the zoneDistribute stencil
  * exchange (reconstruction.C:97-107), syncProcPatches (advection.C:311-393, called once

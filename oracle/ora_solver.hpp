@@ -188,6 +188,9 @@ struct Solver {
         return (prm.mixed_cell_tol < alpha[c]) && (alpha[c] < 1.0 - prm.mixed_cell_tol);
     }
 
+    // overset: cellCellStencil cell types (empty = not an overset mesh); CALCULATED = 0
+    std::vector<label> cellTypes;
+
     // ---------------------------------------------------------------- A1 ----
     void initialize()  // reconstruction.C:634-677
     {
@@ -197,8 +200,9 @@ struct Solver {
         std::fill(interfaceC.begin(), interfaceC.end(), vec());
         std::fill(interfaceS.begin(), interfaceS.end(), vec());
         std::fill(interfaceD.begin(), interfaceD.end(), 0.0);
+        const bool overset = !cellTypes.empty();   // isA<dynamicOversetFvMesh>(mesh_)  (:649-662)
         for (label c = 0; c < mesh.nCells; ++c) {
-            if (isAMixedCell(c)) {
+            if (isAMixedCell(c) && (!overset || cellTypes[c] == 0)) {
                 mixedCells.push_back(c);
                 cellStatus.push_back(-100);
             }

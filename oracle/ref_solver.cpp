@@ -74,13 +74,14 @@ struct Ref
     volScalarField* alpha;
     surfaceScalarField* phi;
     volVectorField* U;
+    volScalarField* cellMask;   // overset: 0 in HOLE cells, 1 elsewhere (registered as "cellMask")
     RefSolver* solver;
     DimensionedField<scalar> Sp, Su;
     std::string log, ctorLog, err;
     // last extracted surface
     std::vector<double> sPts;
     std::vector<int32_t> sOff, sFacePts, sCells;
-    Ref() : alpha(nullptr), phi(nullptr), U(nullptr), solver(nullptr) {}
+    Ref() : alpha(nullptr), phi(nullptr), U(nullptr), cellMask(nullptr), solver(nullptr) {}
     ~Ref()
     {
         delete solver;
@@ -89,6 +90,7 @@ struct Ref
             zoneDistributes.erase(fmp.get());
             oversetStencils.erase(fmp.get());
         }
+        delete cellMask;
         delete U;
         delete phi;
         delete alpha;
@@ -338,9 +340,23 @@ int ref_solver_set_cell_types(void* h, const int32_t* types)
 {
     Ref* r = static_cast<Ref*>(h);
     if (!r) return -1;
-    cellCellStencilObject& o = stubOversetStencil(*r->fmp);
-    o.cellTypes_.setSize(r->fmp->nCells());
-    for (label c = 0; c < r->fmp->nCells(); ++c) o.cellTypes_[c] = types[c];
+    fvMesh& fm = *r->fmp;
+    cellCellStencilObject& o = stubOversetStencil(fm);
+    o.cellTypes_.setSize(fm.nCells());
+    for (label c = 0; c < fm.nCells(); ++c) o.cellTypes_[c] = types[c];
+    // cellMask as dynamicOversetFvMesh keeps it: 0 in holes, 1 elsewhere; zeroGradient patches
+    if (!r->cellMask)
+    {
+        r->cellMask = new volScalarField(IOobject("cellMask", "0", fm), fm, dimensionedScalar(dimless, 1.0));
+        fm.objects_.push_back(std::make_pair(word("cellMask"), static_cast<const void*>(r->cellMask)));
+    }
+    for (label c = 0; c < fm.nCells(); ++c) (*r->cellMask)[c] = (types[c] == cellCellStencil::HOLE) ? 0.0 : 1.0;
+    for (label p = 0; p < r->cellMask->boundaryField().size(); ++p)
+    {
+        const label start = fm.boundaryMesh()[p].start();
+        for (label i = 0; i < r->cellMask->boundaryField()[p].size(); ++i)
+            r->cellMask->boundaryFieldRef()[p][i] = (*r->cellMask)[fm.faceOwner()[start + i]];
+    }
     return 0;
 }
 

@@ -485,6 +485,14 @@ int svof_set_interface(svof_handle* h, const double* N, const double* D)
     return SVOF_OK;
 }
 
+int svof_set_cell_types(svof_handle* h, const int32_t* cell_types)
+{
+    if (!h) return SVOF_ERR_INVALID_ARG;
+    if (!cell_types) h->s.cellTypes.clear();
+    else h->s.cellTypes.assign(cell_types, cell_types + h->s.mesh.nCells);
+    return SVOF_OK;
+}
+
 int svof_map_alpha_field(svof_handle* h, double lower, double upper)
 {
     if (!h) return SVOF_ERR_INVALID_ARG;

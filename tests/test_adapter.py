@@ -77,7 +77,10 @@ def _run_case(lib, lib_path, tmp_path, tag, n=10, steps=4):
     assert npoly == len(s.interface()[2]) and npoly > 0
     nsub = int(np.fromfile(fout, dtype=np.int32, offset=8 * (nC + 3 * nIF) + 4, count=1)[0])
     assert nsub == len(s.subCellFaces()[3]) and nsub > npoly
-    assert log.count("SimPLIC::reconstruction: Number of mixed cells = ") == steps + 1
+    assert log.count("SimPLIC::reconstruction: Number of mixed cells = ") == steps + 3
+    import re
+    kept, n_all, only, restored = re.search(r"overset filter: (\d+) of (\d+) interface cells kept, CALCULATED only (\w+), restored (\d+)", log).groups()
+    assert 0 < int(kept) < int(n_all) == int(restored) == npoly and only == "yes"
     assert log.count("SimPLIC::advection: Before conservative bounding: min(alpha) = ") == steps
     assert log.count("SimPLIC::advection: After  conservative bounding: min(alpha) = ") == steps
     assert "SimPLIC::Mesh face flatness: min/max/avg = " in log

@@ -359,3 +359,102 @@ def test_gpu_deformation_run_32_equals_reference_class(product):
     m = meshmod.hex_block(32)
     steps, n_mixed = _drive_both(m, product, exact_sphere_alpha(m), 0.0, None, n_steps=120, what="CUDA 32^3")
     assert n_mixed > 500
+
+
+# ---- overset meshes: the cell-type filter of initialize() and the face mask of advect() -------------------------------
+def _overset_against_reference(lib, what):
+    """A dynamicOversetFvMesh scenario on one component mesh: a block of HOLE cells with a layer of INTERPOLATED cells
+    around it, the sphere's interface crossing both; phi masked on the faces of the holes, as the reference demands of
+    its callers (advectionTemplates.C:370).  The interface-cell list keeps CALCULATED cells only (reconstruction.C:649-662),
+    dVf *= faceMask (advectionTemplates.C:383-396) runs in the reference; everything bitwise, five steps."""
+    n = 14
+    m = meshmod.hex_block(n)
+    s = SolveVofEqu(m, dict(LEVEQUE_CONTROLS), lib=lib)
+    ref = RefSolver(m, s._params, RefSolver.OVERSET)
+    C_, Cf, Sf, V = s.field(capi.F_C), s.field(capi.F_CF), s.field(capi.F_SF), s.field(capi.F_V)
+    ijk = np.floor(C_ * n).astype(int)
+    lo, hi = np.array([6, 4, 4]), np.array([8, 6, 6])
+    hole = np.all((ijk >= lo) & (ijk <= hi), axis=1)
+    fringe = np.all((ijk >= lo - 1) & (ijk <= hi + 1), axis=1) & ~hole
+    types = np.zeros(m.n_cells, np.int32)
+    types[fringe], types[hole] = 1, 2
+    a0 = exact_sphere_alpha(m)
+    mixed_by_alpha = (a0 > 1e-8) & (a0 < 1 - 1e-8)
+    assert (mixed_by_alpha & fringe).sum() > 10 and (mixed_by_alpha & hole).sum() > 5 and (mixed_by_alpha & (types == 0)).sum() > 30
+    vel = fields.leveque_velocity
+    U0, phi0 = vel(C_), fields.face_flux(Cf, Sf, vel)
+    Ub = vel(Cf[m.n_internal_faces:])
+    # faceMask = localMin(cellMask): 0 where a hole touches the face
+    mask = np.ones(m.n_faces)
+    nIF = m.n_internal_faces
+    mask[:nIF] = np.minimum(~hole[m.owner[:nIF]], ~hole[m.neighbour[:nIF]])
+    mask[nIF:] = ~hole[m.owner[nIF:]]
+    phi0 = phi0 * mask
+    dt = 0.5 * np.cbrt(V.min()) / np.abs(U0).max()
+    s.setPhi(phi0)
+    s.setAlpha(a0)
+    s.setU(U0, Ub)
+    s.setCellTypes(types)
+    ref.setState(a0, phi0, U0, Ub)
+    ref.setCellTypes(types)
+    for k in range(5):
+        s.reconstruct()
+        ref.reconstruct()
+        mc, st, iN, iD, iC, iS = ref.recon()
+        assert np.all(types[mc] == 0)
+        a_now = s.alpha()
+        assert len(mc) < int(((a_now > 1e-8) & (a_now < 1 - 1e-8)).sum()), "the filter must have removed cells"
+        assert np.array_equal(mc, s.mixedCells()) and np.array_equal(st, s.cellStatus()), "%s step %d: interface-cell list" % (what, k)
+        assert np.array_equal(iN[mc], s.interfaceN()[mc]) and np.array_equal(iD, s.interfaceD())
+        assert np.array_equal(iC, s.field(capi.F_INTERFACE_C)) and np.array_equal(iS, s.interfaceS())
+        s.advect(dt)
+        ref.advect(dt)
+        ra, rap, rab = ref.fields()
+        assert np.array_equal(ra, s.alpha()), "%s step %d: alpha differs by %g" % (what, k, np.abs(ra - s.alpha()).max())
+        assert np.array_equal(rap, s.alphaPhi()), "%s step %d: alphaPhi" % (what, k)
+        assert np.array_equal(rab, s.field(capi.F_ALPHA_BOUNDARY))
+    # switching the filter off again restores the plain list
+    s.setCellTypes(None)
+    s.reconstruct()
+    a_now = s.alpha()
+    assert len(s.mixedCells()) == int(((a_now > 1e-8) & (a_now < 1 - 1e-8)).sum())
+    assert s.info(capi.I_ERROR_FLAGS) == 0
+    s.close()
+
+
+def test_oracle_overset_cell_types_match_reference():
+    _overset_against_reference(oracle_lib(), "oracle")
+
+
+@pytest.mark.gpu
+def test_gpu_overset_cell_types_match_reference(product):
+    _overset_against_reference(product, "CUDA")
+
+
+@pytest.mark.gpu
+def test_gpu_overset_filter_inside_the_captured_step(product, oracle):
+    """svof_step_device (CUDA graph) with the cell-type filter: set, stepped, cleared, stepped -- against the oracle."""
+    n = 12
+    m = meshmod.hex_block(n)
+    out = []
+    for lib in (oracle, product):
+        s = SolveVofEqu(m, dict(LEVEQUE_CONTROLS), lib=lib)
+        C_, Cf, Sf = s.field(capi.F_C), s.field(capi.F_CF), s.field(capi.F_SF)
+        types = (np.linalg.norm(C_ - np.array([0.35, 0.35, 0.5]), axis=1) < 0.12).astype(np.int32)
+        s.setPhi(fields.face_flux(Cf, Sf))
+        s.setAlpha(exact_sphere_alpha(m))
+        s.setU(fields.leveque_velocity(C_))
+        rec = []
+        for k in range(9):
+            if k == 2:
+                s.setCellTypes(types)
+            if k == 6:
+                s.setCellTypes(None)
+            s.step(0.01)
+            rec.append((s.alpha(), s.mixedCells()))
+        out.append(rec)
+        s.close()
+    for k, ((ao, mo), (ag, mg)) in enumerate(zip(*out)):
+        assert np.array_equal(mo, mg), "step %d: interface-cell list" % k
+        assert np.array_equal(ao, ag), "step %d: alpha" % k
+    assert len(out[0][3][1]) < len(out[0][1][1]) or len(out[0][3][1]) < len(out[0][7][1])
