@@ -126,6 +126,12 @@ struct svof_handle {
     cudaStream_t stream = nullptr;   // main stream: copies, sparse kernels, timing events
     cudaStream_t streamD = nullptr;  // streaming (dense) kernel only: runs concurrently with the sparse chain
     cudaEvent_t evNear = nullptr, evPlic = nullptr, evDense = nullptr, evInputs = nullptr, evCopy = nullptr;
+    // zero-copy host step, overlapped form ("zc_overlap" option): U rows pulled on their own stream beside the normals / plane
+    // positioning, the streaming kernel forked at the near sets, values that are final after it pushed on its stream
+    cudaStream_t streamU = nullptr;
+    cudaEvent_t evFront = nullptr, evU = nullptr, evPush = nullptr;
+    int zcOverlap = 7;   // bit 0: U rows on their own stream, bit 1: streaming kernel forked at the near sets, bit 2: early pushes
+    bool zcDenseEarly = false;
     bool inputsAfterNear = false, freshRecon = false;
     std::map<std::string, double> hostAcc;  // profile: host wall time per phase of svof_step_host (ms)
     std::chrono::steady_clock::time_point hostT;
@@ -840,6 +846,9 @@ void allocFields(svof_handle* h)
     CK(cudaEventCreateWithFlags(&h->evDense, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evInputs, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evCopy, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evFront, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evU, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evPush, cudaEventDisableTiming));
     h->events.resize(96);
     for (EventPair& e : h->events) {
         CK(cudaEventCreate(&e.a));
@@ -1234,6 +1243,7 @@ void doReconstruct(svof_handle* h)
     LAUNCH(h, k_front_write, h->nScanBlocks, SV_SCAN_WORDS, d, h->mixedBits, h->nWords, h->blockSums, h->capMixed, h->mixedCells,
            h->cellStatus, h->cellSlot, h->ctl, h->near1, h->near2, h->near2List, h->capNear);
     h->epochBumps++;
+    if (h->zcDenseEarly) CK(cudaEventRecord(h->evFront, s));   // zero-copy host step: list and near sets are there
     // the streaming kernel of the coming advect() only needs alpha.oldTime, phi and the near2 bitmap: with the two-stream
     // schedule it may start from here (fork 1) or once the plane-positioning kernel has been issued (fork 2)
     if (h->overlap && h->forkAt == 1) CK(cudaEventRecord(h->evNear, s));
@@ -1265,7 +1275,10 @@ void doAdvect(svof_handle* h, double dt, const double* dSp, const double* dSu)
     //      on its own low-priority stream beside the interface kernels and is joined before k_near_finalize.
     if (!h->freshRecon) LAUNCH(h, k_ctl_reset_dense, 1, 1, h->ctl);  // advect() without a new reconstruct()
     if (h->overlap) {
-        if (h->inputsAfterNear || dSp || dSu || !h->freshRecon) {
+        if (h->zcDenseEarly) {
+            // zero-copy host step: phi was pulled on this very stream and U is not read here -- only the near sets are awaited
+            CK(cudaStreamWaitEvent(sD, h->evFront, 0));
+        } else if (h->inputsAfterNear || dSp || dSu || !h->freshRecon) {
             CK(cudaEventRecord(h->evInputs, sS));
             CK(cudaStreamWaitEvent(sD, h->evInputs, 0));
         } else {
@@ -1524,6 +1537,7 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         CK(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
         CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prHi));
         CK(cudaStreamCreateWithPriority(&h->streamD, cudaStreamNonBlocking, prLo));
+        CK(cudaStreamCreateWithPriority(&h->streamU, cudaStreamNonBlocking, prHi));
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
@@ -1595,6 +1609,10 @@ int svof_destroy(svof_handle* h)
     if (h->evDense) cudaEventDestroy(h->evDense);
     if (h->evInputs) cudaEventDestroy(h->evInputs);
     if (h->evCopy) cudaEventDestroy(h->evCopy);
+    if (h->evFront) cudaEventDestroy(h->evFront);
+    if (h->evU) cudaEventDestroy(h->evU);
+    if (h->evPush) cudaEventDestroy(h->evPush);
+    if (h->streamU) { cudaStreamSynchronize(h->streamU); cudaStreamDestroy(h->streamU); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->streamD) cudaStreamDestroy(h->streamD);
     delete h;
@@ -2245,15 +2263,35 @@ int stepHostZeroCopy(svof_handle* h, double dt, const double* phi, const double*
         h->h2dBytes += 8LL * h->nBF;
         alphaBC(h);
     }
+    // overlapped form: needs the two-stream schedule; isoRDF synchronises with the host inside reconstruct()
+    const int ovm = (h->overlap && h->prm.orientation_method != SVOF_ORIENT_ISO_RDF) ? h->zcOverlap : 0;
+    const bool ovU = ovm & 1, ovD = ovm & 2, ovP = ovm & 4;
+    cudaStream_t sU = h->streamU;
+    CK(cudaMemsetAsync(&h->ctl->nDeltaA, 0, 2 * sizeof(int), st));   // nDeltaA, nDeltaF: before anything that may push
+    h->zcDenseEarly = ovU || ovD;   // (the front event is recorded for either)
     EventPair& e0 = beginTimed(h, 0);
     doReconstruct(h);
     endTimed(h, e0);
     // U rows the interface-velocity interpolation reads: bitmap only (no list to overflow, nothing to read back)
-    CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), st));
-    CK(cudaMemsetAsync(&h->ctl->nUCells, 0, sizeof(int), st));
-    LAUNCH(h, k_mark_u_cells, sparseGrid(h, 256), 256, h->md, h->mixedCells, h->cellStatus, h->ctl, h->uBits, h->uList, 0);
-    LAUNCH(h, k_u_pull, cdiv(h->nC, 256), 256, h->uBits, h->nC, UD, h->U);
-    CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), st));   // leave the bitmap clean for the staged path
+    if (ovU) {
+        // ... marked from the interface-cell list (every interface cell: a superset of the cut ones) as soon as the front
+        // kernels are done, and pulled on a third stream while the normals and the plane positioning run
+        CK(cudaStreamWaitEvent(sU, h->evFront, 0));
+        CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), sU));
+        CK(cudaMemsetAsync(&h->ctl->nUCells, 0, sizeof(int), sU));
+        k_mark_u_cells<<<sparseGrid(h, 256), 256, 0, sU>>>(h->md, h->mixedCells, nullptr, h->ctl, h->uBits, h->uList, 0);
+        k_u_pull<<<cdiv(h->nC, 256), 256, 0, sU>>>(h->uBits, h->nC, UD, h->U);
+        h->launches += 2;
+        CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), sU));
+        CK(cudaEventRecord(h->evU, sU));
+        CK(cudaStreamWaitEvent(st, h->evU, 0));
+    } else {
+        CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), st));
+        CK(cudaMemsetAsync(&h->ctl->nUCells, 0, sizeof(int), st));
+        LAUNCH(h, k_mark_u_cells, sparseGrid(h, 256), 256, h->md, h->mixedCells, h->cellStatus, h->ctl, h->uBits, h->uList, 0);
+        LAUNCH(h, k_u_pull, cdiv(h->nC, 256), 256, h->uBits, h->nC, UD, h->U);
+        CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), st));   // leave the bitmap clean for the staged path
+    }
     h->haveU = true;
     h->uPartial = true;
     h->inputsAfterNear = true;
@@ -2262,21 +2300,43 @@ int stepHostZeroCopy(svof_handle* h, double dt, const double* phi, const double*
     CK(cudaMemsetAsync(&h->ctl->phiUnsafe, 0, sizeof(int), st));
     h->boundPhiBits = bitsCur;   // an out-of-bounds cell with a face outside the bitmap: k_bound_deps reads that entry from the caller's phi
     h->boundPhiHost = phiD;
+    h->zcDenseEarly = ovD;
     EventPair& e1 = beginTimed(h, 1);
     doAdvect(h, dt, nullptr, nullptr);
     endTimed(h, e1);
+    h->zcDenseEarly = false;
     h->boundPhiBits = nullptr;
     h->boundPhiHost = nullptr;
     // results
     const bool pushA = alpha_out && h->hostAlphaSynced == alpha_out;
-    CK(cudaMemsetAsync(&h->ctl->nDeltaA, 0, 2 * sizeof(int), st));
-    if (pushA) LAUNCH(h, k_alpha_push, cdiv(h->nC, 256), 256, h->alphaBuf[h->cur], h->alphaBuf[h->cur ^ 1], h->nC, alphaOutD, h->ctl);
-    else if (alpha_out) {
+    const double* aCur = h->alphaBuf[h->cur];
+    const double* aRef = h->alphaBuf[h->cur ^ 1];
+    if (ovP && (pushA || pushF)) {
+        // final after the streaming kernel: pushed on its stream while the interface chain is still at work ...
+        if (pushA) { k_alpha_push_early<<<cdiv(h->nC, 256), 256, 0, sD>>>(aCur, aRef, h->near2, h->nC, alphaOutD, h->ctl); h->launches++; }
+        if (pushF) {
+            k_alphaphi_push_early<<<cdiv(h->nF, 256), 256, 0, sD>>>(h->md, bitsCur, bitsPrev, h->near2, h->alphaPhi, alphaPhiOutD, h->nF, h->ctl);
+            h->launches++;
+        }
+        CK(cudaEventRecord(h->evPush, sD));
+        // ... final after k_near_finalize: the near2 cells and the faces they own, from the list
+        if (pushA) LAUNCH(h, k_alpha_push_late, sparseGrid(h, 128), 128, h->near2List, h->ctl, aCur, aRef, alphaOutD);
+        if (pushF) {
+            LAUNCH(h, k_alphaphi_push_late, sparseGrid(h, 128), 128, h->md, h->near2List, h->ctl, bitsCur, bitsPrev, h->alphaPhi, alphaPhiOutD);
+            CK(cudaStreamWaitEvent(st, h->evPush, 0));
+            LAUNCH(h, k_alphaphi_push_all, 4 * h->sms, 256, h->alphaPhi, alphaPhiOutD, h->nF, h->ctl);
+        } else {
+            CK(cudaStreamWaitEvent(st, h->evPush, 0));
+        }
+    } else {
+        if (pushA) LAUNCH(h, k_alpha_push, cdiv(h->nC, 256), 256, h->alphaBuf[h->cur], h->alphaBuf[h->cur ^ 1], h->nC, alphaOutD, h->ctl);
+        if (pushF) LAUNCH(h, k_alphaphi_push, cdiv(h->nF, 256), 256, bitsCur, bitsPrev, h->alphaPhi, alphaPhiOutD, h->nF, h->ctl);
+    }
+    if (!pushA && alpha_out) {
         CK(cudaMemcpyAsync(alpha_out, h->alphaBuf[h->cur], sizeof(double) * h->nC, cudaMemcpyDeviceToHost, st));
         h->d2hBytes += 8LL * h->nC;
     }
-    if (pushF) LAUNCH(h, k_alphaphi_push, cdiv(h->nF, 256), 256, bitsCur, bitsPrev, h->alphaPhi, alphaPhiOutD, h->nF, h->ctl);
-    else if (alpha_phi_out) {
+    if (!pushF && alpha_phi_out) {
         CK(cudaMemcpyAsync(alpha_phi_out, h->alphaPhi, sizeof(double) * h->nF, cudaMemcpyDeviceToHost, st));
         h->d2hBytes += 8LL * h->nF;
     }
@@ -2303,6 +2363,7 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     if (!h->haveAlpha) return fail(h, SVOF_ERR_STATE, "svof_step_host: alpha not set");
     API_BEGIN
     CK(cudaSetDevice(h->device));
+    h->zcDenseEarly = false;   // (a failed call may have left it set)
     cudaStream_t st = h->stream;
     // decomposed runs: the sparse-phi forms may redo a step on ONE rank (redoStepWithFullPhi), which would unpair the ranks'
     // NCCL ghost refreshes -- full flux field there
@@ -2705,6 +2766,7 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "dense_v4")) { h->denseV4 = value != 0 && h->dsliced.enabled; for (auto& g : h->graphs) g.sched = -1; return SVOF_OK; }
     if (!strcmp(name, "dense_v3")) { h->denseV3 = value != 0; for (auto& g : h->graphs) g.sched = -1; return SVOF_OK; }
     if (!strcmp(name, "zero_copy")) { h->zeroCopy = value != 0; return SVOF_OK; }
+    if (!strcmp(name, "zc_overlap")) { h->zcOverlap = value; return SVOF_OK; }
     if (!strcmp(name, "sparse_phi_exp")) {
         h->sparsePhiTol = value > 0 ? pow(10.0, -(double)value) : 0.0;
         h->phiBitsReady = false;

@@ -2502,7 +2502,9 @@ __global__ void k_mark_u_cells(MeshDev m, const int* mixedCells, const int* cell
 {
     const int n = ctl->nMixed;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (cellStatus[i] != 0) continue;
+        // cellStatus == nullptr: every interface cell (a superset of the cut ones) -- the zero-copy host step marks the rows
+        // before the plane positioning has run, so that the pull overlaps it
+        if (cellStatus && cellStatus[i] != 0) continue;
         const int c = mixedCells[i];
         for (int k = m.cellPtOff[c]; k < m.cellPtOff[c + 1]; ++k) {
             const int p = m.cellPts[k];
@@ -2638,6 +2640,85 @@ __global__ void k_alphaphi_push(const unsigned int* __restrict__ bitsCur, const 
         const int cnt = all ? 32 : __popc(cur | prev);
         if (cnt) atomicAdd(&ctl->nDeltaF, cnt);
     }
+}
+// ---- the same pushes split by WHEN a value is final.  A cell outside near2 and a face whose owner is outside near2 get their
+// final alpha / alphaPhi from the streaming kernel (snap/clip included), which runs beside the interface kernels: those values
+// ("early") cross PCIe on the streaming kernel's stream while the interface chain is still working.  near2 cells and the faces
+// they own are final after k_near_finalize ("late"): a list-driven kernel at the end of the step.
+__global__ void k_alpha_push_early(const double* __restrict__ cur, const double* __restrict__ ref, const unsigned int* __restrict__ near2,
+                                   int n, double* host, Ctl* ctl)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool changed = false;
+    if (i < n && !bitTest(near2, i)) {
+        const double v = cur[i];
+        changed = __double_as_longlong(v) != __double_as_longlong(ref[i]);
+        if (changed) host[i] = v;
+    }
+    const unsigned int mk = __ballot_sync(0xffffffffu, changed);
+    if ((threadIdx.x & 31) == 0 && mk) atomicAdd(&ctl->nDeltaA, __popc(mk));
+}
+__global__ void k_alpha_push_late(const int* __restrict__ near2List, Ctl* ctl, const double* __restrict__ cur,
+                                  const double* __restrict__ ref, double* host)
+{
+    const int n = ctl->nNear2;
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = near2List[i];
+        const double v = cur[c];
+        if (__double_as_longlong(v) != __double_as_longlong(ref[c])) {
+            host[c] = v;
+            cnt++;
+        }
+    }
+    if (cnt) atomicAdd(&ctl->nDeltaA, cnt);
+}
+__global__ void k_alphaphi_push_early(MeshDev m, const unsigned int* __restrict__ bitsCur, const unsigned int* __restrict__ bitsPrev,
+                                      const unsigned int* __restrict__ near2, const double* __restrict__ alphaPhi, double* host,
+                                      int nFaces, Ctl* ctl)
+{
+    const long long fl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool wrote = false;
+    if (fl < nFaces) {
+        const int w = (int)(fl >> 5);
+        const unsigned int bit = 1u << lane;
+        const unsigned int cur = bitsCur[w], prev = bitsPrev[w];
+        if (((cur | prev) & bit) && !bitTest(near2, __ldg(m.owner + fl))) {
+            host[fl] = (cur & bit) ? alphaPhi[fl] : 0.0;
+            wrote = true;
+        }
+    }
+    const unsigned int mk = __ballot_sync(0xffffffffu, wrote);
+    if (lane == 0 && mk) atomicAdd(&ctl->nDeltaF, __popc(mk));
+}
+__global__ void k_alphaphi_push_late(MeshDev m, const int* __restrict__ near2List, Ctl* ctl, const unsigned int* __restrict__ bitsCur,
+                                     const unsigned int* __restrict__ bitsPrev, const double* __restrict__ alphaPhi, double* host)
+{
+    const int n = ctl->nNear2;
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = near2List[i];
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int f = m.cellFaces[k];
+            if (m.owner[f] != c) continue;
+            const unsigned int bit = 1u << (f & 31);
+            const unsigned int cur = bitsCur[f >> 5], prev = bitsPrev[f >> 5];
+            if ((cur | prev) & bit) {
+                host[f] = (cur & bit) ? alphaPhi[f] : 0.0;
+                cnt++;
+            }
+        }
+    }
+    if (cnt) atomicAdd(&ctl->nDeltaF, cnt);
+}
+// a bounding correction landed on a face outside the bitmap (ctl->packUnsafe, rare): every face is written
+__global__ void k_alphaphi_push_all(const double* __restrict__ alphaPhi, double* host, int nFaces, Ctl* ctl)
+{
+    if (!ctl->packUnsafe) return;
+    for (long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x; f < nFaces; f += (long long)gridDim.x * blockDim.x)
+        host[f] = alphaPhi[f];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ctl->nDeltaF, nFaces);
 }
 // the reverse of k_phi_scatter: packed[k] = field[f] for the marked faces in face order (alphaPhi read-back: alphaPhi can only
 // be non-zero on a face whose upwind cell held liquid, i.e. on the faces the step's phi bitmap marks)

@@ -214,7 +214,8 @@ def test_step_host_matches_split_calls(oracle, product):
     assert s1.info(capi.I_GPU_LAUNCHES) > 0
 
 
-@pytest.mark.parametrize("pinned", [False, True], ids=["pageable caller buffers (staged)", "pinned caller buffers (zero copy)"])
+@pytest.mark.parametrize("pinned", [False, True, "serial"], ids=["pageable caller buffers (staged)", "pinned caller buffers (zero copy)",
+                                                              "pinned caller buffers (zero copy, zc_overlap 0)"])
 @pytest.mark.parametrize("case", ["sphere in an empty box", "half-filled box with inflow/outflow patches",
                                   "sphere in an empty box, Courant number 2", "sphere with negative slivers next to empty cells"])
 def test_step_host_sparse_phi_upload_is_bitwise_the_full_upload(product, case, pinned):
@@ -263,6 +264,8 @@ def test_step_host_sparse_phi_upload_is_bitwise_the_full_upload(product, case, p
     for s in (s1, s2, s3):
         s.setAlpha(a0)
     s3.setOption("sparse_phi", 0)
+    if pinned == "serial":   # the one-stream order of the pulls and pushes (the default overlaps them with the interface kernels)
+        s2.setOption("zc_overlap", 0)
     redone = False
     out2, aphi2, out3, aphi3 = np.empty(m.n_cells), np.empty(m.n_faces), np.empty(m.n_cells), np.empty(m.n_faces)
     if pinned:   # page-locked buffers: the kernels read phi / U and write alpha / alphaPhi in the caller's memory directly
