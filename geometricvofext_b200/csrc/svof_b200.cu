@@ -129,9 +129,13 @@ struct svof_handle {
     // zero-copy host step, overlapped form ("zc_overlap" option): U rows pulled on their own stream beside the normals / plane
     // positioning, the streaming kernel forked at the near sets, values that are final after it pushed on its stream
     cudaStream_t streamU = nullptr;
-    cudaEvent_t evFront = nullptr, evU = nullptr, evPush = nullptr;
-    int zcOverlap = 7;   // bit 0: U rows on their own stream, bit 1: streaming kernel forked at the near sets, bit 2: early pushes
+    cudaEvent_t evFront = nullptr, evU = nullptr, evPush = nullptr, evPhiNear = nullptr;
+    // bit 0: U rows on their own stream, bit 1: streaming kernel forked at the near sets (default: both); measured and NOT adopted:
+    // bit 2: early pushes on the streaming kernel's stream (+0.4 ms), bit 3: phi of all needBounding-cell faces pulled up front
+    // (profiles/r5e/r5f/r5g_e2e_ab_matrix.txt)
+    int zcOverlap = 3;
     bool zcDenseEarly = false;
+    int zcPushCtas = 2;   // resident CTAs per SM of the early push kernels ("zc_push_ctas")
     bool inputsAfterNear = false, freshRecon = false;
     std::map<std::string, double> hostAcc;  // profile: host wall time per phase of svof_step_host (ms)
     std::chrono::steady_clock::time_point hostT;
@@ -849,6 +853,7 @@ void allocFields(svof_handle* h)
     CK(cudaEventCreateWithFlags(&h->evFront, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evU, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evPush, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evPhiNear, cudaEventDisableTiming));
     h->events.resize(96);
     for (EventPair& e : h->events) {
         CK(cudaEventCreate(&e.a));
@@ -1612,6 +1617,7 @@ int svof_destroy(svof_handle* h)
     if (h->evFront) cudaEventDestroy(h->evFront);
     if (h->evU) cudaEventDestroy(h->evU);
     if (h->evPush) cudaEventDestroy(h->evPush);
+    if (h->evPhiNear) cudaEventDestroy(h->evPhiNear);
     if (h->streamU) { cudaStreamSynchronize(h->streamU); cudaStreamDestroy(h->streamU); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->streamD) cudaStreamDestroy(h->streamD);
@@ -2265,7 +2271,7 @@ int stepHostZeroCopy(svof_handle* h, double dt, const double* phi, const double*
     }
     // overlapped form: needs the two-stream schedule; isoRDF synchronises with the host inside reconstruct()
     const int ovm = (h->overlap && h->prm.orientation_method != SVOF_ORIENT_ISO_RDF) ? h->zcOverlap : 0;
-    const bool ovU = ovm & 1, ovD = ovm & 2, ovP = ovm & 4;
+    const bool ovU = ovm & 1, ovD = ovm & 2, ovP = ovm & 4, ovN = (ovm & 8) && (ovm & 1);
     cudaStream_t sU = h->streamU;
     CK(cudaMemsetAsync(&h->ctl->nDeltaA, 0, 2 * sizeof(int), st));   // nDeltaA, nDeltaF: before anything that may push
     h->zcDenseEarly = ovU || ovD;   // (the front event is recorded for either)
@@ -2285,6 +2291,13 @@ int stepHostZeroCopy(svof_handle* h, double dt, const double* phi, const double*
         CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), sU));
         CK(cudaEventRecord(h->evU, sU));
         CK(cudaStreamWaitEvent(st, h->evU, 0));
+        if (ovN) {   // phi on every face of the needBounding cells, once the bitmap kernel is done with the words
+            CK(cudaStreamWaitEvent(sU, h->evCopy, 0));
+            k_phi_pull_near<<<sparseGrid(h, 128), 128, 0, sU>>>(h->md, h->near2List, h->near1, h->ctl, phiD, h->phi, bitsCur);
+            h->launches++;
+            CK(cudaEventRecord(h->evPhiNear, sU));
+            CK(cudaStreamWaitEvent(st, h->evPhiNear, 0));
+        }
     } else {
         CK(cudaMemsetAsync(h->uBits, 0, sizeof(unsigned int) * (h->nWords + 1), st));
         CK(cudaMemsetAsync(&h->ctl->nUCells, 0, sizeof(int), st));
@@ -2313,9 +2326,10 @@ int stepHostZeroCopy(svof_handle* h, double dt, const double* phi, const double*
     const double* aRef = h->alphaBuf[h->cur ^ 1];
     if (ovP && (pushA || pushF)) {
         // final after the streaming kernel: pushed on its stream while the interface chain is still at work ...
-        if (pushA) { k_alpha_push_early<<<cdiv(h->nC, 256), 256, 0, sD>>>(aCur, aRef, h->near2, h->nC, alphaOutD, h->ctl); h->launches++; }
+        if (ovN) CK(cudaStreamWaitEvent(sD, h->evPhiNear, 0));   // the bitmap words are final
+        if (pushA) { k_alpha_push_early<<<h->zcPushCtas * h->sms, 256, 0, sD>>>(aCur, aRef, h->near2, h->nC, alphaOutD, h->ctl); h->launches++; }
         if (pushF) {
-            k_alphaphi_push_early<<<cdiv(h->nF, 256), 256, 0, sD>>>(h->md, bitsCur, bitsPrev, h->near2, h->alphaPhi, alphaPhiOutD, h->nF, h->ctl);
+            k_alphaphi_push_early<<<h->zcPushCtas * h->sms, 256, 0, sD>>>(h->md, bitsCur, bitsPrev, h->near2, h->alphaPhi, alphaPhiOutD, h->nF, h->ctl);
             h->launches++;
         }
         CK(cudaEventRecord(h->evPush, sD));
@@ -2767,6 +2781,7 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     if (!strcmp(name, "dense_v3")) { h->denseV3 = value != 0; for (auto& g : h->graphs) g.sched = -1; return SVOF_OK; }
     if (!strcmp(name, "zero_copy")) { h->zeroCopy = value != 0; return SVOF_OK; }
     if (!strcmp(name, "zc_overlap")) { h->zcOverlap = value; return SVOF_OK; }
+    if (!strcmp(name, "zc_push_ctas")) { h->zcPushCtas = value > 0 ? value : 2; return SVOF_OK; }
     if (!strcmp(name, "sparse_phi_exp")) {
         h->sparsePhiTol = value > 0 ? pow(10.0, -(double)value) : 0.0;
         h->phiBitsReady = false;

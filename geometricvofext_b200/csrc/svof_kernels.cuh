@@ -2600,6 +2600,28 @@ __global__ void k_phi_pull(MeshDev m, const double* __restrict__ alpha, double t
         if (w) atomicAdd(&ctl->nPhiPulled, __popc(w));
     }
 }
+// Every face of a needBounding cell (near1: the interface cells and their face neighbours), marked or not: the bounding of an
+// EMPTY near1 cell that went out of bounds reads phi on all its faces, and a PCIe read issued from inside the sweep would queue
+// behind the result pushes that share the link.  Entries that were not marked yet are pulled, stored and marked.
+__global__ void k_phi_pull_near(MeshDev m, const int* __restrict__ near2List, const unsigned int* __restrict__ near1, Ctl* ctl,
+                                const double* phiHost, double* phiDev, unsigned int* bits)
+{
+    const int n = ctl->nNear2;
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = near2List[i];
+        if (!bitTest(near1, c)) continue;
+        for (int k = m.cellOff[c]; k < m.cellOff[c + 1]; ++k) {
+            const int f = m.cellFaces[k];
+            const unsigned int bit = 1u << (f & 31);
+            if (__ldcg(bits + (f >> 5)) & bit) continue;
+            phiDev[f] = phiHost[f];   // both cells of a face may do this: same value
+            __threadfence();
+            if (!(atomicOr(bits + (f >> 5), bit) & bit)) cnt++;
+        }
+    }
+    if (cnt) atomicAdd(&ctl->nPhiPulled, cnt);
+}
 // rows of U next to cut cells (bitmap from k_mark_u_cells), straight from the caller's buffer
 __global__ void k_u_pull(const unsigned int* __restrict__ uBits, int nCells, const double* UHost, double* UDev)
 {
@@ -2648,15 +2670,23 @@ __global__ void k_alphaphi_push(const unsigned int* __restrict__ bitsCur, const 
 __global__ void k_alpha_push_early(const double* __restrict__ cur, const double* __restrict__ ref, const unsigned int* __restrict__ near2,
                                    int n, double* host, Ctl* ctl)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool changed = false;
-    if (i < n && !bitTest(near2, i)) {
-        const double v = cur[i];
-        changed = __double_as_longlong(v) != __double_as_longlong(ref[i]);
-        if (changed) host[i] = v;
+    // a small persistent grid (the launcher gives it a fraction of every SM): the interface kernels on the other stream must
+    // keep finding free CTA slots while these warps sit on PCIe back-pressure
+    const int lane = threadIdx.x & 31;
+    const long long nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nW = (n + 31) >> 5;
+    int cnt = 0;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nW; w += nWarps) {
+        const int i = (int)(w << 5) + lane;
+        bool changed = false;
+        if (i < n && !((near2[w] >> lane) & 1u)) {
+            const double v = cur[i];
+            changed = __double_as_longlong(v) != __double_as_longlong(ref[i]);
+            if (changed) host[i] = v;
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, changed));
     }
-    const unsigned int mk = __ballot_sync(0xffffffffu, changed);
-    if ((threadIdx.x & 31) == 0 && mk) atomicAdd(&ctl->nDeltaA, __popc(mk));
+    if (lane == 0 && cnt) atomicAdd(&ctl->nDeltaA, cnt);
 }
 __global__ void k_alpha_push_late(const int* __restrict__ near2List, Ctl* ctl, const double* __restrict__ cur,
                                   const double* __restrict__ ref, double* host)
@@ -2677,20 +2707,23 @@ __global__ void k_alphaphi_push_early(MeshDev m, const unsigned int* __restrict_
                                       const unsigned int* __restrict__ near2, const double* __restrict__ alphaPhi, double* host,
                                       int nFaces, Ctl* ctl)
 {
-    const long long fl = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    bool wrote = false;
-    if (fl < nFaces) {
-        const int w = (int)(fl >> 5);
-        const unsigned int bit = 1u << lane;
+    const long long nWarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int nW = (nFaces + 31) >> 5;
+    int cnt = 0;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nW; w += nWarps) {
         const unsigned int cur = bitsCur[w], prev = bitsPrev[w];
-        if (((cur | prev) & bit) && !bitTest(near2, __ldg(m.owner + fl))) {
+        if (!(cur | prev)) continue;   // warp-uniform
+        const long long fl = (w << 5) + lane;
+        const unsigned int bit = 1u << lane;
+        bool wrote = false;
+        if (fl < nFaces && ((cur | prev) & bit) && !bitTest(near2, __ldg(m.owner + fl))) {
             host[fl] = (cur & bit) ? alphaPhi[fl] : 0.0;
             wrote = true;
         }
+        cnt += __popc(__ballot_sync(0xffffffffu, wrote));
     }
-    const unsigned int mk = __ballot_sync(0xffffffffu, wrote);
-    if (lane == 0 && mk) atomicAdd(&ctl->nDeltaF, __popc(mk));
+    if (lane == 0 && cnt) atomicAdd(&ctl->nDeltaF, cnt);
 }
 __global__ void k_alphaphi_push_late(MeshDev m, const int* __restrict__ near2List, Ctl* ctl, const unsigned int* __restrict__ bitsCur,
                                      const unsigned int* __restrict__ bitsPrev, const double* __restrict__ alphaPhi, double* host)

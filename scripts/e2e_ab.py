@@ -18,7 +18,9 @@ a_out, ap_out = capi.pinned_array(lib, (s.nC,)), capi.pinned_array(lib, (s.nF,))
 Ub_h[:] = 0
 ref = None
 for mode in [int(x) for x in (sys.argv[3] if len(sys.argv) > 3 else '0,7,0,7').split(',')]:
-    s.setOption("zc_overlap", mode)
+    s.setOption("zc_overlap", mode % 100)
+    if mode >= 100:
+        s.setOption("zc_push_ctas", mode // 100)
     s.setAlpha(a0)
     ts = []
     for k in range(6 + calls):
