@@ -59,6 +59,28 @@ void solveVofEqu::readControls(svof_params& p) const
         }
         // SVOF_ERR_INVALID_ARG: a key of the same dictionary that belongs to someone else (solver tolerances ...)
     }
+#ifndef OPENFOAM_STUB_H
+    // orientationMethod alphaGrad evaluates fvc::grad(alpha1_, "grad(alpha1)") (reconstruction.C:78) with the CASE's
+    // gradient scheme: hand the fvSchemes entry over ("Gauss linear" | "Gauss pointLinear")
+    if (p.orientation_method == SVOF_ORIENT_ALPHA_GRAD)
+    {
+        ITstream& is = mesh_.gradScheme("grad(alpha1)");
+        std::string text;
+        while (!is.eof())
+        {
+            OStringStream os;
+            os << token(is);
+            if (os.str().empty()) break;
+            text += (text.empty() ? "" : " ") + os.str();
+        }
+        if (svof_params_set(&p, "gradSchemes", text.c_str()) != SVOF_OK)
+        {
+            FatalErrorInFunction
+                << "gradSchemes entry for grad(alpha1) is '" << text << "'; the device path has Gauss linear and Gauss pointLinear"
+                << abort(FatalError);
+        }
+    }
+#endif
 }
 
 //- polyBoundaryMesh + alpha boundary conditions -> svof_patch table

@@ -47,7 +47,7 @@ class SvofParams(C.Structure):
                 ("rdf_tol", C.c_double), ("rdf_rel_tol", C.c_double), ("n_alpha_bounds", C.c_int32),
                 ("clip", C.c_int32), ("orientation_method", C.c_int32), ("split_warped_face", C.c_int32),
                 ("map_alpha_field", C.c_int32), ("write_plic_fields", C.c_int32), ("rdf_iterations", C.c_int32),
-                ("mixed_cell_tol_set", C.c_int32)]
+                ("mixed_cell_tol_set", C.c_int32), ("alpha_grad_scheme", C.c_int32)]
 
 
 class SvofComm(C.Structure):

@@ -1258,7 +1258,7 @@ void doReconstruct(svof_handle* h)
     if (h->prm.orientation_method == SVOF_ORIENT_ISO_RDF)
         rdfNormals(h, alpha);
     else if (h->prm.orientation_method == SVOF_ORIENT_ALPHA_GRAD)
-        LAUNCH(h, k_alpha_grad_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->iN);
+        LAUNCH(h, k_alpha_grad_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->iN, h->prm.alpha_grad_scheme == 1);
     else
         LAUNCH(h, k_ls_normals, g128, 128, d, h->mixedCells, h->ctl, alpha, h->alphaBBuf[h->cb], h->sp, h->iN);
     GEO(h, plic, s, h->plicCtas, d, h->mixedCells, h->ctl, alpha, h->iN, h->sp.split, h->cellStatus, h->iD, h->iC, h->iS);
@@ -1473,6 +1473,7 @@ int svof_params_default(svof_params* p)
     p->rdf_rel_tol = 0.1;
     p->n_alpha_bounds = 10;
     p->clip = 1;
+    p->alpha_grad_scheme = 0;
     p->orientation_method = SVOF_ORIENT_ISO_ALPHA_GRAD;
     p->rdf_iterations = 5;
     return SVOF_OK;
@@ -1506,6 +1507,13 @@ int svof_params_set(svof_params* p, const char* key, const char* value)
         if (v == "alphaGrad") p->orientation_method = SVOF_ORIENT_ALPHA_GRAD;
         else if (v == "isoAlphaGrad" || v == "LS") p->orientation_method = SVOF_ORIENT_ISO_ALPHA_GRAD;
         else if (v == "isoRDF" || v == "RDF") p->orientation_method = SVOF_ORIENT_ISO_RDF;
+        else return SVOF_ERR_BAD_CONFIG;
+        return SVOF_OK;
+    }
+    if (k == "gradSchemes" || k == "grad(alpha1)" || k == "gradScheme") {
+        // the caller's fvSchemes entry for grad(alpha1), read by fvc::grad(alpha1_, "grad(alpha1)") (reconstruction.C:78)
+        if (v == "Gauss linear" || v == "linear") p->alpha_grad_scheme = 0;
+        else if (v == "Gauss pointLinear" || v == "pointLinear") p->alpha_grad_scheme = 1;
         else return SVOF_ERR_BAD_CONFIG;
         return SVOF_OK;
     }

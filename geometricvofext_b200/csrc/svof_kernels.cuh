@@ -683,11 +683,80 @@ __global__ void __launch_bounds__(128) k_rdf_residual(MeshDev m, const int* mixe
 }
 
 // A2, orientationMethod alphaGrad: reconstruction::calcInterfaceNFromRegAlphaGrad (reconstruction.C:74-82),
-// -fvc::grad(alpha1) with `Gauss linear` (OF, recalled: makeWeights, linear interpolate, GaussGrad::calcGrad).
+// volPointInterpolation::interpolate(alpha1) evaluated lazily at one point (OF, recalled; the scalar twin of pointU below)
+__device__ double pointAlpha(const MeshDev& m, int p, const double* __restrict__ alpha, const double* __restrict__ alphaB)
+{
+    const d3 pt = ld3(m.points, p);
+    double val = 0.0;
+    if (!m.isPatchPoint[p]) {
+        const int j0 = m.ptCellOff[p], j1 = m.ptCellOff[p + 1];
+        double sumW = 0.0;
+        for (int j = j0; j < j1; ++j) sumW += 1.0 / mag(pt - ld3(m.C, m.ptCells[j]));
+        for (int j = j0; j < j1; ++j) {
+            const int c = m.ptCells[j];
+            const double pw = (1.0 / mag(pt - ld3(m.C, c))) / sumW;
+            val += pw * alpha[c];
+        }
+        return val;
+    }
+    const int j0 = m.ptBFOff[p], j1 = m.ptBFOff[p + 1];
+    double sumW = 0.0;
+    for (int j = j0; j < j1; ++j) {
+        const int bf = m.ptBFaces[j];
+        if (m.bKind[bf] == 0) sumW += 1.0 / mag(pt - ld3(m.Cf, m.nIF + bf));
+    }
+    for (int j = j0; j < j1; ++j) {
+        const int bf = m.ptBFaces[j];
+        if (m.bKind[bf] != 0) continue;
+        const double pw = (1.0 / mag(pt - ld3(m.Cf, m.nIF + bf))) / sumW;
+        val += pw * alphaB[bf];
+    }
+    return val;
+}
+
+// surfaceInterpolation::weights() of internal face f (OF, recalled)
+__device__ __forceinline__ double linearWeight(const MeshDev& m, int f)
+{
+    const d3 Sf = ld3(m.Sf, f), Cf = ld3(m.Cf, f);
+    const double SfdOwn = fabs(dot(Sf, Cf - ld3(m.C, m.owner[f])));
+    const double SfdNei = fabs(dot(Sf, ld3(m.C, m.neighbour[f]) - Cf));
+    return (fabs(SfdOwn + SfdNei) > SV_ROOTVSMALL) ? SfdNei / (SfdOwn + SfdNei) : 0.5;
+}
+
+// pointLinear<scalar>::correction on internal face f (OF, recalled: pointLinear.C): the face value re-built from the
+// point-interpolated field over the triangles (pi, f[k], f[k-1]) about pi = a C_P + (1 - a) C_N; lin = linearInterpolate(vf)[f].
+// As published, a is mesh.weights() indexed by the OWNER CELL label; the quirk is kept (0.5 where that is no internal face).
+__device__ double pointLinearCorrection(const MeshDev& m, int f, double lin, const double* __restrict__ alpha,
+                                        const double* __restrict__ alphaB)
+{
+    const int P = m.owner[f], N = m.neighbour[f];
+    const double a = (P < m.nIF) ? linearWeight(m, P) : 0.5;
+    const d3 pi = a * ld3(m.C, P) + (1.0 - a) * ld3(m.C, N);
+    const int q0 = m.faceOff[f], nv = m.faceOff[f + 1] - q0;
+    const int pFirst = m.facePts[q0], pLast = m.facePts[q0 + nv - 1];
+    double at = mag(0.5 * cross(ld3(m.points, pFirst) - pi, ld3(m.points, pLast) - pi));
+    double sumAt = at;
+    double sumPsip = at * (1.0 / 3.0) * (lin + pointAlpha(m, pFirst, alpha, alphaB) + pointAlpha(m, pLast, alpha, alphaB));
+    int pPrev = pFirst;
+    double vPrev = pointAlpha(m, pFirst, alpha, alphaB);
+    for (int k = 1; k < nv; ++k) {
+        const int pk = m.facePts[q0 + k];
+        const double vk = pointAlpha(m, pk, alpha, alphaB);
+        at = mag(0.5 * cross(ld3(m.points, pk) - pi, ld3(m.points, pPrev) - pi));
+        sumAt += at;
+        sumPsip += at * (1.0 / 3.0) * (lin + vk + vPrev);
+        pPrev = pk;
+        vPrev = vk;
+    }
+    return sumPsip / sumAt - lin;
+}
+
+// -fvc::grad(alpha1) with `Gauss linear` or `Gauss pointLinear` (OF, recalled: makeWeights, linear interpolate [+ the
+// pointLinear correction], GaussGrad::calcGrad).
 // Thread per mixed cell over its ascending-face row: the order GaussGrad accumulates in (internal faces ascending,
 // then the patches).  Only mixed cells are evaluated (nothing on the path reads the others).
 __global__ void __launch_bounds__(128) k_alpha_grad_normals(MeshDev m, const int* mixedCells, Ctl* ctl, const double* __restrict__ alpha,
-                                                            const double* __restrict__ alphaB, double* iN)
+                                                            const double* __restrict__ alphaB, double* iN, int pointLinear)
 {
     const int n = ctl->nMixed;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -708,7 +777,8 @@ __global__ void __launch_bounds__(128) k_alpha_grad_normals(MeshDev m, const int
                 const double SfdOwn = fabs(dot(Sf, Cf - CP));
                 const double SfdNei = fabs(dot(Sf, CN - Cf));
                 const double w = (fabs(SfdOwn + SfdNei) > SV_ROOTVSMALL) ? SfdNei / (SfdOwn + SfdNei) : 0.5;
-                const double af = w * (aP - aN) + aN;
+                double af = w * (aP - aN) + aN;
+                if (pointLinear) af += pointLinearCorrection(m, f, af, alpha, alphaB);
                 const d3 t = Sf * af;
                 if (isNei) g -= t;
                 else g += t;

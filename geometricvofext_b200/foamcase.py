@@ -208,7 +208,33 @@ class FoamCase:
         d = self.fv_solution["solvers"].lookup(self.alpha_name)
         if d is None:
             raise foamfile.FoamFormatError("fvSolution: no solvers entry matches %s" % self.alpha_name)
-        return {k: v for k, v in d.items() if not isinstance(v, (dict, list, tuple))}
+        ctl = {k: v for k, v in d.items() if not isinstance(v, (dict, list, tuple))}
+        # orientationMethod alphaGrad evaluates fvc::grad(alpha1, "grad(alpha1)") (reconstruction.C:78) with the case's gradient
+        # scheme: system/fvSchemes gradSchemes { grad(alpha1) ...; } or its default entry
+        if str(ctl.get("orientationMethod", "")) == "alphaGrad":
+            sch = self.grad_alpha_scheme()
+            if sch:
+                ctl["gradSchemes"] = sch
+        return ctl
+
+    def grad_alpha_scheme(self):
+        """The gradSchemes entry that applies to grad(alpha1) ('Gauss linear', 'Gauss pointLinear', ...) or None."""
+        path = os.path.join(self.dir, "system", "fvSchemes")
+        if not os.path.isfile(path):
+            return None
+        g = foamfile.read_dict(path).get("gradSchemes")
+        if g is None:
+            return None
+        v = g.lookup("grad(alpha1)") if hasattr(g, "lookup") else g.get("grad(alpha1)")
+        if v is None:   # this reader splits `grad(alpha1) Gauss pointLinear;` into the keyword grad and the list (alpha1)
+            w = g.get("grad")
+            if isinstance(w, (list, tuple)) and len(w) > 1 and list(w[0]) == ["alpha1"]:
+                v = list(w[1:])
+        if v is None:
+            v = g.get("default")
+        if v is None or str(v) == "none":
+            return None
+        return " ".join(str(x) for x in v) if isinstance(v, (list, tuple)) else str(v)
 
     def has_poly_mesh(self):
         return os.path.isfile(os.path.join(self.dir, "constant", "polyMesh", "faces"))

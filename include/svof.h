@@ -122,6 +122,10 @@ typedef struct {
     int32_t write_plic_fields;  /* writePlicFields false */
     int32_t rdf_iterations;     /* iterations     5      (isoRDF only)     */
     int32_t mixed_cell_tol_set; /* internal: explicit mixedCellTol wins over surfCellTol */
+    int32_t alpha_grad_scheme;  /* orientationMethod alphaGrad only: the caller's fvSchemes gradSchemes entry for
+                                 * grad(alpha1) (reconstruction.C:78) -- 0 "Gauss linear" (default; every solver
+                                 * tutorial), 1 "Gauss pointLinear" (tutorials/test/plicVofOrientationFoam/NAG/system/
+                                 * fvSchemes:35).  svof_params_set key "gradSchemes" (or "grad(alpha1)"). */
 } svof_params;
 
 /* One handle <-> one rank <-> one GPU (one MPI rank of the reference).

@@ -244,10 +244,75 @@ struct Solver {
     //   surfaceInterpolation::makeWeights   w = |Sf.(C_N - Cf)| / (|Sf.(Cf - C_P)| + |Sf.(C_N - Cf)|)
     //   linear interpolate                  a_f = w*(a_P - a_N) + a_N ; boundary faces take the patch value
     //   GaussGrad::calcGrad                 faces ascending: grad[P] += Sf*a_f, grad[N] -= Sf*a_f; patches; then /V
+    // With `Gauss pointLinear` (tutorials/test/plicVofOrientationFoam/NAG/system/fvSchemes:35; prm.alpha_grad_scheme 1) the face
+    // value is linear + pointLinear::correction.
     // Only the mixed cells are evaluated: the reference fills every cell, but nothing on the path reads the others.
+    // surfaceInterpolation::weights() of internal face f (OF, recalled)
+    scalar linearWeight(label f) const
+    {
+        const label P = mesh.owner[f], N = mesh.neighbour[f];
+        const scalar SfdOwn = std::fabs(mesh.Sf[f] & (mesh.Cf[f] - mesh.C[P]));
+        const scalar SfdNei = std::fabs(mesh.Sf[f] & (mesh.C[N] - mesh.Cf[f]));
+        return (std::fabs(SfdOwn + SfdNei) > ROOTVSMALL) ? SfdNei / (SfdOwn + SfdNei) : 0.5;
+    }
+
+    // volPointInterpolation::interpolate(alpha1) evaluated lazily at one point (as pointU below)
+    scalar pointAlpha(label p) const
+    {
+        const point& pt = mesh.points[p];
+        if (!mesh.isPatchPoint[p]) {
+            const label n = mesh.pointCells.size(p);
+            const label* pc = mesh.pointCells.row(p);
+            scalar sumW = 0.0;
+            for (label k = 0; k < n; ++k) sumW += 1.0 / mag(pt - mesh.C[pc[k]]);
+            scalar val = 0.0;
+            for (label k = 0; k < n; ++k) {
+                const scalar pw = (1.0 / mag(pt - mesh.C[pc[k]])) / sumW;
+                val += pw * alpha[pc[k]];
+            }
+            return val;
+        }
+        const label n = mesh.pointBFaces.size(p);
+        const label* pf = mesh.pointBFaces.row(p);
+        scalar sumW = 0.0;
+        for (label k = 0; k < n; ++k)
+            if (mesh.isPatchFace[pf[k]]) sumW += 1.0 / mag(pt - mesh.Cf[mesh.nInternalFaces + pf[k]]);
+        scalar val = 0.0;
+        for (label k = 0; k < n; ++k) {
+            if (!mesh.isPatchFace[pf[k]]) continue;
+            const scalar pw = (1.0 / mag(pt - mesh.Cf[mesh.nInternalFaces + pf[k]])) / sumW;
+            val += pw * alphaB[pf[k]];
+        }
+        return val;
+    }
+
+    // pointLinear<scalar>::correction on internal face f (OF, recalled: pointLinear.C): the face value is re-built from the
+    // point-interpolated field over the triangles (pi, f[k], f[k-1]) about pi = a C_P + (1 - a) C_N; `lin` is
+    // linearInterpolate(vf)[f].  As published, a is mesh.weights() indexed by the OWNER CELL label (not by the face); the
+    // quirk is kept (a = 0.5 where that index is not an internal face).
+    scalar pointLinearCorrection(label f, scalar lin) const
+    {
+        const label P = mesh.owner[f], N = mesh.neighbour[f];
+        const scalar a = (P < mesh.nInternalFaces) ? linearWeight(P) : 0.5;
+        const point pi = a * mesh.C[P] + (1.0 - a) * mesh.C[N];
+        const label nv = mesh.faces.size(f);
+        const label* fp = mesh.faces.row(f);
+        auto triMag = [&](const point& b, const point& c) { return mag(0.5 * ((b - pi) ^ (c - pi))); };
+        scalar at = triMag(mesh.points[fp[0]], mesh.points[fp[nv - 1]]);
+        scalar sumAt = at;
+        scalar sumPsip = at * (1.0 / 3.0) * (lin + pointAlpha(fp[0]) + pointAlpha(fp[nv - 1]));
+        for (label k = 1; k < nv; ++k) {
+            at = triMag(mesh.points[fp[k]], mesh.points[fp[k - 1]]);
+            sumAt += at;
+            sumPsip += at * (1.0 / 3.0) * (lin + pointAlpha(fp[k]) + pointAlpha(fp[k - 1]));
+        }
+        return sumPsip / sumAt - lin;
+    }
+
     void calcInterfaceNFromRegAlphaGrad()
     {
         std::vector<label> fs;
+        const bool pointLinear = prm.alpha_grad_scheme == 1;
         for (size_t i = 0; i < mixedCells.size(); ++i) {
             const label celli = mixedCells[i];
             fs.assign(mesh.cells.row(celli), mesh.cells.row(celli) + mesh.cells.size(celli));
@@ -256,17 +321,16 @@ struct Solver {
             for (label f : fs) {
                 if (f < mesh.nInternalFaces) {
                     const label P = mesh.owner[f], N = mesh.neighbour[f];
-                    const scalar SfdOwn = std::fabs(mesh.Sf[f] & (mesh.Cf[f] - mesh.C[P]));
-                    const scalar SfdNei = std::fabs(mesh.Sf[f] & (mesh.C[N] - mesh.Cf[f]));
-                    const scalar w = (std::fabs(SfdOwn + SfdNei) > ROOTVSMALL) ? SfdNei / (SfdOwn + SfdNei) : 0.5;
-                    const scalar af = w * (alpha[P] - alpha[N]) + alpha[N];
+                    const scalar w = linearWeight(f);
+                    scalar af = w * (alpha[P] - alpha[N]) + alpha[N];
+                    if (pointLinear) af += pointLinearCorrection(f, af);   // surfaceInterpolationScheme::interpolate: tsf += correction
                     const vec Sfssf = mesh.Sf[f] * af;
                     if (celli == P) g += Sfssf;
                     else g -= Sfssf;
                 } else {
                     const label bf = f - mesh.nInternalFaces;
                     if (!mesh.isPatchFace[bf]) continue;  // empty patches have no faces in fvMesh
-                    g += mesh.Sf[f] * alphaB[bf];
+                    g += mesh.Sf[f] * alphaB[bf];          // (the correction is zero on uncoupled patches)
                 }
             }
             g /= mesh.V[celli];

@@ -44,6 +44,7 @@ std::ostringstream& stubInfoStream()
 StubFatalError FatalError;
 std::function<vector(const vector&, label)> stubInterpolateCellPoint;
 std::function<void(const fvMesh&, label, labelList&)> stubCpcStencil;
+int stubGradScheme = 0;
 dictionary& stubDynamicMeshDict()
 {
     static dictionary d;
@@ -285,6 +286,7 @@ void ref_solver_destroy(void* h) { delete static_cast<Ref*>(h); }
 static void bindHooks(Ref* r)
 {
     ora::Solver* Sp_ = &r->S;
+    stubGradScheme = r->S.prm.alpha_grad_scheme;
     stubInterpolateCellPoint = [Sp_](const vector& pos, label celli)
     {
         const ora::vec v = Sp_->interpolateU(ora::vec(pos.x(), pos.y(), pos.z()), celli);

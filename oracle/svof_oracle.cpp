@@ -57,6 +57,7 @@ int svof_params_default(svof_params* p)
     p->rdf_rel_tol = 0.1;       // :514
     p->n_alpha_bounds = 10;     // advection.C:455
     p->clip = 1;                // advection.C:457
+    p->alpha_grad_scheme = 0;
     p->orientation_method = SVOF_ORIENT_ISO_ALPHA_GRAD;  // reconstruction.C:507
     p->split_warped_face = 0;   // :504
     p->map_alpha_field = 0;     // :516
@@ -107,6 +108,13 @@ int svof_params_set(svof_params* p, const char* key, const char* value)
         if (v == "alphaGrad") p->orientation_method = SVOF_ORIENT_ALPHA_GRAD;
         else if (v == "isoAlphaGrad" || v == "LS") p->orientation_method = SVOF_ORIENT_ISO_ALPHA_GRAD;
         else if (v == "isoRDF" || v == "RDF") p->orientation_method = SVOF_ORIENT_ISO_RDF;
+        else return SVOF_ERR_BAD_CONFIG;
+        return SVOF_OK;
+    }
+    if (k == "gradSchemes" || k == "grad(alpha1)" || k == "gradScheme") {
+        // the caller's fvSchemes entry for grad(alpha1), read by fvc::grad(alpha1_, "grad(alpha1)") (reconstruction.C:78)
+        if (v == "Gauss linear" || v == "linear") p->alpha_grad_scheme = 0;
+        else if (v == "Gauss pointLinear" || v == "pointLinear") p->alpha_grad_scheme = 1;
         else return SVOF_ERR_BAD_CONFIG;
         return SVOF_OK;
     }

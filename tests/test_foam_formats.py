@@ -298,3 +298,28 @@ def test_cli_block_mesh_writes_a_readable_polymesh(tmp_path):
     assert np.array_equal(m.face_points, ref.face_points) and np.array_equal(m.points, ref.points)
     assert [p.name for p in m.patches] == ["top", "left", "back", "right", "bottom", "front"]
     assert set(m.meta["patch_types"].values()) == {"wall"}
+
+
+def test_case_gradient_scheme_reaches_the_alpha_grad_controls(tmp_path):
+    """orientationMethod alphaGrad runs fvc::grad(alpha1, "grad(alpha1)") with the CASE's scheme (reconstruction.C:78): the
+    fvSchemes entry of the NAG orientation test (tutorials/test/plicVofOrientationFoam/NAG/system/fvSchemes:32-36) must
+    arrive in the solver's controls; LS cases are left alone; `default` applies when grad(alpha1) has no entry of its own."""
+    case = make_case(str(tmp_path / "c"), n=8)
+    schemes = ('FoamFile { version 2.0; format ascii; class dictionary; location "system"; object fvSchemes; }\n'
+               "ddtSchemes { default Euler; }\n"
+               "gradSchemes\n{\n    default         none;\n    grad(alpha1)    Gauss pointLinear;\n}\n")
+    with open(os.path.join(case.dir, "system", "fvSchemes"), "w") as f:
+        f.write(schemes)
+    assert case.grad_alpha_scheme() == "Gauss pointLinear"
+    assert "gradSchemes" not in case.alpha_controls()          # orientationMethod LS in this fvSolution
+    case.fv_solution["solvers"].lookup(case.alpha_name)["orientationMethod"] = "alphaGrad"
+    ctl = case.alpha_controls()
+    assert ctl["gradSchemes"] == "Gauss pointLinear"
+    s = SolveVofEqu(case.mesh(), ctl, lib=oracle_lib())
+    assert s._params.orientation_method == 0 and s._params.alpha_grad_scheme == 1   # SVOF_ORIENT_ALPHA_GRAD, Gauss pointLinear
+    s.close()
+    with open(os.path.join(case.dir, "system", "fvSchemes"), "w") as f:
+        f.write(schemes.replace("default         none;", "default         Gauss linear;").replace("    grad(alpha1)    Gauss pointLinear;\n", ""))
+    assert foamcase.FoamCase(case.dir).grad_alpha_scheme() == "Gauss linear"
+    if os.path.isdir(REF_TUT):
+        assert foamcase.FoamCase(os.path.join(REF_TUT, "test/plicVofOrientationFoam/NAG")).alpha_controls()["gradSchemes"] == "Gauss pointLinear"

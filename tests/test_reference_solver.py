@@ -54,6 +54,14 @@ CASES = {
     "hexes, alphaGrad": lambda: (meshmod.hex_block(14), {"orientationMethod": "alphaGrad"}, None, fields.leveque_velocity, 5, 0.5),
     "warped hexes, alphaGrad": _poly(lambda: meshmod.perturb_points(meshmod.hex_block(10), 0.2, 3), {"orientationMethod": "alphaGrad"}, steps=4),
     "Kelvin cells, alphaGrad": _poly(lambda: meshmod.kelvin_mesh(6), {"orientationMethod": "alphaGrad"}, steps=3),
+    # ... with the NAG test's gradient scheme (Gauss pointLinear: OpenFOAM's, re-stated; the stand-in evaluates it over the whole
+    # field as pointLinear.C does, the implementations lazily per face: the same numbers)
+    "hexes, alphaGrad, Gauss pointLinear": lambda: (meshmod.hex_block(14), {"orientationMethod": "alphaGrad", "gradSchemes": "Gauss pointLinear"},
+                                                    None, fields.leveque_velocity, 5, 0.5),
+    "warped hexes, alphaGrad, Gauss pointLinear": _poly(lambda: meshmod.perturb_points(meshmod.hex_block(10), 0.2, 3),
+                                                        {"orientationMethod": "alphaGrad", "gradSchemes": "Gauss pointLinear"}, steps=4),
+    "Kelvin cells, alphaGrad, Gauss pointLinear": _poly(lambda: meshmod.kelvin_mesh(6),
+                                                        {"orientationMethod": "alphaGrad", "gradSchemes": "Gauss pointLinear"}, steps=3),
     "hexes, isoRDF": lambda: (meshmod.hex_block(16), {"orientationMethod": "isoRDF"}, None, fields.leveque_velocity, 5, 0.5),
     "warped hexes, isoRDF": _poly(lambda: meshmod.perturb_points(meshmod.hex_block(12), 0.2, 3), {"orientationMethod": "isoRDF"}, steps=4),
     "Kelvin cells, RDF, one iteration": _poly(lambda: meshmod.kelvin_mesh(7), {"orientationMethod": "RDF", "iterations": 1}, steps=3),
@@ -66,6 +74,10 @@ for _n in ("every cell cut", "no bounding sweeps", "Courant number 1.5", "2-D: e
 CASES["edge: 2-D, isoRDF"] = lambda: (lambda c: (c[0], {"orientationMethod": "isoRDF"}) + c[2:])(edge_case("2-D: empty front and back"))
 CASES["edge: inflow and outflow patches, alphaGrad"] = \
     lambda: (lambda c: (c[0], {"orientationMethod": "alphaGrad"}) + c[2:])(edge_case("inflow and outflow patches"))
+CASES["edge: inflow and outflow patches, alphaGrad, Gauss pointLinear"] = \
+    lambda: (lambda c: (c[0], {"orientationMethod": "alphaGrad", "gradSchemes": "Gauss pointLinear"}) + c[2:])(edge_case("inflow and outflow patches"))
+CASES["edge: 2-D, alphaGrad, Gauss pointLinear"] = \
+    lambda: (lambda c: (c[0], {"orientationMethod": "alphaGrad", "gradSchemes": "Gauss pointLinear"}) + c[2:])(edge_case("2-D: empty front and back"))
 
 
 def _check_against_reference(case, lib, what, sources=False):
