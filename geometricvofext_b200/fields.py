@@ -79,8 +79,10 @@ class AdvectionDriver:
     """
 
     def __init__(self, solver, velocity=leveque_velocity, period=6.0, max_co=0.5, max_alpha_co=0.5,
-                 max_delta_t=0.2, delta_t0=0.001, fixed_dt=None, write_interval=None, start_time=0.0):
+                 max_delta_t=0.2, delta_t0=0.001, fixed_dt=None, write_interval=None, start_time=0.0, reduce_max=None):
         self.s = solver
+        # decomposed runs: the Courant numbers are gMax over all ranks (CourantNo.H / alphaCourantNo.H reduce)
+        self.reduce_max = reduce_max or (lambda x: x)
         # writeControl adjustableRunTime: Time::adjustDeltaT spreads the time to the next write over equal steps
         self.write_interval, self.start_time, self.write_index, self.write_now = write_interval, start_time, 0, False
         self.period, self.max_co, self.max_alpha_co = period, max_co, max_alpha_co
@@ -113,9 +115,9 @@ class AdvectionDriver:
             return
         SMALL = 1e-15
         sp = self._sum_mag_phi()
-        co = 0.5 * np.max(sp / self.V) * self.dt
+        co = 0.5 * self.reduce_max(np.max(sp / self.V)) * self.dt
         mask = (alpha - 0.01 >= 0) & (0.99 - alpha >= 0)
-        aco = 0.5 * np.max(mask * sp / self.V) * self.dt
+        aco = 0.5 * self.reduce_max(np.max(mask * sp / self.V)) * self.dt
         f = min(self.max_co / (co + SMALL), self.max_alpha_co / (aco + SMALL))
         fact = min(min(f, 1.0 + 0.1 * f), 1.2)
         self.dt = min(fact * self.dt, self.max_delta_t)

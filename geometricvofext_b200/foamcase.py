@@ -393,6 +393,162 @@ def run_plic_vof_advection(case, lib=None, end_time=None, renumber=False, alpha0
     return out
 
 
+# ---- decomposed cases: processor*/ directories --------------------------------------------------------------------------
+def read_cell_proc_addressing(case, n_procs=None):
+    """cell -> rank map of a decomposed case from processor*/constant/polyMesh/cellProcAddressing (the file of processor r
+    lists, for each of its cells in local order, the cell's label in the undecomposed mesh)."""
+    case = case if isinstance(case, FoamCase) else FoamCase(case)
+    procs = sorted(int(d[len("processor"):]) for d in os.listdir(case.dir)
+                   if d.startswith("processor") and d[len("processor"):].isdigit())
+    if n_procs is not None:
+        procs = [r for r in procs if r < n_procs]
+    if not procs or procs != list(range(len(procs))):
+        raise foamfile.FoamFormatError("%s: processor directories %s are not 0..N-1" % (case.dir, procs))
+    addr = [foamfile.read_labels(os.path.join(case.dir, "processor%d" % r, "constant", "polyMesh", "cellProcAddressing")) for r in procs]
+    n = sum(len(a) for a in addr)
+    cell_rank = np.full(n, -1, np.int32)
+    for r, a in enumerate(addr):
+        cell_rank[a] = r
+    if (cell_rank < 0).any():
+        raise foamfile.FoamFormatError("cellProcAddressing files do not cover every cell exactly once")
+    return cell_rank, addr
+
+
+def decompose_case(case, n_procs, cell_rank=None, weights=None, lib=None, fmt=None):
+    """What this driver needs of `decomposePar`: processorR/constant/polyMesh/cellProcAddressing and processorR/0/alpha.water for
+    R = 0..n_procs-1.  The cell -> rank map is given (a scotch map read elsewhere) or comes from the library's weighted recursive
+    bisection (svof_partition_rcb).  The processor meshes themselves are not written: the device decomposition
+    (svof_decompose: ghost layers instead of processor patches) is cut from the undecomposed mesh by every rank."""
+    from . import multigpu as mg
+    case = case if isinstance(case, FoamCase) else FoamCase(case)
+    mesh = case.mesh()
+    if cell_rank is None:
+        cell_rank = mg.partition_rcb(mesh, n_procs, weights=weights, lib=lib)
+    cell_rank = np.asarray(cell_rank, np.int32)
+    alpha0, _ = case.read_alpha(mesh)
+    fmt = fmt or str(case.control_dict.get("writeFormat", "binary"))
+    for r in range(n_procs):
+        own = np.nonzero(cell_rank == r)[0].astype(np.int32)       # ascending, as decomposePar numbers a processor's cells
+        pdir = os.path.join(case.dir, "processor%d" % r)
+        foamfile.write_labels(os.path.join(pdir, "constant", "polyMesh", "cellProcAddressing"), own, "cellProcAddressing",
+                              "constant/polyMesh", fmt=fmt)
+        foamfile.write_field(os.path.join(pdir, "0", case.alpha_name), "volScalarField", case.alpha_name, alpha0[own], {},
+                             fmt=fmt, location="0")
+    return cell_rank
+
+
+class _RankSolver:
+    """The members fields.AdvectionDriver uses, on one rank of a decomposed run (multigpu.DecomposedSolveVofEqu)."""
+
+    def __init__(self, ds):
+        self.ds, self.s = ds, ds.s
+        self.mesh, self.nC, self.nF, self.nIF, self.nBF = ds.s.mesh, ds.s.nC, ds.s.nF, ds.s.nIF, ds.s.nBF
+
+    def field(self, which):
+        return self.s.field(which)
+
+    def alpha(self):
+        return self.s.alpha()
+
+    def setPhi(self, phi):
+        self.ds.setPhi(phi)
+
+    def setU(self, U, Ub=None):
+        self.ds.setU(U, Ub)
+
+    def reconstruct(self):
+        self.ds.reconstruct()
+
+    def advect(self, dt):
+        self.ds.advect(dt)
+
+
+def run_plic_vof_advection_decomposed(case, rank, world, lib=None, device=None, end_time=None, write=True, log=None):
+    """plicVofAdvectionFoam -parallel on a decomposed case, one call per rank (torch.distributed initialised by the caller:
+    gloo for the CPU engine, nccl on GPUs).  Rank r reads processor<r>/constant/polyMesh/cellProcAddressing and
+    processor<r>/0/alpha.water, cuts its part (owned cells + ghost layers) out of the undecomposed mesh, runs the time loop
+    with globally reduced Courant numbers and writes processor<r>/<time>/alpha.water for its own cells in processor order --
+    what reconstructPar reads."""
+    import torch
+    import torch.distributed as dist
+    from . import multigpu as mg
+    case = case if isinstance(case, FoamCase) else FoamCase(case)
+    log = log or (lambda *a: None)
+    cd = case.control_dict
+    mesh = case.mesh()
+    cell_rank, addr = read_cell_proc_addressing(case, world)
+    if len(addr) != world:
+        raise foamfile.FoamFormatError("%d processor directories for %d ranks" % (len(addr), world))
+    try:
+        case.read_alpha(mesh)            # the patch conditions come from the undecomposed 0/alpha.water
+    except FileNotFoundError:
+        pass
+    controls = case.alpha_controls()
+    sub, maps = mg.decompose(mesh, cell_rank, rank, mg.default_layers(controls))   # host utility of the product library
+    ds = mg.DecomposedSolveVofEqu(sub, maps, controls, rank, world, lib=lib, device=device)
+    pdir = os.path.join(case.dir, "processor%d" % rank)
+    f0 = foamfile.read_field(os.path.join(pdir, "0", case.alpha_name))
+    mine = np.asarray(addr[rank], np.int64)                     # processor-local order -> global label
+    a_proc = f0.internal_array(len(mine))
+    cell_global = np.asarray(maps["cell_global"], np.int64)
+    pos = np.searchsorted(cell_global, mine)                     # sub-mesh numbering preserves the global order
+    assert np.array_equal(cell_global[pos], mine), "cellProcAddressing does not match the rank's owned cells"
+    a_local = np.zeros(sub.n_cells)
+    a_local[pos] = a_proc
+    ds.setAlpha(a_local)
+    ds.exchange_alpha()                                          # ghost values from their owners
+
+    def gmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64)
+        if device is not None and dist.get_backend() == "nccl":
+            t = t.cuda(device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    rs = _RankSolver(ds)
+    adjust = str(cd.get("adjustTimeStep", "no")).lower() in ("yes", "true", "on", "1")
+    drv = fields.AdvectionDriver(
+        rs, period=float(controls.get("period", 0.0)), max_co=float(cd.get("maxCo", 1.0)),
+        max_alpha_co=float(cd.get("maxAlphaCo", 1.0)), max_delta_t=float(cd.get("maxDeltaT", 1e30)),
+        delta_t0=float(cd.get("deltaT", 1e-3)), fixed_dt=None if adjust else float(cd.get("deltaT", 1e-3)), reduce_max=gmax)
+    drv.t = drv.start_time = float(cd.get("startTime", 0.0))
+    t_end = float(end_time if end_time is not None else cd.get("endTime"))
+    w_int = float(cd.get("writeInterval", t_end))
+    if not (adjust and str(cd.get("writeControl", "adjustableRunTime")) == "adjustableRunTime"):
+        raise NotImplementedError("the decomposed driver follows writeControl adjustableRunTime with adjustTimeStep (the reference's cases)")
+    drv.write_interval = w_int
+    ds.reconstruct()
+    fmt = str(cd.get("writeFormat", "binary"))
+    written = []
+    while drv.running(t_end):
+        drv.step(end_time=t_end)
+        ds.s.synchronize()
+        if drv.write_now or not drv.running(t_end):
+            name = _time_name(drv.t)
+            vol = ds.volume()
+            if write:
+                foamfile.write_field(os.path.join(pdir, name, case.alpha_name), "volScalarField", case.alpha_name,
+                                     ds.s.alpha()[pos], {}, fmt=fmt, location=name)
+            written.append(name)
+            if rank == 0:
+                log("Time = %s  steps %d  Phase-1 volume = %.15g" % (name, drv.steps, vol))
+    out = {"steps": drv.steps, "end_time": drv.t, "written": written, "n_owned": len(mine), "volume": ds.volume()}
+    ds.close()
+    return out
+
+
+def reconstruct_par(case, time_name, n_procs=None):
+    """reconstructPar for alpha: the undecomposed field of <time> from processor*/<time>/alpha.water."""
+    case = case if isinstance(case, FoamCase) else FoamCase(case)
+    cell_rank, addr = read_cell_proc_addressing(case, n_procs)
+    out = np.empty(len(cell_rank))
+    for r, a in enumerate(addr):
+        f = foamfile.read_field(os.path.join(case.dir, "processor%d" % r, time_name, case.alpha_name))
+        out[a] = f.internal_array(len(a))
+    return out
+
+
 def calc_vof_advection_errors(case, exact_dir=None, exact_name=None, mesh=None, cell_volumes=None):
     """calcVofAdvectionErrors (updateErrors.H): per written time with an exact field,
     (time, E_v, alphaMin, 1-alphaMax, E_s).  The exact field is <time>/alpha.water.exact in the case, or
@@ -428,8 +584,40 @@ def main(argv=None):
     b = sub.add_parser("blockMesh", help="system/blockMeshDict -> constant/polyMesh")
     b.add_argument("case")
     b.add_argument("--renumber", action="store_true")
+    d = sub.add_parser("decompose", help="processor*/constant/polyMesh/cellProcAddressing + processor*/0/alpha.water (weighted bisection)")
+    d.add_argument("case")
+    d.add_argument("n", type=int)
+    pr = sub.add_parser("parallel", help="one rank of a decomposed case; launch with python -m torch.distributed.run --nproc-per-node N "
+                                        "-m geometricvofext_b200.foamcase parallel <case> (nccl on GPUs, gloo with --cpu-engine <oracle .so>)")
+    pr.add_argument("case")
+    pr.add_argument("--end-time", type=float, default=None)
+    pr.add_argument("--cpu-engine", default=None, help="path of a library exporting include/svof.h to run on the host (tests)")
     args = ap.parse_args(argv)
     case = FoamCase(args.case)
+    if args.cmd == "decompose":
+        if not case.has_poly_mesh():
+            foamfile.write_polymesh(case.mesh(), case.dir)
+        cr = decompose_case(case, args.n)
+        print("cells per processor:", np.bincount(cr, minlength=args.n).tolist())
+        return 0
+    if args.cmd == "parallel":
+        import torch.distributed as dist
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        if args.cpu_engine:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+            out = run_plic_vof_advection_decomposed(case, rank, world, lib=capi.load(args.cpu_engine), end_time=args.end_time,
+                                                    log=print)
+        else:
+            import torch
+            dev = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(dev)
+            dist.init_process_group("nccl", rank=rank, world_size=world)
+            out = run_plic_vof_advection_decomposed(case, rank, world, device=dev, end_time=args.end_time, log=print)
+        if rank == 0:
+            print("End: %d steps" % out["steps"])
+        dist.barrier()
+        dist.destroy_process_group()
+        return 0
     if args.cmd == "blockMesh":
         m = case.mesh(renumber=args.renumber)
         print(foamfile.write_polymesh(m, case.dir, fmt=str(case.control_dict.get("writeFormat", "binary"))))

@@ -466,6 +466,14 @@ def read_labels(path):
     return _as_array(lists[0], np.int64).astype(np.int32)
 
 
+def write_labels(path, labels, obj, location, fmt="binary", note=None):
+    """A labelList file (cellProcAddressing ...)."""
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(_header("labelList", obj, location, fmt, note))
+        f.write(_list_bytes(np.asarray(labels).astype(np.int32), fmt))
+
+
 def read_faces(path):
     """faces -> (offsets[nF+1], labels): ascii faceList `N ( 4(a b c d) ... )` or binary faceCompactList."""
     hdr, lists = parse_file(path, "label")

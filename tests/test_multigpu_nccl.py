@@ -98,3 +98,41 @@ def test_two_gpus_match_single_gpu(tmp_path, kind, n, steps):
         assert abs(d["v1"] - vref) <= 1e-13 * abs(vref)
     assert not np.isnan(got).any()
     assert np.abs(got - ref).max() <= 1e-12
+
+
+def _case_worker(rank, world, case_dir, port):
+    import torch
+    import torch.distributed as dist
+    from geometricvofext_b200 import foamcase
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    out = foamcase.run_plic_vof_advection_decomposed(case_dir, rank, world, device=rank)
+    np.savez(os.path.join(case_dir, "run_rank%d.npz" % rank), steps=out["steps"], written=np.array(out["written"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 CUDA devices")
+def test_two_gpus_run_a_decomposed_case_directory(tmp_path):
+    """processor*/ directories (cellProcAddressing, 0/alpha.water) on two GPUs with the library's NCCL ghost refresh: the
+    reconstructed field equals the single-GPU run of the same case directory."""
+    import torch.multiprocessing as mp
+    from common import fields
+    from geometricvofext_b200 import foamcase, foamfile
+    from test_foam_formats import make_case
+    case = make_case(str(tmp_path / "c"), n=24, end=0.01, wi=0.005)
+    mesh = case.mesh()
+    a0 = fields.sphere_alpha_quadrature(mesh)
+    case.write_alpha(mesh, "0", a0)
+    foamfile.write_polymesh(mesh, case.dir)
+    foamcase.decompose_case(case, 2, weights=1.0 + 50.0 * ((a0 > 0) & (a0 < 1)))
+    serial = foamcase.run_plic_vof_advection(case)
+    mp.spawn(_case_worker, args=(2, case.dir, 29950 + os.getpid() % 40), nprocs=2, join=True)
+    for r in range(2):
+        d = np.load(os.path.join(case.dir, "run_rank%d.npz" % r))
+        assert int(d["steps"]) == serial["steps"] and d["written"].tolist() == serial["written"]
+    for name in serial["written"]:
+        got = foamcase.reconstruct_par(case, name)
+        ref = foamfile.read_field(os.path.join(case.dir, name, case.alpha_name)).internal_array(mesh.n_cells)
+        assert np.abs(got - ref).max() <= 1e-12

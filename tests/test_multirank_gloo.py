@@ -169,3 +169,48 @@ def test_gloo_ranks_match_single_domain(tmp_path, kind, world, n, steps, layers)
     assert np.abs(got - ref).max() <= 1e-12, "decomposed run differs from single domain by %g" % np.abs(got - ref).max()
     if kind == "hex10":
         assert max_sweeps >= 2, "the case must exercise several bounding sweeps (got %d)" % max_sweeps
+
+
+# ---- a decomposed CASE DIRECTORY: processor*/ with cellProcAddressing, run the way plicVofAdvectionFoam -parallel runs -----------
+def _case_worker(rank, world, case_dir, port):
+    import torch.distributed as dist
+    from common import oracle_lib
+    from geometricvofext_b200 import foamcase
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    out = foamcase.run_plic_vof_advection_decomposed(case_dir, rank, world, lib=oracle_lib())
+    np.savez(os.path.join(case_dir, "run_rank%d.npz" % rank), steps=out["steps"], written=np.array(out["written"]), volume=out["volume"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_decomposed_case_directory_run_equals_the_serial_case_run(tmp_path, world):
+    """decomposePar's files (processorR/constant/polyMesh/cellProcAddressing, processorR/0/alpha.water) -> one process per
+    rank over gloo, adaptive time loop with globally reduced Courant numbers -> processorR/<time>/alpha.water ->
+    reconstructPar: the field equals the serial run of the same case (same steps, same write times, alpha <= 1e-12)."""
+    import torch.multiprocessing as mp
+    from common import fields, oracle_lib
+    from geometricvofext_b200 import foamcase, foamfile
+    from test_foam_formats import make_case
+    case = make_case(str(tmp_path / "c"), n=14, end=0.01, wi=0.005)
+    mesh = case.mesh()
+    a0 = fields.sphere_alpha_quadrature(mesh)
+    case.write_alpha(mesh, "0", a0)
+    foamfile.write_polymesh(mesh, case.dir)            # the undecomposed mesh every rank cuts its part from
+    # interface cells weigh more, as in the strong-scaling bench: the parts are not equal slabs
+    cell_rank = foamcase.decompose_case(case, world, weights=1.0 + 50.0 * ((a0 > 0) & (a0 < 1)))
+    assert sorted(np.unique(cell_rank).tolist()) == list(range(world))
+    cr2, addr = foamcase.read_cell_proc_addressing(case)
+    assert np.array_equal(cr2, cell_rank) and all(np.all(np.diff(a) > 0) for a in addr)
+    serial = foamcase.run_plic_vof_advection(case, lib=oracle_lib())
+    port = 29900 + (os.getpid() % 400) + world
+    mp.spawn(_case_worker, args=(world, case.dir, port), nprocs=world, join=True)
+    for r in range(world):
+        d = np.load(os.path.join(case.dir, "run_rank%d.npz" % r))
+        assert int(d["steps"]) == serial["steps"] and d["written"].tolist() == serial["written"]
+        assert abs(float(d["volume"]) - serial["volume"]) <= 1e-13 * abs(serial["volume"])
+    for name in serial["written"]:
+        got = foamcase.reconstruct_par(case, name)
+        ref = foamfile.read_field(os.path.join(case.dir, name, case.alpha_name)).internal_array(mesh.n_cells)
+        assert np.abs(got - ref).max() <= 1e-12, "time %s: decomposed case run differs from the serial one by %g" % (name, np.abs(got - ref).max())
+    assert np.abs(got - a0).max() > 1e-3          # the interface really moved
