@@ -150,6 +150,26 @@ def parity_block(s, m, a0, dt, ref, label):
     return out
 
 
+SCHED_SETTLE_STEPS = 24
+
+
+def settle_schedule(s, a_start, dt, args):
+    """svof_step_device picks its two-stream schedule at run time (streaming kernel forked at the near sets and uncapped, or
+    forked after plane positioning with 4 resident CTAs per SM): it measures 4 steps of each during the first 20 calls.  Those
+    calls are made here, untimed, from the same start field; the timed windows then start from that field again.
+    Returns None when the selection is off (an explicit --overlap)."""
+    if args.overlap >= 0 or args.no_sched_auto:
+        return None
+    s.setOption("sched_auto", 1)
+    s.setAlpha(a_start)
+    for _ in range(SCHED_SETTLE_STEPS):
+        s.step(dt)
+    s.synchronize()
+    v = int(s.info(capi.I_SCHEDULE))
+    return {"first_window": v, "meaning": "100*fork + resident streaming CTAs per SM (0 = uncapped); chosen by the library from 4 timed "
+                                          "steps of each schedule (svof_set_option sched_auto)"}
+
+
 def advance_on_device(s, U0, phi0, t_end, dt, torch):
     """plicVof.H loop with phi(t), U(t) refreshed on the device every step (updateU.H:59-69 scales the steady field)."""
     dev = torch.device("cuda", 0)
@@ -213,6 +233,7 @@ def run_ours(args):
     dense_ms = (s.info(capi.I_DENSE_KERNEL_MS) - d0) / max(1.0, s.info(capi.I_DENSE_KERNEL_LAUNCHES) - dn0)
     recon_s, adv_s = s.reconstructionTime(), s.advectionTime()
     s.setOption("overlap", 1 if args.overlap < 0 else args.overlap)   # the product's default schedule (two streams) from here on
+    sched_sel = settle_schedule(s, a0, dt, args)
     # ---- device-resident leg: inputs already in HBM, the call a user makes for that case (svof_step_device:
     #      reconstruct + advect replayed as one CUDA graph) ----
     s.setAlpha(a0)          # every leg runs the same steps of the same problem: from t = 0
@@ -295,6 +316,12 @@ def run_ours(args):
         del U1, phi1
         s.setPhi(phi)        # the timed window uses the same frozen flux field as the first one
         s.setU(U, Ub)
+        if sched_sel is not None:       # 4.5 times the interface cells of the first window: let the library measure again
+            s.setOption("sched_retune", 1)
+            for _ in range(SCHED_SETTLE_STEPS):
+                s.step(dt)
+            s.synchronize()
+            sched_sel["late_window"] = int(s.info(capi.I_SCHEDULE))
         a_late = s.alpha()
         for _ in range(2 + args.warmup):
             s.step(dt)
@@ -327,6 +354,7 @@ def run_ours(args):
                    "timing": "CUDA events on the handle's stream around %d steps" % args.steps,
                    "schedule": "svof_step_device: one CUDA-graph launch per step (%d kernels inside), streaming kernel on a second "
                                "stream beside the interface kernels" % (launches // max(1, args.steps)),
+                   "schedule_selected": sched_sel,
                    "ms_per_step_plain_launches": ms_plain.value / args.steps,
                    "reconstruct_ms": 1e3 * recon_s / (args.steps + args.warmup), "advect_ms": 1e3 * adv_s / (args.steps + args.warmup),
                    "setup_s": setup_s,
@@ -440,6 +468,7 @@ def run_workload(args):
     s.synchronize()
     dense_ms = (s.info(capi.I_DENSE_KERNEL_MS) - d0) / max(1.0, s.info(capi.I_DENSE_KERNEL_LAUNCHES) - dn0)
     s.setOption("overlap", 1 if args.overlap < 0 else args.overlap)
+    sched_sel = settle_schedule(s, a1, dt, args)
     s.setAlpha(a1)
     for _ in range(2 + args.warmup):
         s.step(dt)
@@ -493,7 +522,8 @@ def run_workload(args):
         "config": {"workload": desc, "cells": m.n_cells, "faces": m.n_faces, "dt": dt, "controls": ctl, "mixed_cells": n_mixed,
                    "near_cells": n_near, "develop_steps": args.develop_steps, "error_flags": err, "setup_s": setup_s,
                    "l2": "inputs larger than L2 (%.2f GB per step)" % (B / 1e9),
-                   "schedule": "svof_step_device: one CUDA-graph launch per step (%d kernels inside)" % (launches // max(1, args.steps))},
+                   "schedule": "svof_step_device: one CUDA-graph launch per step (%d kernels inside)" % (launches // max(1, args.steps)),
+                   "schedule_selected": sched_sel},
         "clocks": clk,
         "e2e": {"value": m.n_cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps},
@@ -636,6 +666,7 @@ def main():
     ap.add_argument("--mixed-weight", type=float, default=float(os.environ.get("SVOF_BENCH_MIXED_WEIGHT", "1000")),
                     help="partition weight of an interface cell relative to a bulk cell (strong scaling)")
     ap.add_argument("--overlap", type=int, default=-1, help="two-stream schedule (library option 'overlap'); -1: library default")
+    ap.add_argument("--no-sched-auto", action="store_true", help="keep the library's default schedule instead of its run-time selection")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

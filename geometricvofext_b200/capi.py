@@ -26,7 +26,7 @@ BC_ZERO_GRADIENT, BC_FIXED_VALUE, BC_INLET_OUTLET = 0, 1, 2
 (I_N_MIXED, I_MIN_ALPHA_BEFORE, I_MAX_ALPHA_M1_BEFORE, I_MIN_ALPHA_AFTER, I_MAX_ALPHA_M1_AFTER, I_N_BOUND_SWEEPS,
  I_RECONSTRUCTION_TIME, I_ADVECTION_TIME, I_ALPHA_MAPPING_TIME, I_VOLUME, I_GPU_LAUNCHES, I_FLATNESS_MIN,
  I_FLATNESS_MAX, I_FLATNESS_AVG, I_DEVICE_BYTES, I_ERROR_FLAGS, I_DENSE_KERNEL_MS, I_DENSE_KERNEL_LAUNCHES,
- I_N_NEAR, I_H2D_BYTES, I_D2H_BYTES, I_VOLUME_OWNED, I_HALO_BYTES, I_RDF_ITERATIONS) = range(24)
+ I_N_NEAR, I_H2D_BYTES, I_D2H_BYTES, I_VOLUME_OWNED, I_HALO_BYTES, I_RDF_ITERATIONS, I_SCHEDULE) = range(25)
 
 
 class SvofPatch(C.Structure):

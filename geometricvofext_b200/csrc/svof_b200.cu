@@ -267,8 +267,18 @@ struct svof_handle {
     long long launches = 0;
     // svof_step_device: one captured CUDA graph per (alpha buffer parity, patch-value buffer parity, mixed bitmap valid), valid for one dt
     struct StepGraph { cudaGraphExec_t exec = nullptr; double dt = 0; long long nLaunches = 0; int sched = -1; };
-    StepGraph graphs[8];
+    StepGraph graphs[16];   // [schedule slot of the run-time selection][buffer parities, bitmap valid]
     bool capturing = false;
+    // run-time schedule selection of svof_step_device ("sched_auto"): the default schedule (slot 0: streaming kernel forked at
+    // the near sets, uncapped) against slot 1 (forked after plane positioning, 4 resident CTAs per SM) -- which one wins
+    // depends on how the interface chain compares with the streaming pass (profiles/r4a, r4b, r4g: 1.10 vs 1.17 ms at 256^3
+    // LeVeque; the filled dam-break box prefers the uncapped kernel).  Both give bitwise the same results.
+    int tuneMode = 1, tunePhase = 0, tuneSlot = 0;
+    bool schedUser = false, retune = false;
+    long long tuneSteps = 0;
+    int fork0 = 1, dense0 = 0;          // slot 0 as configured
+    double tuneMs[2] = {0, 0};
+    cudaEvent_t evT[4] = {nullptr, nullptr, nullptr, nullptr};
     double reconTime = 0, advTime = 0, lastReconMs = 0, lastAdvMs = 0;
     double flatMin = 1, flatMax = 1, flatAvg = 1;
     std::vector<EventPair> events;
@@ -854,6 +864,7 @@ void allocFields(svof_handle* h)
     CK(cudaEventCreateWithFlags(&h->evU, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evPush, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->evPhiNear, cudaEventDisableTiming));
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&h->evT[i]));
     h->events.resize(96);
     for (EventPair& e : h->events) {
         CK(cudaEventCreate(&e.a));
@@ -1555,7 +1566,9 @@ int svof_create(const svof_mesh* mesh, const svof_params* params, const svof_com
         CK(cudaGetDeviceProperties(&prop, h->device));
         h->sms = prop.multiProcessorCount;
         h->overlap = getenv("SVOF_OVERLAP") ? atoi(getenv("SVOF_OVERLAP")) : 1;  // default on (round 2: 1.173 vs 1.206 ms/step at 256^3)
-        if (getenv("SVOF_FORK")) h->forkAt = atoi(getenv("SVOF_FORK"));
+        if (getenv("SVOF_FORK")) { h->forkAt = atoi(getenv("SVOF_FORK")); h->schedUser = true; }
+        if (getenv("SVOF_OVERLAP") || getenv("SVOF_DENSE_CTAS")) h->schedUser = true;
+        if (getenv("SVOF_SCHED_AUTO")) h->tuneMode = atoi(getenv("SVOF_SCHED_AUTO")) != 0;
         if (getenv("SVOF_BOUND_LANES")) h->boundLanes = atoi(getenv("SVOF_BOUND_LANES")) != 0;
         if (getenv("SVOF_UN0") && !strcmp(getenv("SVOF_UN0"), "group")) h->un0Group = true;   // measured 84 us against 77 us: opt-in
         if (getenv("SVOF_DENSE_CTAS")) h->denseCtas = atoi(getenv("SVOF_DENSE_CTAS"));
@@ -1626,6 +1639,7 @@ int svof_destroy(svof_handle* h)
     if (h->evU) cudaEventDestroy(h->evU);
     if (h->evPush) cudaEventDestroy(h->evPush);
     if (h->evPhiNear) cudaEventDestroy(h->evPhiNear);
+    for (int i = 0; i < 4; ++i) if (h->evT[i]) cudaEventDestroy(h->evT[i]);
     if (h->streamU) { cudaStreamSynchronize(h->streamU); cudaStreamDestroy(h->streamU); }
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->streamD) cudaStreamDestroy(h->streamD);
@@ -1951,6 +1965,48 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
     API_END(h)
 }
 
+namespace {
+void tuneUse(svof_handle* h, int slot)
+{
+    h->tuneSlot = slot;
+    h->forkAt = slot ? 2 : h->fork0;
+    h->denseCtas = slot ? 4 : h->dense0;
+}
+// called once per svof_step_device before the step is enqueued
+void tuneAdvance(svof_handle* h)
+{
+    if (!h->tuneMode || h->schedUser || h->halo.active || !h->overlap || h->useStaged || h->denseV3 || h->denseV4 || h->dfast.enabled) return;
+    cudaStream_t st = h->stream;
+    switch (h->tunePhase) {
+        case 0:   // slot 0 warming up (its graphs are captured during these steps)
+            if (h->tuneSteps == 0) { h->fork0 = h->forkAt; h->dense0 = h->denseCtas; tuneUse(h, 0); }
+            if (h->tuneSteps >= 6) { CK(cudaEventRecord(h->evT[0], st)); h->tunePhase = 1; h->tuneSteps = 0; }
+            break;
+        case 1:   // slot 0 timed
+            if (h->tuneSteps >= 4) { CK(cudaEventRecord(h->evT[1], st)); tuneUse(h, 1); h->tunePhase = 2; h->tuneSteps = 0; }
+            break;
+        case 2:   // slot 1 warming up
+            if (h->tuneSteps >= 6) { CK(cudaEventRecord(h->evT[2], st)); h->tunePhase = 3; h->tuneSteps = 0; }
+            break;
+        case 3:   // slot 1 timed, then the decision (the one host wait of the selection)
+            if (h->tuneSteps >= 4) {
+                CK(cudaEventRecord(h->evT[3], st));
+                CK(cudaEventSynchronize(h->evT[3]));
+                float a = 0, b = 0;
+                CK(cudaEventElapsedTime(&a, h->evT[0], h->evT[1]));
+                CK(cudaEventElapsedTime(&b, h->evT[2], h->evT[3]));
+                h->tuneMs[0] = a / 4.0; h->tuneMs[1] = b / 4.0;
+                tuneUse(h, (b < 0.98 * a) ? 1 : 0);   // the alternative has to win by 2 %
+                h->tunePhase = 4; h->tuneSteps = 0; h->retune = false;
+            }
+            break;
+        default:  // settled: measure again now and then (the interface grows and shrinks during a run), or on request
+            if (h->retune || h->tuneSteps >= 4096) { tuneUse(h, 0); h->tunePhase = 0; h->tuneSteps = 1; h->retune = false; }
+            break;
+    }
+}
+}  // namespace
+
 // reconstruct() + advect(dt) with device-resident inputs as ONE CUDA-graph launch.  The step is ~27 dependent launches,
 // most of them a few microseconds long; replaying a captured graph removes the per-launch gaps.  Every launch size is
 // host-known and every count lives on the device, so the captured graph is valid for any state of the fields; it is
@@ -1968,7 +2024,9 @@ int svof_step_device(svof_handle* h, double dt)
     }
     API_BEGIN
     CK(cudaSetDevice(h->device));
-    svof_handle::StepGraph& g = h->graphs[h->cur * 4 + h->cb * 2 + (h->bitsValid ? 1 : 0)];
+    tuneAdvance(h);
+    h->tuneSteps++;
+    svof_handle::StepGraph& g = h->graphs[h->tuneSlot * 8 + h->cur * 4 + h->cb * 2 + (h->bitsValid ? 1 : 0)];
     if (!g.exec || g.dt != dt || g.sched != schedKey(h)) {
         if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
         // run the first step of this kind with plain launches (warms every lazily initialised launcher), then capture
@@ -2719,6 +2777,12 @@ int svof_get_info(svof_handle* h, int which, double* out)
         }
         case SVOF_I_HALO_BYTES: *out = 8.0 * h->halo.cells.nRecv; return SVOF_OK;
         case SVOF_I_RDF_ITERATIONS: *out = (double)h->rdfIterations; return SVOF_OK;
+        case SVOF_I_SCHEDULE: {
+            const double v = 100.0 * h->forkAt + h->denseCtas;
+            const bool measuring = h->tuneMode && !h->schedUser && !h->halo.active && h->overlap && h->tunePhase < 4;
+            *out = measuring ? -v : v;
+            return SVOF_OK;
+        }
         case SVOF_I_GPU_LAUNCHES: *out = (double)h->launches; return SVOF_OK;
         case SVOF_I_FLATNESS_MIN: *out = h->flatMin; return SVOF_OK;
         case SVOF_I_FLATNESS_MAX: *out = h->flatMax; return SVOF_OK;
@@ -2775,13 +2839,20 @@ int svof_set_option(svof_handle* h, const char* name, int value)
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->streamD));
     CK(cudaStreamSynchronize(h->stream));
-    if (!strcmp(name, "overlap")) { h->overlap = value; return SVOF_OK; }
-    if (!strcmp(name, "fork")) { h->forkAt = value; return SVOF_OK; }
-    if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; return SVOF_OK; }
-    if (!strcmp(name, "dense_threads")) { h->denseThreads = value; return SVOF_OK; }
-    if (!strcmp(name, "dense_l2")) { h->denseL2 = value; return SVOF_OK; }
-    if (!strcmp(name, "dense_split")) { h->denseSplit = value; return SVOF_OK; }
-    if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; return SVOF_OK; }
+    // an explicit schedule option switches the run-time selection of svof_step_device off ("sched_auto 1" switches it back on)
+    if (!strcmp(name, "sched_auto")) {
+        h->tuneMode = value != 0; h->schedUser = false; h->tunePhase = 0; h->tuneSteps = 0;
+        if (h->tuneSlot) tuneUse(h, 0);
+        return SVOF_OK;
+    }
+    if (!strcmp(name, "sched_retune")) { h->retune = true; return SVOF_OK; }
+    if (!strcmp(name, "overlap")) { h->overlap = value; h->schedUser = true; return SVOF_OK; }
+    if (!strcmp(name, "fork")) { h->forkAt = value; h->schedUser = true; return SVOF_OK; }
+    if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; h->schedUser = true; return SVOF_OK; }
+    if (!strcmp(name, "dense_threads")) { h->denseThreads = value; h->schedUser = true; return SVOF_OK; }
+    if (!strcmp(name, "dense_l2")) { h->denseL2 = value; h->schedUser = true; return SVOF_OK; }
+    if (!strcmp(name, "dense_split")) { h->denseSplit = value; h->schedUser = true; return SVOF_OK; }
+    if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; h->schedUser = true; return SVOF_OK; }
     if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
     if (!strcmp(name, "bound_lanes")) { h->boundLanes = value != 0; for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }

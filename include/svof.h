@@ -255,6 +255,8 @@ typedef enum {
     SVOF_I_VOLUME_OWNED = 21,    /* sum(alpha*V) over the cells this rank owns (== VOLUME without ghosts) */
     SVOF_I_HALO_BYTES = 22,      /* bytes this rank receives per ghost refresh    */
     SVOF_I_RDF_ITERATIONS = 23,  /* isoRDF: iterations the last reconstruct ran (reconstruction.C:228-399) */
+    SVOF_I_SCHEDULE = 24,        /* svof_step_device: schedule in use, 100*fork + resident streaming CTAs per SM (0 = uncapped);
+                                  * negative while the run-time selection ("sched_auto") is still measuring */
     SVOF_I_COUNT_
 } svof_info;
 

@@ -398,6 +398,40 @@ def test_overlap_schedule_is_bitwise_identical(product):
         assert np.array_equal(a, b)
 
 
+def test_schedule_selection_of_the_graph_step_is_bitwise_neutral(product, oracle):
+    """svof_step_device measures its two schedules at run time (6 + 4 steps of the default, 6 + 4 of the alternative, then the
+    decision; `sched_retune` repeats it): every step on the way -- plain-launch capture steps, both schedules' graphs, the
+    switch back -- must equal the oracle bitwise, an explicit schedule option must switch the selection off, and the
+    result must be reported."""
+    m = meshmod.hex_block(24)
+    so, sg = SolveVofEqu(m, LEVEQUE_CONTROLS, lib=oracle), SolveVofEqu(m, LEVEQUE_CONTROLS, lib=product)
+    a0 = exact_sphere_alpha(m)
+    C, Cf, Sf = so.field(capi.F_C), so.field(capi.F_CF), so.field(capi.F_SF)
+    U0, phi0 = fields.leveque_velocity(C), fields.face_flux(Cf, Sf)
+    dt = 0.25 / 24
+    for s in (so, sg):
+        s.setAlpha(a0)
+        s.setPhi(phi0)
+        s.setU(U0)
+    seen = set()
+    for k in range(52):
+        if k == 26:
+            sg.setOption("sched_retune", 1)
+        if k == 48:
+            sg.setOption("fork", 2)          # explicit choice: selection off, schedule as given
+        so.reconstruct()
+        so.advect(dt)
+        sg.step(dt)
+        seen.add(int(sg.info(capi.I_SCHEDULE)))
+        assert np.array_equal(so.alpha(), sg.alpha()), "step %d (schedule %d)" % (k, int(sg.info(capi.I_SCHEDULE)))
+        assert np.array_equal(so.alphaPhi(), sg.alphaPhi()), "step %d" % k
+        if k in (24, 47):
+            assert int(sg.info(capi.I_SCHEDULE)) in (100, 204), "settled after 21 calls: %d" % int(sg.info(capi.I_SCHEDULE))
+    assert -100 in seen and -204 in seen, "both schedules were measured: %s" % sorted(seen)
+    assert int(sg.info(capi.I_SCHEDULE)) in (200, 204)
+    assert sg.info(capi.I_ERROR_FLAGS) == 0
+
+
 def test_graph_step_is_bitwise_the_two_calls(product):
     """svof_step_device (one CUDA-graph launch per step in the steady state) against reconstruct() + advect()."""
     m = meshmod.hex_block(32)
