@@ -2444,6 +2444,13 @@ int svof_step_host(svof_handle* h, double dt, const double* phi, const double* U
     API_BEGIN
     CK(cudaSetDevice(h->device));
     h->zcDenseEarly = false;   // (a failed call may have left it set)
+    // the run-time schedule selection belongs to svof_step_device: the host step keeps the schedule as configured
+    struct SchedGuard {
+        svof_handle* h; int f, d; bool on;
+        explicit SchedGuard(svof_handle* h_) : h(h_), f(h_->forkAt), d(h_->denseCtas), on(h_->tuneMode && !h_->schedUser && h_->tuneSlot != 0)
+        { if (on) { h->forkAt = h->fork0; h->denseCtas = h->dense0; } }
+        ~SchedGuard() { if (on) { h->forkAt = f; h->denseCtas = d; } }
+    } schedGuard(h);
     cudaStream_t st = h->stream;
     // decomposed runs: the sparse-phi forms may redo a step on ONE rank (redoStepWithFullPhi), which would unpair the ranks'
     // NCCL ghost refreshes -- full flux field there
