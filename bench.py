@@ -150,12 +150,12 @@ def parity_block(s, m, a0, dt, ref, label):
     return out
 
 
-SCHED_SETTLE_STEPS = 24
+SCHED_SETTLE_STEPS = 40
 
 
 def settle_schedule(s, a_start, dt, args):
     """svof_step_device picks its two-stream schedule at run time (streaming kernel forked at the near sets and uncapped, or
-    forked after plane positioning with 4 resident CTAs per SM): it measures 4 steps of each during the first 20 calls.  Those
+    forked after plane positioning with 4 resident CTAs per SM): it measures 12 steps of each during the first 36 calls.  Those
     calls are made here, untimed, from the same start field; the timed windows then start from that field again.
     Returns None when the selection is off (an explicit --overlap)."""
     if args.overlap >= 0 or args.no_sched_auto:
@@ -166,7 +166,7 @@ def settle_schedule(s, a_start, dt, args):
         s.step(dt)
     s.synchronize()
     v = int(s.info(capi.I_SCHEDULE))
-    return {"first_window": v, "meaning": "100*fork + resident streaming CTAs per SM (0 = uncapped); chosen by the library from 4 timed "
+    return {"first_window": v, "meaning": "100*fork + resident streaming CTAs per SM (0 = uncapped); chosen by the library from 12 timed "
                                           "steps of each schedule (svof_set_option sched_auto)"}
 
 

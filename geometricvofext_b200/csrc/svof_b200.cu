@@ -270,7 +270,7 @@ struct svof_handle {
     StepGraph graphs[16];   // [schedule slot of the run-time selection][buffer parities, bitmap valid]
     bool capturing = false;
     // run-time schedule selection of svof_step_device ("sched_auto"): the default schedule (slot 0: streaming kernel forked at
-    // the near sets, uncapped) against slot 1 (forked after plane positioning, 4 resident CTAs per SM) -- which one wins
+    // the near sets, uncapped) against slot 1 (forked after plane positioning, 4 resident CTAs per SM), 6 warm + 12 timed steps each -- which one wins
     // depends on how the interface chain compares with the streaming pass (profiles/r4a, r4b, r4g: 1.10 vs 1.17 ms at 256^3
     // LeVeque; the filled dam-break box prefers the uncapped kernel).  Both give bitwise the same results.
     int tuneMode = 1, tunePhase = 0, tuneSlot = 0;
@@ -1966,6 +1966,7 @@ int svof_advect(svof_handle* h, double dt, const double* Sp, const double* Su)
 }
 
 namespace {
+constexpr int kTuneTimed = 12;   // timed steps per schedule (4 were too few next to a clock sampler: profiles/r5k)
 void tuneUse(svof_handle* h, int slot)
 {
     h->tuneSlot = slot;
@@ -1983,20 +1984,23 @@ void tuneAdvance(svof_handle* h)
             if (h->tuneSteps >= 6) { CK(cudaEventRecord(h->evT[0], st)); h->tunePhase = 1; h->tuneSteps = 0; }
             break;
         case 1:   // slot 0 timed
-            if (h->tuneSteps >= 4) { CK(cudaEventRecord(h->evT[1], st)); tuneUse(h, 1); h->tunePhase = 2; h->tuneSteps = 0; }
+            if (h->tuneSteps >= kTuneTimed) { CK(cudaEventRecord(h->evT[1], st)); tuneUse(h, 1); h->tunePhase = 2; h->tuneSteps = 0; }
             break;
         case 2:   // slot 1 warming up
             if (h->tuneSteps >= 6) { CK(cudaEventRecord(h->evT[2], st)); h->tunePhase = 3; h->tuneSteps = 0; }
             break;
         case 3:   // slot 1 timed, then the decision (the one host wait of the selection)
-            if (h->tuneSteps >= 4) {
+            if (h->tuneSteps >= kTuneTimed) {
                 CK(cudaEventRecord(h->evT[3], st));
                 CK(cudaEventSynchronize(h->evT[3]));
                 float a = 0, b = 0;
                 CK(cudaEventElapsedTime(&a, h->evT[0], h->evT[1]));
                 CK(cudaEventElapsedTime(&b, h->evT[2], h->evT[3]));
-                h->tuneMs[0] = a / 4.0; h->tuneMs[1] = b / 4.0;
+                h->tuneMs[0] = a / kTuneTimed; h->tuneMs[1] = b / kTuneTimed;
                 tuneUse(h, (b < 0.98 * a) ? 1 : 0);   // the alternative has to win by 2 %
+                if (getenv("SVOF_SCHED_DEBUG"))
+                    fprintf(stderr, "[svof sched] default %.4f ms/step, alternative %.4f ms/step -> %s\n", h->tuneMs[0], h->tuneMs[1],
+                            h->tuneSlot ? "alternative" : "default");
                 h->tunePhase = 4; h->tuneSteps = 0; h->retune = false;
             }
             break;

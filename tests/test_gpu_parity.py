@@ -399,7 +399,7 @@ def test_overlap_schedule_is_bitwise_identical(product):
 
 
 def test_schedule_selection_of_the_graph_step_is_bitwise_neutral(product, oracle):
-    """svof_step_device measures its two schedules at run time (6 + 4 steps of the default, 6 + 4 of the alternative, then the
+    """svof_step_device measures its two schedules at run time (6 + 12 steps of the default, 6 + 12 of the alternative, then the
     decision; `sched_retune` repeats it): every step on the way -- plain-launch capture steps, both schedules' graphs, the
     switch back -- must equal the oracle bitwise, an explicit schedule option must switch the selection off, and the
     result must be reported."""
@@ -414,10 +414,10 @@ def test_schedule_selection_of_the_graph_step_is_bitwise_neutral(product, oracle
         s.setPhi(phi0)
         s.setU(U0)
     seen = set()
-    for k in range(52):
-        if k == 26:
+    for k in range(84):
+        if k == 42:
             sg.setOption("sched_retune", 1)
-        if k == 48:
+        if k == 80:
             sg.setOption("fork", 2)          # explicit choice: selection off, schedule as given
         so.reconstruct()
         so.advect(dt)
@@ -425,8 +425,8 @@ def test_schedule_selection_of_the_graph_step_is_bitwise_neutral(product, oracle
         seen.add(int(sg.info(capi.I_SCHEDULE)))
         assert np.array_equal(so.alpha(), sg.alpha()), "step %d (schedule %d)" % (k, int(sg.info(capi.I_SCHEDULE)))
         assert np.array_equal(so.alphaPhi(), sg.alphaPhi()), "step %d" % k
-        if k in (24, 47):
-            assert int(sg.info(capi.I_SCHEDULE)) in (100, 204), "settled after 21 calls: %d" % int(sg.info(capi.I_SCHEDULE))
+        if k in (40, 79):
+            assert int(sg.info(capi.I_SCHEDULE)) in (100, 204), "settled after 37 calls: %d" % int(sg.info(capi.I_SCHEDULE))
     assert -100 in seen and -204 in seen, "both schedules were measured: %s" % sorted(seen)
     assert int(sg.info(capi.I_SCHEDULE)) in (200, 204)
     assert sg.info(capi.I_ERROR_FLAGS) == 0
