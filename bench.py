@@ -316,13 +316,14 @@ def run_ours(args):
         del U1, phi1
         s.setPhi(phi)        # the timed window uses the same frozen flux field as the first one
         s.setU(U, Ub)
-        if sched_sel is not None:       # 4.5 times the interface cells of the first window: let the library measure again
-            s.setOption("sched_retune", 1)
+        a_late = s.alpha()
+        if sched_sel is not None:       # 4.5 times the interface cells of the first window: let the library measure again,
+            s.setOption("sched_retune", 1)   # then start the window from the same field (as settle_schedule does for the first one)
             for _ in range(SCHED_SETTLE_STEPS):
                 s.step(dt)
             s.synchronize()
             sched_sel["late_window"] = int(s.info(capi.I_SCHEDULE))
-        a_late = s.alpha()
+            s.setAlpha(a_late)
         for _ in range(2 + args.warmup):
             s.step(dt)
         s.synchronize()
