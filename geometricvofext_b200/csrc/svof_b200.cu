@@ -1973,6 +1973,12 @@ void tuneUse(svof_handle* h, int slot)
     h->forkAt = slot ? 2 : h->fork0;
     h->denseCtas = slot ? 4 : h->dense0;
 }
+// an explicit schedule option: the run-time selection steps aside and hands back the schedule as configured
+void schedByUser(svof_handle* h)
+{
+    if (!h->schedUser && h->tuneSlot != 0) tuneUse(h, 0);
+    h->schedUser = true;
+}
 // called once per svof_step_device before the step is enqueued
 void tuneAdvance(svof_handle* h)
 {
@@ -2857,13 +2863,13 @@ int svof_set_option(svof_handle* h, const char* name, int value)
         return SVOF_OK;
     }
     if (!strcmp(name, "sched_retune")) { h->retune = true; return SVOF_OK; }
-    if (!strcmp(name, "overlap")) { h->overlap = value; h->schedUser = true; return SVOF_OK; }
-    if (!strcmp(name, "fork")) { h->forkAt = value; h->schedUser = true; return SVOF_OK; }
-    if (!strcmp(name, "dense_ctas")) { h->denseCtas = value; h->schedUser = true; return SVOF_OK; }
-    if (!strcmp(name, "dense_threads")) { h->denseThreads = value; h->schedUser = true; return SVOF_OK; }
-    if (!strcmp(name, "dense_l2")) { h->denseL2 = value; h->schedUser = true; return SVOF_OK; }
-    if (!strcmp(name, "dense_split")) { h->denseSplit = value; h->schedUser = true; return SVOF_OK; }
-    if (!strcmp(name, "plic_ctas")) { h->plicCtas = value; h->schedUser = true; return SVOF_OK; }
+    if (!strcmp(name, "overlap")) { schedByUser(h); h->overlap = value; return SVOF_OK; }
+    if (!strcmp(name, "fork")) { schedByUser(h); h->forkAt = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_ctas")) { schedByUser(h); h->denseCtas = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_threads")) { schedByUser(h); h->denseThreads = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_l2")) { schedByUser(h); h->denseL2 = value; return SVOF_OK; }
+    if (!strcmp(name, "dense_split")) { schedByUser(h); h->denseSplit = value; return SVOF_OK; }
+    if (!strcmp(name, "plic_ctas")) { schedByUser(h); h->plicCtas = value; return SVOF_OK; }
     if (!strcmp(name, "un0_group")) { h->un0Group = value != 0; return SVOF_OK; }
     if (!strcmp(name, "bound_lanes")) { h->boundLanes = value != 0; for (auto& g : h->graphs) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; } return SVOF_OK; }
     if (!strcmp(name, "profile")) { h->prof = value != 0; return SVOF_OK; }
